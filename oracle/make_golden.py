@@ -1,0 +1,226 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) on CPU.
+
+Run in the build container only (the reference does not travel to the GPU box):
+
+    python oracle/make_golden.py            # writes tests/golden/
+
+Needs `oracle/ref_shim` (timm-0.4.5 / matplotlib import shim) ahead of /root/reference on sys.path.
+Weights and inputs come from `transformer4sed_b200.utils.synth` (seed -> tensors, independent of
+construction order) so the tests can rebuild bit-identical inputs without storing them; each fixture
+also stores input checksums so an RNG drift is detected rather than mis-read as a parity failure.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path[:0] = [os.path.join(HERE, "ref_shim"), "/root/reference", ROOT]
+warnings.filterwarnings("ignore")
+
+from src.models.passt.passt_feature_extraction import PasstFeatureExtractor  # noqa: E402
+from src.models.passt.passt_sed import PaSST_SED  # noqa: E402
+from src.models.transformer.mask import MlmModule  # noqa: E402
+from src.models.transformer.transformerXL import RelPositionMultiheadAttention  # noqa: E402
+
+from transformer4sed_b200.utils import synth  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+torch.set_num_threads(os.cpu_count())
+
+
+def f32(t):
+    return t.detach().float().cpu().numpy()
+
+
+def checksum(t):
+    t = t.detach().double().flatten()
+    return np.array([t.sum().item(), t.abs().sum().item(), t[::997].sum().item()], dtype=np.float64)
+
+
+def golden_frontend():
+    ext = PasstFeatureExtractor(n_mels=128, sr=32000, win_length=800, hopsize=320, n_fft=1024, htk=False, fmin=0.0,
+                                fmax=None, wav_norm=True, fmin_aug_range=10, fmax_aug_range=2000).eval()
+    out = {}
+    # (a) two 2 s clips, (b) one full 10 s clip, (c) ragged/edge lengths, (d) silence + DC + impulse
+    wav_a = synth.synth_wav(2, 64000, seed=11)
+    wav_b = synth.synth_wav(1, 320000, seed=12)
+    out["a_in_ck"], out["b_in_ck"] = checksum(wav_a), checksum(wav_b)
+    out["a_power"], out["a_logmel"] = f32(ext(wav_a)), f32(ext.normalize(ext(wav_a)))
+    out["b_logmel"] = f32(ext.normalize(ext(wav_b)))
+    for n in (1025, 1345, 3201, 32001):  # shortest reflect-paddable, non-multiples of hop
+        w = synth.synth_wav(1, n, seed=100 + n)
+        out[f"c{n}_in_ck"] = checksum(w)
+        out[f"c{n}_logmel"] = f32(ext.normalize(ext(w)))
+    w = torch.zeros(3, 16000)
+    w[1] += 0.25
+    w[2, 5000] = 1.0
+    out["d_logmel"] = f32(ext.normalize(ext(w)))
+    # train-mode mel-basis jitter: record the draws and the result (fmin=3, fmax=15000+1000-417)
+    import torchaudio
+    mb, _ = torchaudio.compliance.kaldi.get_mel_banks(128, 1024, 32000, 3.0, 15583.0, vtln_low=100.0, vtln_high=-500.,
+                                                      vtln_warp_factor=1.0)
+    out["jit_basis_rowsum"] = f32(mb.sum(1))
+    out["jit_basis_first_nz"] = (mb > 0).float().argmax(1).numpy().astype(np.int32)
+    np.savez_compressed(os.path.join(OUT, "frontend_passt.npz"), **out)
+    print("frontend_passt.npz", {k: v.shape for k, v in out.items()})
+
+
+def golden_frontend_16k():
+    import torchaudio.transforms as T
+    ms = T.MelSpectrogram(sample_rate=16000, n_fft=2048, win_length=2048, hop_length=256, f_min=0, f_max=8000, n_mels=128,
+                          window_fn=torch.hamming_window, wkwargs={"periodic": False}, power=1)
+    adb = T.AmplitudeToDB(stype="amplitude")
+    adb.amin = 1e-5
+    w = synth.synth_wav(2, 48000, seed=21)
+    np.savez_compressed(os.path.join(OUT, "frontend_dcase16k.npz"), in_ck=checksum(w),
+                        db=f32(adb(ms(w)).clamp(min=-50, max=80)))
+
+
+def build_ref(kw, seed):
+    net = PaSST_SED(load_pretrained_model=False, **kw)
+    sd = synth.synth_state_dict_like(net, seed)
+    net.load_state_dict(sd, strict=True)
+    return net, sd
+
+
+def grads_summary(net):
+    names, norms, heads = [], [], []
+    for n, p in sorted(net.named_parameters()):
+        if p.grad is None:
+            continue
+        g = p.grad.detach().double().flatten()
+        names.append(n)
+        norms.append(g.norm().item())
+        h = np.zeros(8)
+        h[: min(8, g.numel())] = g[:8].numpy()
+        heads.append(h)
+    return np.array(names), np.array(norms), np.stack(heads)
+
+
+def golden_model(tag, kw, seed, batch):
+    net, sd = build_ref(kw, seed)
+    net.eval()
+    ext = net.get_feature_extractor().eval()
+    wav = synth.synth_wav(batch, 320000, seed=seed + 1)
+    mel = ext.normalize(ext(wav))
+    labels = synth.synth_strong_labels(batch, 10, 1000, seed + 2)
+    weak_labels = (labels.sum(-1) > 0).float()
+    pad_mask = torch.zeros(batch, 1000, dtype=torch.bool)
+    pad_mask[-1, 900:] = True
+    hooks = {}
+    net.decoder.register_forward_hook(lambda m, i, o: hooks.__setitem__("decoder_out", o))
+    for p in net.parameters():
+        p.grad = None
+    bb = net.backbone(mel.unsqueeze(1))
+    with torch.no_grad():  # pad_mask path is eval-only upstream: the in-place fill breaks autograd (passt_sed.py:289-290)
+        s_pad, w_pad, _ = net(mel, temp_w=1, pad_mask=pad_mask)
+    strong, weak, other = net(mel, temp_w=1)
+    bce = torch.nn.BCELoss()
+    loss = bce(strong, labels) + 0.5 * bce(weak, weak_labels) + 2.0 * bce(other["at_out"], weak_labels)
+    loss.backward()
+    gn, gnorm, ghead = grads_summary(net)
+    s2, w2, _ = net(mel, temp_w=0.5)  # val kwargs temperature, no pad mask
+    out = dict(
+        wav_ck=checksum(wav), mel_ck=checksum(mel), sd_ck=checksum(torch.cat([v.flatten() for _, v in sorted(sd.items())])),
+        strong=f32(strong), weak=f32(weak), at_out=f32(other["at_out"]), loss=np.array(loss.item()),
+        strong_t05=f32(s2), weak_t05=f32(w2), strong_pad=f32(s_pad), weak_pad=f32(w_pad),
+        argmax=strong.argmax(dim=1).numpy().astype(np.int8),
+        layer_feat=f32(bb["layer10_out"].transpose(1, 2)[:, ::17, ::4]),
+        frame=f32(bb["frame"].transpose(1, 2)[:, ::17, ::4]),
+        frame_before_mask=f32(other["frame_before_mask"][:, ::8, ::4]),
+        decoder_out=f32(hooks["decoder_out"][:, ::8, ::4]),
+        grad_names=gn, grad_norms=gnorm, grad_heads=ghead,
+    )
+    np.savez_compressed(os.path.join(OUT, f"matsed_{tag}.npz"), **out)
+    print(f"matsed_{tag}.npz loss={loss.item():.6f}", "strong range", strong.min().item(), strong.max().item())
+
+
+def golden_mlm(tag, kw, seed, batch):
+    """MAT-SED pre-train forward (mlm=True): needs the synthetic PaSST checkpoint on disk."""
+    import tempfile
+    from src.models.passt.passt import PaSST
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "pretrained_model"))
+        os.chdir(d)
+        try:
+            bb = PaSST(u_patchout=0, s_patchout_t=0, s_patchout_f=0, img_size=(128, 998), patch_size=16, stride=10,
+                       in_chans=1, num_classes=527, embed_dim=kw.get("embed_dim", 768), depth=12, num_heads=12,
+                       mlp_ratio=4, qkv_bias=True, distilled=True)
+            torch.save(bb.state_dict(), "pretrained_model/passt-s-f128-p16-s10-ap.476-swa.pt")
+            net = PaSST_SED(load_pretrained_model=True, **kw)
+        finally:
+            os.chdir(cwd)
+    sd = synth.synth_state_dict_like(net, seed)
+    net.load_state_dict(sd, strict=True)
+    net.train()  # masking is train-time; all dropouts are 0, patchout 0
+    ext = net.get_feature_extractor().eval()
+    wav = synth.synth_wav(batch, 320000, seed=seed + 1)
+    mel = ext.normalize(ext(wav))
+    dec_in = {}
+    net.decoder.register_forward_pre_hook(lambda m, i: dec_in.__setitem__("x", i[0]))
+    torch.manual_seed(seed + 3)
+    pred, other = net(mel)
+    torch.manual_seed(seed + 3)
+    noise = torch.rand(batch, 100)  # the first draw inside block_mask (mask.py:96)
+    probs = torch.rand(batch * 1000)  # mask.py:71
+    m = other["mask_id_seq"]
+    n_rand = int((m.view(-1) & (probs >= 0.8) & (probs < 0.9)).sum())
+    rand_idx = torch.randint(0, batch * 1000, (n_rand,))  # mask.py:79
+    fbm = other["frame_before_mask"]
+    loss = torch.nn.MSELoss()(fbm[m], pred[m])
+    out = dict(wav_ck=checksum(wav), noise=f32(noise), probs=f32(probs), rand_idx=rand_idx.numpy().astype(np.int32),
+               decoder_in=f32(dec_in["x"][:, ::8, ::4]), mask=np.packbits(m.numpy()), masked_frac=np.array(m.float().mean().item()),
+               decoder_in_equals_input=np.array(bool(torch.equal(dec_in["x"], fbm))),
+               pred=f32(pred[:, ::8, ::4]), at_out=f32(other["at_out"]), loss=np.array(loss.item()))
+    np.savez_compressed(os.path.join(OUT, f"matsed_mlm_{tag}_b{batch}.npz"), **out)
+    print(f"matsed_mlm_{tag}.npz loss={loss.item():.6f} masked={m.float().mean().item():.3f} noop={out['decoder_in_equals_input']}")
+
+
+def golden_ops():
+    out = {}
+    # rel_shift identity vs as_strided (transformerXL.py:289-297)
+    att = RelPositionMultiheadAttention(embed_dim=48, num_heads=4)
+    x = torch.arange(2 * 4 * 7 * 13, dtype=torch.float32).reshape(2, 4, 7, 13)
+    out["rel_shift_in"], out["rel_shift_out"] = f32(x), f32(att.rel_shift(x))
+    # block_mask with the RNG draw recorded (mask.py:93-100)
+    mm = MlmModule(mask_rate=0.75, strategy="block", block_width=10, device="cpu")
+    torch.manual_seed(5)
+    mask = mm.block_mask(4, 1000, 10)
+    torch.manual_seed(5)
+    out["block_noise"], out["block_mask"] = f32(torch.rand(4, 100)), np.packbits(mask.numpy())
+    # one relative-position attention layer, small (T=50, D=48, H=4)
+    from src.models.transformer_decoder import TransformerXLDecoder
+    dec = TransformerXLDecoder(input_dim=48, seq_len=50, decoder_layer_num=2, num_heads=4)
+    sd = synth.synth_state_dict_like(dec, 9)
+    dec.load_state_dict(sd)
+    xin = synth.synth_tensor(9, "txl_in", (3, 50, 48))
+    out["txl_in_ck"], out["txl_out"] = checksum(xin), f32(dec.eval()(xin))
+    np.savez_compressed(os.path.join(OUT, "ops.npz"), **out)
+    print("ops.npz")
+
+
+if __name__ == "__main__":
+    os.makedirs(OUT, exist_ok=True)
+    small = dict(embed_dim=192, decoder_dim=192, decoder="transformerXL", decoder_layer_num=1, at_adapter=True,
+                 f_pool="mean_pool", mlm=False)
+    base = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_adapter=True, decoder="transformerXL",
+                decoder_layer_num=3, decoder_pos_emd_len=1000, mlm=False)  # config/mat-sed/base/finetune2.yaml:53-62
+    pre = dict(base, mlm=True, mlm_dict=dict(strategy="block", block_width=10, mask_rate=0.75, out_dim=768))  # pretrain.yaml:39-52
+    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "mlm"]
+    if "frontend" in which:
+        golden_frontend()
+        golden_frontend_16k()
+    if "ops" in which:
+        golden_ops()
+    if "small" in which:
+        golden_model("small", small, seed=3, batch=2)
+    if "base" in which:
+        golden_model("base", base, seed=4, batch=1)
+    if "mlm" in which:
+        golden_mlm("base", pre, seed=6, batch=2)  # B>1: upstream masking is a silent no-op
+        golden_mlm("base", pre, seed=6, batch=1)  # B=1: reshape is a view, masking applies

@@ -1,0 +1,241 @@
+"""Oracle: MAT-SED (`PaSST_SED`) forward as plain functions over a state dict (CPU, torch fp32/fp64).
+
+Test infrastructure only (see oracle/__init__.py).  Each function cites the reference lines it follows.
+State-dict keys are the reference's.  Autograd works through everything here, so the
+oracle also provides reference gradients.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def layer_norm(x, sd, prefix, eps):
+    return F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], eps)
+
+
+def linear(x, sd, prefix, bias=True):
+    return F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"] if bias else None)
+
+
+# ------------------------------------------------------------------------------------------------
+# PaSST backbone  (reference src/models/passt/passt.py)
+# ------------------------------------------------------------------------------------------------
+def patch_embed_tokens(mel, sd, p="backbone."):
+    """mel [B,128,T] -> tokens [B, 2+F*Tp, D]; patch conv (:302-315) + time/freq pos (:503-519) +
+    cls/dist tokens (:560-569).  Eval path: time pos-embed cropped from offset 0 (:511), or the
+    patch grid cropped to the table's 99 columns (:515)."""
+    x = F.conv2d(mel.unsqueeze(1), sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"], stride=10)
+    tpos = sd[p + "time_new_pos_embed"]
+    if x.shape[-1] < tpos.shape[-1]:
+        tpos = tpos[:, :, :, :x.shape[-1]]
+    else:
+        x = x[:, :, :, :tpos.shape[-1]]
+    x = x + tpos + sd[p + "freq_new_pos_embed"]
+    B, D, Fd, Td = x.shape
+    x = x.flatten(2).transpose(1, 2)
+    cls = sd[p + "cls_token"].expand(B, -1, -1) + sd[p + "new_pos_embed"][:, :1]
+    dist = sd[p + "dist_token"].expand(B, -1, -1) + sd[p + "new_pos_embed"][:, 1:]
+    return torch.cat((cls, dist, x), dim=1), Fd, Td
+
+
+def vit_attention(x, sd, p, num_heads):
+    """passt.py:330-344: fused qkv, scale hd^-1/2, softmax, proj."""
+    B, N, C = x.shape
+    hd = C // num_heads
+    qkv = linear(x, sd, p + "qkv").reshape(B, N, 3, num_heads, hd).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = ((q @ k.transpose(-2, -1)) * hd ** -0.5).softmax(dim=-1)
+    return linear((attn @ v).transpose(1, 2).reshape(B, N, C), sd, p + "proj")
+
+
+def vit_mlp(x, sd, p):
+    """passt.py:270-276 (exact-erf GELU)."""
+    return linear(F.gelu(linear(x, sd, p + "fc1")), sd, p + "fc2")
+
+
+def vit_block(x, sd, p, num_heads, eps=1e-6):
+    """passt.py:360-363: pre-norm residual block, LayerNorm eps 1e-6 (:410)."""
+    x = x + vit_attention(layer_norm(x, sd, p + "norm1", eps), sd, p + "attn.", num_heads)
+    x = x + vit_mlp(layer_norm(x, sd, p + "norm2", eps), sd, p + "mlp.")
+    return x
+
+
+def passt_backbone(mel, sd, depth=12, num_heads=12, feature_layer=10, p="backbone."):
+    """passt.py:492-583.  Returns (layer{feature_layer}_out [B,N,D], final-norm tokens [B,N,D], F, T')."""
+    x, Fd, Td = patch_embed_tokens(mel, sd, p)
+    feat = None
+    for k in range(depth):
+        x = vit_block(x, sd, f"{p}blocks.{k}.", num_heads)
+        if k + 1 == feature_layer:
+            feat = x
+    return feat, layer_norm(x, sd, p + "norm", 1e-6), Fd, Td
+
+
+# ------------------------------------------------------------------------------------------------
+# Frame sequence  (reference src/models/passt/passt_sed.py:199-218, 258-259, 23-34)
+# ------------------------------------------------------------------------------------------------
+def mha_pool(x, sd, p, num_heads):
+    """pooling.py:37-51 AttentionPooling: one learned query over keys x [B',K,C] via nn.MultiheadAttention."""
+    Bp, K, C = x.shape
+    hd = C // num_heads
+    w, b = sd[p + "frequency_att.in_proj_weight"], sd[p + "frequency_att.in_proj_bias"]
+    q = F.linear(sd[p + "f_att_token"].reshape(1, C), w[:C], b[:C])  # batch independent
+    k = F.linear(x, w[C:2 * C], b[C:2 * C]).reshape(Bp, K, num_heads, hd).transpose(1, 2)
+    v = F.linear(x, w[2 * C:], b[2 * C:]).reshape(Bp, K, num_heads, hd).transpose(1, 2)
+    q = q.reshape(1, num_heads, 1, hd)
+    attn = ((q * hd ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1)  # [B',H,1,K]
+    o = (attn @ v).transpose(1, 2).reshape(Bp, C)
+    return F.linear(o, sd[p + "frequency_att.out_proj.weight"], sd[p + "frequency_att.out_proj.bias"])
+
+
+def f_pool(feat, sd, Fd, Td, mode="mean_pool"):
+    """passt_sed.py:199-218: drop cls/dist, out_norm (eps 1e-5), pool over the F patch rows."""
+    x = layer_norm(feat[:, 2:], sd, "out_norm", 1e-5)
+    B, _, C = x.shape
+    x = x.reshape(B, Fd, Td, C)
+    if mode == "mean_pool":
+        return x.mean(dim=1)
+    if mode == "attention":
+        return mha_pool(x.transpose(1, 2).reshape(B * Td, Fd, C), sd, "f_pool_module.", 6).reshape(B, Td, C)
+    raise NotImplementedError(mode)
+
+
+def pad_interpolate(x, ratio=10):
+    """passt_sed.py:258-259 + InterpolateModule (:23-34): repeat last frame, F.interpolate(linear,
+    align_corners=False) x ratio."""
+    x = torch.cat((x, x[:, -1:, :]), dim=1)
+    if ratio == 1:
+        return x
+    return F.interpolate(x.transpose(1, 2), scale_factor=ratio, mode="linear").transpose(1, 2)
+
+
+# ------------------------------------------------------------------------------------------------
+# TransformerXL context network  (reference src/models/transformer/transformerXL.py,
+# src/models/transformer_decoder.py:74-122)
+# ------------------------------------------------------------------------------------------------
+def rel_pos_table(T, d_model, dtype=torch.float32):
+    """transformerXL.py:68-101,120-126: rows k=0..2T-2 hold relative position T-1-k
+    (sin on even, cos on odd channels)."""
+    rel = torch.arange(T - 1, -T, -1, dtype=torch.float32).unsqueeze(1)
+    div = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float32) * -(math.log(10000.0) / d_model))
+    pe = torch.zeros(2 * T - 1, d_model)
+    pe[:, 0::2] = torch.sin(rel * div)
+    pe[:, 1::2] = torch.cos(rel * div)
+    return pe.to(dtype)
+
+
+def rel_shift(bd):
+    """transformerXL.py:254-297: out[..., i, j] = bd[..., i, T-1-i+j]."""
+    T = bd.shape[-2]
+    idx = (T - 1 - torch.arange(T).unsqueeze(1)) + torch.arange(T).unsqueeze(0)
+    return bd.gather(-1, idx.expand(bd.shape[:-2] + (T, T)))
+
+
+def relpos_attention(x, pos, sd, p, num_heads):
+    """transformerXL.py:299-593 with query=key=value=x [B,T,C] (we keep batch-major; the reference's
+    (T,B,C) permutes are layout only).  score = ((q+u)k^T + shift((q+v)p^T)) * hd^-1/2."""
+    B, T, C = x.shape
+    hd = C // num_heads
+    q, k, v = linear(x, sd, p + "in_proj").chunk(3, dim=-1)
+    q = q.reshape(B, T, num_heads, hd)
+    k = k.reshape(B, T, num_heads, hd).permute(0, 2, 3, 1)
+    v = v.reshape(B, T, num_heads, hd).transpose(1, 2)
+    pp = F.linear(pos, sd[p + "linear_pos.weight"]).reshape(-1, num_heads, hd).permute(1, 2, 0)  # [H,hd,2T-1]
+    qu = (q + sd[p + "pos_bias_u"]).transpose(1, 2)
+    qv = (q + sd[p + "pos_bias_v"]).transpose(1, 2)
+    ac = qu @ k
+    bd = rel_shift(qv @ pp)
+    attn = ((ac + bd) * hd ** -0.5).softmax(dim=-1)
+    o = (attn @ v).transpose(1, 2).reshape(B, T, C)
+    return linear(o, sd, p + "out_proj")
+
+
+def txl_block(x, pos, sd, p, num_heads):
+    """transformerXL.py:31-35: residual taken from the NORMALISED input; timm Mlp ratio 1."""
+    x = layer_norm(x, sd, p + "norm1", 1e-5)
+    x = x + relpos_attention(x, pos, sd, p + "attn.", num_heads)
+    x = x + vit_mlp(layer_norm(x, sd, p + "norm2", 1e-5), sd, p + "mlp.")
+    return x
+
+
+def txl_decoder(x, sd, n_layers, num_heads=12, p="decoder."):
+    """transformer_decoder.py:110-122 + RelPositionalEncoding.forward (transformerXL.py:104-127)."""
+    B, T, C = x.shape
+    pos = rel_pos_table(T, C, x.dtype)
+    x = x * math.sqrt(C)
+    for i in range(n_layers):
+        x = txl_block(x, pos, sd, f"{p}encoder_blocks.{i}.", num_heads)
+    return x
+
+
+# ------------------------------------------------------------------------------------------------
+# Heads and losses
+# ------------------------------------------------------------------------------------------------
+def sed_head(x, sd, temp_w=1.0, pad_mask=None):
+    """passt_sed.py:285-296: classifier, sigmoid(x/temp), zero padded frames, linear-softmax pool."""
+    p = torch.sigmoid(linear(x, sd, "classifier") / temp_w)
+    if pad_mask is not None:
+        p = p.masked_fill(pad_mask.unsqueeze(-1) if pad_mask.dim() == 2 else pad_mask, 0.0)
+    weak = torch.clamp((p * p).sum(dim=1) / p.sum(dim=1), 1e-7, 1.0)
+    return p.transpose(1, 2), weak
+
+
+def at_branch(frame, sd):
+    """passt_sed.py:236-240,276-278: AttentionPooling(12 heads) over final-norm patch tokens -> Linear -> sigmoid."""
+    emb = mha_pool(frame[:, 2:], sd, "at_adpater.0.", 12)
+    return torch.sigmoid(F.linear(emb, sd["at_adpater.1.weight"], sd["at_adpater.1.bias"]))
+
+
+def mlm_head(x, sd):
+    """passt_sed.py:194-196: Linear-GELU-Linear."""
+    return linear(F.gelu(linear(x, sd, "mlm_mlp.0")), sd, "mlm_mlp.2")
+
+
+def block_mask_from_noise(noise, mask_rate, block_width, seq_len):
+    """mask.py:93-100 with the `torch.rand` draw injected: threshold at sorted-noise index int(n*rate)."""
+    n_seg = noise.shape[1]
+    thr = noise.sort()[0][:, min(int(n_seg * mask_rate), n_seg - 1)]
+    m = torch.zeros(noise.shape[0], seq_len, dtype=torch.bool)
+    m[:, :n_seg * block_width] = (noise <= thr.unsqueeze(-1)).repeat_interleave(block_width, dim=1)
+    return m
+
+
+def apply_mask(x, mask_id, probs, rand_idx, mask_token, style=(0.8, 0.1, 0.1), strict_upstream=False):
+    """mask.py:62-83 with RNG draws injected.  strict_upstream=True reproduces the upstream no-op for
+    non-contiguous inputs: the masked sequence equals the input."""
+    if strict_upstream:
+        return x
+    B, T, C = x.shape
+    flat = x.reshape(-1, C)
+    m = mask_id.reshape(-1)
+    out = flat.clone()
+    mm = m & (probs < style[0])
+    out[mm] = mask_token.reshape(1, C).to(out.dtype)
+    rm = m & (probs >= style[0]) & (probs < style[0] + style[1])
+    out[rm] = flat[rand_idx[: int(rm.sum())]]
+    return out.reshape(B, T, C)
+
+
+def mat_sed_forward(mel, sd, decoder_layers=3, feature_layer=10, f_pool_mode="mean_pool", decode_ratio=10,
+                    temp_w=1.0, pad_mask=None, mlm=False, decoder_input_override=None, stages=None):
+    """PaSST_SED.forward (passt_sed.py:242-296), encoder_win=False.  Returns (strong, weak, other) or
+    (pred, other) in MLM mode.  `stages` (dict) receives intermediate tensors when given."""
+    feat, frame, Fd, Td = passt_backbone(mel, sd, feature_layer=feature_layer)
+    x = pad_interpolate(f_pool(feat, sd, Fd, Td, f_pool_mode), decode_ratio)
+    other = {"frame_before_mask": x}
+    dec_in = x if decoder_input_override is None else decoder_input_override(x, other)
+    y = txl_decoder(dec_in, sd, decoder_layers)
+    if "at_adpater.1.weight" in sd:
+        other["at_out"] = at_branch(frame, sd)
+    if stages is not None:
+        stages.update(layer_feat=feat, frame=frame, frame_before_mask=x, decoder_out=y)
+    if mlm:
+        return mlm_head(y, sd), other
+    strong, weak = sed_head(y, sd, temp_w, pad_mask)
+    return strong, weak, other
+
+
+def bce(p, y):
+    """torch.nn.BCELoss semantics (log clamped at -100), mean reduction (finetune/train.py:166-173)."""
+    return -(y * torch.clamp(p.log(), min=-100.0) + (1 - y) * torch.clamp((1 - p).log(), min=-100.0)).mean()

@@ -1,0 +1,110 @@
+"""CPU: oracle MAT-SED model vs golden vectors from the unmodified reference (small + base + MLM + ops)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import checksum
+from oracle import frontend as F
+from oracle import model as M
+from transformer4sed_b200 import schema
+from transformer4sed_b200.utils import synth
+
+torch.set_num_threads(max(1, __import__("os").cpu_count()))
+
+
+def _sd(shapes, seed, grad=False):
+    sd = synth.synth_state_dict(shapes, seed)
+    if grad:
+        for v in sd.values():
+            v.requires_grad_(True)
+    return sd
+
+
+def _run(tag, shapes, seed, batch, decoder_layers, golden):
+    g = golden(f"matsed_{tag}.npz")
+    sd = _sd(shapes, seed, grad=True)
+    np.testing.assert_allclose(checksum(torch.cat([v.flatten() for _, v in sorted(sd.items())])), g["sd_ck"], rtol=1e-12)
+    wav = synth.synth_wav(batch, 320000, seed=seed + 1)
+    np.testing.assert_allclose(checksum(wav), g["wav_ck"], rtol=1e-12)
+    mel = F.passt_logmel(wav)
+    np.testing.assert_allclose(checksum(mel), g["mel_ck"], rtol=1e-9)
+    labels = synth.synth_strong_labels(batch, 10, 1000, seed + 2)
+    weak_labels = (labels.sum(-1) > 0).float()
+    st = {}
+    strong, weak, other = M.mat_sed_forward(mel, sd, decoder_layers=decoder_layers, stages=st)
+    tol = dict(rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(st["layer_feat"][:, ::17, ::4].detach().numpy(), g["layer_feat"], **tol)
+    np.testing.assert_allclose(st["frame"][:, ::17, ::4].detach().numpy(), g["frame"], **tol)
+    np.testing.assert_allclose(other["frame_before_mask"][:, ::8, ::4].detach().numpy(), g["frame_before_mask"], **tol)
+    np.testing.assert_allclose(st["decoder_out"][:, ::8, ::4].detach().numpy(), g["decoder_out"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(strong.detach().numpy(), g["strong"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(weak.detach().numpy(), g["weak"], rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(other["at_out"].detach().numpy(), g["at_out"], rtol=1e-4, atol=1e-6)
+    assert (strong.argmax(dim=1).numpy() == g["argmax"]).all()
+    loss = M.bce(strong, labels) + 0.5 * M.bce(weak, weak_labels) + 2.0 * M.bce(other["at_out"], weak_labels)
+    np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-5)
+    loss.backward()
+    for name, norm, head in zip(g["grad_names"], g["grad_norms"], g["grad_heads"]):
+        gr = sd[str(name)].grad
+        assert gr is not None, name
+        np.testing.assert_allclose(gr.double().norm().item(), norm, rtol=2e-3, atol=1e-7, err_msg=str(name))
+        n = min(8, gr.numel())
+        np.testing.assert_allclose(gr.flatten()[:n].double().numpy(), head[:n], rtol=5e-3, atol=1e-5 * max(norm, 1e-3), err_msg=str(name))
+    with torch.no_grad():
+        pad = torch.zeros(batch, 1000, dtype=torch.bool)
+        pad[-1, 900:] = True
+        sp, wp, _ = M.mat_sed_forward(mel, sd, decoder_layers=decoder_layers, pad_mask=pad)
+        np.testing.assert_allclose(sp.numpy(), g["strong_pad"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(wp.numpy(), g["weak_pad"], rtol=1e-4, atol=1e-6)
+        s5, w5, _ = M.mat_sed_forward(mel, sd, decoder_layers=decoder_layers, temp_w=0.5)
+        np.testing.assert_allclose(s5.numpy(), g["strong_t05"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(w5.numpy(), g["weak_t05"], rtol=1e-4, atol=1e-6)
+
+
+def test_small_config(golden):
+    _run("small", schema.mat_sed_shapes(embed_dim=192, decoder_dim=192, decoder_layer_num=1), 3, 2, 1, golden)
+
+
+def test_base_config(golden):
+    _run("base", schema.mat_sed_shapes(), 4, 1, 3, golden)
+
+
+@pytest.mark.parametrize("batch", [1, 2])
+def test_mlm_pretrain(golden, batch):
+    """B>1: upstream masking is a silent no-op; B=1: masking applies (refined: the
+    `reshape(-1,C)` of the cloned non-contiguous tensor is a view only when B==1)."""
+    g = golden(f"matsed_mlm_base_b{batch}.npz")
+    seed = 6
+    sd = _sd(schema.mat_sed_shapes(mlm=True), seed)
+    wav = synth.synth_wav(batch, 320000, seed=seed + 1)
+    np.testing.assert_allclose(checksum(wav), g["wav_ck"], rtol=1e-12)
+    mel = F.passt_logmel(wav)
+    noise = torch.from_numpy(g["noise"])
+    mask = M.block_mask_from_noise(noise, 0.75, 10, 1000)
+    assert (np.packbits(mask.numpy()) == g["mask"]).all()
+    noop = bool(g["decoder_in_equals_input"])
+    assert noop == (batch > 1)
+
+    def dec_in(x, other):
+        return M.apply_mask(x, mask, torch.from_numpy(g["probs"]), torch.from_numpy(g["rand_idx"]).long(),
+                            sd["mask_token"], style=(0.8, 0.1, 0.1), strict_upstream=noop)
+
+    with torch.no_grad():
+        pred, other = M.mat_sed_forward(mel, sd, mlm=True, decoder_input_override=dec_in)
+        np.testing.assert_allclose(dec_in(other["frame_before_mask"], None)[:, ::8, ::4].numpy(), g["decoder_in"], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(pred[:, ::8, ::4].numpy(), g["pred"], rtol=1e-3, atol=1e-3)
+        fbm = other["frame_before_mask"]
+        loss = torch.nn.functional.mse_loss(fbm[mask], pred[mask])
+        np.testing.assert_allclose(loss.item(), g["loss"], rtol=1e-4)
+
+
+def test_ops(golden):
+    g = golden("ops.npz")
+    np.testing.assert_array_equal(M.rel_shift(torch.from_numpy(g["rel_shift_in"])).numpy(), g["rel_shift_out"])
+    m = M.block_mask_from_noise(torch.from_numpy(g["block_noise"]), 0.75, 10, 1000)
+    assert (np.packbits(m.numpy()) == g["block_mask"]).all()
+    sd = synth.synth_state_dict(schema.txl_decoder_shapes(48, 2, num_heads=4, prefix=""), 9)
+    xin = synth.synth_tensor(9, "txl_in", (3, 50, 48))
+    np.testing.assert_allclose(checksum(xin), g["txl_in_ck"], rtol=1e-12)
+    out = M.txl_decoder(xin, sd, 2, num_heads=4, p="")
+    np.testing.assert_allclose(out.numpy(), g["txl_out"], rtol=1e-4, atol=1e-5)

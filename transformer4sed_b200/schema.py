@@ -1,0 +1,86 @@
+"""State-dict schema of the reference models as {key: shape}.
+
+The drop-in promise is that checkpoints move between the reference and this package unchanged, so
+the key names (including the upstream spelling ``at_adpater``) and shapes are part of the boundary.
+"""
+
+
+def _ln(d, p, dim):
+    d[p + ".weight"] = (dim,)
+    d[p + ".bias"] = (dim,)
+
+
+def _lin(d, p, n_out, n_in, bias=True):
+    d[p + ".weight"] = (n_out, n_in)
+    if bias:
+        d[p + ".bias"] = (n_out,)
+
+
+def passt_shapes(embed_dim=768, depth=12, mlp_ratio=4, f_dim=12, t_dim=99, patch=16, num_classes=527, prefix="backbone."):
+    """reference src/models/passt/passt.py:366-455 (distilled=True)."""
+    d, D, p = {}, embed_dim, prefix
+    d[p + "cls_token"] = (1, 1, D)
+    d[p + "dist_token"] = (1, 1, D)
+    d[p + "new_pos_embed"] = (1, 2, D)
+    d[p + "freq_new_pos_embed"] = (1, D, f_dim, 1)
+    d[p + "time_new_pos_embed"] = (1, D, 1, t_dim)
+    d[p + "patch_embed.proj.weight"] = (D, 1, patch, patch)
+    d[p + "patch_embed.proj.bias"] = (D,)
+    for i in range(depth):
+        b = f"{p}blocks.{i}."
+        _ln(d, b + "norm1", D)
+        _lin(d, b + "attn.qkv", 3 * D, D)
+        _lin(d, b + "attn.proj", D, D)
+        _ln(d, b + "norm2", D)
+        _lin(d, b + "mlp.fc1", int(D * mlp_ratio), D)
+        _lin(d, b + "mlp.fc2", D, int(D * mlp_ratio))
+    _ln(d, p + "norm", D)
+    _ln(d, p + "head.0", D)
+    _lin(d, p + "head.1", num_classes, D)
+    _lin(d, p + "head_dist", num_classes, D)
+    return d
+
+
+def attention_pooling_shapes(prefix, dim):
+    """reference src/models/pooling.py:37-44."""
+    d = {prefix + "f_att_token": (1, 1, dim),
+         prefix + "frequency_att.in_proj_weight": (3 * dim, dim),
+         prefix + "frequency_att.in_proj_bias": (3 * dim,)}
+    _lin(d, prefix + "frequency_att.out_proj", dim, dim)
+    return d
+
+
+def txl_decoder_shapes(dim, n_layers, num_heads=12, mlp_ratio=1, prefix="decoder."):
+    """reference src/models/transformer_decoder.py:74-94, src/models/transformer/transformerXL.py:23-28,148-178."""
+    d = {}
+    for i in range(n_layers):
+        b = f"{prefix}encoder_blocks.{i}."
+        _ln(d, b + "norm1", dim)
+        _ln(d, b + "norm2", dim)
+        d[b + "attn.pos_bias_u"] = (num_heads, dim // num_heads)
+        d[b + "attn.pos_bias_v"] = (num_heads, dim // num_heads)
+        _lin(d, b + "attn.in_proj", 3 * dim, dim)
+        _lin(d, b + "attn.out_proj", dim, dim)
+        _lin(d, b + "attn.linear_pos", dim, dim, bias=False)
+        _lin(d, b + "mlp.fc1", int(dim * mlp_ratio), dim)
+        _lin(d, b + "mlp.fc2", dim, int(dim * mlp_ratio))
+    return d
+
+
+def mat_sed_shapes(embed_dim=768, decoder_dim=768, decoder_layer_num=3, class_num=10, at_adapter=True,
+                   f_pool="mean_pool", mlm=False, mlm_out_dim=768):
+    """reference src/models/passt/passt_sed.py:39-148 (decoder='transformerXL')."""
+    d = passt_shapes(embed_dim)
+    _ln(d, "out_norm", embed_dim)
+    if f_pool == "attention":
+        d.update(attention_pooling_shapes("f_pool_module.", embed_dim))
+    if mlm:
+        d["mask_token"] = (1, 1, decoder_dim)
+        _lin(d, "mlm_mlp.0", decoder_dim, decoder_dim)
+        _lin(d, "mlm_mlp.2", mlm_out_dim, decoder_dim)
+    d.update(txl_decoder_shapes(decoder_dim, decoder_layer_num))
+    _lin(d, "classifier", class_num, decoder_dim)
+    if at_adapter:
+        d.update(attention_pooling_shapes("at_adpater.0.", embed_dim))
+        _lin(d, "at_adpater.1", class_num, embed_dim)
+    return d
