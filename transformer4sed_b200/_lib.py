@@ -1,0 +1,105 @@
+"""ctypes binding of libt4s.so (the C ABI declared in include/t4s.h).
+
+There is no CPU fallback: if the library is missing, cannot be loaded, or the device is not
+sm_100, every op raises.  `load()` is lazy so that CPU-only tooling (schema, synthetic weights,
+config handling) can import the package on a box without a GPU.
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libt4s.so")
+_lock = threading.Lock()
+_lib = None
+_device_ok = set()
+
+c_void_p, c_int, c_size_t, c_float = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_float
+
+
+class T4sError(RuntimeError):
+    pass
+
+
+class MelParams(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in ("n_fft", "win_length", "hop", "n_mels", "preemphasis", "wav_norm", "magnitude",
+                                     "out_mode", "out_dtype")]
+
+
+def _declare(lib):
+    P, I, Z, F = c_void_p, c_int, c_size_t, c_float
+    sigs = {
+        "t4s_version": (I, []),
+        "t4s_last_error": (ctypes.c_char_p, []),
+        "t4s_device_check": (I, []),
+        "t4s_sm_count": (I, []),
+        "t4s_wav_peak": (I, [P, P, I, I, P]),
+        "t4s_mel_tables_bytes": (Z, [I, I]),
+        "t4s_mel_tables_init": (I, [P, P, I, I, P]),
+        "t4s_mel_forward": (I, [P, P, P, P, P, P, P, I, P, I, I, I, ctypes.POINTER(MelParams), P]),
+        "t4s_mel_normalize": (I, [P, P, Z, P]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return sigs
+
+
+def load():
+    """Return the loaded library, building it first if the sources are newer and nvcc is present."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            try:
+                from . import build as _build
+                _build.build()
+            except Exception as e:  # noqa: BLE001
+                raise T4sError(f"libt4s.so is missing at {LIB_PATH} and could not be built ({e}); "
+                               "run `python -m transformer4sed_b200.build`.  There is no CPU fallback.") from e
+        try:
+            lib = ctypes.CDLL(LIB_PATH)
+        except OSError as e:
+            raise T4sError(f"cannot load {LIB_PATH}: {e}.  There is no CPU fallback.") from e
+        _declare(lib)
+        _lib = lib
+    return _lib
+
+
+def exported_symbols():
+    """Names declared in include/t4s.h, parsed from the header (used by the CPU ABI test)."""
+    import re
+    hdr = open(os.path.join(os.path.dirname(_HERE), "include", "t4s.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(t4s_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().t4s_last_error().decode(errors="replace")
+        raise T4sError(f"{what} failed with code {rc}: {msg}")
+
+
+def ensure_device(t):
+    """Validate that tensor `t` lives on an sm_100 CUDA device and make it current."""
+    import torch
+    if not t.is_cuda:
+        raise T4sError("transformer4sed_b200 ops need CUDA tensors on a B200 (sm_100a); there is no CPU fallback")
+    idx = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    if idx not in _device_ok:
+        with torch.cuda.device(idx):
+            check(load().t4s_device_check(), "t4s_device_check")
+        _device_ok.add(idx)
+    return idx
+
+
+def stream_ptr():
+    import torch
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
