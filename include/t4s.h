@@ -73,6 +73,54 @@ int t4s_mel_forward(const float* wav, const float* peak, const void* tables,
 /* normalize only: out = (ln(in + 1e-5) + 4.5) / 5  (passt_feature_extraction.py:91-94). */
 int t4s_mel_normalize(const float* in, float* out, size_t n, void* stream);
 
+/* ---- K3: tcgen05 / TMA GEMM with fused epilogue -----------------------------------------------------------
+ * C[z][M,N] = act(alpha * A[z][M,K] . B[z][N,K]^T + bias[N]) + residual[z][M,N]
+ * Both operands are K-major ("x @ W^T", exactly nn.Linear's layout), bf16 (tcgen05 kind::f16) or fp32 (kind::tf32),
+ * fp32 accumulation in TMEM.  Replaces every nn.Linear / torch.matmul / bmm on the path:
+ *   src/models/passt/passt.py:270-276 (Mlp fc1+GELU, fc2), :333,:342 (qkv, proj), :336,:341 (q k^T, attn v),
+ *   :302-315 (patch-embed conv as GEMM), src/models/transformer/transformerXL.py:372-374 (in_proj), :487 (linear_pos),
+ *   :510-513 (matrix_ac / matrix_bd), :566-576 (bmm, out_proj), src/models/passt/passt_sed.py:194-196 (mlm_mlp).
+ * z = (z1, z2) is a two-level batch index (e.g. clip, head); an operand with nb == 1 at a level is broadcast.
+ */
+typedef struct {
+  const void* ptr;  /* element (row 0, k 0) of batch (0,0) */
+  int64_t rows;     /* M for A, N for B */
+  int64_t ld;       /* K-major: elements between consecutive rows (K contiguous);
+                       MN-major: elements between consecutive K indices (rows contiguous) */
+  int64_t nb1, stride1, nb2, stride2; /* batch extents and strides in elements */
+  int mn_major;     /* 0: stored [rows][K]; 1: stored [K][rows] (transposed operand, no copy needed for dgrad/wgrad) */
+} T4sOperand;
+
+typedef struct {
+  void* ptr;        /* NULL = absent */
+  int dtype;        /* T4S_F32 or T4S_BF16 */
+  int64_t ld, stride1, stride2;
+} T4sMatrix;
+
+#define T4S_ACT_NONE 0
+#define T4S_ACT_GELU 1
+
+typedef struct {
+  int M, N, K;
+  int in_dtype;       /* T4S_BF16 or T4S_F32 (tf32 tensor-core math) */
+  int nb1, nb2;       /* batch grid; total batches = nb1 * nb2 */
+  int split_k;        /* >1: K is cut into split_k ranges; range s writes its partial product to C + s*c_split_stride
+                         (epilogue extras apply to every partial; use t4s_reduce_splits afterwards) */
+  int64_t c_split_stride;
+  T4sOperand A, B;
+  T4sMatrix C;        /* output (required) */
+  T4sMatrix aux;      /* optional second output: alpha*acc + bias, i.e. the pre-activation (saved for backward) */
+  T4sMatrix residual; /* optional, added after the activation; may alias C (accumulate) */
+  const float* bias;  /* optional [N] fp32 */
+  float alpha;
+  int act;
+} T4sGemm;
+
+int t4s_gemm(const T4sGemm* g, void* stream);
+
+/* out[i] = (accumulate ? out[i] : 0) + sum_s ws[s*n + i]   (fp32; finishes a split-K weight-gradient GEMM) */
+int t4s_reduce_splits(const float* ws, int splits, size_t n, float* out, int accumulate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,22 @@ class MelParams(ctypes.Structure):
                                      "out_mode", "out_dtype")]
 
 
+class Operand(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("rows", ctypes.c_int64), ("ld", ctypes.c_int64), ("nb1", ctypes.c_int64),
+                ("stride1", ctypes.c_int64), ("nb2", ctypes.c_int64), ("stride2", ctypes.c_int64), ("mn_major", c_int)]
+
+
+class Matrix(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("dtype", c_int), ("ld", ctypes.c_int64), ("stride1", ctypes.c_int64),
+                ("stride2", ctypes.c_int64)]
+
+
+class Gemm(ctypes.Structure):
+    _fields_ = [("M", c_int), ("N", c_int), ("K", c_int), ("in_dtype", c_int), ("nb1", c_int), ("nb2", c_int),
+                ("split_k", c_int), ("c_split_stride", ctypes.c_int64), ("A", Operand), ("B", Operand), ("C", Matrix),
+                ("aux", Matrix), ("residual", Matrix), ("bias", c_void_p), ("alpha", c_float), ("act", c_int)]
+
+
 def _declare(lib):
     P, I, Z, F = c_void_p, c_int, c_size_t, c_float
     sigs = {
@@ -38,6 +54,8 @@ def _declare(lib):
         "t4s_mel_tables_init": (I, [P, P, I, I, P]),
         "t4s_mel_forward": (I, [P, P, P, P, P, P, P, I, P, I, I, I, ctypes.POINTER(MelParams), P]),
         "t4s_mel_normalize": (I, [P, P, Z, P]),
+        "t4s_gemm": (I, [ctypes.POINTER(Gemm), P]),
+        "t4s_reduce_splits": (I, [P, I, Z, P, I, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -1,0 +1,488 @@
+// K3: persistent warp-specialised tcgen05 GEMM with TMA-fed shared-memory pipeline and a fused epilogue.
+//
+//   C[z] = act(alpha * A[z] . B[z]^T + bias) + residual[z]      A:[M,K]  B:[N,K]  (both K-major), fp32 accumulate in TMEM
+//
+// CTA = 8 warps, one CTA per SM, walking 128 x BN output tiles (m fastest so neighbouring CTAs share the B tile in L2):
+//   warp 0    TMA producer: 4-D tensor maps (k, row, batch1, batch2), SWIZZLE_128B boxes -> NS-stage smem ring
+//   warp 1    MMA issuer:   one lane issues tcgen05.mma (M=128, N=BN, K=32 B per instruction), commits to mbarriers
+//   warp 2    TMEM allocator (2 x BN fp32 columns: accumulator double buffer, epilogue overlaps the next mainloop)
+//   warps 4-7 epilogue: tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> bias / GELU / residual ->
+//             coalesced 16-byte stores (row-predicated, so ragged M/N tiles and TMA zero-fill compose)
+// bf16 inputs use kind::f16, fp32 inputs use kind::tf32 (tensor map type TFLOAT32 rounds on load).
+#include <algorithm>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace t4s {
+namespace gemm {
+
+constexpr int kBM = 128;
+constexpr int kThreads = 256;
+constexpr int kEpiStride = 36;  // floats; 16-byte accesses are conflict-free both ways
+constexpr int kEpiBytesPerWarp = 32 * kEpiStride * 4;
+
+struct MatArg {
+  void* ptr;
+  long long ld, s1, s2;
+  int dtype;
+  int vec;  // 16-byte (fp32) / 8-byte (bf16) vector access is legal
+};
+
+struct Args {
+  int M, N, K, nb1, nb2;
+  int a_b1, a_b2, b_b1, b_b2;  // 1 if the operand really has that batch level (else coordinate 0)
+  int tiles_m, tiles_n;
+  int split_k, kb_per_split;   // K range of split s: k-blocks [s*kb_per_split, min(kblocks, (s+1)*kb_per_split))
+  long long c_split;           // elements between partial outputs
+  long long total_tiles;
+  MatArg C, aux, res;
+  const float* bias;
+  float alpha;
+  int act;
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStageA = kBM * 128;
+  static constexpr int kStageB = BN * 128;
+  static constexpr int kStage = kStageA + kStageB;
+  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmem = 1024 /*align slack*/ + kStages * kStage + 4 * kEpiBytesPerWarp + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__device__ __forceinline__ void store4(const MatArg& m, long long off, int ncols_valid, float4 v) {
+  if (m.dtype == T4S_F32) {
+    float* p = reinterpret_cast<float*>(m.ptr) + off;
+    if (m.vec && ncols_valid >= 4) {
+      *reinterpret_cast<float4*>(p) = v;
+    } else {
+      if (ncols_valid > 0) p[0] = v.x;
+      if (ncols_valid > 1) p[1] = v.y;
+      if (ncols_valid > 2) p[2] = v.z;
+      if (ncols_valid > 3) p[3] = v.w;
+    }
+  } else {
+    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(m.ptr) + off;
+    if (m.vec && ncols_valid >= 4) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+      uint2 u;
+      u.x = *reinterpret_cast<uint32_t*>(&lo);
+      u.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(p) = u;
+    } else {
+      if (ncols_valid > 0) p[0] = __float2bfloat16_rn(v.x);
+      if (ncols_valid > 1) p[1] = __float2bfloat16_rn(v.y);
+      if (ncols_valid > 2) p[2] = __float2bfloat16_rn(v.z);
+      if (ncols_valid > 3) p[3] = __float2bfloat16_rn(v.w);
+    }
+  }
+}
+
+__device__ __forceinline__ float4 load4(const MatArg& m, long long off, int ncols_valid) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (m.dtype == T4S_F32) {
+    const float* p = reinterpret_cast<const float*>(m.ptr) + off;
+    if (m.vec && ncols_valid >= 4) {
+      v = *reinterpret_cast<const float4*>(p);
+    } else {
+      if (ncols_valid > 0) v.x = p[0];
+      if (ncols_valid > 1) v.y = p[1];
+      if (ncols_valid > 2) v.z = p[2];
+      if (ncols_valid > 3) v.w = p[3];
+    }
+  } else {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(m.ptr) + off;
+    if (m.vec && ncols_valid >= 4) {
+      uint2 u = *reinterpret_cast<const uint2*>(p);
+      __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&u.x), hi = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+      v = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+    } else {
+      if (ncols_valid > 0) v.x = __bfloat162float(p[0]);
+      if (ncols_valid > 1) v.y = __bfloat162float(p[1]);
+      if (ncols_valid > 2) v.z = __bfloat162float(p[2]);
+      if (ncols_valid > 3) v.w = __bfloat162float(p[3]);
+    }
+  }
+  return v;
+}
+
+template <int BN, bool kTf32, bool kAMn, bool kBMn>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+  using C = Cfg<BN>;
+  constexpr int kBK = kTf32 ? 32 : 64;   // K elements per pipeline stage
+  constexpr int kRowEl = kTf32 ? 32 : 64; // elements per 128-byte swizzle row
+  constexpr int kBoxBytes = kBK * 128;    // one MN-major box: kBK rows (K) x 128 B (M/N)
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = ptx::smem_u32(smem_raw);
+  unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + C::kStages * C::kStageA;
+  float* sEpi = reinterpret_cast<float*>(smem + C::kStages * C::kStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStage + 4 * kEpiBytesPerWarp);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + C::kStages;
+  uint64_t* tfull = bars + 2 * C::kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks_all = (a.K + kBK - 1) / kBK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) {
+      ptx::mbar_init(&full[i], 1);
+      ptx::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&tfull[i], 1);
+      ptx::mbar_init(&tempty[i], 4);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long tiles_per_batch = (long long)a.tiles_m * a.tiles_n;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+        const int zs = (int)(tile / tiles_per_batch);
+        const int r = (int)(tile - (long long)zs * tiles_per_batch);
+        const int m0 = (r % a.tiles_m) * kBM, n0 = (r / a.tiles_m) * BN;
+        const int nbz = a.nb1 * a.nb2;
+        const int sp = zs / nbz, z = zs - sp * nbz;
+        const int z1 = z % a.nb1, z2 = z / a.nb1;
+        const int kb0 = sp * a.kb_per_split, kb1 = min(kblocks_all, kb0 + a.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
+          const int az1 = a.a_b1 ? z1 : 0, az2 = a.a_b2 ? z2 : 0, bz1 = a.b_b1 ? z1 : 0, bz2 = a.b_b2 ? z2 : 0;
+          if (kAMn) {
+#pragma unroll
+            for (int j = 0; j < kBM / kRowEl; ++j)
+              ptx::tma_load_4d(sA + s * C::kStageA + j * kBoxBytes, &tmA, &full[s], m0 + j * kRowEl, kb * kBK, az1, az2);
+          } else {
+            ptx::tma_load_4d(sA + s * C::kStageA, &tmA, &full[s], kb * kBK, m0, az1, az2);
+          }
+          if (kBMn) {
+#pragma unroll
+            for (int j = 0; j < BN / kRowEl; ++j)
+              ptx::tma_load_4d(sB + s * C::kStageB + j * kBoxBytes, &tmB, &full[s], n0 + j * kRowEl, kb * kBK, bz1, bz2);
+          } else {
+            ptx::tma_load_4d(sB + s * C::kStageB, &tmB, &full[s], kb * kBK, n0, bz1, bz2);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idesc = ptx::umma_idesc(kTf32 ? 2 : 1, kBM, BN, kAMn ? 1 : 0, kBMn ? 1 : 0);
+    // per-instruction K step (16 bf16 / 8 tf32 = 32 bytes of K): K-major advances 32 B inside the swizzled row,
+    // MN-major advances whole rows (16 or 8 rows of 128 B); in 16-byte descriptor units.
+    constexpr uint32_t kStepA = kAMn ? (kTf32 ? 64u : 128u) : 2u;
+    constexpr uint32_t kStepB = kBMn ? (kTf32 ? 64u : 128u) : 2u;
+    uint32_t it = 0, ai = 0;
+    for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ai) {
+      const int as = ai & 1;
+      const uint32_t aph = (ai >> 1) & 1;
+      const int sp = (int)(tile / (tiles_per_batch * a.nb1 * a.nb2));
+      const int kb0 = sp * a.kb_per_split, kb1 = min(kblocks_all, kb0 + a.kb_per_split);
+      ptx::mbar_wait(&tempty[as], aph ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % C::kStages;
+        const uint32_t ph = (it / C::kStages) & 1;
+        ptx::mbar_wait(&full[s], ph);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint64_t adesc = ptx::umma_desc_sw128(ptx::smem_u32(sA + s * C::kStageA), kAMn ? kBoxBytes : 16, 1024);
+          const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sB + s * C::kStageB), kBMn ? kBoxBytes : 16, 1024);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (kTf32)
+              ptx::mma_tf32(d_tmem, adesc + kStepA * k, bdesc + kStepB * k, idesc, acc);
+            else
+              ptx::mma_f16(d_tmem, adesc + kStepA * k, bdesc + kStepB * k, idesc, acc);
+          }
+          ptx::tc_commit(&empty[s]);                    // frees the smem stage when these MMAs retire
+          if (kb == kb1 - 1) ptx::tc_commit(&tfull[as]);  // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp - 4;  // TMEM lane quarter this warp may access
+    float* st = sEpi + q * 32 * kEpiStride;
+    uint32_t ai = 0;
+    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
+    for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ai) {
+      const int zs = (int)(tile / tiles_per_batch);
+      const int r = (int)(tile - (long long)zs * tiles_per_batch);
+      const int m0 = (r % a.tiles_m) * kBM, n0 = (r / a.tiles_m) * BN;
+      const int nbz = a.nb1 * a.nb2;
+      const int sp = zs / nbz, z = zs - sp * nbz;
+      const int z1 = z % a.nb1, z2 = z / a.nb1;
+      const int as = ai & 1;
+      const uint32_t aph = (ai >> 1) & 1;
+      ptx::mbar_wait(&tfull[as], aph);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      const long long c_base = (long long)z1 * a.C.s1 + (long long)z2 * a.C.s2 + (long long)sp * a.c_split;
+      const long long x_base = (long long)z1 * a.aux.s1 + (long long)z2 * a.aux.s2;
+      const long long r_base = (long long)z1 * a.res.s1 + (long long)z2 * a.res.s2;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= a.N) break;  // warp-uniform
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_row + c0, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(st + lane * kEpiStride + 4 * j) =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+        const int gcol = n0 + c0 + c4;
+        const int nvalid = a.N - gcol;  // may be <= 0
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (a.bias && nvalid > 0) {
+          b4.x = a.bias[gcol];
+          if (nvalid > 1) b4.y = a.bias[gcol + 1];
+          if (nvalid > 2) b4.z = a.bias[gcol + 2];
+          if (nvalid > 3) b4.w = a.bias[gcol + 3];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = rsub + 4 * i;
+          const int grow = m0 + q * 32 + row;
+          float4 x = *reinterpret_cast<const float4*>(st + row * kEpiStride + c4);
+          if (grow < a.M && nvalid > 0) {
+            x.x = fmaf(a.alpha, x.x, b4.x);
+            x.y = fmaf(a.alpha, x.y, b4.y);
+            x.z = fmaf(a.alpha, x.z, b4.z);
+            x.w = fmaf(a.alpha, x.w, b4.w);
+            if (a.aux.ptr) store4(a.aux, x_base + (long long)grow * a.aux.ld + gcol, nvalid, x);
+            if (a.act == T4S_ACT_GELU) {
+              x.x = gelu_erf(x.x);
+              x.y = gelu_erf(x.y);
+              x.z = gelu_erf(x.z);
+              x.w = gelu_erf(x.w);
+            }
+            if (a.res.ptr) {
+              float4 rr = load4(a.res, r_base + (long long)grow * a.res.ld + gcol, nvalid);
+              x.x += rr.x;
+              x.y += rr.y;
+              x.z += rr.z;
+              x.w += rr.w;
+            }
+            store4(a.C, c_base + (long long)grow * a.C.ld + gcol, nvalid, x);
+          }
+        }
+        __syncwarp();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 4-D map (k, row, b1, b2) with a [box_k x box_rows x 1 x 1] SWIZZLE_128B box; out-of-range elements read as zero.
+static int make_map(CUtensorMap* m, const T4sOperand& op, int K, int esize, bool tf32, int box_k, int box_rows, const char* name) {
+  const bool mn = op.mn_major != 0;
+  const long long inner = mn ? op.rows : K, outer = mn ? K : op.rows;  // inner = contiguous dimension
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return T4S_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) || (op.ld * esize) % 16 || op.ld < inner) {
+    set_error("t4s_gemm: operand %s needs a 16-byte aligned base and pitch >= its contiguous extent (ld=%lld, extent=%lld)", name,
+              (long long)op.ld, inner);
+    return T4S_ERR_ARG;
+  }
+  const long long nb1 = std::max<long long>(1, op.nb1), nb2 = std::max<long long>(1, op.nb2);
+  long long s1 = nb1 > 1 ? op.stride1 : op.ld, s2 = nb2 > 1 ? op.stride2 : op.ld;
+  if ((s1 * esize) % 16 || (s2 * esize) % 16 || s1 <= 0 || s2 <= 0) {
+    set_error("t4s_gemm: operand %s batch strides must be positive multiples of 16 bytes", name);
+    return T4S_ERR_ARG;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)inner, (cuuint64_t)outer, (cuuint64_t)nb1, (cuuint64_t)nb2};
+  cuuint64_t strides[3] = {(cuuint64_t)(op.ld * esize), (cuuint64_t)(s1 * esize), (cuuint64_t)(s2 * esize)};
+  // K-major: box = [box_k of K (128 B)] x [box_rows rows]; MN-major: box = [128 B of rows] x [box_k K-rows]
+  cuuint32_t box[4] = {(cuuint32_t)(mn ? 128 / esize : box_k), (cuuint32_t)(mn ? box_k : box_rows), 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMapDataType dt = esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  CUresult rc = enc(m, dt, 4, const_cast<void*>(op.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (K=%d rows=%lld ld=%lld nb=%lldx%lld)", name, (int)rc, K,
+              (long long)op.rows, (long long)op.ld, nb1, nb2);
+    return T4S_ERR_CUDA;
+  }
+  return T4S_OK;
+}
+
+static MatArg mat_arg(const T4sMatrix& m) {
+  MatArg o;
+  o.ptr = m.ptr;
+  o.ld = m.ld;
+  o.s1 = m.stride1;
+  o.s2 = m.stride2;
+  o.dtype = m.dtype;
+  const int align = m.dtype == T4S_F32 ? 16 : 8;
+  o.vec = m.ptr && !(reinterpret_cast<uintptr_t>(m.ptr) % align) && !(m.ld % 4) && !(m.stride1 % 4) && !(m.stride2 % 4);
+  return o;
+}
+
+template <int BN, bool kTf32, bool kAMn, bool kBMn>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, Args& a, cudaStream_t st) {
+  a.tiles_m = (a.M + kBM - 1) / kBM;
+  a.tiles_n = (a.N + BN - 1) / BN;
+  const int bk = kTf32 ? 32 : 64;
+  const int kblocks = (a.K + bk - 1) / bk;
+  a.kb_per_split = (kblocks + a.split_k - 1) / a.split_k;
+  a.split_k = (kblocks + a.kb_per_split - 1) / a.kb_per_split;  // drop empty trailing splits
+  a.total_tiles = (long long)a.tiles_m * a.tiles_n * a.nb1 * a.nb2 * a.split_k;
+  const int grid = (int)std::min<long long>(a.total_tiles, sm_count());
+  auto kern = gemm_kernel<BN, kTf32, kAMn, kBMn>;
+  T4S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
+  kern<<<grid, kThreads, Cfg<BN>::kSmem, st>>>(tmA, tmB, a);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+}  // namespace gemm
+}  // namespace t4s
+
+extern "C" int t4s_gemm(const T4sGemm* g, void* stream) {
+  using namespace t4s::gemm;
+  T4S_REQUIRE(g, "t4s_gemm: null descriptor");
+  T4S_REQUIRE(g->M > 0 && g->N > 0 && g->K > 0 && g->nb1 > 0 && g->nb2 > 0, "t4s_gemm: M, N, K and batch counts must be positive");
+  T4S_REQUIRE(g->A.ptr && g->B.ptr && g->C.ptr, "t4s_gemm: A, B and C are required");
+  T4S_REQUIRE(g->in_dtype == T4S_BF16 || g->in_dtype == T4S_F32, "t4s_gemm: in_dtype must be T4S_BF16 or T4S_F32");
+  T4S_REQUIRE(g->A.rows == g->M && g->B.rows == g->N, "t4s_gemm: operand rows must equal M / N");
+  for (const T4sMatrix* m : {&g->C, &g->aux, &g->residual})
+    T4S_REQUIRE(!m->ptr || m->dtype == T4S_F32 || m->dtype == T4S_BF16, "t4s_gemm: bad output dtype");
+  const bool tf32 = g->in_dtype == T4S_F32;
+  const int esize = tf32 ? 4 : 2, bk = tf32 ? 32 : 64;
+  const int BN = g->N > 128 ? 256 : (g->N > 64 ? 128 : 64);
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, g->A, g->K, esize, tf32, bk, kBM, "A");
+  if (rc) return rc;
+  rc = make_map(&tmB, g->B, g->K, esize, tf32, bk, BN, "B");
+  if (rc) return rc;
+  Args a;
+  a.M = g->M; a.N = g->N; a.K = g->K; a.nb1 = g->nb1; a.nb2 = g->nb2;
+  a.a_b1 = g->A.nb1 > 1; a.a_b2 = g->A.nb2 > 1; a.b_b1 = g->B.nb1 > 1; a.b_b2 = g->B.nb2 > 1;
+  T4S_REQUIRE((!a.a_b1 || g->A.nb1 == g->nb1) && (!a.a_b2 || g->A.nb2 == g->nb2) && (!a.b_b1 || g->B.nb1 == g->nb1) &&
+                  (!a.b_b2 || g->B.nb2 == g->nb2), "t4s_gemm: operand batch extents must be 1 or match nb1/nb2");
+  a.C = mat_arg(g->C); a.aux = mat_arg(g->aux); a.res = mat_arg(g->residual);
+  a.bias = g->bias; a.alpha = g->alpha; a.act = g->act;
+  a.split_k = g->split_k > 1 ? g->split_k : 1;
+  a.c_split = g->c_split_stride;
+  T4S_REQUIRE(a.split_k == 1 || (g->c_split_stride > 0 && !g->bias && !g->residual.ptr && !g->aux.ptr && g->act == T4S_ACT_NONE),
+              "t4s_gemm: split_k needs c_split_stride and a plain epilogue");
+  cudaStream_t st = t4s::as_stream(stream);
+  const int variant = (tf32 ? 4 : 0) | (g->A.mn_major ? 2 : 0) | (g->B.mn_major ? 1 : 0);
+#define T4S_GEMM_CASE(V, TF, AM, BM_)                                         \
+  case V:                                                                     \
+    if (BN == 256) return launch<256, TF, AM, BM_>(tmA, tmB, a, st);          \
+    if (BN == 128) return launch<128, TF, AM, BM_>(tmA, tmB, a, st);          \
+    return launch<64, TF, AM, BM_>(tmA, tmB, a, st);
+  switch (variant) {
+    T4S_GEMM_CASE(0, false, false, false)
+    T4S_GEMM_CASE(1, false, false, true)
+    T4S_GEMM_CASE(2, false, true, false)
+    T4S_GEMM_CASE(3, false, true, true)
+    T4S_GEMM_CASE(4, true, false, false)
+    T4S_GEMM_CASE(5, true, false, true)
+    T4S_GEMM_CASE(6, true, true, false)
+    T4S_GEMM_CASE(7, true, true, true)
+  }
+#undef T4S_GEMM_CASE
+  return T4S_ERR_ARG;
+}
+
+namespace t4s {
+namespace gemm {
+__global__ void reduce_splits_kernel(const float* __restrict__ ws, int splits, size_t n, float* __restrict__ out, int accumulate) {
+  size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+  for (; i < n; i += stride) {
+    if (i + 4 <= n) {
+      float4 acc = accumulate ? *reinterpret_cast<const float4*>(out + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int s = 0; s < splits; ++s) {
+        float4 v = *reinterpret_cast<const float4*>(ws + (size_t)s * n + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(out + i) = acc;
+    } else {
+      for (size_t j = i; j < n; ++j) {
+        float acc = accumulate ? out[j] : 0.f;
+        for (int s = 0; s < splits; ++s) acc += ws[(size_t)s * n + j];
+        out[j] = acc;
+      }
+    }
+  }
+}
+}  // namespace gemm
+}  // namespace t4s
+
+extern "C" int t4s_reduce_splits(const float* ws, int splits, size_t n, float* out, int accumulate, void* stream) {
+  T4S_REQUIRE(ws && out && splits > 0, "t4s_reduce_splits: bad arguments");
+  T4S_REQUIRE(n % 4 == 0 && !(reinterpret_cast<uintptr_t>(ws) & 15) && !(reinterpret_cast<uintptr_t>(out) & 15),
+              "t4s_reduce_splits: n must be a multiple of 4 and buffers 16-byte aligned");
+  if (n == 0) return T4S_OK;
+  const int grid = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)t4s::sm_count() * 8);
+  t4s::gemm::reduce_splits_kernel<<<grid, 256, 0, t4s::as_stream(stream)>>>(ws, splits, n, out, accumulate);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}

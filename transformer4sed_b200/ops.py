@@ -1,0 +1,92 @@
+"""Python-side launchers for the libt4s kernels (raw device pointers through ctypes; torch is plumbing only).
+
+Everything here runs on the current CUDA stream of the tensor's device and raises `T4sError` on any
+failure; there is no CPU implementation.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import Gemm, Matrix, Operand
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_GELU = 0, 1
+
+
+def dtype_code(dt):
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise _lib.T4sError(f"unsupported dtype {dt}: libt4s kernels take float32 or bfloat16")
+
+
+def _esize(t):
+    return t.element_size()
+
+
+class Op:
+    """Strided view of a GEMM operand inside tensor `t` (K-major unless mn_major)."""
+
+    def __init__(self, t, rows, ld, offset=0, nb1=1, stride1=0, nb2=1, stride2=0, mn_major=False):
+        self.t, self.rows, self.ld, self.offset = t, rows, ld, offset
+        self.nb1, self.stride1, self.nb2, self.stride2, self.mn_major = nb1, stride1, nb2, stride2, mn_major
+
+    def c(self):
+        return Operand(ctypes.c_void_p(self.t.data_ptr() + self.offset * _esize(self.t)), self.rows, self.ld, self.nb1,
+                       self.stride1, self.nb2, self.stride2, int(self.mn_major))
+
+
+class Out:
+    """Strided view of an output / residual / aux matrix."""
+
+    def __init__(self, t, ld, offset=0, stride1=0, stride2=0):
+        self.t, self.ld, self.offset, self.stride1, self.stride2 = t, ld, offset, stride1, stride2
+
+    def c(self):
+        return Matrix(ctypes.c_void_p(self.t.data_ptr() + self.offset * _esize(self.t)), dtype_code(self.t.dtype), self.ld,
+                      self.stride1, self.stride2)
+
+
+_NULL_MAT = Matrix(ctypes.c_void_p(0), 0, 0, 0, 0)
+
+
+def gemm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, bias=None, aux: Out = None, residual: Out = None, alpha=1.0,
+         act=ACT_NONE, split_k=1, c_split_stride=0):
+    """C[z] = act(alpha * A[z] @ B[z]^T + bias) + residual[z] on tensor cores (tcgen05)."""
+    _lib.ensure_device(A.t)
+    if A.t.dtype != B.t.dtype:
+        raise _lib.T4sError("gemm operands must share a dtype")
+    g = Gemm()
+    g.M, g.N, g.K, g.in_dtype, g.nb1, g.nb2 = M, N, K, dtype_code(A.t.dtype), nb1, nb2
+    g.split_k, g.c_split_stride = split_k, c_split_stride
+    g.A, g.B, g.C = A.c(), B.c(), C.c()
+    g.aux = aux.c() if aux is not None else _NULL_MAT
+    g.residual = residual.c() if residual is not None else _NULL_MAT
+    if bias is not None and bias.dtype != torch.float32:
+        raise _lib.T4sError("gemm bias must be float32")
+    g.bias = ctypes.c_void_p(bias.data_ptr()) if bias is not None else ctypes.c_void_p(0)
+    g.alpha, g.act = float(alpha), act
+    with torch.cuda.device(A.t.device):
+        _lib.check(_lib.load().t4s_gemm(ctypes.byref(g), _lib.stream_ptr()), "t4s_gemm")
+
+
+def reduce_splits(ws, splits, n, out, accumulate=False):
+    _lib.ensure_device(ws)
+    with torch.cuda.device(ws.device):
+        _lib.check(_lib.load().t4s_reduce_splits(_lib.ptr(ws), splits, n, _lib.ptr(out), int(accumulate), _lib.stream_ptr()),
+                   "t4s_reduce_splits")
+
+
+def linear_nt(x, w, bias=None, out_dtype=None, act=ACT_NONE, residual=None, aux_dtype=None, alpha=1.0):
+    """y[M,N] = act(alpha * x[M,K] @ w[N,K]^T + bias) + residual; returns (y, aux or None)."""
+    M, K = x.shape
+    N = w.shape[0]
+    out_dtype = out_dtype or x.dtype
+    y = torch.empty(M, N, dtype=out_dtype, device=x.device)
+    aux = torch.empty(M, N, dtype=aux_dtype, device=x.device) if aux_dtype is not None else None
+    gemm(Op(x, M, x.stride(0)), Op(w, N, w.stride(0)), Out(y, N), M, N, K, bias=bias,
+         aux=Out(aux, N) if aux is not None else None,
+         residual=Out(residual, residual.stride(0)) if residual is not None else None, alpha=alpha, act=act)
+    return y, aux
