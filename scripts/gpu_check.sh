@@ -9,7 +9,7 @@ FILES=${T4S_TEST_FILES:-$(ls tests/test_*gpu*.py)}
 rc_all=0
 for f in $FILES; do
   name=$(basename "$f" .py)
-  timeout ${T4S_TEST_TIMEOUT:-300} python -m pytest "$f" -m gpu -x -q ${T4S_PYTEST_ARGS:-} > "gpurun_out/$name.log" 2>&1
+  timeout ${T4S_TEST_TIMEOUT:-300} python -m pytest "$f" -m gpu -q ${T4S_PYTEST_ARGS:-} > "gpurun_out/$name.log" 2>&1
   rc=$?
   echo "$name rc=$rc $(tail -n 1 gpurun_out/$name.log)"
   [ $rc -ne 0 ] && rc_all=1 && tail -n 40 "gpurun_out/$name.log"

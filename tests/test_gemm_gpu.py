@@ -19,7 +19,7 @@ def _rand(shape, dtype, seed):
 def _tol(dtype, K):
     # bf16 inputs are exact in the reference too (we upcast the same bf16 values); error is fp32 accumulation order only.
     # tf32 rounds fp32 inputs to 10 mantissa bits: rel 2^-11 per operand -> ~ sqrt(K) * 2^-11 * |a||b| absolute.
-    return (2e-3 if dtype == torch.bfloat16 else 1.5e-3 * (K ** 0.5) / 8)
+    return (2e-3 if dtype == torch.bfloat16 else 4e-3 * (K ** 0.5) / 8)
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
@@ -104,7 +104,7 @@ def test_gemm_split_k_weight_gradient():
         dw = torch.ones(Nout, Kin, device="cuda")
         ops.reduce_splits(ws, S, Nout * Kin, dw, accumulate=True)
         ref = dy.double().t() @ x.double() + 1.0
-        assert (dw.double() - ref).abs().max().item() < (5e-3 if dtype == torch.bfloat16 else 0.15)
+        assert (dw.double() - ref).abs().max().item() < (5e-3 if dtype == torch.bfloat16 else 0.3)
 
 
 def test_gemm_rejects_bad_arguments():

@@ -216,8 +216,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
         if (lane == 0) {
-          const uint64_t adesc = ptx::umma_desc_sw128(ptx::smem_u32(sA + s * C::kStageA), kAMn ? kBoxBytes : 16, 1024);
-          const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sB + s * C::kStageB), kBMn ? kBoxBytes : 16, 1024);
+          // tf32 MN-major: 32-byte-atom swizzle, 4-row K groups (512 B); everything else: SWIZZLE_128B, 8-row groups
+          const uint64_t adesc = ptx::umma_desc_sw128(ptx::smem_u32(sA + s * C::kStageA), kAMn ? kBoxBytes : 16,
+                                                      (kAMn && kTf32) ? 512 : 1024, (kAMn && kTf32) ? 1 : 2);
+          const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sB + s * C::kStageB), kBMn ? kBoxBytes : 16,
+                                                      (kBMn && kTf32) ? 512 : 1024, (kBMn && kTf32) ? 1 : 2);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
@@ -361,7 +364,8 @@ static int make_map(CUtensorMap* m, const T4sOperand& op, int K, int esize, bool
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUtensorMapDataType dt = esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : (tf32 ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
   CUresult rc = enc(m, dt, 4, const_cast<void*>(op.ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    (mn && esize == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (K=%d rows=%lld ld=%lld nb=%lldx%lld)", name, (int)rc, K,
               (long long)op.rows, (long long)op.ld, nb1, nb2);

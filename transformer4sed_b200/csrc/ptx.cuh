@@ -116,13 +116,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 //   K-major  (rows = M/N index, 128 B of K per row): 8-row groups 1024 B apart (SBO); LBO unused.
 //   MN-major (rows = K index, 128 B of M/N per row): 8-row K groups 1024 B apart (SBO); successive 128-byte-wide
 //            M/N blocks are separate boxes LBO bytes apart (canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   MN-major 32-bit (tf32) operands must use the 32-byte-atom variant (SWIZZLE_128B_BASE32B, TMA SWIZZLE_128B_ATOM_32B):
+//            32-byte chunks XOR (row % 4), K groups of 4 rows 512 B apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);  // start address, 16-byte units
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
   d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;             // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 // Instruction descriptor for kind::f16 / kind::tf32 with fp32 accumulate.  fmt: 0 = f16, 1 = bf16, 2 = tf32.
