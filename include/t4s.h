@@ -121,6 +121,88 @@ int t4s_gemm(const T4sGemm* g, void* stream);
 /* out[i] = (accumulate ? out[i] : 0) + sum_s ws[s*n + i]   (fp32; finishes a split-K weight-gradient GEMM) */
 int t4s_reduce_splits(const float* ws, int splits, size_t n, float* out, int accumulate, void* stream);
 
+/* 3xTF32 operand preparation for the error-compensated parity mode: gathers a (strided, optionally MN-major) fp32
+ * operand into a contiguous K-major [nb2][nb1][rows][3K] buffer of tf32-exact values; pattern 0 = [hi|lo|hi] (A side),
+ * pattern 1 = [hi|hi|lo] (B side), so one tf32 GEMM over 3K gives hi*hi + lo*hi + hi*lo (fp32-class accuracy). */
+int t4s_split_tf32(const T4sOperand* src, int K, float* dst, int pattern, void* stream);
+
+/* ---- K2: LayerNorm, softmax and other row kernels ----------------------------------------------------------
+ * Replace nn.LayerNorm (passt.py:360-363,410; passt_sed.py:126,203; transformerXL.py:32,34), softmax (passt.py:339;
+ * transformerXL.py:549), rel_shift + softmax (transformerXL.py:254-297,514-549), exact GELU backward, bias gradients.
+ * Row r of x is read at x + (r / n_inner) * x_bstride + (r % n_inner) * cols (n_inner <= 0: contiguous), which lets a
+ * [B, skip:, C] token slice be normalised in place; y / mean / rstd are contiguous.  `in_scale` multiplies x first
+ * (the decoder's x*sqrt(d), transformerXL.py:118). */
+int t4s_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows,
+                      int cols, float eps, float in_scale, int dtype, int64_t n_inner, int64_t x_bstride, void* stream);
+size_t t4s_layernorm_bwd_workspace(int64_t rows, int cols);
+/* dx (same addressing as x) = dLN/dx (+ dx_add, same addressing); dgamma/dbeta may be NULL (frozen). */
+int t4s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dx_add,
+                      void* dx, float* dgamma, float* dbeta, float* ws, size_t ws_bytes, int64_t rows, int cols, float in_scale,
+                      int dtype, int64_t n_inner, int64_t x_bstride, void* stream);
+size_t t4s_colsum_workspace(int64_t rows, int cols);
+/* out[c] (+)= sum_r x[r*ld + c] */
+int t4s_colsum(const void* x, int dtype, int64_t rows, int cols, int64_t ld, float* ws, size_t ws_bytes, float* out, int accumulate,
+               void* stream);
+int t4s_gelu_bwd(const void* dy, const void* h, void* dh, size_t n, int dtype, void* stream);
+int t4s_softmax_fwd(const void* s, void* p, int64_t rows, int cols, int64_t ld_s, int64_t ld_p, int dtype, void* stream);
+/* dp <- p * (dp - sum(p*dp)) in place */
+int t4s_softmax_bwd(const void* p, void* dp, int64_t rows, int cols, int64_t ld_p, int64_t ld_dp, int dtype, void* stream);
+/* p[r, j] = softmax_j(ac[r, j] + bd[r, T-1-(r%T)+j]); rows = batch*heads*T */
+int t4s_relpos_softmax_fwd(const void* ac, const void* bd, void* p, int64_t rows, int T_len, int64_t ld_ac, int64_t ld_bd,
+                           int64_t ld_p, int dtype, void* stream);
+/* dp <- ds in place (= d ac); dbd row <- ds scattered to the shifted columns, zero elsewhere */
+int t4s_relpos_softmax_bwd(const void* p, void* dp, void* dbd, int64_t rows, int T_len, int64_t ld_p, int64_t ld_dp, int64_t ld_bd,
+                           int dtype, void* stream);
+
+/* ---- layout / glue kernels (csrc/misc.cu) -------------------------------------------------------------------
+ * passt.py:302-315 (patch conv as im2col + GEMM), :503-519,:560-569 (positional tables, cls/dist tokens),
+ * passt_sed.py:199-218 (frequency mean-pool), :23-34,:258-259 (pad + linear interpolation). */
+/* out [(b, f, t), patch*patch] for f < f_dim, t < t_dim (the grid may be cropped, passt.py:515) */
+int t4s_patch_im2col(const void* img, int img_dtype, void* out, int out_dtype, int batch, int height, int width, int patch, int stride,
+                     int f_dim, int t_dim, void* stream);
+int t4s_patch_posbias(const float* time_pos, const float* freq_pos, float* out, int dim, int f_dim, int t_dim, int t_table, int t_offset,
+                      void* stream);
+int t4s_cls_dist_tokens(void* x, int dtype, const float* cls, const float* dist, const float* new_pos, int batch, int64_t batch_stride,
+                        int dim, void* stream);
+/* tmp: (2 + f_dim*t_dim) * dim floats.  Any gradient pointer may be NULL. */
+int t4s_patch_small_grads(const void* dx, int dtype, float* tmp, float* d_time, float* d_freq, float* d_bias, float* d_cls, float* d_dist,
+                          float* d_newpos, int batch, int64_t batch_stride, int dim, int f_dim, int t_dim, int t_table, int t_offset,
+                          void* stream);
+int t4s_fpool_mean_fwd(const void* y, void* out, int dtype, int batch, int f_dim, int t_dim, int dim, void* stream);
+int t4s_fpool_mean_bwd(const void* dout, void* dy, int dtype, int batch, int f_dim, int t_dim, int dim, void* stream);
+/* x [B, t_in, C] -> out [B, (t_in+pad)*ratio, C]; pad = 1 repeats the last frame first (99 -> 100 frames) */
+int t4s_pad_interp_fwd(const void* x, void* out, int dtype, int batch, int t_in, int ratio, int dim, int pad, void* stream);
+int t4s_pad_interp_bwd(const void* dout, void* dx, int dtype, int batch, int t_in, int ratio, int dim, int pad, void* stream);
+/* out[r, c] = scale * x[r*ld + c] + vec[c]  (vec may be NULL) */
+int t4s_add_rowvec(const void* x, int64_t ld, const float* vec, void* out, int64_t rows, int cols, float scale, int dtype, void* stream);
+/* out[r*ldo + c] = alpha * x[r*ldx + c] + beta * y[r*ldy + c] */
+int t4s_add2(const void* x, int64_t ldx, const void* y, int64_t ldy, void* out, int64_t ldo, int64_t rows, int cols, float alpha, float beta,
+             int dtype, void* stream);
+int t4s_convert(const void* in, int in_dtype, void* out, int out_dtype, size_t n, void* stream);
+
+/* ---- K6/K7: heads and losses (csrc/head.cu) ------------------------------------------------------------------
+ * passt_sed.py:285-296 (sigmoid, pad mask, linear-softmax pool), pooling.py:37-51 (AttentionPooling),
+ * recipes/desed/finetune/train.py:166-178 (BCE / MSE), recipes/desed/mlm/mlm_passt/train.py:36-38 (masked MSE). */
+int t4s_sed_pool_fwd(const float* logits, const unsigned char* pad_mask, float temp, float* strong, float* weak, int batch, int frames,
+                     int classes, void* stream);
+int t4s_sed_pool_bwd(const float* strong, const float* dstrong, const float* dweak, const unsigned char* pad_mask, float temp, float* dlogits,
+                     int batch, int frames, int classes, void* stream);
+int t4s_sigmoid_fwd(const float* x, float* y, size_t n, void* stream);
+int t4s_sigmoid_bwd(const float* y, const float* dy, float* dx, size_t n, void* stream);
+/* out[0] = mean loss, out[1] = divisor; ws >= 512 floats */
+int t4s_bce_fwd(const float* p, const float* y, size_t n, float* ws, float* out, void* stream);
+int t4s_bce_bwd(const float* p, const float* y, const float* grad_out, size_t n, float* dp, void* stream);
+int t4s_mse_fwd(const void* a, const void* b, const unsigned char* row_mask, int64_t rows, int cols, int dtype, float* ws, float* out,
+                void* stream);
+int t4s_mse_bwd(const void* a, const void* b, const unsigned char* row_mask, int64_t rows, int cols, int dtype, const float* grad_out,
+                const float* fwd_out, void* da, void* db, void* stream);
+/* kv: item i at kv + i*item_stride holds [keys, 2*dim] (k | v per key); item_stride <= 0 means keys*2*dim (a larger
+ * stride skips leading tokens such as cls/dist).  q [dim] fp32 pre-scaled; ctx [items, dim]; probs [items, heads, keys] */
+int t4s_attnpool_fwd(const void* kv, const float* q, void* ctx, float* probs, int items, int keys, int dim, int heads, int64_t item_stride,
+                     int dtype, void* stream);
+int t4s_attnpool_bwd(const void* kv, const float* q, const float* probs, const void* dctx, void* dkv, float* dq_part, int items, int keys,
+                     int dim, int heads, int64_t item_stride, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,146 @@
+"""GPU parity proper: the drop-in `PaSST_SED` (CUDA kernels through the C ABI) against the golden vectors recorded from
+the UNMODIFIED reference (tests/golden/, oracle/make_golden.py) and against the CPU oracle on fresh inputs.
+
+Contract (BASELINE.json north_star): bit-exact frame-label argmax, <= 1e-3 relative on activations / loss.  That contract
+is checked in the strict `tf32x3` mode (error-compensated tensor-core GEMMs, fp32 activations).  The bf16 performance mode
+is checked against the same vectors with bf16-sized tolerances and its argmax tie-rate is reported, not asserted exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import checksum
+from transformer4sed_b200 import schema
+from transformer4sed_b200.utils import synth
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(embed_dim=192, decoder_dim=192, decoder="transformerXL", decoder_layer_num=1, at_adapter=True, f_pool="mean_pool", mlm=False)
+BASE = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_adapter=True, decoder="transformerXL", decoder_layer_num=3,
+            decoder_pos_emd_len=1000, mlm=False)
+PRE = dict(BASE, mlm=True, mlm_dict=dict(strategy="block", block_width=10, mask_rate=0.75, out_dim=768))
+
+
+def build(kw, seed):
+    from transformer4sed_b200.src_models.passt.passt_sed import PaSST_SED
+    net = PaSST_SED(load_pretrained_model=False, **kw)
+    sd = synth.synth_state_dict_like(net, seed)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda(), sd
+
+
+def relmax(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def run_golden(tag, kw, seed, batch, golden, mode):
+    from transformer4sed_b200 import functional as F
+    g = golden(f"matsed_{tag}.npz")
+    F.set_precision(mode)
+    try:
+        net, sd = build(kw, seed)
+        np.testing.assert_allclose(checksum(torch.cat([v.flatten() for _, v in sorted(sd.items())])), g["sd_ck"], rtol=1e-12)
+        net.eval()
+        ext = net.get_feature_extractor().eval()
+        wav = synth.synth_wav(batch, 320000, seed=seed + 1)
+        np.testing.assert_allclose(checksum(wav), g["wav_ck"], rtol=1e-12)
+        mel = ext.normalize(ext(wav.cuda()))
+        labels = synth.synth_strong_labels(batch, 10, 1000, seed + 2).cuda()
+        weak_labels = (labels.sum(-1) > 0).float()
+        cap = {}
+        net.decoder.register_forward_hook(lambda m, i, o: cap.__setitem__("decoder_out", o))
+        net.interpolate_module.register_forward_hook(lambda m, i, o: cap.__setitem__("interp", o))
+        strong, weak, other = net(mel, temp_w=1)
+        loss = F.bce_loss(strong, labels) + 0.5 * F.bce_loss(weak, weak_labels) + 2.0 * F.bce_loss(other["at_out"], weak_labels)
+        loss.backward()
+        res = dict(
+            strong=relmax(strong, g["strong"]), weak=relmax(weak, g["weak"]), at_out=relmax(other["at_out"], g["at_out"]),
+            fbm=relmax(other["frame_before_mask"].float()[:, ::8, ::4], g["frame_before_mask"]),
+            dec=relmax(cap["decoder_out"].float()[:, ::8, ::4], g["decoder_out"]),
+            loss=abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])),
+            argmax_mismatch=float((strong.argmax(dim=1).cpu().numpy() != g["argmax"]).mean()),
+        )
+        assert torch.equal(cap["interp"], other["frame_before_mask"])
+        gerr = {}
+        params = dict(net.named_parameters())
+        for name, norm, head in zip(g["grad_names"], g["grad_norms"], g["grad_heads"]):
+            p = params[str(name)]
+            assert p.grad is not None, name
+            gn = p.grad.double().norm().item()
+            n = min(8, p.grad.numel())
+            gerr[str(name)] = max(abs(gn - norm) / max(norm, 1e-9),
+                                  float(np.abs(p.grad.flatten()[:n].double().cpu().numpy() - head[:n]).max()) / max(norm, 1e-9))
+        res["grad_worst"] = max(gerr.values())
+        res["grad_worst_name"] = max(gerr, key=gerr.get)
+        with torch.no_grad():
+            pad = torch.zeros(batch, 1000, dtype=torch.bool, device="cuda")
+            pad[-1, 900:] = True
+            sp, wp, _ = net(mel, temp_w=1, pad_mask=pad)
+            s5, w5, _ = net(mel, temp_w=0.5)
+        res["pad"] = max(relmax(sp, g["strong_pad"]), relmax(wp, g["weak_pad"]))
+        res["t05"] = max(relmax(s5, g["strong_t05"]), relmax(w5, g["weak_t05"]))
+        return res
+    finally:
+        F.set_precision("bf16")
+
+
+@pytest.mark.parametrize("tag,kw,seed,batch", [("small", SMALL, 3, 2), ("base", BASE, 4, 1)])
+def test_strict_mode_meets_contract(golden, tag, kw, seed, batch):
+    r = run_golden(tag, kw, seed, batch, golden, "tf32x3")
+    print(tag, "tf32x3", r)
+    for k in ("strong", "weak", "at_out", "fbm", "dec", "loss", "pad", "t05"):
+        assert r[k] < 1e-3, (k, r)
+    assert r["argmax_mismatch"] == 0.0, r
+    assert r["grad_worst"] < 5e-3, r
+
+
+@pytest.mark.parametrize("tag,kw,seed,batch", [("small", SMALL, 3, 2), ("base", BASE, 4, 1)])
+def test_tf32_mode(golden, tag, kw, seed, batch):
+    r = run_golden(tag, kw, seed, batch, golden, "tf32")
+    print(tag, "tf32", r)
+    for k in ("strong", "weak", "at_out", "loss"):
+        assert r[k] < 1e-2, (k, r)
+    assert r["argmax_mismatch"] < 0.01, r
+
+
+@pytest.mark.parametrize("tag,kw,seed,batch", [("small", SMALL, 3, 2), ("base", BASE, 4, 1)])
+def test_bf16_mode(golden, tag, kw, seed, batch):
+    r = run_golden(tag, kw, seed, batch, golden, "bf16")
+    print(tag, "bf16", r)
+    for k in ("strong", "weak", "at_out"):
+        assert r[k] < 6e-2, (k, r)
+    assert r["loss"] < 2e-2, r
+    assert r["argmax_mismatch"] < 0.05, r
+    assert r["grad_worst"] < 0.25, r
+
+
+def test_mlm_pretrain_forward_matches_reference(golden):
+    """MAT-SED pre-training (mlm=True): same mask as the reference for the same torch seed; B>1 keeps the upstream no-op."""
+    from transformer4sed_b200 import functional as F
+    g = golden("matsed_mlm_base_b2.npz")
+    F.set_precision("tf32x3")
+    try:
+        net, _ = build(PRE, 6)
+        net.train()
+        ext = net.get_feature_extractor().eval()
+        wav = synth.synth_wav(2, 320000, seed=7)
+        mel = ext.normalize(ext(wav.cuda()))
+        # the reference draws on the CPU generator; replay its first draw to fix the mask, then check ours reproduces the loss
+        torch.manual_seed(9)
+        pred, other = net(mel)
+        mask_ref = torch.from_numpy(np.unpackbits(g["mask"])[:2000].astype(bool)).view(2, 1000)
+        from oracle import model as OM
+        mask_from_noise = OM.block_mask_from_noise(torch.from_numpy(g["noise"]), 0.75, 10, 1000)
+        assert torch.equal(mask_ref, mask_from_noise)
+        assert abs(other["mask_id_seq"].float().mean().item() - float(g["masked_frac"])) < 1e-6   # 76 of 100 blocks
+        assert relmax(pred.float()[:, ::8, ::4], g["pred"]) < 1e-3
+        assert relmax(other["at_out"], g["at_out"]) < 1e-3
+        fbm = other["frame_before_mask"]
+        loss = F.mse_loss(fbm.detach(), pred, mask_ref.cuda())
+        assert abs(loss.item() - float(g["loss"])) / float(g["loss"]) < 1e-3
+        loss.backward()
+        assert net.mask_token.grad is None   # upstream no-op masking: the mask token never reaches the decoder
+        assert net.mlm_mlp[2].weight.grad is not None
+    finally:
+        F.set_precision("bf16")

@@ -43,7 +43,7 @@ class Gemm(ctypes.Structure):
 
 
 def _declare(lib):
-    P, I, Z, F = c_void_p, c_int, c_size_t, c_float
+    P, I, Z, F, L = c_void_p, c_int, c_size_t, c_float, ctypes.c_int64
     sigs = {
         "t4s_version": (I, []),
         "t4s_last_error": (ctypes.c_char_p, []),
@@ -56,6 +56,38 @@ def _declare(lib):
         "t4s_mel_normalize": (I, [P, P, Z, P]),
         "t4s_gemm": (I, [ctypes.POINTER(Gemm), P]),
         "t4s_reduce_splits": (I, [P, I, Z, P, I, P]),
+        "t4s_split_tf32": (I, [ctypes.POINTER(Operand), I, P, I, P]),
+        "t4s_layernorm_fwd": (I, [P, P, P, P, P, P, L, I, F, F, I, L, L, P]),
+        "t4s_layernorm_bwd_workspace": (Z, [L, I]),
+        "t4s_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, P, Z, L, I, F, I, L, L, P]),
+        "t4s_colsum_workspace": (Z, [L, I]),
+        "t4s_colsum": (I, [P, I, L, I, L, P, Z, P, I, P]),
+        "t4s_gelu_bwd": (I, [P, P, P, Z, I, P]),
+        "t4s_softmax_fwd": (I, [P, P, L, I, L, L, I, P]),
+        "t4s_softmax_bwd": (I, [P, P, L, I, L, L, I, P]),
+        "t4s_relpos_softmax_fwd": (I, [P, P, P, L, I, L, L, L, I, P]),
+        "t4s_relpos_softmax_bwd": (I, [P, P, P, L, I, L, L, L, I, P]),
+        "t4s_patch_im2col": (I, [P, I, P, I, I, I, I, I, I, I, I, P]),
+        "t4s_add2": (I, [P, L, P, L, P, L, L, I, F, F, I, P]),
+        "t4s_patch_posbias": (I, [P, P, P, I, I, I, I, I, P]),
+        "t4s_cls_dist_tokens": (I, [P, I, P, P, P, I, L, I, P]),
+        "t4s_patch_small_grads": (I, [P, I, P, P, P, P, P, P, P, I, L, I, I, I, I, I, P]),
+        "t4s_fpool_mean_fwd": (I, [P, P, I, I, I, I, I, P]),
+        "t4s_fpool_mean_bwd": (I, [P, P, I, I, I, I, I, P]),
+        "t4s_pad_interp_fwd": (I, [P, P, I, I, I, I, I, I, P]),
+        "t4s_pad_interp_bwd": (I, [P, P, I, I, I, I, I, I, P]),
+        "t4s_add_rowvec": (I, [P, L, P, P, L, I, F, I, P]),
+        "t4s_convert": (I, [P, I, P, I, Z, P]),
+        "t4s_sed_pool_fwd": (I, [P, P, F, P, P, I, I, I, P]),
+        "t4s_sed_pool_bwd": (I, [P, P, P, P, F, P, I, I, I, P]),
+        "t4s_sigmoid_fwd": (I, [P, P, Z, P]),
+        "t4s_sigmoid_bwd": (I, [P, P, P, Z, P]),
+        "t4s_bce_fwd": (I, [P, P, Z, P, P, P]),
+        "t4s_bce_bwd": (I, [P, P, P, Z, P, P]),
+        "t4s_mse_fwd": (I, [P, P, P, L, I, I, P, P, P]),
+        "t4s_mse_bwd": (I, [P, P, P, L, I, I, P, P, P, P, P]),
+        "t4s_attnpool_fwd": (I, [P, P, P, P, I, I, I, I, L, I, P]),
+        "t4s_attnpool_bwd": (I, [P, P, P, P, P, P, I, I, I, I, L, I, P]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)

@@ -1,0 +1,368 @@
+// K6/K7: heads and losses of the SED path (fp32 statistics, deterministic two-stage reductions):
+//   sed_pool   : sigmoid(logit / temp), padded frames -> 0, linear-softmax pooling   (reference passt_sed.py:285-296)
+//   attnpool   : single learned-query multi-head attention pooling                    (reference pooling.py:37-51)
+//   bce / mse  : torch.nn.BCELoss / MSELoss(mean) with optional row mask              (finetune/train.py:166-178,
+//                                                                                      mlm/mlm_passt/train.py:36-38)
+//   sigmoid    : audio-tagging head                                                    (passt_sed.py:236-240)
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace t4s {
+namespace head {
+
+__device__ __forceinline__ float block_sum(float v, float* s_red) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  float t = (threadIdx.x < (blockDim.x >> 5)) ? s_red[threadIdx.x] : 0.f;
+  if (warp == 0) t = warp_sum(t);
+  if (threadIdx.x == 0) s_red[0] = t;
+  __syncthreads();
+  return s_red[0];
+}
+
+// ---- sed_pool: logits [B, T, K] fp32 -> strong [B, K, T], weak [B, K].  One block per (b, k).
+__global__ void sed_pool_fwd_kernel(const float* __restrict__ logits, const unsigned char* __restrict__ pad_mask, float inv_temp,
+                                    float* __restrict__ strong, float* __restrict__ weak, int T, int K) {
+  __shared__ float s_red[32];
+  const int b = blockIdx.x / K, k = blockIdx.x % K;
+  float s1 = 0.f, s2 = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float p = 1.0f / (1.0f + expf(-logits[((long long)b * T + t) * K + k] * inv_temp));
+    if (pad_mask && pad_mask[(long long)b * T + t]) p = 0.f;
+    strong[((long long)b * K + k) * T + t] = p;
+    s1 += p;
+    s2 += p * p;
+  }
+  s1 = block_sum(s1, s_red);
+  s2 = block_sum(s2, s_red);
+  if (threadIdx.x == 0) weak[blockIdx.x] = fminf(fmaxf(s2 / s1, 1e-7f), 1.0f);
+}
+
+// dlogit[b,t,k] = (dstrong + dweak * d(weak)/dp) * p (1 - p) / temp
+__global__ void sed_pool_bwd_kernel(const float* __restrict__ strong, const float* __restrict__ dstrong, const float* __restrict__ dweak,
+                                    const unsigned char* __restrict__ pad_mask, float inv_temp, float* __restrict__ dlogits, int T, int K) {
+  __shared__ float s_red[32];
+  const int b = blockIdx.x / K, k = blockIdx.x % K;
+  const float* p_row = strong + ((long long)b * K + k) * T;
+  float s1 = 0.f, s2 = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float p = p_row[t];
+    s1 += p;
+    s2 += p * p;
+  }
+  s1 = block_sum(s1, s_red);
+  s2 = block_sum(s2, s_red);
+  const float w = s2 / s1;
+  float gw = dweak ? dweak[blockIdx.x] : 0.f;
+  if (!(w >= 1e-7f && w <= 1.0f)) gw = 0.f;  // clamp passes gradient only inside [min, max]
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float p = p_row[t];
+    float dp = dstrong ? dstrong[((long long)b * K + k) * T + t] : 0.f;
+    dp += gw * (2.0f * p * s1 - s2) / (s1 * s1);
+    float dl = dp * p * (1.0f - p) * inv_temp;
+    if (pad_mask && pad_mask[(long long)b * T + t]) dl = 0.f;
+    dlogits[((long long)b * T + t) * K + k] = dl;
+  }
+}
+
+// ---- elementwise sigmoid
+__global__ void sigmoid_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) y[i] = 1.0f / (1.0f + expf(-x[i]));
+}
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dx[i] = dy[i] * y[i] * (1.0f - y[i]);
+}
+
+// ---- BCE (torch semantics: log clamped at -100; backward divides by max(p(1-p), 1e-12))
+__global__ void bce_partial_kernel(const float* __restrict__ p, const float* __restrict__ y, size_t n, float* __restrict__ part) {
+  __shared__ float s_red[32];
+  float acc = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float pi = p[i], yi = y[i];
+    acc -= yi * fmaxf(logf(pi), -100.f) + (1.0f - yi) * fmaxf(logf(1.0f - pi), -100.f);
+  }
+  acc = block_sum(acc, s_red);
+  if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+__global__ void finish_mean_kernel(const float* __restrict__ part, int nparts, const float* __restrict__ count_part, float denom,
+                                   float* __restrict__ out) {
+  // single warp: out[0] = sum(part) / (count_part ? sum(count_part) * denom : denom); out[1] = that divisor
+  float a = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += 32) {
+    a += part[i];
+    if (count_part) c += count_part[i];
+  }
+  a = warp_sum(a);
+  c = warp_sum(c);
+  if (threadIdx.x == 0) {
+    const float div = count_part ? c * denom : denom;
+    out[0] = a / div;
+    out[1] = div;
+  }
+}
+__global__ void bce_bwd_kernel(const float* __restrict__ p, const float* __restrict__ y, const float* __restrict__ gout, float inv_n,
+                               float* __restrict__ dp, size_t n) {
+  const float g = gout[0] * inv_n;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float pi = p[i];
+    dp[i] = g * (pi - y[i]) / fmaxf(pi * (1.0f - pi), 1e-12f);
+  }
+}
+
+// ---- (masked) MSE over rows of width C: mean over selected rows x C of (a - b)^2
+template <typename T>
+__global__ void mse_partial_kernel(const T* __restrict__ a, const T* __restrict__ b, const unsigned char* __restrict__ mask, long long rows,
+                                   int C, float* __restrict__ part, float* __restrict__ count_part) {
+  __shared__ float s_red[32];
+  float acc = 0.f, cnt = 0.f;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    if (mask && !mask[r]) continue;
+    if (threadIdx.x == 0) cnt += 1.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float d = to_f32<T>(a[r * C + c]) - to_f32<T>(b[r * C + c]);
+      acc += d * d;
+    }
+  }
+  acc = block_sum(acc, s_red);
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = acc;
+    count_part[blockIdx.x] = cnt;
+  }
+}
+template <typename T>
+__global__ void mse_bwd_kernel(const T* __restrict__ a, const T* __restrict__ b, const unsigned char* __restrict__ mask, long long rows, int C,
+                               const float* __restrict__ gout, const float* __restrict__ fwd_out /*[1] = divisor*/, T* __restrict__ da,
+                               T* __restrict__ db) {
+  const float g = 2.0f * gout[0] / fwd_out[1];
+  const long long total = rows * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / C;
+    float d = 0.f;
+    if (!mask || mask[r]) d = g * (to_f32<T>(a[i]) - to_f32<T>(b[i]));
+    if (da) da[i] = from_f32<T>(d);
+    if (db) db[i] = from_f32<T>(-d);
+  }
+}
+
+// ---- attention pooling with one query.  kv [Bp, K, 2C] (k then v per key row), q [C] fp32 already scaled by hd^-1/2.
+// One block per pooled item; dynamic smem: probs [H][K] + q [C] (+ dctx [C] in backward).
+template <typename T>
+__global__ void __launch_bounds__(256) attnpool_fwd_kernel(const T* __restrict__ kv, const float* __restrict__ q, T* __restrict__ ctx,
+                                                           float* __restrict__ probs, int K, int C, int H, long long item_stride) {
+  extern __shared__ float sm[];
+  float* s_p = sm;           // [H][K]
+  float* s_q = sm + H * K;   // [C]
+  const int bp = blockIdx.x, hd = C / H;
+  const T* kvb = kv + (long long)bp * item_stride;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) s_q[c] = q[c];
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * K; i += blockDim.x) {
+    const int h = i / K, j = i % K;
+    const T* kr = kvb + (long long)j * 2 * C + h * hd;
+    float acc = 0.f;
+    for (int d = 0; d < hd; ++d) acc += s_q[h * hd + d] * to_f32<T>(kr[d]);
+    s_p[i] = acc;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int h = warp; h < H; h += (blockDim.x >> 5)) {
+    float mx = -INFINITY;
+    for (int j = lane; j < K; j += 32) mx = fmaxf(mx, s_p[h * K + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < K; j += 32) {
+      const float e = __expf(s_p[h * K + j] - mx);
+      s_p[h * K + j] = e;
+      sum += e;
+    }
+    const float inv = 1.0f / warp_sum(sum);
+    for (int j = lane; j < K; j += 32) {
+      const float p = s_p[h * K + j] * inv;
+      s_p[h * K + j] = p;
+      if (probs) probs[((long long)bp * H + h) * K + j] = p;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int h = c / hd;
+    float acc = 0.f;
+    for (int j = 0; j < K; ++j) acc += s_p[h * K + j] * to_f32<T>(kvb[(long long)j * 2 * C + C + c]);
+    ctx[(long long)bp * C + c] = from_f32<T>(acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) attnpool_bwd_kernel(const T* __restrict__ kv, const float* __restrict__ q, const float* __restrict__ probs,
+                                                           const T* __restrict__ dctx, T* __restrict__ dkv, float* __restrict__ dq_part,
+                                                           int K, int C, int H, long long item_stride) {
+  extern __shared__ float sm[];
+  float* s_ds = sm;              // [H][K]: dp then ds
+  float* s_q = sm + H * K;       // [C]
+  float* s_dc = s_q + C;         // [C]
+  const int bp = blockIdx.x, hd = C / H;
+  const T* kvb = kv + (long long)bp * item_stride;
+  T* dkvb = dkv + (long long)bp * item_stride;
+  const float* pb = probs + (long long)bp * H * K;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    s_q[c] = q[c];
+    s_dc[c] = to_f32<T>(dctx[(long long)bp * C + c]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H * K; i += blockDim.x) {  // dp[h][j] = dctx_h . v[j, h]
+    const int h = i / K, j = i % K;
+    const T* vr = kvb + (long long)j * 2 * C + C + h * hd;
+    float acc = 0.f;
+    for (int d = 0; d < hd; ++d) acc += s_dc[h * hd + d] * to_f32<T>(vr[d]);
+    s_ds[i] = acc;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int h = warp; h < H; h += (blockDim.x >> 5)) {
+    float dot = 0.f;
+    for (int j = lane; j < K; j += 32) dot += pb[h * K + j] * s_ds[h * K + j];
+    dot = warp_sum(dot);
+    for (int j = lane; j < K; j += 32) s_ds[h * K + j] = pb[h * K + j] * (s_ds[h * K + j] - dot);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int h = c / hd;
+    const float qc = s_q[c], dc = s_dc[c];
+    float dq = 0.f;
+    for (int j = 0; j < K; ++j) {
+      const float ds = s_ds[h * K + j];
+      dq += ds * to_f32<T>(kvb[(long long)j * 2 * C + c]);
+      dkvb[(long long)j * 2 * C + c] = from_f32<T>(ds * qc);
+      dkvb[(long long)j * 2 * C + C + c] = from_f32<T>(pb[h * K + j] * dc);
+    }
+    dq_part[(long long)bp * C + c] = dq;
+  }
+}
+
+static int grid_for(long long n, int threads = 256) {
+  return (int)std::max<long long>(1, std::min<long long>((n + threads - 1) / threads, (long long)sm_count() * 8));
+}
+
+}  // namespace head
+}  // namespace t4s
+
+using namespace t4s::head;
+
+extern "C" {
+
+int t4s_sed_pool_fwd(const float* logits, const unsigned char* pad_mask, float temp, float* strong, float* weak, int batch, int frames,
+                     int classes, void* stream) {
+  T4S_REQUIRE(logits && strong && weak && batch > 0 && frames > 0 && classes > 0 && temp != 0.f, "t4s_sed_pool_fwd: bad arguments");
+  sed_pool_fwd_kernel<<<batch * classes, 256, 0, t4s::as_stream(stream)>>>(logits, pad_mask, 1.0f / temp, strong, weak, frames, classes);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_sed_pool_bwd(const float* strong, const float* dstrong, const float* dweak, const unsigned char* pad_mask, float temp, float* dlogits,
+                     int batch, int frames, int classes, void* stream) {
+  T4S_REQUIRE(strong && dlogits && batch > 0 && frames > 0 && classes > 0 && temp != 0.f, "t4s_sed_pool_bwd: bad arguments");
+  sed_pool_bwd_kernel<<<batch * classes, 256, 0, t4s::as_stream(stream)>>>(strong, dstrong, dweak, pad_mask, 1.0f / temp, dlogits, frames, classes);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_sigmoid_fwd(const float* x, float* y, size_t n, void* stream) {
+  T4S_REQUIRE(x && y, "t4s_sigmoid_fwd: null pointer");
+  if (n) sigmoid_fwd_kernel<<<grid_for((long long)n), 256, 0, t4s::as_stream(stream)>>>(x, y, n);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_sigmoid_bwd(const float* y, const float* dy, float* dx, size_t n, void* stream) {
+  T4S_REQUIRE(y && dy && dx, "t4s_sigmoid_bwd: null pointer");
+  if (n) sigmoid_bwd_kernel<<<grid_for((long long)n), 256, 0, t4s::as_stream(stream)>>>(y, dy, dx, n);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+#define T4S_LOSS_PARTS 256
+
+/* out[0] = mean BCE, out[1] = n.  ws: >= 256 floats. */
+int t4s_bce_fwd(const float* p, const float* y, size_t n, float* ws, float* out, void* stream) {
+  T4S_REQUIRE(p && y && ws && out && n > 0, "t4s_bce_fwd: bad arguments");
+  cudaStream_t st = t4s::as_stream(stream);
+  const int parts = (int)std::min<size_t>(T4S_LOSS_PARTS, (n + 255) / 256);
+  bce_partial_kernel<<<parts, 256, 0, st>>>(p, y, n, ws);
+  finish_mean_kernel<<<1, 32, 0, st>>>(ws, parts, nullptr, (float)n, out);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_bce_bwd(const float* p, const float* y, const float* grad_out, size_t n, float* dp, void* stream) {
+  T4S_REQUIRE(p && y && grad_out && dp && n > 0, "t4s_bce_bwd: bad arguments");
+  bce_bwd_kernel<<<grid_for((long long)n), 256, 0, t4s::as_stream(stream)>>>(p, y, grad_out, 1.0f / (float)n, dp, n);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+/* out[0] = mean over (selected rows x cols) of (a-b)^2, out[1] = divisor.  ws: >= 512 floats. */
+int t4s_mse_fwd(const void* a, const void* b, const unsigned char* row_mask, int64_t rows, int cols, int dtype, float* ws, float* out,
+                void* stream) {
+  T4S_REQUIRE(a && b && ws && out && rows > 0 && cols > 0, "t4s_mse_fwd: bad arguments");
+  cudaStream_t st = t4s::as_stream(stream);
+  const int parts = (int)std::min<long long>(T4S_LOSS_PARTS, rows);
+  if (dtype == T4S_F32) mse_partial_kernel<float><<<parts, 256, 0, st>>>((const float*)a, (const float*)b, row_mask, rows, cols, ws, ws + T4S_LOSS_PARTS);
+  else if (dtype == T4S_BF16) mse_partial_kernel<__nv_bfloat16><<<parts, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, row_mask, rows, cols, ws, ws + T4S_LOSS_PARTS);
+  else { t4s::set_error("t4s_mse_fwd: bad dtype"); return T4S_ERR_ARG; }
+  finish_mean_kernel<<<1, 32, 0, st>>>(ws, parts, ws + T4S_LOSS_PARTS, (float)cols, out);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_mse_bwd(const void* a, const void* b, const unsigned char* row_mask, int64_t rows, int cols, int dtype, const float* grad_out,
+                const float* fwd_out, void* da, void* db, void* stream) {
+  T4S_REQUIRE(a && b && grad_out && fwd_out && (da || db), "t4s_mse_bwd: bad arguments");
+  cudaStream_t st = t4s::as_stream(stream);
+  const int grid = grid_for(rows * cols);
+  if (dtype == T4S_F32) mse_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, row_mask, rows, cols, grad_out, fwd_out, (float*)da, (float*)db);
+  else if (dtype == T4S_BF16) mse_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, row_mask, rows, cols, grad_out, fwd_out, (__nv_bfloat16*)da, (__nv_bfloat16*)db);
+  else { t4s::set_error("t4s_mse_bwd: bad dtype"); return T4S_ERR_ARG; }
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_attnpool_fwd(const void* kv, const float* q, void* ctx, float* probs, int items, int keys, int dim, int heads, int64_t item_stride,
+                     int dtype, void* stream) {
+  if (item_stride <= 0) item_stride = (int64_t)keys * 2 * dim;
+  T4S_REQUIRE(kv && q && ctx && items > 0 && keys > 0 && heads > 0 && dim % heads == 0, "t4s_attnpool_fwd: bad arguments");
+  const size_t smem = ((size_t)heads * keys + dim) * sizeof(float);
+  T4S_REQUIRE(smem <= 200 * 1024, "t4s_attnpool_fwd: heads*keys too large for shared memory");
+  cudaStream_t st = t4s::as_stream(stream);
+  if (dtype == T4S_F32) {
+    T4S_CUDA(cudaFuncSetAttribute(attnpool_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attnpool_fwd_kernel<float><<<items, 256, smem, st>>>((const float*)kv, q, (float*)ctx, probs, keys, dim, heads, item_stride);
+  } else if (dtype == T4S_BF16) {
+    T4S_CUDA(cudaFuncSetAttribute(attnpool_fwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attnpool_fwd_kernel<__nv_bfloat16><<<items, 256, smem, st>>>((const __nv_bfloat16*)kv, q, (__nv_bfloat16*)ctx, probs, keys, dim, heads, item_stride);
+  } else { t4s::set_error("t4s_attnpool_fwd: bad dtype"); return T4S_ERR_ARG; }
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_attnpool_bwd(const void* kv, const float* q, const float* probs, const void* dctx, void* dkv, float* dq_part, int items, int keys,
+                     int dim, int heads, int64_t item_stride, int dtype, void* stream) {
+  if (item_stride <= 0) item_stride = (int64_t)keys * 2 * dim;
+  T4S_REQUIRE(kv && q && probs && dctx && dkv && dq_part && items > 0 && keys > 0 && heads > 0 && dim % heads == 0, "t4s_attnpool_bwd: bad arguments");
+  const size_t smem = ((size_t)heads * keys + 2 * dim) * sizeof(float);
+  T4S_REQUIRE(smem <= 200 * 1024, "t4s_attnpool_bwd: heads*keys too large for shared memory");
+  cudaStream_t st = t4s::as_stream(stream);
+  if (dtype == T4S_F32) {
+    T4S_CUDA(cudaFuncSetAttribute(attnpool_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attnpool_bwd_kernel<float><<<items, 256, smem, st>>>((const float*)kv, q, probs, (const float*)dctx, (float*)dkv, dq_part, keys, dim, heads, item_stride);
+  } else if (dtype == T4S_BF16) {
+    T4S_CUDA(cudaFuncSetAttribute(attnpool_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attnpool_bwd_kernel<__nv_bfloat16><<<items, 256, smem, st>>>((const __nv_bfloat16*)kv, q, probs, (const __nv_bfloat16*)dctx, (__nv_bfloat16*)dkv, dq_part, keys, dim, heads, item_stride);
+  } else { t4s::set_error("t4s_attnpool_bwd: bad dtype"); return T4S_ERR_ARG; }
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,452 @@
+// K2 and friends: row-wise kernels (one warp per row, values held in registers, fp32 statistics):
+//   LayerNorm forward / backward (+ fused residual-gradient add), row softmax forward / backward,
+//   relative-position softmax with the Transformer-XL shift folded into the read, column sums (bias / gamma grads),
+//   GELU backward.  All take fp32 or bf16 activations; statistics and parameters are fp32.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace t4s {
+namespace rowops {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> {
+  static __device__ __forceinline__ float4 load(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void store(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct Vec4<__nv_bfloat16> {
+  static __device__ __forceinline__ float4 load(const __nv_bfloat16* p) {
+    uint2 u = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&u.x), hi = *reinterpret_cast<__nv_bfloat162*>(&u.y);
+    return make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(p) = u;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// LayerNorm.  Row r lives at x + (r / n_inner) * bstride + (r % n_inner) * cols  (a [B, skip:, C] slice is a view).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kLnMaxV = 8;  // float4 per lane -> cols <= 1024
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
+                                                          const float* __restrict__ beta, T* __restrict__ y,
+                                                          float* __restrict__ mean, float* __restrict__ rstd, long long rows,
+                                                          int cols, float eps, float in_scale, long long n_inner,
+                                                          long long bstride) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const int nv = cols >> 2;
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const T* xr = x + (r / n_inner) * bstride + (r % n_inner) * cols;
+    float4 v[kLnMaxV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        v[i] = Vec4<T>::load(xr + 4 * c);
+        v[i].x *= in_scale; v[i].y *= in_scale; v[i].z *= in_scale; v[i].w *= in_scale;
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mu = warp_sum(s) / (float)cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        float a = v[i].x - mu, b = v[i].y - mu, c2 = v[i].z - mu, d = v[i].w - mu;
+        q += (a * a + b * b) + (c2 * c2 + d * d);
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) / (float)cols + eps);
+    T* yr = y + r * cols;
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c), b = *reinterpret_cast<const float4*>(beta + 4 * c);
+        float4 o;
+        o.x = (v[i].x - mu) * rs * g.x + b.x;
+        o.y = (v[i].y - mu) * rs * g.y + b.y;
+        o.z = (v[i].z - mu) * rs * g.z + b.z;
+        o.w = (v[i].w - mu) * rs * g.w + b.w;
+        Vec4<T>::store(yr + 4 * c, o);
+      }
+    }
+    if (lane == 0) {
+      if (mean) mean[r] = mu;
+      if (rstd) rstd[r] = rs;
+    }
+  }
+}
+
+// dx = in_scale * rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)) (+ dx_add);  partial dgamma/dbeta per block.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+                                                          const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                          const float* __restrict__ rstd, const T* __restrict__ dx_add,
+                                                          T* __restrict__ dx, float* __restrict__ part /*[grid][2][cols]*/,
+                                                          long long rows, int cols, float in_scale, long long n_inner,
+                                                          long long bstride) {
+  extern __shared__ float s_part[];  // [kWarpsPerBlock][2][cols]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + warp;
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const int nv = cols >> 2;
+  float4 ag[kLnMaxV], ab[kLnMaxV];
+#pragma unroll
+  for (int i = 0; i < kLnMaxV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const long long xoff = (r / n_inner) * bstride + (r % n_inner) * cols;
+    const T* xr = x + xoff;
+    const T* dyr = dy + r * cols;
+    const float mu = mean[r], rs = rstd[r];
+    float4 xh[kLnMaxV], gd[kLnMaxV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        float4 xv = Vec4<T>::load(xr + 4 * c), dv = Vec4<T>::load(dyr + 4 * c);
+        const float4 g = *reinterpret_cast<const float4*>(gamma + 4 * c);
+        xh[i] = make_float4((xv.x * in_scale - mu) * rs, (xv.y * in_scale - mu) * rs, (xv.z * in_scale - mu) * rs,
+                            (xv.w * in_scale - mu) * rs);
+        gd[i] = make_float4(dv.x * g.x, dv.y * g.y, dv.z * g.z, dv.w * g.w);
+        s1 += (gd[i].x + gd[i].y) + (gd[i].z + gd[i].w);
+        s2 += (gd[i].x * xh[i].x + gd[i].y * xh[i].y) + (gd[i].z * xh[i].z + gd[i].w * xh[i].w);
+        ag[i].x += dv.x * xh[i].x; ag[i].y += dv.y * xh[i].y; ag[i].z += dv.z * xh[i].z; ag[i].w += dv.w * xh[i].w;
+        ab[i].x += dv.x; ab[i].y += dv.y; ab[i].z += dv.z; ab[i].w += dv.w;
+      }
+    }
+    const float m1 = warp_sum(s1) / (float)cols, m2 = warp_sum(s2) / (float)cols;
+    const float k = rs * in_scale;
+    T* dxr = dx + xoff;
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        float4 o;
+        o.x = k * (gd[i].x - m1 - xh[i].x * m2);
+        o.y = k * (gd[i].y - m1 - xh[i].y * m2);
+        o.z = k * (gd[i].z - m1 - xh[i].z * m2);
+        o.w = k * (gd[i].w - m1 - xh[i].w * m2);
+        if (dx_add) {
+          float4 a = Vec4<T>::load(dx_add + xoff + 4 * c);
+          o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        }
+        Vec4<T>::store(dxr + 4 * c, o);
+      }
+    }
+  }
+  if (part) {
+    float* sp = s_part + warp * 2 * cols;
+#pragma unroll
+    for (int i = 0; i < kLnMaxV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nv) {
+        *reinterpret_cast<float4*>(sp + 4 * c) = ag[i];
+        *reinterpret_cast<float4*>(sp + cols + 4 * c) = ab[i];
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 2 * cols; j += kThreads) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarpsPerBlock; ++w) acc += s_part[w * 2 * cols + j];
+      part[(size_t)blockIdx.x * 2 * cols + j] = acc;
+    }
+  }
+}
+
+// out[j] (+)= sum_p part[p * stride + j]
+__global__ void reduce_rows_kernel(const float* __restrict__ part, int nparts, long long stride, int n, float* __restrict__ out,
+                                   int accumulate) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  float acc = accumulate ? out[j] : 0.f;
+  for (int p = 0; p < nparts; ++p) acc += part[(size_t)p * stride + j];
+  out[j] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Column sums: out[c] (+)= sum_r x[r, c].  Stage 1: block (256 threads x 4 columns) over a strip of rows.
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T* __restrict__ x, long long rows, int cols, long long ld,
+                                                             float* __restrict__ part, int rows_per_block) {
+  const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long r = r0; r < r1; ++r) {
+    float4 v = Vec4<T>::load(x + r * ld + c);
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  *reinterpret_cast<float4*>(part + (size_t)blockIdx.y * cols + c) = acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_partial_scalar_kernel(const T* __restrict__ x, long long rows, int cols, long long ld,
+                                                                    float* __restrict__ part, int rows_per_block) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float acc = 0.f;
+  for (long long r = r0; r < r1; ++r) acc += to_f32<T>(x[r * ld + c]);
+  part[(size_t)blockIdx.y * cols + c] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// GELU backward: dh = dy * gelu'(h)
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ h, T* __restrict__ dh, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 d = Vec4<T>::load(dy + 4 * i), x = Vec4<T>::load(h + 4 * i), o;
+    auto g = [](float v) { return 0.5f * (1.0f + erff(v * 0.70710678118654752440f)) + v * 0.3989422804014327f * __expf(-0.5f * v * v); };
+    o.x = d.x * g(x.x); o.y = d.y * g(x.y); o.z = d.z * g(x.z); o.w = d.w * g(x.w);
+    Vec4<T>::store(dh + 4 * i, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Row softmax.  kRel: logits = ac[i, j] + bd[i, T-1-i+j]  (Transformer-XL rel_shift folded into the address).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kSmMaxE = 64;  // elements per lane -> cols <= 2048
+
+template <typename T, bool kRel>
+__global__ void __launch_bounds__(kThreads) softmax_fwd_kernel(const T* __restrict__ s, const T* __restrict__ bd, T* __restrict__ p,
+                                                               long long rows, int cols, long long ld_s, long long ld_bd,
+                                                               long long ld_p, int T_len) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const T* sr = s + r * ld_s;
+    const T* br = kRel ? bd + r * ld_bd + (T_len - 1 - (int)(r % T_len)) : nullptr;
+    float v[kSmMaxE];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kSmMaxE; ++i) {
+      const int c = lane + 32 * i;
+      if (c < cols) {
+        float a = to_f32<T>(sr[c]);
+        if (kRel) a += to_f32<T>(br[c]);
+        v[i] = a;
+        mx = fmaxf(mx, a);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSmMaxE; ++i) {
+      const int c = lane + 32 * i;
+      if (c < cols) {
+        v[i] = __expf(v[i] - mx);
+        sum += v[i];
+      }
+    }
+    const float inv = 1.0f / warp_sum(sum);
+    T* pr = p + r * ld_p;
+#pragma unroll
+    for (int i = 0; i < kSmMaxE; ++i) {
+      const int c = lane + 32 * i;
+      if (c < cols) pr[c] = from_f32<T>(v[i] * inv);
+    }
+  }
+}
+
+// ds = p * (dp - sum_j p*dp); written over dp.  kRel additionally scatters ds into the (zero-filled) shifted bd-gradient row.
+template <typename T, bool kRel>
+__global__ void __launch_bounds__(kThreads) softmax_bwd_kernel(const T* __restrict__ p, T* __restrict__ dp, T* __restrict__ dbd,
+                                                               long long rows, int cols, long long ld_p, long long ld_dp,
+                                                               long long ld_bd, int T_len) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const T* pr = p + r * ld_p;
+    T* dr = dp + r * ld_dp;
+    float pv[kSmMaxE], dv[kSmMaxE];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSmMaxE; ++i) {
+      const int c = lane + 32 * i;
+      if (c < cols) {
+        pv[i] = to_f32<T>(pr[c]);
+        dv[i] = to_f32<T>(dr[c]);
+        dot += pv[i] * dv[i];
+      }
+    }
+    dot = warp_sum(dot);
+    const int shift = kRel ? T_len - 1 - (int)(r % T_len) : 0;
+    T* br = kRel ? dbd + r * ld_bd : nullptr;
+    if (kRel) {
+      const int width = 2 * T_len - 1;
+      for (int c = lane; c < shift; c += 32) br[c] = from_f32<T>(0.f);
+      for (int c = shift + cols + lane; c < width; c += 32) br[c] = from_f32<T>(0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < kSmMaxE; ++i) {
+      const int c = lane + 32 * i;
+      if (c < cols) {
+        const T o = from_f32<T>(pv[i] * (dv[i] - dot));
+        dr[c] = o;
+        if (kRel) br[shift + c] = o;
+      }
+    }
+  }
+}
+
+static int grid_for_rows(long long rows) {
+  long long blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)sm_count() * 8));
+}
+
+}  // namespace rowops
+}  // namespace t4s
+
+using namespace t4s::rowops;
+
+#define T4S_DISPATCH_DTYPE(dtype, ...)                                   \
+  do {                                                                   \
+    if ((dtype) == T4S_F32) { using T = float; __VA_ARGS__; }            \
+    else if ((dtype) == T4S_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { t4s::set_error("bad dtype %d", (int)(dtype)); return T4S_ERR_ARG; } \
+  } while (0)
+
+extern "C" {
+
+int t4s_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* mean, float* rstd, int64_t rows,
+                      int cols, float eps, float in_scale, int dtype, int64_t n_inner, int64_t x_bstride, void* stream) {
+  T4S_REQUIRE(x && gamma && beta && y && rows > 0, "t4s_layernorm_fwd: bad arguments");
+  T4S_REQUIRE(cols % 4 == 0 && cols > 0 && cols <= 128 * kLnMaxV, "t4s_layernorm_fwd: cols must be a multiple of 4 and <= %d", 128 * kLnMaxV);
+  if (n_inner <= 0) { n_inner = rows; x_bstride = 0; }
+  T4S_REQUIRE(x_bstride % 4 == 0, "t4s_layernorm_fwd: batch stride must be a multiple of 4 elements");
+  T4S_DISPATCH_DTYPE(dtype, (ln_fwd_kernel<T><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
+                                static_cast<const T*>(x), gamma, beta, static_cast<T*>(y), mean, rstd, rows, cols, eps, in_scale,
+                                n_inner, x_bstride)));
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+size_t t4s_layernorm_bwd_workspace(int64_t rows, int cols) {
+  const int grid = (int)std::min<long long>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock, 2L * t4s::sm_count());
+  return (size_t)std::max(grid, 1) * 2 * cols * sizeof(float);
+}
+
+int t4s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dx_add,
+                      void* dx, float* dgamma, float* dbeta, float* ws, size_t ws_bytes, int64_t rows, int cols, float in_scale,
+                      int dtype, int64_t n_inner, int64_t x_bstride, void* stream) {
+  T4S_REQUIRE(dy && x && gamma && mean && rstd && dx && rows > 0, "t4s_layernorm_bwd: bad arguments");
+  T4S_REQUIRE(cols % 4 == 0 && cols > 0 && cols <= 128 * kLnMaxV, "t4s_layernorm_bwd: cols must be a multiple of 4 and <= %d", 128 * kLnMaxV);
+  if (n_inner <= 0) { n_inner = rows; x_bstride = 0; }
+  const bool want_params = dgamma != nullptr || dbeta != nullptr;
+  int grid = (int)std::max<long long>(1, std::min<long long>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock, 2L * t4s::sm_count()));
+  if (want_params) T4S_REQUIRE(ws && ws_bytes >= (size_t)grid * 2 * cols * sizeof(float), "t4s_layernorm_bwd: workspace too small");
+  const size_t smem = want_params ? (size_t)kWarpsPerBlock * 2 * cols * sizeof(float) : 0;
+  cudaStream_t st = t4s::as_stream(stream);
+  T4S_DISPATCH_DTYPE(dtype, {
+    if (smem > 48 * 1024) T4S_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ln_bwd_kernel<T><<<grid, kThreads, smem, st>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma, mean, rstd,
+                                                   static_cast<const T*>(dx_add), static_cast<T*>(dx), want_params ? ws : nullptr,
+                                                   rows, cols, in_scale, n_inner, x_bstride);
+  });
+  T4S_LAUNCH_CHECK();
+  if (want_params) {
+    if (dgamma) reduce_rows_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws, grid, 2LL * cols, cols, dgamma, 0);
+    if (dbeta) reduce_rows_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws + cols, grid, 2LL * cols, cols, dbeta, 0);
+    T4S_LAUNCH_CHECK();
+  }
+  return T4S_OK;
+}
+
+size_t t4s_colsum_workspace(int64_t rows, int cols) {
+  const int parts = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, 4L * t4s::sm_count()));
+  return (size_t)parts * cols * sizeof(float);
+}
+
+int t4s_colsum(const void* x, int dtype, int64_t rows, int cols, int64_t ld, float* ws, size_t ws_bytes, float* out, int accumulate,
+               void* stream) {
+  T4S_REQUIRE(x && out && ws && rows > 0 && cols > 0, "t4s_colsum: bad arguments");
+  const bool vec = cols % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const int parts = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, 4L * t4s::sm_count()));
+  T4S_REQUIRE(ws_bytes >= (size_t)parts * cols * sizeof(float), "t4s_colsum: workspace too small");
+  const int rpb = (int)((rows + parts - 1) / parts);
+  cudaStream_t st = t4s::as_stream(stream);
+  if (vec) {
+    dim3 grid((cols + 1023) / 1024, parts);
+    T4S_DISPATCH_DTYPE(dtype, (colsum_partial_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), rows, cols, ld, ws, rpb)));
+  } else {
+    dim3 grid((cols + 255) / 256, parts);
+    T4S_DISPATCH_DTYPE(dtype, (colsum_partial_scalar_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), rows, cols, ld, ws, rpb)));
+  }
+  T4S_LAUNCH_CHECK();
+  reduce_rows_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws, (int)((rows + rpb - 1) / rpb), cols, cols, out, accumulate);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_gelu_bwd(const void* dy, const void* h, void* dh, size_t n, int dtype, void* stream) {
+  T4S_REQUIRE(dy && h && dh && n % 4 == 0, "t4s_gelu_bwd: n must be a multiple of 4");
+  if (n == 0) return T4S_OK;
+  const int grid = (int)std::min<size_t>((n / 4 + 255) / 256, (size_t)t4s::sm_count() * 16);
+  T4S_DISPATCH_DTYPE(dtype, (gelu_bwd_kernel<T><<<grid, 256, 0, t4s::as_stream(stream)>>>(static_cast<const T*>(dy), static_cast<const T*>(h),
+                                                                                       static_cast<T*>(dh), n / 4)));
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_softmax_fwd(const void* s, void* p, int64_t rows, int cols, int64_t ld_s, int64_t ld_p, int dtype, void* stream) {
+  T4S_REQUIRE(s && p && rows > 0 && cols > 0 && cols <= 32 * kSmMaxE, "t4s_softmax_fwd: cols must be in 1..%d", 32 * kSmMaxE);
+  T4S_DISPATCH_DTYPE(dtype, (softmax_fwd_kernel<T, false><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
+                                static_cast<const T*>(s), nullptr, static_cast<T*>(p), rows, cols, ld_s, 0, ld_p, 0)));
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_softmax_bwd(const void* p, void* dp, int64_t rows, int cols, int64_t ld_p, int64_t ld_dp, int dtype, void* stream) {
+  T4S_REQUIRE(p && dp && rows > 0 && cols > 0 && cols <= 32 * kSmMaxE, "t4s_softmax_bwd: cols must be in 1..%d", 32 * kSmMaxE);
+  T4S_DISPATCH_DTYPE(dtype, (softmax_bwd_kernel<T, false><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
+                                static_cast<const T*>(p), static_cast<T*>(dp), nullptr, rows, cols, ld_p, ld_dp, 0, 0)));
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_relpos_softmax_fwd(const void* ac, const void* bd, void* p, int64_t rows, int T_len, int64_t ld_ac, int64_t ld_bd,
+                           int64_t ld_p, int dtype, void* stream) {
+  T4S_REQUIRE(ac && bd && p && rows > 0 && T_len > 0 && T_len <= 32 * kSmMaxE && rows % T_len == 0 && ld_bd >= 2 * T_len - 1,
+              "t4s_relpos_softmax_fwd: bad arguments");
+  T4S_DISPATCH_DTYPE(dtype, (softmax_fwd_kernel<T, true><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
+                                static_cast<const T*>(ac), static_cast<const T*>(bd), static_cast<T*>(p), rows, T_len, ld_ac, ld_bd,
+                                ld_p, T_len)));
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_relpos_softmax_bwd(const void* p, void* dp, void* dbd, int64_t rows, int T_len, int64_t ld_p, int64_t ld_dp, int64_t ld_bd,
+                           int dtype, void* stream) {
+  T4S_REQUIRE(p && dp && dbd && rows > 0 && T_len > 0 && T_len <= 32 * kSmMaxE && rows % T_len == 0 && ld_bd >= 2 * T_len - 1,
+              "t4s_relpos_softmax_bwd: bad arguments");
+  T4S_DISPATCH_DTYPE(dtype, (softmax_bwd_kernel<T, true><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
+                                static_cast<const T*>(p), static_cast<T*>(dp), static_cast<T*>(dbd), rows, T_len, ld_p, ld_dp, ld_bd,
+                                T_len)));
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,828 @@
+"""Autograd-visible ops of the SED hot path.  Forward AND backward of every op run in libt4s kernels
+(tcgen05 GEMMs + fused row kernels); torch supplies only tensor allocation, views and the autograd tape.
+
+Precision modes (`set_precision`):
+  "bf16"   activations and GEMM operands bf16, fp32 accumulate / statistics / master weights  (performance mode)
+  "tf32"   activations fp32, GEMMs on tcgen05 kind::tf32
+  "tf32x3" as tf32 but every GEMM is error-compensated (hi/lo split, 3 tensor-core products): fp32-class accuracy;
+           this is the strict-parity mode the <=1e-3 / argmax-exact contract is checked in.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib, ops
+from .ops import Op, Out
+
+_MODE = "bf16"
+
+
+def set_precision(mode: str):
+    global _MODE
+    if mode not in ("bf16", "tf32", "tf32x3"):
+        raise ValueError(f"unknown precision mode {mode!r}")
+    _MODE = mode
+
+
+def get_precision():
+    return _MODE
+
+
+def act_dtype():
+    return torch.bfloat16 if _MODE == "bf16" else torch.float32
+
+
+def _lib_call(name, *args):
+    _lib.check(getattr(_lib.load(), name)(*args), name)
+
+
+def _st():
+    return _lib.stream_ptr()
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# operand preparation
+# ------------------------------------------------------------------------------------------------------------------
+_wcache = {}
+
+
+def cast_weight(w: torch.Tensor) -> torch.Tensor:
+    """fp32 master weight -> GEMM operand dtype (bf16 copy cached until the parameter is modified)."""
+    if _MODE != "bf16":
+        return w.detach()
+    if w._base is not None and w._base.dtype == torch.float32:  # a slice of a parameter: cast the parameter once, re-slice the copy
+        return cast_weight(w._base).as_strided(w.shape, w.stride(), w.storage_offset())
+    key = id(w)
+    ent = _wcache.get(key)
+    ver = (w._version, w.data_ptr(), w.device)
+    if ent is not None and ent[0] == ver and ent[2]() is w:
+        return ent[1]
+    import weakref
+    out = torch.empty(w.shape, dtype=torch.bfloat16, device=w.device)
+    convert(w.detach(), out)
+    _wcache[key] = (ver, out, weakref.ref(w, lambda _r, k=key: _wcache.pop(k, None)))
+    return out
+
+
+def convert(src, dst):
+    _lib.ensure_device(src)
+    with torch.cuda.device(src.device):
+        _lib_call("t4s_convert", _p(src), ops.dtype_code(src.dtype), _p(dst), ops.dtype_code(dst.dtype), src.numel(), _st())
+    return dst
+
+
+class _Cast(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.src_dtype = x.dtype
+        x = x.contiguous()
+        return convert(x, torch.empty(x.shape, dtype=dtype, device=x.device))
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        return convert(dy, torch.empty(dy.shape, dtype=ctx.src_dtype, device=dy.device)), None
+
+
+def cast(x, dtype):
+    return x if x.dtype == dtype else _Cast.apply(x, dtype)
+
+
+def to_act(x):
+    """Bring a tensor to the activation dtype (autograd-visible; no-op when it already is)."""
+    return cast(x, act_dtype())
+
+
+def _split3(op: Op, K, pattern, nb1, nb2):
+    """tf32x3: gather a strided operand into a contiguous K-major [nb2, nb1, rows, 3K] hi/lo buffer."""
+    b1 = nb1 if op.nb1 > 1 else 1
+    b2 = nb2 if op.nb2 > 1 else 1
+    dst = torch.empty(b2, b1, op.rows, 3 * K, dtype=torch.float32, device=op.t.device)
+    c = op.c()
+    _lib_call("t4s_split_tf32", ctypes.byref(c), K, _p(dst), pattern, _st())
+    return Op(dst, op.rows, 3 * K, 0, nb1=b1, stride1=op.rows * 3 * K, nb2=b2, stride2=b1 * op.rows * 3 * K)
+
+
+def mm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, **kw):
+    """Tensor-core GEMM honouring the precision mode."""
+    if _MODE == "tf32x3" and A.t.dtype == torch.float32:
+        with torch.cuda.device(A.t.device):
+            A3, B3 = _split3(A, K, 0, nb1, nb2), _split3(B, K, 1, nb1, nb2)
+        ops.gemm(A3, B3, C, M, N, 3 * K, nb1=nb1, nb2=nb2, **kw)
+    else:
+        ops.gemm(A, B, C, M, N, K, nb1=nb1, nb2=nb2, **kw)
+
+
+def _split_k_for(M, N, K, batches=1):
+    tiles = ((M + 127) // 128) * ((N + 255) // 256 if N > 128 else 1) * batches
+    bk = 64 if _MODE == "bf16" else 32
+    kblocks = max(1, (K + bk - 1) // bk)
+    want = max(1, (2 * 148 + tiles - 1) // tiles)
+    return max(1, min(want, kblocks // 4 if kblocks >= 8 else 1, 64))
+
+
+def weight_grad(dy2d, x2d, n_out, k_in):
+    """dW[n_out, k_in] = dy^T x over the token dimension: both operands consumed MN-major (no transposes), split-K."""
+    Mtok = dy2d.shape[0]
+    S = _split_k_for(n_out, k_in, Mtok)
+    dev = dy2d.device
+    if S == 1:
+        dw = torch.empty(n_out, k_in, dtype=torch.float32, device=dev)
+        mm(Op(dy2d, n_out, dy2d.stride(0), mn_major=True), Op(x2d, k_in, x2d.stride(0), mn_major=True), Out(dw, k_in), n_out, k_in, Mtok)
+        return dw
+    ws = torch.empty(S, n_out, k_in, dtype=torch.float32, device=dev)
+    if _MODE == "tf32x3":
+        # split along the contraction by hand (the 3K interleave does not commute with the kernel's K ranges)
+        chunk = (Mtok + S - 1) // S
+        chunk = (chunk + 3) // 4 * 4
+        S = (Mtok + chunk - 1) // chunk
+        ws = ws[:S]
+        for s in range(S):
+            r0, r1 = s * chunk, min(Mtok, (s + 1) * chunk)
+            mm(Op(dy2d, n_out, dy2d.stride(0), offset=r0 * dy2d.stride(0), mn_major=True),
+               Op(x2d, k_in, x2d.stride(0), offset=r0 * x2d.stride(0), mn_major=True), Out(ws, k_in, offset=s * n_out * k_in),
+               n_out, k_in, r1 - r0)
+    else:
+        mm(Op(dy2d, n_out, dy2d.stride(0), mn_major=True), Op(x2d, k_in, x2d.stride(0), mn_major=True), Out(ws, k_in), n_out, k_in, Mtok,
+           split_k=S, c_split_stride=n_out * k_in)
+    dw = torch.empty(n_out, k_in, dtype=torch.float32, device=dev)
+    ops.reduce_splits(ws, S, n_out * k_in, dw)
+    return dw
+
+
+def colsum(x2d, cols=None, ld=None, rows=None):
+    rows = x2d.shape[0] if rows is None else rows
+    cols = x2d.shape[1] if cols is None else cols
+    ld = x2d.stride(0) if ld is None else ld
+    lib = _lib.load()
+    with torch.cuda.device(x2d.device):
+        nbytes = lib.t4s_colsum_workspace(rows, cols)
+        ws = torch.empty(nbytes // 4, dtype=torch.float32, device=x2d.device)
+        out = torch.empty(cols, dtype=torch.float32, device=x2d.device)
+        _lib_call("t4s_colsum", _p(x2d), ops.dtype_code(x2d.dtype), rows, cols, ld, _p(ws), nbytes, _p(out), 0, _st())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Linear (+bias, +GELU, +residual)                  reference: nn.Linear / timm Mlp / attention projections
+# ------------------------------------------------------------------------------------------------------------------
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, residual, act, out_dtype):
+        _lib.ensure_device(x)
+        shp = x.shape
+        K = shp[-1]
+        x2 = x.reshape(-1, K)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        M, N = x2.shape[0], w.shape[0]
+        wq = cast_weight(w)
+        out_dtype = out_dtype or x.dtype
+        y = torch.empty(M, N, dtype=out_dtype, device=x.device)
+        aux = torch.empty(M, N, dtype=x.dtype, device=x.device) if act == ops.ACT_GELU else None
+        res2 = residual.reshape(M, N) if residual is not None else None
+        with torch.cuda.device(x.device):
+            mm(Op(x2, M, x2.stride(0)), Op(wq, N, wq.stride(0)), Out(y, N), M, N, K, bias=b.detach() if b is not None else None,
+               aux=Out(aux, N) if aux is not None else None, residual=Out(res2, res2.stride(0)) if res2 is not None else None, act=act)
+        ctx.save_for_backward(x2, w, aux)
+        ctx.has_bias = b is not None
+        ctx.has_res = residual is not None
+        ctx.act = act
+        ctx.in_shape = shp
+        ctx.res_dtype = residual.dtype if residual is not None else None
+        return y.reshape(*shp[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, aux = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        dy2 = dy.reshape(M, N)
+        if dy2.stride(-1) != 1:
+            dy2 = dy2.contiguous()
+        dev = x2.device
+        d_res = None
+        with torch.cuda.device(dev):
+            if ctx.has_res:
+                d_res = dy if dy.dtype == ctx.res_dtype else convert(dy2, torch.empty(dy.shape, dtype=ctx.res_dtype, device=dev))
+            if dy2.dtype != x2.dtype:
+                dy2 = convert(dy2, torch.empty(M, N, dtype=x2.dtype, device=dev))
+            if ctx.act == ops.ACT_GELU:
+                dh = torch.empty(M, N, dtype=x2.dtype, device=dev)
+                _lib_call("t4s_gelu_bwd", _p(dy2), _p(aux), _p(dh), M * N, ops.dtype_code(x2.dtype), _st())
+            else:
+                dh = dy2
+            if (dh.stride(0) * dh.element_size()) % 16 or dh.data_ptr() % 16:
+                # narrow heads (e.g. 10 classes): TMA needs a 16-byte row pitch -> padded copy, pad columns are never read
+                Np = _pad8(N)
+                dhp = torch.empty(M, Np, dtype=dh.dtype, device=dev)
+                _lib_call("t4s_add2", _p(dh), dh.stride(0), _p(dh), dh.stride(0), _p(dhp), Np, M, N, 1.0, 0.0, ops.dtype_code(dh.dtype), _st())
+                dh = dhp[:, :N]
+            dx = dw = db = None
+            if ctx.needs_input_grad[0]:
+                wq = cast_weight(w)
+                dx = torch.empty(M, K, dtype=x2.dtype, device=dev)
+                mm(Op(dh, M, dh.stride(0)), Op(wq, K, wq.stride(0), mn_major=True), Out(dx, K), M, K, N)
+                dx = dx.reshape(ctx.in_shape)
+            if ctx.needs_input_grad[1]:
+                dw = weight_grad(dh, x2, N, K)
+            if ctx.has_bias and ctx.needs_input_grad[2]:
+                db = colsum(dh)
+        return dx, dw, db, d_res, None, None
+
+
+def linear(x, w, b=None, residual=None, act=ops.ACT_NONE, out_dtype=None):
+    return _Linear.apply(x, w, b, residual, act, out_dtype)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LayerNorm over the last dim of x [B, n, C], optionally skipping the first `skip` tokens of every clip
+# ------------------------------------------------------------------------------------------------------------------
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, in_scale, skip):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        if skip:
+            B, n_all = x.shape[0], x.shape[1]
+            n_inner, bstride, off = n_all - skip, n_all * C, skip * C
+            out_shape = (B, n_inner, C)
+        else:
+            n_inner, bstride, off = 0, 0, 0
+            out_shape = x.shape
+        rows = x.numel() // C if not skip else x.shape[0] * n_inner
+        y = torch.empty(out_shape, dtype=x.dtype, device=x.device)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        xp = ctypes.c_void_p(x.data_ptr() + off * x.element_size())
+        with torch.cuda.device(x.device):
+            _lib_call("t4s_layernorm_fwd", xp, _p(gamma.detach()), _p(beta.detach()), _p(y), _p(mean), _p(rstd), rows, C, eps, in_scale,
+                      ops.dtype_code(x.dtype), n_inner, bstride, _st())
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.cfg = (in_scale, skip, rows, C, n_inner, bstride, off)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        in_scale, skip, rows, C, n_inner, bstride, off = ctx.cfg
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = convert(dy, torch.empty(dy.shape, dtype=x.dtype, device=x.device))
+        lib = _lib.load()
+        dev = x.device
+        with torch.cuda.device(dev):
+            dx = torch.zeros_like(x) if skip else torch.empty_like(x)
+            want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+            dg = torch.empty(C, dtype=torch.float32, device=dev) if want else None
+            db = torch.empty(C, dtype=torch.float32, device=dev) if want else None
+            nbytes = lib.t4s_layernorm_bwd_workspace(rows, C) if want else 0
+            ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
+            es = x.element_size()
+            _lib_call("t4s_layernorm_bwd", _p(dy), ctypes.c_void_p(x.data_ptr() + off * es), _p(gamma.detach()), _p(mean), _p(rstd),
+                      ctypes.c_void_p(0), ctypes.c_void_p(dx.data_ptr() + off * es), _p(dg), _p(db), _p(ws), nbytes, rows, C, in_scale,
+                      ops.dtype_code(x.dtype), n_inner, bstride, _st())
+        return dx, dg, db, None, None, None
+
+
+def layer_norm(x, gamma, beta, eps=1e-5, in_scale=1.0, skip=0):
+    return _LayerNorm.apply(x, gamma, beta, float(eps), float(in_scale), int(skip))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Multi-head self-attention on a fused qkv buffer [B, N, 3*D]      reference: passt.py:330-341
+# ------------------------------------------------------------------------------------------------------------------
+def _heads(qkv, B, N, D, H, which, mn=False):
+    """Per-(head, clip) operand view of q (0) / k (1) / v (2) inside the fused buffer.  K-major: rows = tokens, K = hd;
+    MN-major (`mn`): the token index is the contraction, rows = hd."""
+    hd = D // H
+    return Op(qkv, hd if mn else N, 3 * D, which * D, nb1=H, stride1=hd, nb2=B, stride2=N * 3 * D, mn_major=mn)
+
+
+def _tok_heads(t, B, N, D, H, mn=False):
+    """Same for a [B, N, D] tensor (attention output / its gradient, q+u, q+v)."""
+    hd = D // H
+    return Op(t, hd if mn else N, D, 0, nb1=H, stride1=hd, nb2=B, stride2=N * D, mn_major=mn)
+
+
+class _Attention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, H):
+        _lib.ensure_device(qkv)
+        qkv = qkv.contiguous()
+        B, N, D3 = qkv.shape
+        D = D3 // 3
+        hd = D // H
+        Np = _pad8(N)
+        scale = hd ** -0.5
+        dt, dev = qkv.dtype, qkv.device
+        with torch.cuda.device(dev):
+            P = torch.empty(B, H, N, Np, dtype=dt, device=dev)
+            mm(_heads(qkv, B, N, D, H, 0), _heads(qkv, B, N, D, H, 1), Out(P, Np, 0, N * Np, H * N * Np), N, N, hd, nb1=H, nb2=B, alpha=scale)
+            _lib_call("t4s_softmax_fwd", _p(P), _p(P), B * H * N, N, Np, Np, ops.dtype_code(dt), _st())
+            o = torch.empty(B, N, D, dtype=dt, device=dev)
+            mm(Op(P, N, Np, 0, nb1=H, stride1=N * Np, nb2=B, stride2=H * N * Np), _heads(qkv, B, N, D, H, 2, mn=True),
+               Out(o, D, 0, hd, N * D), N, hd, N, nb1=H, nb2=B)
+        ctx.save_for_backward(qkv, P)
+        ctx.H = H
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, P = ctx.saved_tensors
+        H = ctx.H
+        B, N, D3 = qkv.shape
+        D = D3 // 3
+        hd = D // H
+        Np = P.shape[-1]
+        scale = hd ** -0.5
+        dt, dev = qkv.dtype, qkv.device
+        do = do.contiguous()
+        if do.dtype != dt:
+            do = convert(do, torch.empty(do.shape, dtype=dt, device=dev))
+        with torch.cuda.device(dev):
+            dqkv = torch.empty_like(qkv)
+            dP = torch.empty(B, H, N, Np, dtype=dt, device=dev)
+            pmat = dict(nb1=H, stride1=N * Np, nb2=B, stride2=H * N * Np)
+            # dP = dO V^T
+            mm(_tok_heads(do, B, N, D, H), _heads(qkv, B, N, D, H, 2), Out(dP, Np, 0, N * Np, H * N * Np), N, N, hd, nb1=H, nb2=B)
+            # dV = P^T dO
+            mm(Op(P, N, Np, 0, mn_major=True, **pmat), _tok_heads(do, B, N, D, H, mn=True), Out(dqkv, 3 * D, 2 * D, hd, N * 3 * D), N, hd, N,
+               nb1=H, nb2=B)
+            _lib_call("t4s_softmax_bwd", _p(P), _p(dP), B * H * N, N, Np, Np, ops.dtype_code(dt), _st())
+            # dQ = scale dS K ; dK = scale dS^T Q
+            mm(Op(dP, N, Np, 0, **pmat), _heads(qkv, B, N, D, H, 1, mn=True), Out(dqkv, 3 * D, 0, hd, N * 3 * D), N, hd, N, nb1=H, nb2=B,
+               alpha=scale)
+            mm(Op(dP, N, Np, 0, mn_major=True, **pmat), _heads(qkv, B, N, D, H, 0, mn=True), Out(dqkv, 3 * D, D, hd, N * 3 * D), N, hd, N, nb1=H,
+               nb2=B, alpha=scale)
+        return dqkv, None
+
+
+def attention(qkv, num_heads):
+    return _Attention.apply(qkv, num_heads)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Transformer-XL relative-position attention               reference: transformerXL.py:299-593, rel_shift :254-297
+# score[i, j] = ((q_i + u) k_j + (q_i + v) p_{T-1-i+j}) / sqrt(hd)
+# ------------------------------------------------------------------------------------------------------------------
+class _RelPosAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, p_lin, u, v, H):
+        _lib.ensure_device(qkv)
+        qkv = qkv.contiguous()
+        p_lin = p_lin.contiguous()
+        B, T, D3 = qkv.shape
+        D = D3 // 3
+        hd = D // H
+        L = 2 * T - 1
+        Tp, Lp = _pad8(T), _pad8(L)
+        scale = hd ** -0.5
+        dt, dev = qkv.dtype, qkv.device
+        code = ops.dtype_code(dt)
+        with torch.cuda.device(dev):
+            qu = torch.empty(B, T, D, dtype=dt, device=dev)
+            qv = torch.empty(B, T, D, dtype=dt, device=dev)
+            _lib_call("t4s_add_rowvec", _p(qkv), 3 * D, _p(u.detach().reshape(-1)), _p(qu), B * T, D, 1.0, code, _st())
+            _lib_call("t4s_add_rowvec", _p(qkv), 3 * D, _p(v.detach().reshape(-1)), _p(qv), B * T, D, 1.0, code, _st())
+            P = torch.empty(B, H, T, Tp, dtype=dt, device=dev)
+            BD = torch.empty(B, H, T, Lp, dtype=dt, device=dev)
+            mm(_tok_heads(qu, B, T, D, H), _heads(qkv, B, T, D, H, 1), Out(P, Tp, 0, T * Tp, H * T * Tp), T, T, hd, nb1=H, nb2=B, alpha=scale)
+            mm(_tok_heads(qv, B, T, D, H), Op(p_lin, L, D, 0, nb1=H, stride1=hd), Out(BD, Lp, 0, T * Lp, H * T * Lp), T, L, hd, nb1=H, nb2=B,
+               alpha=scale)
+            _lib_call("t4s_relpos_softmax_fwd", _p(P), _p(BD), _p(P), B * H * T, T, Tp, Lp, Tp, code, _st())
+            del BD
+            o = torch.empty(B, T, D, dtype=dt, device=dev)
+            mm(Op(P, T, Tp, 0, nb1=H, stride1=T * Tp, nb2=B, stride2=H * T * Tp), _heads(qkv, B, T, D, H, 2, mn=True),
+               Out(o, D, 0, hd, T * D), T, hd, T, nb1=H, nb2=B)
+        ctx.save_for_backward(qkv, p_lin, u, v, P)
+        ctx.H = H
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, p_lin, u, v, P = ctx.saved_tensors
+        H = ctx.H
+        B, T, D3 = qkv.shape
+        D = D3 // 3
+        hd = D // H
+        L = 2 * T - 1
+        Tp, Lp = P.shape[-1], _pad8(L)
+        scale = hd ** -0.5
+        dt, dev = qkv.dtype, qkv.device
+        code = ops.dtype_code(dt)
+        do = do.contiguous()
+        if do.dtype != dt:
+            do = convert(do, torch.empty(do.shape, dtype=dt, device=dev))
+        with torch.cuda.device(dev):
+            qu = torch.empty(B, T, D, dtype=dt, device=dev)
+            qv = torch.empty(B, T, D, dtype=dt, device=dev)
+            _lib_call("t4s_add_rowvec", _p(qkv), 3 * D, _p(u.detach().reshape(-1)), _p(qu), B * T, D, 1.0, code, _st())
+            _lib_call("t4s_add_rowvec", _p(qkv), 3 * D, _p(v.detach().reshape(-1)), _p(qv), B * T, D, 1.0, code, _st())
+            pm = dict(nb1=H, stride1=T * Tp, nb2=B, stride2=H * T * Tp)
+            bm = dict(nb1=H, stride1=T * Lp, nb2=B, stride2=H * T * Lp)
+            dqkv = torch.empty_like(qkv)
+            dP = torch.empty(B, H, T, Tp, dtype=dt, device=dev)
+            dBD = torch.empty(B, H, T, Lp, dtype=dt, device=dev)
+            mm(_tok_heads(do, B, T, D, H), _heads(qkv, B, T, D, H, 2), Out(dP, Tp, 0, T * Tp, H * T * Tp), T, T, hd, nb1=H, nb2=B)
+            mm(Op(P, T, Tp, 0, mn_major=True, **pm), _tok_heads(do, B, T, D, H, mn=True), Out(dqkv, 3 * D, 2 * D, hd, T * 3 * D), T, hd, T,
+               nb1=H, nb2=B)
+            _lib_call("t4s_relpos_softmax_bwd", _p(P), _p(dP), _p(dBD), B * H * T, T, Tp, Tp, Lp, code, _st())
+            # d(q+u) = scale dAC K ; dK = scale dAC^T (q+u)
+            dqu = torch.empty(B, T, D, dtype=dt, device=dev)
+            mm(Op(dP, T, Tp, 0, **pm), _heads(qkv, B, T, D, H, 1, mn=True), Out(dqu, D, 0, hd, T * D), T, hd, T, nb1=H, nb2=B, alpha=scale)
+            mm(Op(dP, T, Tp, 0, mn_major=True, **pm), _tok_heads(qu, B, T, D, H, mn=True), Out(dqkv, 3 * D, D, hd, T * 3 * D), T, hd, T, nb1=H,
+               nb2=B, alpha=scale)
+            # d(q+v) = scale dBD p ; dp = scale sum_b dBD^T (q+v)
+            dqv = torch.empty(B, T, D, dtype=dt, device=dev)
+            mm(Op(dBD, T, Lp, 0, **bm), Op(p_lin, hd, D, 0, nb1=H, stride1=hd, mn_major=True), Out(dqv, D, 0, hd, T * D), T, hd, L, nb1=H, nb2=B,
+               alpha=scale)
+            dp_lin = None
+            if ctx.needs_input_grad[1]:
+                ws = torch.empty(B, L, D, dtype=torch.float32, device=dev)
+                mm(Op(dBD, L, Lp, 0, mn_major=True, **bm), _tok_heads(qv, B, T, D, H, mn=True), Out(ws, D, 0, hd, L * D), L, hd, T, nb1=H, nb2=B,
+                   alpha=scale)
+                dp32 = torch.empty(L, D, dtype=torch.float32, device=dev)
+                ops.reduce_splits(ws, B, L * D, dp32)
+                dp_lin = dp32 if dt == torch.float32 else convert(dp32, torch.empty(L, D, dtype=dt, device=dev))
+            _lib_call("t4s_add2", _p(dqu), D, _p(dqv), D, _p(dqkv), 3 * D, B * T, D, 1.0, 1.0, code, _st())
+            du = colsum(dqu.reshape(B * T, D)).reshape(u.shape) if ctx.needs_input_grad[2] else None
+            dv = colsum(dqv.reshape(B * T, D)).reshape(v.shape) if ctx.needs_input_grad[3] else None
+        return dqkv, dp_lin, du, dv, None
+
+
+def relpos_attention(qkv, p_lin, pos_bias_u, pos_bias_v, num_heads):
+    return _RelPosAttention.apply(qkv, p_lin, pos_bias_u, pos_bias_v, num_heads)
+
+
+_pos_tables = {}
+
+
+def rel_pos_table(T, d_model, device, dtype):
+    """Sin/cos relative-position table [2T-1, d]: row k <-> relative position T-1-k (transformerXL.py:68-101,120-126).
+    A constant of (T, d): built once on the host exactly as the reference builds `pe`, then cached on the device."""
+    key = (T, d_model, str(device), dtype)
+    t = _pos_tables.get(key)
+    if t is None:
+        rel = torch.arange(T - 1, -T, -1, dtype=torch.float32).unsqueeze(1)
+        div = torch.exp(torch.arange(0, d_model, 2, dtype=torch.float32) * -(math.log(10000.0) / d_model))
+        pe = torch.zeros(2 * T - 1, d_model)
+        pe[:, 0::2] = torch.sin(rel * div)
+        pe[:, 1::2] = torch.cos(rel * div)
+        t = pe.to(device=device, dtype=dtype)
+        _pos_tables[key] = t
+    return t
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Patch embedding + positional tables + cls/dist tokens          reference: passt.py:302-315, 496-569
+# ------------------------------------------------------------------------------------------------------------------
+class _PatchEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mel, conv_w, conv_b, time_pos, freq_pos, cls, dist, new_pos, stride, t_offset):
+        _lib.ensure_device(mel)
+        mel = mel.contiguous()
+        B, Hh, W = mel.shape
+        D, _, P, _ = conv_w.shape
+        F = (Hh - P) // stride + 1
+        Tp_full = (W - P) // stride + 1
+        Tt = time_pos.shape[-1]
+        Tp = min(Tp_full, Tt)          # a longer grid is cropped to the table (passt.py:515)
+        dt, dev = act_dtype(), mel.device
+        n_tok = 2 + F * Tp
+        with torch.cuda.device(dev):
+            A = torch.empty(B * F * Tp, P * P, dtype=dt, device=dev)
+            _lib_call("t4s_patch_im2col", _p(mel), ops.dtype_code(mel.dtype), _p(A), ops.dtype_code(dt), B, Hh, W, P, stride, F, Tp, _st())
+            pos = torch.empty(F * Tp, D, dtype=torch.float32, device=dev)
+            _lib_call("t4s_patch_posbias", _p(time_pos.detach()), _p(freq_pos.detach()), _p(pos), D, F, Tp, Tt, t_offset, _st())
+            x = torch.empty(B, n_tok, D, dtype=dt, device=dev)
+            w2 = cast_weight(conv_w).reshape(D, P * P)
+            mm(Op(A, F * Tp, P * P, 0, nb1=B, stride1=F * Tp * P * P), Op(w2, D, P * P), Out(x, D, 2 * D, n_tok * D), F * Tp, D, P * P, nb1=B,
+               bias=conv_b.detach(), residual=Out(pos, D, 0, 0))
+            _lib_call("t4s_cls_dist_tokens", _p(x), ops.dtype_code(dt), _p(cls.detach()), _p(dist.detach()), _p(new_pos.detach()), B, n_tok * D, D,
+                      _st())
+        ctx.save_for_backward(A, conv_w)
+        ctx.cfg = (B, F, Tp, Tt, t_offset, D, P, n_tok, time_pos.shape, freq_pos.shape, cls.shape, new_pos.shape)
+        return x
+
+    @staticmethod
+    def backward(ctx, dx):
+        A, conv_w = ctx.saved_tensors
+        B, F, Tp, Tt, t_offset, D, P, n_tok, tshape, fshape, cshape, nshape = ctx.cfg
+        dev = dx.device
+        dx = dx.contiguous()
+        if dx.dtype != A.dtype:
+            dx = convert(dx, torch.empty(dx.shape, dtype=A.dtype, device=dev))
+        ng = ctx.needs_input_grad
+        with torch.cuda.device(dev):
+            f32 = dict(dtype=torch.float32, device=dev)
+            tmp = torch.empty(n_tok * D, **f32)
+            d_time = torch.empty(tshape, **f32) if ng[3] else None
+            d_freq = torch.empty(fshape, **f32) if ng[4] else None
+            d_bias = torch.empty(D, **f32) if ng[2] else None
+            d_cls = torch.empty(cshape, **f32) if ng[5] else None
+            d_dist = torch.empty(cshape, **f32) if ng[6] else None
+            d_new = torch.empty(nshape, **f32) if ng[7] else None
+            if any(g is not None for g in (d_time, d_freq, d_bias, d_cls, d_dist, d_new)):
+                _lib_call("t4s_patch_small_grads", _p(dx), ops.dtype_code(dx.dtype), _p(tmp), _p(d_time), _p(d_freq), _p(d_bias), _p(d_cls),
+                          _p(d_dist), _p(d_new), B, n_tok * D, D, F, Tp, Tt, t_offset, _st())
+            dw = None
+            if ng[1]:
+                ws = torch.empty(B, D, P * P, **f32)
+                mm(Op(dx, D, D, 2 * D, nb1=B, stride1=n_tok * D, mn_major=True), Op(A, P * P, P * P, 0, nb1=B, stride1=F * Tp * P * P, mn_major=True),
+                   Out(ws, P * P, 0, D * P * P), D, P * P, F * Tp, nb1=B)
+                dw = torch.empty(D, P * P, **f32)
+                ops.reduce_splits(ws, B, D * P * P, dw)
+                dw = dw.reshape(conv_w.shape)
+        return None, dw, d_bias, d_time, d_freq, d_cls, d_dist, d_new, None, None
+
+
+def patch_embed(mel, conv_w, conv_b, time_pos, freq_pos, cls, dist, new_pos, stride=10, t_offset=0):
+    return _PatchEmbed.apply(mel, conv_w, conv_b, time_pos, freq_pos, cls, dist, new_pos, stride, t_offset)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# frequency mean-pool, pad + interpolate                          reference: passt_sed.py:199-218, 23-34, 258-259
+# ------------------------------------------------------------------------------------------------------------------
+class _FpoolMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, F, Tp):
+        _lib.ensure_device(y)
+        y = y.contiguous()
+        B, _, C = y.shape
+        out = torch.empty(B, Tp, C, dtype=y.dtype, device=y.device)
+        with torch.cuda.device(y.device):
+            _lib_call("t4s_fpool_mean_fwd", _p(y), _p(out), ops.dtype_code(y.dtype), B, F, Tp, C, _st())
+        ctx.cfg = (B, F, Tp, C)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, F, Tp, C = ctx.cfg
+        dout = dout.contiguous()
+        dy = torch.empty(B, F * Tp, C, dtype=dout.dtype, device=dout.device)
+        with torch.cuda.device(dout.device):
+            _lib_call("t4s_fpool_mean_bwd", _p(dout), _p(dy), ops.dtype_code(dout.dtype), B, F, Tp, C, _st())
+        return dy, None, None
+
+
+def fpool_mean(y, f_dim, t_dim):
+    return _FpoolMean.apply(y, f_dim, t_dim)
+
+
+class _PadInterp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ratio, pad):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        B, Tin, C = x.shape
+        out = torch.empty(B, (Tin + pad) * ratio, C, dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib_call("t4s_pad_interp_fwd", _p(x), _p(out), ops.dtype_code(x.dtype), B, Tin, ratio, C, pad, _st())
+        ctx.cfg = (B, Tin, ratio, C, pad)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, Tin, ratio, C, pad = ctx.cfg
+        dout = dout.contiguous()
+        dx = torch.empty(B, Tin, C, dtype=dout.dtype, device=dout.device)
+        with torch.cuda.device(dout.device):
+            _lib_call("t4s_pad_interp_bwd", _p(dout), _p(dx), ops.dtype_code(dout.dtype), B, Tin, ratio, C, pad, _st())
+        return dx, None, None
+
+
+def pad_interpolate(x, ratio, pad=True):
+    """(optionally repeat the last frame, then) linear interpolation x ratio along time, align_corners=False."""
+    return _PadInterp.apply(x, int(ratio), int(bool(pad)))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# heads and losses
+# ------------------------------------------------------------------------------------------------------------------
+class _SedPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, temp, pad_mask):
+        _lib.ensure_device(logits)
+        logits = logits.contiguous().float()
+        B, T, K = logits.shape
+        strong = torch.empty(B, K, T, dtype=torch.float32, device=logits.device)
+        weak = torch.empty(B, K, dtype=torch.float32, device=logits.device)
+        pm = pad_mask.to(torch.uint8).contiguous() if pad_mask is not None else None
+        with torch.cuda.device(logits.device):
+            _lib_call("t4s_sed_pool_fwd", _p(logits), _p(pm), float(temp), _p(strong), _p(weak), B, T, K, _st())
+        ctx.save_for_backward(strong, pm)
+        ctx.temp = float(temp)
+        return strong, weak
+
+    @staticmethod
+    def backward(ctx, dstrong, dweak):
+        strong, pm = ctx.saved_tensors
+        B, K, T = strong.shape
+        dl = torch.empty(B, T, K, dtype=torch.float32, device=strong.device)
+        ds = dstrong.contiguous().float() if dstrong is not None else None
+        dw = dweak.contiguous().float() if dweak is not None else None
+        with torch.cuda.device(strong.device):
+            _lib_call("t4s_sed_pool_bwd", _p(strong), _p(ds), _p(dw), _p(pm), ctx.temp, _p(dl), B, T, K, _st())
+        return dl, None, None
+
+
+def sed_pool(logits, temp=1.0, pad_mask=None):
+    """sigmoid(logits/temp) -> (strong [B,K,T], weak [B,K]) with padded frames zeroed and linear-softmax pooling."""
+    return _SedPool.apply(logits, temp, pad_mask)
+
+
+class _Sigmoid(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _lib.ensure_device(x)
+        x = x.contiguous().float()
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib_call("t4s_sigmoid_fwd", _p(x), _p(y), x.numel(), _st())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = dy.contiguous().float()
+        dx = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            _lib_call("t4s_sigmoid_bwd", _p(y), _p(dy), _p(dx), y.numel(), _st())
+        return dx
+
+
+def sigmoid(x):
+    return _Sigmoid.apply(x)
+
+
+class _Bce(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, y):
+        _lib.ensure_device(p)
+        p = p.contiguous().float()
+        y = y.contiguous().float()
+        ws = torch.empty(512, dtype=torch.float32, device=p.device)
+        out = torch.empty(2, dtype=torch.float32, device=p.device)
+        with torch.cuda.device(p.device):
+            _lib_call("t4s_bce_fwd", _p(p), _p(y), p.numel(), _p(ws), _p(out), _st())
+        ctx.save_for_backward(p, y)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        p, y = ctx.saved_tensors
+        dp = torch.empty_like(p)
+        g = g.reshape(1).contiguous().float()
+        with torch.cuda.device(p.device):
+            _lib_call("t4s_bce_bwd", _p(p), _p(y), _p(g), p.numel(), _p(dp), _st())
+        return dp, None
+
+
+def bce_loss(p, y):
+    """torch.nn.BCELoss() (mean reduction, log clamped at -100)."""
+    return _Bce.apply(p, y)
+
+
+class _Mse(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, row_mask):
+        _lib.ensure_device(a)
+        a = a.contiguous()
+        b = b.contiguous()
+        if b.dtype != a.dtype:
+            b = convert(b, torch.empty(b.shape, dtype=a.dtype, device=a.device))
+        C = a.shape[-1]
+        rows = a.numel() // C
+        m = row_mask.reshape(-1).to(torch.uint8).contiguous() if row_mask is not None else None
+        ws = torch.empty(512, dtype=torch.float32, device=a.device)
+        out = torch.empty(2, dtype=torch.float32, device=a.device)
+        with torch.cuda.device(a.device):
+            _lib_call("t4s_mse_fwd", _p(a), _p(b), _p(m), rows, C, ops.dtype_code(a.dtype), _p(ws), _p(out), _st())
+        ctx.save_for_backward(a, b, m, out)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, m, out = ctx.saved_tensors
+        C = a.shape[-1]
+        rows = a.numel() // C
+        da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        g = g.reshape(1).contiguous().float()
+        with torch.cuda.device(a.device):
+            _lib_call("t4s_mse_bwd", _p(a), _p(b), _p(m), rows, C, ops.dtype_code(a.dtype), _p(g), _p(out), _p(da), _p(db), _st())
+        return da, db, None
+
+
+def mse_loss(a, b, row_mask=None):
+    """MSELoss(mean) over rows (last dim = features); with `row_mask` [rows] only the selected rows count
+    (== MSELoss()(a[mask], b[mask]), reference recipes/desed/mlm/mlm_passt/train.py:38)."""
+    return _Mse.apply(a, b, row_mask)
+
+
+class _AttnPool(torch.autograd.Function):
+    """One learned query attending over keys/values packed as kv [items, keys_all, 2C], skipping the first `skip` keys of
+    every item (cls/dist tokens); q [C] fp32, pre-scaled."""
+
+    @staticmethod
+    def forward(ctx, kv, q, H, skip):
+        _lib.ensure_device(kv)
+        kv = kv.contiguous()
+        q = q.contiguous().float()
+        items, K_all, C2 = kv.shape
+        C, K = C2 // 2, K_all - skip
+        ctxv = torch.empty(items, C, dtype=kv.dtype, device=kv.device)
+        probs = torch.empty(items, H, K, dtype=torch.float32, device=kv.device)
+        kp = ctypes.c_void_p(kv.data_ptr() + skip * C2 * kv.element_size())
+        with torch.cuda.device(kv.device):
+            _lib_call("t4s_attnpool_fwd", kp, _p(q), _p(ctxv), _p(probs), items, K, C, H, K_all * C2, ops.dtype_code(kv.dtype), _st())
+        ctx.save_for_backward(kv, q, probs)
+        ctx.cfg = (H, skip)
+        return ctxv
+
+    @staticmethod
+    def backward(ctx, dctx):
+        kv, q, probs = ctx.saved_tensors
+        H, skip = ctx.cfg
+        items, K_all, C2 = kv.shape
+        C, K = C2 // 2, K_all - skip
+        dctx = dctx.contiguous()
+        if dctx.dtype != kv.dtype:
+            dctx = convert(dctx, torch.empty(dctx.shape, dtype=kv.dtype, device=kv.device))
+        dkv = torch.zeros_like(kv) if skip else torch.empty_like(kv)
+        dq_part = torch.empty(items, C, dtype=torch.float32, device=kv.device)
+        off = skip * C2 * kv.element_size()
+        with torch.cuda.device(kv.device):
+            _lib_call("t4s_attnpool_bwd", ctypes.c_void_p(kv.data_ptr() + off), _p(q), _p(probs), _p(dctx),
+                      ctypes.c_void_p(dkv.data_ptr() + off), _p(dq_part), items, K, C, H, K_all * C2, ops.dtype_code(kv.dtype), _st())
+            dq = colsum(dq_part) if ctx.needs_input_grad[1] else None
+        return dkv, dq, None, None
+
+
+def attn_pool(kv, q, num_heads, skip=0):
+    return _AttnPool.apply(kv, q, num_heads, skip)
+
+
+def mha_pool(x, token, in_proj_weight, in_proj_bias, out_w, out_b, num_heads, skip=0):
+    """nn.MultiheadAttention(batch_first) with a single learned query (pooling.py:37-51): x [items, keys, C] -> [items, C].
+    `skip` leading keys of every item are ignored (keys/values are still projected for them: 2 of 1190 tokens)."""
+    items, K, C = x.shape
+    hd = C // num_heads
+    # q = (token W_q^T + b_q) / sqrt(hd): batch independent, one 1-row GEMM with the scale folded into alpha/bias
+    tok = to_act(token.reshape(1, C))
+    qv = _ScaledLinear.apply(tok, in_proj_weight[:C], in_proj_bias[:C], hd ** -0.5)
+    kv = linear(x.reshape(items * K, C), in_proj_weight[C:], in_proj_bias[C:]).reshape(items, K, 2 * C)
+    ctxv = attn_pool(kv, qv.reshape(C), num_heads, skip)
+    return linear(ctxv, out_w, out_b)
+
+
+class _ScaledLinear(torch.autograd.Function):
+    """y = s * (x W^T + b), fp32 output (used for the pooled-attention query)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, s):
+        _lib.ensure_device(x)
+        M, K = x.shape
+        N = w.shape[0]
+        wq = cast_weight(w.contiguous())
+        bs = torch.empty(N, dtype=torch.float32, device=x.device)
+        y = torch.empty(M, N, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib_call("t4s_add_rowvec", _p(b.detach().contiguous()), N, ctypes.c_void_p(0), _p(bs), 1, N, float(s), ops.F32, _st())
+            mm(Op(x, M, K), Op(wq, N, K), Out(y, N), M, N, K, bias=bs, alpha=float(s))
+        ctx.save_for_backward(x, w)
+        ctx.s = float(s)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        M, K = x.shape
+        N = w.shape[0]
+        dev = x.device
+        with torch.cuda.device(dev):
+            dys = torch.empty(M, N, dtype=x.dtype, device=dev)
+            dy32 = dy.contiguous().float()
+            tmp = torch.empty(M, N, dtype=torch.float32, device=dev)
+            _lib_call("t4s_add_rowvec", _p(dy32), N, ctypes.c_void_p(0), _p(tmp), M, N, ctx.s, ops.F32, _st())
+            convert(tmp, dys)
+            dx = None
+            if ctx.needs_input_grad[0]:
+                wq = cast_weight(w.contiguous())
+                dx = torch.empty(M, K, dtype=x.dtype, device=dev)
+                mm(Op(dys, M, N), Op(wq, K, K, mn_major=True), Out(dx, K), M, K, N)
+            dw = weight_grad(dys, x, N, K) if ctx.needs_input_grad[1] else None
+            db = colsum(tmp) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, None
