@@ -122,9 +122,9 @@ int t4s_gemm(const T4sGemm* g, void* stream);
 int t4s_reduce_splits(const float* ws, int splits, size_t n, float* out, int accumulate, void* stream);
 
 /* 3xTF32 operand preparation for the error-compensated parity mode: gathers a (strided, optionally MN-major) fp32
- * operand into a contiguous K-major [nb2][nb1][rows][3K] buffer of tf32-exact values; pattern 0 = [hi|lo|hi] (A side),
+ * operand into a contiguous K-major [nb2][nb1][rows][ld_dst] buffer of tf32-exact values; pattern 0 = [hi|lo|hi] (A side),
  * pattern 1 = [hi|hi|lo] (B side), so one tf32 GEMM over 3K gives hi*hi + lo*hi + hi*lo (fp32-class accuracy). */
-int t4s_split_tf32(const T4sOperand* src, int K, float* dst, int pattern, void* stream);
+int t4s_split_tf32(const T4sOperand* src, int K, float* dst, int64_t ld_dst /* row pitch of dst, >= 3K */, int pattern, void* stream);
 
 /* ---- K2: LayerNorm, softmax and other row kernels ----------------------------------------------------------
  * Replace nn.LayerNorm (passt.py:360-363,410; passt_sed.py:126,203; transformerXL.py:32,34), softmax (passt.py:339;

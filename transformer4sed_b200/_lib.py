@@ -56,7 +56,7 @@ def _declare(lib):
         "t4s_mel_normalize": (I, [P, P, Z, P]),
         "t4s_gemm": (I, [ctypes.POINTER(Gemm), P]),
         "t4s_reduce_splits": (I, [P, I, Z, P, I, P]),
-        "t4s_split_tf32": (I, [ctypes.POINTER(Operand), I, P, I, P]),
+        "t4s_split_tf32": (I, [ctypes.POINTER(Operand), I, P, L, I, P]),
         "t4s_layernorm_fwd": (I, [P, P, P, P, P, P, L, I, F, F, I, L, L, P]),
         "t4s_layernorm_bwd_workspace": (Z, [L, I]),
         "t4s_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, P, Z, L, I, F, I, L, L, P]),

@@ -393,7 +393,11 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, Args& a, cudaS
   const int bk = kTf32 ? 32 : 64;
   const int kblocks = (a.K + bk - 1) / bk;
   a.kb_per_split = (kblocks + a.split_k - 1) / a.split_k;
-  a.split_k = (kblocks + a.kb_per_split - 1) / a.kb_per_split;  // drop empty trailing splits
+  if ((kblocks + a.kb_per_split - 1) / a.kb_per_split != a.split_k) {
+    // an empty trailing split would leave its partial output unwritten: the caller must pick a split count that divides evenly
+    set_error("t4s_gemm: split_k=%d leaves empty splits for %d k-blocks (use ceil(kblocks / ceil(kblocks / split_k)))", a.split_k, kblocks);
+    return T4S_ERR_ARG;
+  }
   a.total_tiles = (long long)a.tiles_m * a.tiles_n * a.nb1 * a.nb2 * a.split_k;
   const int grid = (int)std::min<long long>(a.total_tiles, sm_count());
   auto kern = gemm_kernel<BN, kTf32, kAMn, kBMn>;

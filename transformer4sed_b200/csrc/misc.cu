@@ -209,7 +209,7 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 __global__ void split_tf32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long rows, int K, long long ld,
-                                  int nb1, long long s1, int nb2, long long s2, int mn_major, int pattern) {
+                                  int nb1, long long s1, int nb2, long long s2, int mn_major, int pattern, long long ld_dst) {
   const long long per_batch = rows * K;
   const long long total = per_batch * nb1 * nb2;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -220,7 +220,7 @@ __global__ void split_tf32_kernel(const float* __restrict__ src, float* __restri
     else          { row = e / K;  k = e - row * K; }
     const float v = src[(long long)z1 * s1 + (long long)z2 * s2 + (mn_major ? k * ld + row : row * ld + k)];
     const float hi = tf32_rna(v), lo = tf32_rna(v - hi);
-    float* d = dst + (z * rows + row) * 3LL * K + k;
+    float* d = dst + (z * rows + row) * ld_dst + k;
     d[0] = hi;
     d[K] = pattern == 0 ? lo : hi;
     d[2LL * K] = pattern == 0 ? hi : lo;
@@ -356,12 +356,12 @@ int t4s_convert(const void* in, int in_dtype, void* out, int out_dtype, size_t n
   return T4S_OK;
 }
 
-int t4s_split_tf32(const T4sOperand* src, int K, float* dst, int pattern, void* stream) {
-  T4S_REQUIRE(src && src->ptr && dst && K > 0 && (pattern == 0 || pattern == 1), "t4s_split_tf32: bad arguments");
+int t4s_split_tf32(const T4sOperand* src, int K, float* dst, int64_t ld_dst, int pattern, void* stream) {
+  T4S_REQUIRE(src && src->ptr && dst && K > 0 && ld_dst >= 3LL * K && (pattern == 0 || pattern == 1), "t4s_split_tf32: bad arguments");
   const int nb1 = (int)std::max<int64_t>(1, src->nb1), nb2 = (int)std::max<int64_t>(1, src->nb2);
   const long long total = (long long)src->rows * K * nb1 * nb2;
   split_tf32_kernel<<<grid_for(total), 256, 0, t4s::as_stream(stream)>>>(static_cast<const float*>(src->ptr), dst, src->rows, K, src->ld, nb1,
-                                                                        src->stride1, nb2, src->stride2, src->mn_major, pattern);
+                                                                        src->stride1, nb2, src->stride2, src->mn_major, pattern, ld_dst);
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }

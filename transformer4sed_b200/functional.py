@@ -106,10 +106,11 @@ def _split3(op: Op, K, pattern, nb1, nb2):
     """tf32x3: gather a strided operand into a contiguous K-major [nb2, nb1, rows, 3K] hi/lo buffer."""
     b1 = nb1 if op.nb1 > 1 else 1
     b2 = nb2 if op.nb2 > 1 else 1
-    dst = torch.empty(b2, b1, op.rows, 3 * K, dtype=torch.float32, device=op.t.device)
+    ld = (3 * K + 3) // 4 * 4  # 16-byte row pitch for TMA
+    dst = torch.empty(b2, b1, op.rows, ld, dtype=torch.float32, device=op.t.device)
     c = op.c()
-    _lib_call("t4s_split_tf32", ctypes.byref(c), K, _p(dst), pattern, _st())
-    return Op(dst, op.rows, 3 * K, 0, nb1=b1, stride1=op.rows * 3 * K, nb2=b2, stride2=b1 * op.rows * 3 * K)
+    _lib_call("t4s_split_tf32", ctypes.byref(c), K, _p(dst), ld, pattern, _st())
+    return Op(dst, op.rows, ld, 0, nb1=b1, stride1=op.rows * ld, nb2=b2, stride2=b1 * op.rows * ld)
 
 
 def mm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, **kw):
@@ -127,7 +128,9 @@ def _split_k_for(M, N, K, batches=1):
     bk = 64 if _MODE == "bf16" else 32
     kblocks = max(1, (K + bk - 1) // bk)
     want = max(1, (2 * 148 + tiles - 1) // tiles)
-    return max(1, min(want, kblocks // 4 if kblocks >= 8 else 1, 64))
+    s = max(1, min(want, kblocks // 4 if kblocks >= 8 else 1, 64))
+    per = (kblocks + s - 1) // s
+    return (kblocks + per - 1) // per  # no empty trailing split
 
 
 def weight_grad(dy2d, x2d, n_out, k_in):
