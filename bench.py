@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native Transformer4SED hot path.
+
+Metric (BASELINE.json): 10 s-clips/s of a MAT-SED base training step (fused STFT->mel front end + PaSST encoder +
+TransformerXL context net + frame classifier, forward + losses + backward + gradient all-reduce + AdamW) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--precision bf16|tf32|tf32x3]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
+`--impl reference` times the reference's own CPU path (the oracle port of it: the reference is Python and does not travel to
+the GPU box) on the host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+BASE_KW = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_adapter=True, decoder="transformerXL",
+               decoder_layer_num=3, decoder_pos_emd_len=1000, mlm=False)  # config/mat-sed/base/finetune2.yaml:53-62
+N_SAMPLES = 320000       # 10 s @ 32 kHz (the model asserts 1000 frames: reference passt_sed.py:260)
+FWD_GFLOP_PER_CLIP = 297.3
+MIX = (16, 6, 21, 21)    # strong, synthetic, weak, unlabeled of a 64-clip DESED batch (finetune1.yaml:12 ratio 3:1:4:4)
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:  # noqa: BLE001
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_labels(batch, seed):
+    from transformer4sed_b200.utils import synth
+    y = synth.synth_strong_labels(batch, 10, 1000, seed)
+    return y, (y.sum(-1) > 0).float()
+
+
+def sub_batches(batch):
+    s = [round(batch * m / sum(MIX)) for m in MIX]
+    n_strong = max(1, s[0] + s[1])
+    n_weak = max(1, min(batch - n_strong, s[2])) if batch > 1 else 0
+    return n_strong, n_weak
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from transformer4sed_b200 import _lib, functional as F, ops
+    from transformer4sed_b200.src_models.passt.passt_sed import PaSST_SED
+    from transformer4sed_b200.training import ParamArena, mat_sed_param_groups
+    from transformer4sed_b200.utils import synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    F.set_precision(args.precision)
+    B = args.batch
+
+    torch.manual_seed(1234)
+    net = PaSST_SED(load_pretrained_model=False, **BASE_KW)
+    net.load_state_dict(synth.synth_state_dict_like(net, 4), strict=True)   # identical on every rank
+    net = net.to(dev).train()
+    ext = net.get_feature_extractor().eval()
+    arena = ParamArena(net, mat_sed_param_groups(net), shadow_bf16=(args.precision == "bf16"))
+
+    n_distinct = min(B, 8)
+    wav_host = synth.synth_wav(n_distinct, N_SAMPLES, seed=1234 + rank).repeat((B + n_distinct - 1) // n_distinct, 1)[:B].contiguous()
+    wav_pinned = [wav_host.clone().pin_memory() for _ in range(2)]
+    wav_dev = wav_host.to(dev)
+    y, yw = make_labels(B, 99 + rank)
+    y, yw = y.to(dev), yw.to(dev)
+    n_s, n_w = sub_batches(B)
+
+    def train_step(wav):
+        mel = ext.logmel(wav)
+        strong, weak, other = net(mel)
+        loss = F.bce_loss(strong[:n_s], y[:n_s])
+        if n_w:
+            loss = loss + 0.5 * F.bce_loss(weak[n_s:n_s + n_w], yw[n_s:n_s + n_w])
+        loss = loss + 2.0 * F.bce_loss(other["at_out"][:n_s + n_w], yw[:n_s + n_w])
+        loss.backward()
+        arena.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        train_step(wav_dev)
+    barrier()
+    lib = _lib.load()
+    # ---- timed region 1: inputs resident in HBM ------------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.t4s_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = train_step(wav_dev)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = lib.t4s_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- timed region 2: end to end from pinned host memory (H2D of the clips + D2H of the loss every step) -------
+    copy_stream = torch.cuda.Stream(dev)
+    bufs = [torch.empty_like(wav_dev) for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            bufs[i % 2].copy_(wav_pinned[i % 2], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    prefetch(0)
+    loss_val = 0.0
+    for i in range(args.steps):
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        if i + 1 < args.steps:
+            copy_stream.wait_stream(torch.cuda.current_stream())  # buffer (i+1)%2 was read by step i-1, already enqueued
+            prefetch(i + 1)
+        loss_val = train_step(bufs[i % 2]).item()                 # D2H read of the step's loss
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = t.tolist()
+
+    # ---- instrumented step: per-launch device time of the dominant kernel (tcgen05 GEMM) and of the front end ------
+    roof, mel_roof, breakdown = None, None, None
+    if rank == 0:
+        roof, mel_roof, breakdown = instrumented_step(train_step, wav_dev, ext, ops, B)
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_reference_sample(target_seconds=15.0)
+    if rank == 0:
+        clips = B * world * args.steps
+        pk, pk_src = peaks()
+        value = clips / (ms / 1e3)
+        out = {
+            "metric": "10s-clips/sec fwd+bwd MAT-SED", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"bf16": "bf16", "tf32": "tf32", "tf32x3": "tf32x3"}[args.precision], "data": "synthetic",
+            "config": {"workload": "MAT-SED base (config/mat-sed/base/finetune2.yaml init_kwargs, all 100.95 M params trainable), "
+                                   f"DESED-shape synthetic batch={B}/GPU of 10 s @ 32 kHz clips (320000 samples -> 1000 frames), step = fused "
+                                   "STFT+mel front end + student fwd + BCE strong/weak/AT losses + bwd + grad all-reduce + fused AdamW",
+                       "global_batch": B * world, "per_gpu_batch": B, "sample_rate_note": "BASELINE.json says 16 kHz; every reference recipe is "
+                       "32 kHz and the model asserts 1000 frames (SURVEY §0.1, §8d)", "parallelism": f"dp{world}",
+                       "l2_policy": "inputs larger than L2 (82 MB of clips + GBs of activations per step)", "loss": float(loss_val),
+                       "tc_frac_of_sustained_bf16": value / world * 3 * FWD_GFLOP_PER_CLIP / 1e3 / pk["bf16_tflops_sustained"],
+                       "peaks": pk_src},
+            "clocks": clocks,
+            "e2e": {"value": clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": roof, "roofline_mel": mel_roof, "kernel_time_breakdown_ms": breakdown,
+            "cpu_baseline": cpu_base,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def instrumented_step(train_step, wav_dev, ext, ops, B):
+    """One extra step with every C-ABI launch group bracketed by CUDA events on the launching stream."""
+    from transformer4sed_b200 import _lib
+    pk, pk_src = peaks()
+    recs = []
+    orig_gemm = ops.gemm
+    orig_check = _lib.check
+
+    def gemm_timed(A, Bop, C, M, N, K, nb1=1, nb2=1, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        orig_gemm(A, Bop, C, M, N, K, nb1=nb1, nb2=nb2, **kw)
+        e.record()
+        recs.append(("gemm", s, e, 2.0 * M * N * K * nb1 * nb2))
+
+    ops.gemm = gemm_timed
+    import transformer4sed_b200.functional as F
+    F.ops.gemm = gemm_timed
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    try:
+        torch.cuda.synchronize()
+        t0.record()
+        train_step(wav_dev)
+        t1.record()
+        torch.cuda.synchronize()
+    finally:
+        ops.gemm = orig_gemm
+        F.ops.gemm = orig_gemm
+        _lib.check = orig_check
+    gemm_ms = sum(s.elapsed_time(e) for _, s, e, _ in recs)
+    gemm_flops = sum(f for *_, f in recs)
+    step_ms = t0.elapsed_time(t1)
+    # front end alone, L2 flushed between iterations
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=wav_dev.device)
+    ts = []
+    for _ in range(5):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        ext.logmel(wav_dev)
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    mel_ms = statistics.median(ts)
+    mel_bytes = B * (4 * N_SAMPLES + 4 * 128 * 1000)
+    roof = {"bound": "tensor", "kernel": "t4s::gemm::gemm_kernel (tcgen05, all GEMM launches of one step)", "achieved": gemm_flops / gemm_ms / 1e9,
+            "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": gemm_flops / gemm_ms / 1e9 / pk["bf16_tflops_sustained"], "traffic": None,
+            "launches": len(recs), "gemm_ms_per_step": gemm_ms, "share_of_step": gemm_ms / step_ms, "peak_source": pk_src + " (sustained bf16)",
+            "how": "CUDA events around every t4s_gemm launch of one extra instrumented step; flops = 2MNK per launch"}
+    mel_roof = {"bound": "hbm", "kernel": "t4s::mel::mel_kernel (+peak kernel)", "achieved": mel_bytes / mel_ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": mel_bytes / mel_ms / 1e6 / pk["hbm_gbs"], "traffic": None, "ms": mel_ms, "clips_per_s": B / mel_ms * 1e3,
+                "algorithmic_bytes_per_clip": 4 * N_SAMPLES + 4 * 128 * 1000, "peak_source": pk_src}
+    return roof, mel_roof, {"step_instrumented": step_ms, "gemm": gemm_ms, "front_end": mel_ms, "other": step_ms - gemm_ms - mel_ms}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle port) on the host cores
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_step_fn(batch, threads):
+    from oracle import frontend as OF
+    from oracle import model as OM
+    from transformer4sed_b200 import schema
+    from transformer4sed_b200.utils import synth
+    torch.set_num_threads(threads)
+    sd = synth.synth_state_dict(schema.mat_sed_shapes(), 4)
+    for v in sd.values():
+        v.requires_grad_(True)
+    wav = synth.synth_wav(min(batch, 4), N_SAMPLES, seed=1234).repeat((batch + 3) // 4, 1)[:batch]
+    y, yw = make_labels(batch, 99)
+
+    def step():
+        for v in sd.values():
+            v.grad = None
+        mel = OF.passt_logmel(wav)
+        strong, weak, other = OM.mat_sed_forward(mel, sd, decoder_layers=3)
+        loss = OM.bce(strong, y) + 0.5 * OM.bce(weak, yw) + 2.0 * OM.bce(other["at_out"], yw)
+        loss.backward()
+        return loss.item()
+
+    return step
+
+
+def cpu_reference_sample(target_seconds=15.0):
+    threads = os.cpu_count() or 1
+    step = cpu_step_fn(1, threads)
+    t0 = time.perf_counter()
+    step()
+    t1 = time.perf_counter() - t0
+    batch = max(1, min(8, int(target_seconds / max(t1, 1e-3))))
+    if batch > 1:
+        step = cpu_step_fn(batch, threads)
+        t0 = time.perf_counter()
+        step()
+        t1 = time.perf_counter() - t0
+    return {"value": batch / t1, "unit": "clips/s", "cores": threads, "kind": "port",
+            "sample": f"1 fwd+bwd step of the fp32 CPU oracle (oracle/model.py, same model/loss) on {batch} clip(s), {t1:.1f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    probe = cpu_step_fn(1, threads)
+    t0 = time.perf_counter()
+    probe()
+    t1 = time.perf_counter() - t0
+    budget = 150.0
+    batch = max(1, min(4, int(budget / ((args.steps + args.warmup) * max(t1, 1e-3)))))
+    step = cpu_step_fn(batch, threads)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = step()
+    dt = time.perf_counter() - t0
+    value = batch * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": "10s-clips/sec fwd+bwd MAT-SED", "value": value, "unit": "clips/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"MAT-SED base, same model / losses as the CUDA arm, bounded sample: {batch} clip(s) of 10 s @ 32 kHz per step on the "
+                               "host CPU (the reference is pure PyTorch; timed through the oracle port because /root/reference does not travel)",
+                   "global_batch": batch, "loss": loss},
+        "cpu_baseline": {"value": value, "unit": "clips/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} timed steps x {batch} clip(s), torch.set_num_threads({threads})"},
+        "e2e": {"value": value, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "tf32x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

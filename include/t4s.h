@@ -203,6 +203,19 @@ int t4s_attnpool_fwd(const void* kv, const float* q, void* ctx, float* probs, in
 int t4s_attnpool_bwd(const void* kv, const float* q, const float* probs, const void* dctx, void* dkv, float* dq_part, int items, int keys,
                      int dim, int heads, int64_t item_stride, int dtype, void* stream);
 
+/* ---- K9: parameter-side kernels of a training step (csrc/optim.cu) ------------------------------------------------
+ * torch.optim.AdamW semantics (recipes/desed/setting.py:254-258) over a flat fp32 arena; `bf16_shadow` (optional) receives the
+ * updated weights as bf16 GEMM operands in the same pass; `grad_scale` folds the 1/world_size of the gradient all-reduce. */
+int t4s_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, void* bf16_shadow, size_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* teacher = alpha*teacher + (1-alpha)*student  (src/utils/scheduler.py:125-130) */
+int t4s_ema_update(float* teacher, const float* student, void* bf16_shadow, size_t n, float alpha, void* stream);
+/* Gather per-tensor gradients into the flat all-reduce buffer.  table (DEVICE memory): n_entries x {const float* src (NULL = zero fill),
+ * int64 offset, int64 n}. */
+int t4s_grad_pack(const void* table, int n_entries, float* flat, void* stream);
+/* number of kernel launches issued by this library in this process so far */
+long long t4s_launch_count(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -49,6 +49,10 @@ def _declare(lib):
         "t4s_last_error": (ctypes.c_char_p, []),
         "t4s_device_check": (I, []),
         "t4s_sm_count": (I, []),
+        "t4s_launch_count": (ctypes.c_longlong, []),
+        "t4s_adamw_step": (I, [P, P, P, P, P, Z, F, F, F, F, F, I, F, P]),
+        "t4s_ema_update": (I, [P, P, P, Z, F, P]),
+        "t4s_grad_pack": (I, [P, I, P, P]),
         "t4s_wav_peak": (I, [P, P, I, I, P]),
         "t4s_mel_tables_bytes": (Z, [I, I]),
         "t4s_mel_tables_init": (I, [P, P, I, I, P]),

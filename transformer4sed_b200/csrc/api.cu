@@ -5,6 +5,7 @@
 #include "common.cuh"
 
 namespace t4s {
+long long g_launches = 0;
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -50,5 +51,7 @@ int t4s_device_check(void) {
 }
 
 int t4s_sm_count(void) { return t4s::sm_count(); }
+
+long long t4s_launch_count(void) { return t4s::g_launches; }
 
 }  // extern "C"

@@ -18,7 +18,12 @@ int sm_count();
     if (_e != cudaSuccess) return ::t4s::cuda_fail(_e, #expr, __FILE__, __LINE__); \
   } while (0)
 
-#define T4S_LAUNCH_CHECK() T4S_CUDA(cudaGetLastError())
+extern long long g_launches;  // kernels launched by this library (bench.py reports it as gpu_launches)
+#define T4S_LAUNCH_CHECK()          \
+  do {                              \
+    ++::t4s::g_launches;            \
+    T4S_CUDA(cudaGetLastError());   \
+  } while (0)
 
 #define T4S_REQUIRE(cond, ...)          \
   do {                                  \

@@ -291,6 +291,7 @@ int t4s_bce_fwd(const float* p, const float* y, size_t n, float* ws, float* out,
   cudaStream_t st = t4s::as_stream(stream);
   const int parts = (int)std::min<size_t>(T4S_LOSS_PARTS, (n + 255) / 256);
   bce_partial_kernel<<<parts, 256, 0, st>>>(p, y, n, ws);
+  T4S_LAUNCH_CHECK();
   finish_mean_kernel<<<1, 32, 0, st>>>(ws, parts, nullptr, (float)n, out);
   T4S_LAUNCH_CHECK();
   return T4S_OK;
@@ -312,6 +313,7 @@ int t4s_mse_fwd(const void* a, const void* b, const unsigned char* row_mask, int
   if (dtype == T4S_F32) mse_partial_kernel<float><<<parts, 256, 0, st>>>((const float*)a, (const float*)b, row_mask, rows, cols, ws, ws + T4S_LOSS_PARTS);
   else if (dtype == T4S_BF16) mse_partial_kernel<__nv_bfloat16><<<parts, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, row_mask, rows, cols, ws, ws + T4S_LOSS_PARTS);
   else { t4s::set_error("t4s_mse_fwd: bad dtype"); return T4S_ERR_ARG; }
+  T4S_LAUNCH_CHECK();
   finish_mean_kernel<<<1, 32, 0, st>>>(ws, parts, ws + T4S_LOSS_PARTS, (float)cols, out);
   T4S_LAUNCH_CHECK();
   return T4S_OK;

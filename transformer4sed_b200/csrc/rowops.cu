@@ -368,9 +368,14 @@ int t4s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   });
   T4S_LAUNCH_CHECK();
   if (want_params) {
-    if (dgamma) reduce_rows_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws, grid, 2LL * cols, cols, dgamma, 0);
-    if (dbeta) reduce_rows_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws + cols, grid, 2LL * cols, cols, dbeta, 0);
-    T4S_LAUNCH_CHECK();
+    if (dgamma) {
+      reduce_rows_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws, grid, 2LL * cols, cols, dgamma, 0);
+      T4S_LAUNCH_CHECK();
+    }
+    if (dbeta) {
+      reduce_rows_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws + cols, grid, 2LL * cols, cols, dbeta, 0);
+      T4S_LAUNCH_CHECK();
+    }
   }
   return T4S_OK;
 }

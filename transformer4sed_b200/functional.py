@@ -59,6 +59,9 @@ def cast_weight(w: torch.Tensor) -> torch.Tensor:
     """fp32 master weight -> GEMM operand dtype (bf16 copy cached until the parameter is modified)."""
     if _MODE != "bf16":
         return w.detach()
+    shadow = getattr(w, "_t4s_shadow", None)  # kept fresh by the fused AdamW kernel (training.ParamArena)
+    if shadow is not None:
+        return shadow
     if w._base is not None and w._base.dtype == torch.float32:  # a slice of a parameter: cast the parameter once, re-slice the copy
         return cast_weight(w._base).as_strided(w.shape, w.stride(), w.storage_offset())
     key = id(w)

@@ -1,0 +1,117 @@
+"""Parameter arena, fused AdamW and the data-parallel gradient exchange (one process per GPU).
+
+Replaces the reference's single-process `nn.DataParallel` + `torch.optim.AdamW` (recipes/desed/setting.py:254-258):
+parameters live in one flat fp32 arena (grouped by LR group), gradients are packed into one flat buffer by a libt4s kernel,
+all-reduced ONCE over NCCL/NVLink, and a fused AdamW kernel updates the master weights and refreshes the bf16 GEMM-operand
+shadow in the same pass.  The path shards by clip with no activation exchange, so the all-reduce is the only collective.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from . import functional as F
+
+
+def _align(n, a=8):  # 16 bytes for the bf16 shadow (TMA base alignment)
+    return (n + a - 1) // a * a
+
+
+class ParamArena:
+    def __init__(self, module: torch.nn.Module, groups, shadow_bf16=True, betas=(0.9, 0.999), eps=1e-8):
+        """groups: list of dicts {name, params (list of nn.Parameter), lr, weight_decay}.  Parameters not listed are frozen."""
+        self.groups = []
+        dev = next(module.parameters()).device
+        _lib.ensure_device(next(module.parameters()))
+        total = 0
+        layout = []
+        for g in groups:
+            start = total
+            for p in g["params"]:
+                if not p.requires_grad:
+                    continue
+                layout.append((p, total))
+                total = _align(total + p.numel())
+            self.groups.append(dict(name=g["name"], lr=float(g["lr"]), weight_decay=float(g["weight_decay"]), start=start, end=total))
+        self.n = total
+        self.device = dev
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.shadow = torch.empty(total, dtype=torch.bfloat16, device=dev) if shadow_bf16 else None
+        self.layout = layout
+        with torch.no_grad():
+            for p, off in layout:
+                view = self.flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                if self.shadow is not None:
+                    p._t4s_shadow = self.shadow[off:off + p.numel()].view(p.shape)
+        if self.shadow is not None:
+            F.convert(self.flat, self.shadow)
+        self.betas, self.eps, self.step_count = betas, eps, 0
+        self._table_host = torch.empty(len(layout), 3, dtype=torch.int64).pin_memory()
+        self._table_dev = torch.empty(len(layout), 3, dtype=torch.int64, device=dev)
+
+    def pack_grads(self):
+        """Gather every parameter's .grad into the flat buffer (missing grads -> zeros) with one kernel."""
+        t = self._table_host
+        for i, (p, off) in enumerate(self.layout):
+            g = p.grad
+            if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
+                g = g.float().contiguous()
+                p.grad = g
+            t[i, 0] = g.data_ptr() if g is not None else 0
+            t[i, 1] = off
+            t[i, 2] = p.numel()
+        self._table_dev.copy_(t, non_blocking=True)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.load().t4s_grad_pack(_lib.ptr(self._table_dev), len(self.layout), _lib.ptr(self.grad), _lib.stream_ptr()),
+                       "t4s_grad_pack")
+
+    def all_reduce(self):
+        """The path's single collective: sum of the packed gradients over ranks (NCCL over NVLink / NVSwitch)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grad)
+            return dist.get_world_size()
+        return 1
+
+    def step(self, lr_scale=1.0):
+        self.pack_grads()
+        world = self.all_reduce()
+        self.step_count += 1
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            for g in self.groups:
+                n = g["end"] - g["start"]
+                if n == 0:
+                    continue
+                o4, o2 = g["start"] * 4, g["start"] * 2
+                _lib.check(lib.t4s_adamw_step(
+                    ctypes.c_void_p(self.flat.data_ptr() + o4), ctypes.c_void_p(self.grad.data_ptr() + o4),
+                    ctypes.c_void_p(self.exp_avg.data_ptr() + o4), ctypes.c_void_p(self.exp_avg_sq.data_ptr() + o4),
+                    ctypes.c_void_p(self.shadow.data_ptr() + o2) if self.shadow is not None else ctypes.c_void_p(0), n,
+                    g["lr"] * lr_scale, self.betas[0], self.betas[1], self.eps, g["weight_decay"], self.step_count, 1.0 / world,
+                    _lib.stream_ptr()), "t4s_adamw_step")
+        for p, _ in self.layout:
+            p.grad = None
+
+
+def mat_sed_param_groups(net, lr_encoder=5e-6, lr_decoder=1e-4, lr_head=1e-4, weight_decay=1e-4):
+    """The three LR groups of config/mat-sed/base/finetune2.yaml:88-101 (encoder / decoder / head), by parameter-name prefix
+    as reference recipes/desed/finetune/passt/setting.py:28-103 assigns them."""
+    enc, dec, head = [], [], []
+    for name, p in net.named_parameters():
+        if name.startswith("backbone.head"):
+            continue  # PaSST classification heads are not on the SED path (no gradient): keep them out of the arena
+        if name.startswith("backbone.") or name.startswith("out_norm."):
+            enc.append(p)
+        elif name.startswith("decoder.") or name.startswith("mask_token") or name.startswith("f_pool_module."):
+            dec.append(p)
+        else:
+            head.append(p)
+    return [dict(name="encoder", params=enc, lr=lr_encoder, weight_decay=weight_decay),
+            dict(name="decoder", params=dec, lr=lr_decoder, weight_decay=weight_decay),
+            dict(name="head", params=head, lr=lr_head, weight_decay=weight_decay)]
