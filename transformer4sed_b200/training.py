@@ -17,22 +17,43 @@ def _align(n, a=8):  # 16 bytes for the bf16 shadow (TMA base alignment)
     return (n + a - 1) // a * a
 
 
+def flat_layout(groups):
+    """Deterministic arena layout shared by every rank: [(param, element offset)], per-group [start, end) ranges, total size.
+    Offsets are 8-element (16-byte in bf16) aligned; frozen parameters are skipped."""
+    total, layout, ranges = 0, [], []
+    for g in groups:
+        start = total
+        for p in g["params"]:
+            if not p.requires_grad:
+                continue
+            layout.append((p, total))
+            total = _align(total + p.numel())
+        ranges.append(dict(name=g["name"], lr=float(g["lr"]), weight_decay=float(g["weight_decay"]), start=start, end=total))
+    return layout, ranges, total
+
+
+def shard_for_rank(n_items, rank, world):
+    """Contiguous shard [lo, hi) of a global batch for `rank` (clips are independent: SURVEY §8e)."""
+    per = (n_items + world - 1) // world
+    lo = min(n_items, rank * per)
+    return lo, min(n_items, lo + per)
+
+
+def all_reduce_flat(buf):
+    """The path's single collective: in-place sum of the packed gradient buffer over ranks; returns the world size."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(buf)
+        return dist.get_world_size()
+    return 1
+
+
 class ParamArena:
     def __init__(self, module: torch.nn.Module, groups, shadow_bf16=True, betas=(0.9, 0.999), eps=1e-8):
         """groups: list of dicts {name, params (list of nn.Parameter), lr, weight_decay}.  Parameters not listed are frozen."""
-        self.groups = []
         dev = next(module.parameters()).device
         _lib.ensure_device(next(module.parameters()))
-        total = 0
-        layout = []
-        for g in groups:
-            start = total
-            for p in g["params"]:
-                if not p.requires_grad:
-                    continue
-                layout.append((p, total))
-                total = _align(total + p.numel())
-            self.groups.append(dict(name=g["name"], lr=float(g["lr"]), weight_decay=float(g["weight_decay"]), start=start, end=total))
+        layout, self.groups, total = flat_layout(groups)
         self.n = total
         self.device = dev
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
@@ -71,12 +92,8 @@ class ParamArena:
                        "t4s_grad_pack")
 
     def all_reduce(self):
-        """The path's single collective: sum of the packed gradients over ranks (NCCL over NVLink / NVSwitch)."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grad)
-            return dist.get_world_size()
-        return 1
+        """Sum of the packed gradients over ranks (NCCL over NVLink / NVSwitch)."""
+        return all_reduce_flat(self.grad)
 
     def step(self, lr_scale=1.0):
         self.pack_grads()
