@@ -154,6 +154,36 @@ int t4s_relpos_softmax_fwd(const void* ac, const void* bd, void* p, int64_t rows
 int t4s_relpos_softmax_bwd(const void* p, void* dp, void* dbd, int64_t rows, int T_len, int64_t ld_p, int64_t ld_dp, int64_t ld_bd,
                            int dtype, void* stream);
 
+/* ---- K4: fused multi-head self-attention (csrc/attn.cu) ------------------------------------------------------
+ * Replaces passt.py:330-341 (Attention.forward: q k^T * hd^-0.5 -> softmax -> . v) forward and backward without ever
+ * materialising the [B, H, N, N] score / probability matrices: S and P tiles live in TMEM / shared memory
+ * (tcgen05.mma for QK^T, PV, dP, dV, dK, dQ; online softmax in the TMEM-load epilogue warps).  bf16 operands, fp32
+ * accumulation and statistics; head_dim must be 64.  Element (b, n, h, d) of q is q[b*q_bs + n*q_ld + h*64 + d]
+ * (likewise k, v, o, do, dq, dk, dv), so q/k/v may be slices of one fused [B, N, 3*H*64] buffer; all bases and pitches
+ * must be multiples of 8 elements (16 bytes).
+ * lse [B, H, Nl] and delta [B, H, Nl] are fp32 with Nl = t4s_attn_padded_len(N); lse is in log2 units
+ * (log2 sum_j exp(scale * q.k_j)), written by the forward and consumed by the backward. */
+typedef struct {
+  int batch, heads, tokens, head_dim;
+  float scale;
+  const void* q; int64_t q_ld, q_bs;
+  const void* k; int64_t k_ld, k_bs;
+  const void* v; int64_t v_ld, v_bs;
+  void* o;       int64_t o_ld, o_bs;
+  float* lse;
+} T4sAttn;
+typedef struct {
+  T4sAttn fwd;          /* q, k, v, o, lse as given to / produced by t4s_attn_fwd */
+  const void* d_o; int64_t do_ld, do_bs;
+  float* delta;         /* workspace [B, H, Nl]: rowsum(dO * O), filled by the call */
+  void* dq; int64_t dq_ld, dq_bs;
+  void* dk; int64_t dk_ld, dk_bs;
+  void* dv; int64_t dv_ld, dv_bs;
+} T4sAttnBwd;
+int64_t t4s_attn_padded_len(int tokens);
+int t4s_attn_fwd(const T4sAttn* a, void* stream);
+int t4s_attn_bwd(const T4sAttnBwd* a, void* stream);
+
 /* ---- layout / glue kernels (csrc/misc.cu) -------------------------------------------------------------------
  * passt.py:302-315 (patch conv as im2col + GEMM), :503-519,:560-569 (positional tables, cls/dist tokens),
  * passt_sed.py:199-218 (frequency mean-pool), :23-34,:258-259 (pad + linear interpolation). */

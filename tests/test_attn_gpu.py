@@ -1,0 +1,90 @@
+"""GPU: fused tcgen05 attention (csrc/attn.cu, reference passt.py:330-341) forward and backward against a float64
+PyTorch reference of softmax(q k^T / sqrt(hd)) v on the same bf16 inputs, through the C ABI (t4s_attn_fwd / t4s_attn_bwd).
+Covers ragged token counts (TMA zero fill + masked key columns), a single partial tile, several heads / clips, large
+logits (online-softmax rescaling), and agreement with the unfused GEMM + softmax path."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(qkv, H):
+    B, N, D3 = qkv.shape
+    D = D3 // 3
+    hd = D // H
+    q, k, v = qkv.reshape(B, N, 3, H, hd).permute(2, 0, 3, 1, 4)
+    p = ((q @ k.transpose(-1, -2)) * hd ** -0.5).softmax(-1)
+    return (p @ v).permute(0, 2, 1, 3).reshape(B, N, D)
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+@pytest.mark.parametrize("B,N,H,scale", [(1, 128, 1, 1.0), (1, 37, 3, 1.0), (2, 200, 2, 1.0), (1, 256, 1, 4.0),
+                                         (2, 1190, 12, 1.0), (2, 1000, 12, 2.0), (3, 385, 2, 0.3)])
+def test_fused_attention_matches_reference(B, N, H, scale):
+    from transformer4sed_b200 import functional as F
+    F.set_precision("bf16")
+    D = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(N * 7 + H)
+    qkv = (torch.randn(B, N, 3 * D, generator=g, device="cuda") * scale).to(torch.bfloat16).requires_grad_(True)
+    w = torch.randn(B, N, D, generator=g, device="cuda").to(torch.bfloat16)
+    o = F.attention(qkv, H)
+    assert o.dtype == torch.bfloat16 and o.shape == (B, N, D)
+    o.backward(w)
+    qr = qkv.detach().double().requires_grad_(True)
+    o_ref = _ref(qr, H)
+    o_ref.backward(w.double())
+    assert torch.isfinite(o.float()).all() and torch.isfinite(qkv.grad.float()).all()
+    assert _rel(o, o_ref) < 1.5e-2
+    for name, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+        e = _rel(qkv.grad[..., sl], qr.grad[..., sl])
+        assert e < 2.5e-2, f"{name}: rel err {e:.3e}"
+
+
+def test_fused_matches_unfused_path():
+    from transformer4sed_b200 import functional as F
+    F.set_precision("bf16")
+    B, N, H = 2, 602, 12
+    g = torch.Generator(device="cuda").manual_seed(5)
+    base = torch.randn(B, N, 3 * 64 * H, generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randn(B, N, 64 * H, generator=g, device="cuda").to(torch.bfloat16)
+    outs = []
+    try:
+        for fused in (True, False):
+            F.set_fused_attention(fused)
+            x = base.clone().requires_grad_(True)
+            o = F.attention(x, H)
+            o.backward(w)
+            outs.append((o.float(), x.grad.float()))
+    finally:
+        F.set_fused_attention(True)
+    assert _rel(outs[0][0], outs[1][0]) < 2e-2
+    assert _rel(outs[0][1], outs[1][1]) < 3e-2
+
+
+def test_fused_attention_is_deterministic():
+    from transformer4sed_b200 import functional as F
+    F.set_precision("bf16")
+    g = torch.Generator(device="cuda").manual_seed(9)
+    base = torch.randn(2, 1190, 3 * 768, generator=g, device="cuda").to(torch.bfloat16)
+    w = torch.randn(2, 1190, 768, generator=g, device="cuda").to(torch.bfloat16)
+    res = []
+    for _ in range(2):
+        x = base.clone().requires_grad_(True)
+        o = F.attention(x, 12)
+        o.backward(w)
+        res.append((o.clone(), x.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+def test_attention_abi_rejects_bad_arguments():
+    import ctypes
+    from transformer4sed_b200 import _lib
+    lib = _lib.load()
+    a = _lib.Attn()
+    a.batch, a.heads, a.tokens, a.head_dim = 1, 1, 16, 32
+    assert lib.t4s_attn_fwd(ctypes.byref(a), None) != 0
+    assert b"head_dim" in lib.t4s_last_error()

@@ -42,6 +42,22 @@ class Gemm(ctypes.Structure):
                 ("aux", Matrix), ("residual", Matrix), ("bias", c_void_p), ("alpha", c_float), ("act", c_int)]
 
 
+class Attn(ctypes.Structure):
+    _fields_ = [("batch", c_int), ("heads", c_int), ("tokens", c_int), ("head_dim", c_int), ("scale", c_float),
+                ("q", c_void_p), ("q_ld", ctypes.c_int64), ("q_bs", ctypes.c_int64),
+                ("k", c_void_p), ("k_ld", ctypes.c_int64), ("k_bs", ctypes.c_int64),
+                ("v", c_void_p), ("v_ld", ctypes.c_int64), ("v_bs", ctypes.c_int64),
+                ("o", c_void_p), ("o_ld", ctypes.c_int64), ("o_bs", ctypes.c_int64),
+                ("lse", c_void_p)]
+
+
+class AttnBwd(ctypes.Structure):
+    _fields_ = [("fwd", Attn), ("d_o", c_void_p), ("do_ld", ctypes.c_int64), ("do_bs", ctypes.c_int64), ("delta", c_void_p),
+                ("dq", c_void_p), ("dq_ld", ctypes.c_int64), ("dq_bs", ctypes.c_int64),
+                ("dk", c_void_p), ("dk_ld", ctypes.c_int64), ("dk_bs", ctypes.c_int64),
+                ("dv", c_void_p), ("dv_ld", ctypes.c_int64), ("dv_bs", ctypes.c_int64)]
+
+
 def _declare(lib):
     P, I, Z, F, L = c_void_p, c_int, c_size_t, c_float, ctypes.c_int64
     sigs = {
@@ -60,6 +76,9 @@ def _declare(lib):
         "t4s_mel_normalize": (I, [P, P, Z, P]),
         "t4s_gemm": (I, [ctypes.POINTER(Gemm), P]),
         "t4s_reduce_splits": (I, [P, I, Z, P, I, P]),
+        "t4s_attn_padded_len": (L, [I]),
+        "t4s_attn_fwd": (I, [ctypes.POINTER(Attn), P]),
+        "t4s_attn_bwd": (I, [ctypes.POINTER(AttnBwd), P]),
         "t4s_split_tf32": (I, [ctypes.POINTER(Operand), I, P, L, I, P]),
         "t4s_layernorm_fwd": (I, [P, P, P, P, P, P, L, I, F, F, I, L, L, P]),
         "t4s_layernorm_bwd_workspace": (Z, [L, I]),

@@ -1,0 +1,705 @@
+// K4: fused multi-head self-attention, forward and backward, on tcgen05 / TMEM / TMA (head_dim 64, bf16 operands).
+//
+// No [N, N] matrix ever reaches HBM.  Per (clip, head) the kernels walk 128 x 128 score tiles:
+//
+//   forward   CTA = one 128-query tile.  S = Q K_j^T (tcgen05, fp32 in TMEM) -> 4 softmax warps (thread = query row) read S
+//             with tcgen05.ld, keep the running max / sum, write P_j (bf16) into a SWIZZLE_128B shared-memory tile ->
+//             O_j = P_j V_j (tcgen05, V consumed MN-major straight from its [keys, hd] TMA tile) -> the same warps fold O_j
+//             into fp32 registers with the online-softmax rescale.  2 CTAs per SM (256 TMEM columns, 112 KB smem each) so
+//             one CTA's MMAs overlap the other's exponentials.  Also emits lse (log2 units) for the backward.
+//   bwd dK/dV CTA = one 128-key tile, loops over query tiles: S^T = K Q_i^T, dP^T = V dO_i^T (thread = key row),
+//             P^T = exp2(S^T*c - lse_i), dS^T = P^T (dP^T - delta_i) -> shared memory (bf16) ->
+//             dV += P^T dO_i, dK += dS^T Q_i accumulate in TMEM across the whole loop.
+//   bwd dQ    CTA = one 128-query tile, loops over key tiles: S, dP, dS as above (thread = query row), dQ += dS K_j in TMEM.
+//             (S / dP are recomputed once more instead of pushing dQ through global atomics: deterministic results.)
+//   Both backward kernels run 8 softmax warps (two per TMEM lane quarter, each taking half of the 128 columns), one TMA
+//   producer warp and one MMA-issuing warp; S/dP for tile t+1 are issued before the dV/dK (dQ) MMAs of tile t so the
+//   tensor pipe stays busy while the exponentials run.
+//
+// Out-of-range rows are handled by TMA zero fill (loads) and row predicates (stores); out-of-range key columns are masked.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace t4s {
+namespace attn {
+
+constexpr int kHd = 64;
+constexpr int kTile = 128;
+constexpr int kTileBytes = kTile * kHd * 2;  // one [128 rows x 64] bf16 SWIZZLE_128B tile
+constexpr int kPBytes = 2 * kTileBytes;      // one [128 x 128] bf16 tile = two 64-column sub-tiles
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+// Row r, columns [col0, col0 + 32) of a K-major [128 x 128] bf16 operand tile (two SWIZZLE_128B sub-tiles of 64 columns).
+__device__ __forceinline__ void store_row_chunk(unsigned char* tile, int r, int col0, const uint32_t (&pk)[16]) {
+  unsigned char* base = tile + (col0 >> 6) * kTileBytes + r * 128;
+  const int ch0 = (col0 & 63) >> 3;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int ch = (ch0 + q) ^ (r & 7);
+    *reinterpret_cast<uint4*>(base + ch * 16) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+  }
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ptx::smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+// D[128 x N] (+)= A[128 x 64] . B[N x 64]^T, both K-major tiles (4 instructions of K = 16)
+__device__ __forceinline__ void mma_k64(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool accumulate) {
+  const uint64_t adesc = ptx::umma_desc_sw128(a_addr, 16, 1024), bdesc = ptx::umma_desc_sw128(b_addr, 16, 1024);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) ptx::mma_f16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
+}
+// D[128 x 64] (+)= A[128 x 128] . B, A a K-major [128 x 128] tile written by the softmax warps, B a [128 rows(K) x 64] tile
+// consumed MN-major (8 instructions of K = 16 rows = 2048 bytes each).
+__device__ __forceinline__ void mma_k128_mn(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, uint32_t idesc, bool accumulate) {
+  const uint64_t bdesc = ptx::umma_desc_sw128(b_addr, 8192, 1024);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const uint64_t adesc = ptx::umma_desc_sw128(a_addr + (k >> 2) * kTileBytes, 16, 1024) + 2 * (k & 3);
+    ptx::mma_f16(d_tmem, adesc, bdesc + 128 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
+  }
+}
+constexpr uint32_t kIdescS = ptx::umma_idesc(1, 128, 128, 0, 0);   // 128 x 128, both K-major
+constexpr uint32_t kIdescPV = ptx::umma_idesc(1, 128, 64, 0, 1);   // 128 x 64, B MN-major
+
+struct Args {
+  int N, Nl, n_tiles, H;
+  float sl2;    // scale * log2(e)
+  float scale;
+  __nv_bfloat16* o;  long long o_ld, o_bs;
+  float* lse;        // [B, H, Nl], log2 units
+  const float* delta;
+  __nv_bfloat16* dq; long long dq_ld, dq_bs;
+  __nv_bfloat16* dk; long long dk_ld, dk_bs;
+  __nv_bfloat16* dv; long long dv_ld, dv_bs;
+};
+
+__device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const float (&v)[64], float mul) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    uint4 u;
+    u.x = pack_bf16(v[8 * q] * mul, v[8 * q + 1] * mul);
+    u.y = pack_bf16(v[8 * q + 2] * mul, v[8 * q + 3] * mul);
+    u.z = pack_bf16(v[8 * q + 4] * mul, v[8 * q + 5] * mul);
+    u.w = pack_bf16(v[8 * q + 6] * mul, v[8 * q + 7] * mul);
+    reinterpret_cast<uint4*>(dst)[q] = u;
+  }
+}
+__device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (&v)[32], float mul) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    uint4 u;
+    u.x = pack_bf16(__uint_as_float(v[8 * q]) * mul, __uint_as_float(v[8 * q + 1]) * mul);
+    u.y = pack_bf16(__uint_as_float(v[8 * q + 2]) * mul, __uint_as_float(v[8 * q + 3]) * mul);
+    u.z = pack_bf16(__uint_as_float(v[8 * q + 4]) * mul, __uint_as_float(v[8 * q + 5]) * mul);
+    u.w = pack_bf16(__uint_as_float(v[8 * q + 6]) * mul, __uint_as_float(v[8 * q + 7]) * mul);
+    reinterpret_cast<uint4*>(dst)[q] = u;
+  }
+}
+
+// ======================================================================================================
+// forward
+// ======================================================================================================
+namespace fwd {
+constexpr int kThreads = 192;
+constexpr int oQ = 0, oK = oQ + kTileBytes, oV = oK + 2 * kTileBytes, oP = oV + 2 * kTileBytes, oBar = oP + kPBytes;
+constexpr int kSmem = oBar + 128;
+constexpr int kTmemCols = 256;  // S: [0,128)  O: [128,192), [192,256)
+enum { bQFull = 0, bKvFull = 1, bKvEmpty = 3, bSFull = 5, bSFree = 6, bPFull = 7, bOFull = 8, bOFree = 10, bCount = 12 };
+}  // namespace fwd
+
+__global__ void __launch_bounds__(fwd::kThreads, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const Args a) {
+  using namespace fwd;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = a.n_tiles;
+
+  if (threadIdx.x == 0) {
+    if (ptx::smem_u32(smem) & 1023u) {
+      printf("t4s attn_fwd: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    ptx::mbar_init(&bars[bQFull], 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars[bKvFull + i], 1);
+      ptx::mbar_init(&bars[bKvEmpty + i], 1);
+      ptx::mbar_init(&bars[bOFull + i], 1);
+      ptx::mbar_init(&bars[bOFree + i], 4);
+    }
+    ptx::mbar_init(&bars[bSFull], 1);
+    ptx::mbar_init(&bars[bSFree], 4);
+    ptx::mbar_init(&bars[bPFull], 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+  }
+  if (warp == 5) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars[bQFull], kTileBytes);
+      ptx::tma_load_4d(smem + oQ, &tmQ, &bars[bQFull], 0, q0, h, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        ptx::mbar_wait(&bars[bKvEmpty + s], ((j >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bars[bKvFull + s], 2 * kTileBytes);
+        ptx::tma_load_4d(smem + oK + s * kTileBytes, &tmK, &bars[bKvFull + s], 0, j * kTile, h, b);
+        ptx::tma_load_4d(smem + oV + s * kTileBytes, &tmV, &bars[bKvFull + s], 0, j * kTile, h, b);
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t sQ = ptx::smem_u32(smem + oQ), sK = ptx::smem_u32(smem + oK), sV = ptx::smem_u32(smem + oV),
+                   sP = ptx::smem_u32(smem + oP);
+    ptx::mbar_wait(&bars[bQFull], 0);
+    ptx::mbar_wait(&bars[bKvFull + 0], 0);
+    ptx::tc_fence_after();
+    if (lane == 0) {
+      mma_k64(tmem, sQ, sK, kIdescS, false);
+      ptx::tc_commit(&bars[bSFull]);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      if (j + 1 < n_tiles) {
+        ptx::mbar_wait(&bars[bKvFull + (s ^ 1)], ((j + 1) >> 1) & 1);
+        ptx::mbar_wait(&bars[bSFree], j & 1);  // softmax warps have read S_j out of TMEM
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          mma_k64(tmem, sQ, sK + (s ^ 1) * kTileBytes, kIdescS, false);
+          ptx::tc_commit(&bars[bSFull]);
+        }
+        __syncwarp();
+      }
+      ptx::mbar_wait(&bars[bPFull], j & 1);                       // P_j is in shared memory
+      ptx::mbar_wait(&bars[bOFree + s], ((j >> 1) & 1) ^ 1);      // O buffer s was folded (tile j-2)
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        mma_k128_mn(tmem + 128 + 64 * s, sP, sV + s * kTileBytes, kIdescPV, false);
+        ptx::tc_commit(&bars[bKvEmpty + s]);
+        ptx::tc_commit(&bars[bOFull + s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- softmax / accumulate warps: thread = query row ----------------
+    const int r = warp * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    const float sl2 = a.sl2;
+
+    auto fold = [&](int jj) {  // acc = acc * alpha_prev + O_jj
+      const int s = jj & 1;
+      ptx::mbar_wait(&bars[bOFull + s], (jj >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld_32x32(t_lane + 128 + 64 * s, v0);
+      ptx::tmem_ld_32x32(t_lane + 128 + 64 * s + 32, v1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[bOFree + s]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(v0[i]));
+        acc[32 + i] = fmaf(acc[32 + i], alpha_prev, __uint_as_float(v1[i]));
+      }
+    };
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int nvalid = a.N - j * kTile;  // key columns of this tile that exist (>= 1)
+      const bool full = nvalid >= kTile;
+      ptx::mbar_wait(&bars[bSFull], j & 1);
+      ptx::tc_fence_after();
+      // pass 1: running max
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
+        ptx::tmem_ld_wait();
+        if (nvalid >= 32 * c + 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * c + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = ex2((m - m_new) * sl2);  // 0 on the first tile (m = -inf)
+      const float mneg = -m_new * sl2;
+      // the previous tile's P V product must have retired before P is overwritten; fold it in while we are here
+      if (j > 0) fold(j - 1);
+      // pass 2: exponentials, row sum, P tile
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
+        ptx::tmem_ld_wait();
+        if (c == 3) {  // S_j fully read: the MMA warp may overwrite it with S_{j+1}
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars[bSFree]);
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, mneg));
+          float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, mneg));
+          if (!full) {
+            if (32 * c + 2 * i >= nvalid) p0 = 0.f;
+            if (32 * c + 2 * i + 1 >= nvalid) p1 = 0.f;
+          }
+          rs += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
+        }
+        store_row_chunk(smem + oP, r, 32 * c, pk);
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[bPFull]);
+      l = fmaf(l, alpha, rs);
+      m = m_new;
+      alpha_prev = alpha;
+    }
+    fold(n_tiles - 1);
+    const int row = q0 + r;
+    const float inv = 1.f / l;
+    a.lse[((long long)b * a.H + h) * a.Nl + row] = fmaf(m, sl2, log2f(l));
+    if (row < a.N) store_row64(a.o + (long long)b * a.o_bs + (long long)row * a.o_ld + h * kHd, acc, inv);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+// ======================================================================================================
+// backward: delta = rowsum(dO * O)
+// ======================================================================================================
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long o_ld, long long o_bs,
+                                  const __nv_bfloat16* __restrict__ d_o, long long do_ld, long long do_bs,
+                                  float* __restrict__ delta, int B, int H, int N, int Nl) {
+  const long long wg = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (wg >= (long long)B * Nl) return;
+  const int b = (int)(wg / Nl), n = (int)(wg % Nl);
+  if (n >= N) {
+    for (int hh = lane; hh < H; hh += 32) delta[((long long)b * H + hh) * Nl + n] = 0.f;
+    return;
+  }
+  const int chunks = H * 8;  // 16-byte chunks per token row
+  const __nv_bfloat16* op = o + (long long)b * o_bs + (long long)n * o_ld;
+  const __nv_bfloat16* dp = d_o + (long long)b * do_bs + (long long)n * do_ld;
+  for (int c0 = 0; c0 < chunks; c0 += 32) {
+    const int c = c0 + lane;
+    float s = 0.f;
+    if (c < chunks) {
+      const uint4 x = reinterpret_cast<const uint4*>(op)[c], y = reinterpret_cast<const uint4*>(dp)[c];
+      const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&x);
+      const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&y);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 xf = __bfloat1622float2(xp[i]), yf = __bfloat1622float2(yp[i]);
+        s = fmaf(xf.x, yf.x, s);
+        s = fmaf(xf.y, yf.y, s);
+      }
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if ((lane & 7) == 0 && c < chunks) delta[((long long)b * H + (c >> 3)) * Nl + n] = s;
+  }
+}
+
+// ======================================================================================================
+// backward kernels (shared layout)
+// ======================================================================================================
+namespace bwd {
+constexpr int kThreads = 320;  // warps 0-7 softmax (two column halves), 8 TMA, 9 MMA
+// resident pair (K,V for dKV / Q,dO for dQ), streamed pair x 2 stages, two [128x128] bf16 operand tiles, lse/delta stages
+constexpr int oRes = 0, oStr = oRes + 2 * kTileBytes, oP = oStr + 4 * kTileBytes, oDs = oP + kPBytes, oStat = oDs + kPBytes,
+              oBar = oStat + 2 * 2 * kTile * 4;
+constexpr int kSmem = oBar + 128;
+constexpr int kTmemCols = 512;  // S: [0,128)  dP: [128,256)  acc0: [256,320)  acc1: [320,384)
+enum { bResFull = 0, bStrFull = 1, bStrEmpty = 3, bSFull = 5, bSFree = 6, bPFull = 7, bPFree = 8, bAccFull = 9, bCount = 10 };
+}  // namespace bwd
+
+// kDq = false: dK/dV kernel (resident K_j, V_j; streams Q_i, dO_i, lse_i, delta_i; thread = key row)
+// kDq = true : dQ kernel    (resident Q_i, dO_i; streams K_j, V_j;                  thread = query row)
+template <bool kDq>
+__global__ void __launch_bounds__(bwd::kThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const Args a) {
+  using namespace bwd;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = a.n_tiles;
+  const long long stat_base = ((long long)b * a.H + h) * a.Nl;
+
+  if (threadIdx.x == 0) {
+    if (ptx::smem_u32(smem) & 1023u) {
+      printf("t4s attn_bwd: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    ptx::mbar_init(&bars[bResFull], 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars[bStrFull + i], 1);
+      ptx::mbar_init(&bars[bStrEmpty + i], 1);
+    }
+    ptx::mbar_init(&bars[bSFull], 1);
+    ptx::mbar_init(&bars[bSFree], 8);
+    ptx::mbar_init(&bars[bPFull], 8);
+    ptx::mbar_init(&bars[bPFree], 1);
+    ptx::mbar_init(&bars[bAccFull], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 8 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+    ptx::prefetch_tmap(&tmDO);
+  }
+  if (warp == 9) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // shared-memory roles.  X = operand that pairs with K-major "S" product, Y = operand that pairs with the "dP" product.
+  //   dKV: resident (K_j, V_j), streamed (Q_i, dO_i):  S^T = K Q^T,  dP^T = V dO^T,  dV += P^T dO,  dK += dS^T Q
+  //   dQ : resident (Q_i, dO_i), streamed (K_j, V_j):  S   = Q K^T,  dP   = dO V^T,  dQ += dS K
+  unsigned char* sRes0 = smem + oRes;               // K_j  | Q_i
+  unsigned char* sRes1 = smem + oRes + kTileBytes;  // V_j  | dO_i
+  float* sStat = reinterpret_cast<float*>(smem + oStat);  // [stage][lse(128) | delta(128)]  (dKV only)
+
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars[bResFull], 2 * kTileBytes);
+      if (kDq) {
+        ptx::tma_load_4d(sRes0, &tmQ, &bars[bResFull], 0, t0, h, b);
+        ptx::tma_load_4d(sRes1, &tmDO, &bars[bResFull], 0, t0, h, b);
+      } else {
+        ptx::tma_load_4d(sRes0, &tmK, &bars[bResFull], 0, t0, h, b);
+        ptx::tma_load_4d(sRes1, &tmV, &bars[bResFull], 0, t0, h, b);
+      }
+      for (int i = 0; i < n_tiles; ++i) {
+        const int s = i & 1;
+        unsigned char* st0 = smem + oStr + s * 2 * kTileBytes;
+        ptx::mbar_wait(&bars[bStrEmpty + s], ((i >> 1) & 1) ^ 1);
+        if (kDq) {
+          ptx::mbar_arrive_expect_tx(&bars[bStrFull + s], 2 * kTileBytes);
+          ptx::tma_load_4d(st0, &tmK, &bars[bStrFull + s], 0, i * kTile, h, b);
+          ptx::tma_load_4d(st0 + kTileBytes, &tmV, &bars[bStrFull + s], 0, i * kTile, h, b);
+        } else {
+          ptx::mbar_arrive_expect_tx(&bars[bStrFull + s], 2 * kTileBytes + 2 * kTile * 4);
+          ptx::tma_load_4d(st0, &tmQ, &bars[bStrFull + s], 0, i * kTile, h, b);
+          ptx::tma_load_4d(st0 + kTileBytes, &tmDO, &bars[bStrFull + s], 0, i * kTile, h, b);
+          bulk_load(sStat + s * 2 * kTile, a.lse + stat_base + i * kTile, kTile * 4, &bars[bStrFull + s]);
+          bulk_load(sStat + s * 2 * kTile + kTile, a.delta + stat_base + i * kTile, kTile * 4, &bars[bStrFull + s]);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t r0 = ptx::smem_u32(sRes0), r1 = ptx::smem_u32(sRes1), str = ptx::smem_u32(smem + oStr),
+                   sP = ptx::smem_u32(smem + oP), sDs = ptx::smem_u32(smem + oDs);
+    ptx::mbar_wait(&bars[bResFull], 0);
+    ptx::mbar_wait(&bars[bStrFull + 0], 0);
+    ptx::tc_fence_after();
+    if (lane == 0) {
+      mma_k64(tmem, r0, str, kIdescS, false);                      // S / S^T
+      mma_k64(tmem + 128, r1, str + kTileBytes, kIdescS, false);   // dP / dP^T
+      ptx::tc_commit(&bars[bSFull]);
+    }
+    __syncwarp();
+    for (int i = 0; i < n_tiles; ++i) {
+      const int s = i & 1;
+      if (i + 1 < n_tiles) {
+        const uint32_t nx = str + (s ^ 1) * 2 * kTileBytes;
+        ptx::mbar_wait(&bars[bStrFull + (s ^ 1)], ((i + 1) >> 1) & 1);
+        ptx::mbar_wait(&bars[bSFree], i & 1);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          mma_k64(tmem, r0, nx, kIdescS, false);
+          mma_k64(tmem + 128, r1, nx + kTileBytes, kIdescS, false);
+          ptx::tc_commit(&bars[bSFull]);
+        }
+        __syncwarp();
+      }
+      ptx::mbar_wait(&bars[bPFull], i & 1);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        const uint32_t cur = str + s * 2 * kTileBytes;
+        if (kDq) {
+          mma_k128_mn(tmem + 256, sDs, cur, kIdescPV, i > 0);                  // dQ += dS K_j
+        } else {
+          mma_k128_mn(tmem + 256, sP, cur + kTileBytes, kIdescPV, i > 0);      // dV += P^T dO_i
+          mma_k128_mn(tmem + 320, sDs, cur, kIdescPV, i > 0);                  // dK += dS^T Q_i
+        }
+        ptx::tc_commit(&bars[bStrEmpty + s]);
+        ptx::tc_commit(&bars[bPFree]);
+        if (i == n_tiles - 1) ptx::tc_commit(&bars[bAccFull]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- softmax warps: thread = row of this CTA's tile, column half g ----------------
+    const int wq = warp & 3, g = warp >> 2;
+    const int r = wq * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(wq * 32) << 16);
+    const float sl2 = a.sl2;
+    float my_lse = 0.f, my_delta = 0.f;
+    if (kDq) {
+      my_lse = a.lse[stat_base + t0 + r];
+      my_delta = a.delta[stat_base + t0 + r];
+    }
+    for (int i = 0; i < n_tiles; ++i) {
+      const int s = i & 1;
+      const float* st = sStat + s * 2 * kTile;
+      if (!kDq) ptx::mbar_wait(&bars[bStrFull + s], (i >> 1) & 1);  // lse / delta of this query tile have landed
+      ptx::mbar_wait(&bars[bSFull], i & 1);
+      ptx::tc_fence_after();
+      ptx::mbar_wait(&bars[bPFree], (i & 1) ^ 1);  // previous tile's MMAs have finished reading the P / dS tiles
+      const int nvalid = a.N - i * kTile;          // dQ: key columns that exist
+      const bool full = nvalid >= kTile;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int col0 = 64 * g + 32 * c;
+        uint32_t vs[32], vp[32];
+        ptx::tmem_ld_32x32(t_lane + col0, vs);
+        ptx::tmem_ld_32x32(t_lane + 128 + col0, vp);
+        ptx::tmem_ld_wait();
+        if (c == 1) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars[bSFree]);
+        }
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float ls[4], dl[4];
+          if (kDq) {
+            ls[0] = ls[1] = ls[2] = ls[3] = my_lse;
+            dl[0] = dl[1] = dl[2] = dl[3] = my_delta;
+          } else {
+            const float4 L = *reinterpret_cast<const float4*>(st + col0 + 4 * q);
+            const float4 Dv = *reinterpret_cast<const float4*>(st + kTile + col0 + 4 * q);
+            ls[0] = L.x; ls[1] = L.y; ls[2] = L.z; ls[3] = L.w;
+            dl[0] = Dv.x; dl[1] = Dv.y; dl[2] = Dv.z; dl[3] = Dv.w;
+          }
+          float p[4], d[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            p[e] = ex2(fmaf(__uint_as_float(vs[4 * q + e]), sl2, -ls[e]));
+            if (kDq && !full && col0 + 4 * q + e >= nvalid) p[e] = 0.f;
+            d[e] = p[e] * (__uint_as_float(vp[4 * q + e]) - dl[e]);
+          }
+          pp[2 * q] = pack_bf16(p[0], p[1]);
+          pp[2 * q + 1] = pack_bf16(p[2], p[3]);
+          pd[2 * q] = pack_bf16(d[0], d[1]);
+          pd[2 * q + 1] = pack_bf16(d[2], d[3]);
+        }
+        if (!kDq) store_row_chunk(smem + oP, r, col0, pp);
+        store_row_chunk(smem + oDs, r, col0, pd);
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[bPFull]);
+    }
+    // ---- write the accumulators: each column half takes 32 of the 64 head-dim columns ----
+    ptx::mbar_wait(&bars[bAccFull], 0);
+    ptx::tc_fence_after();
+    const int row = t0 + r;
+    uint32_t v[32];
+    ptx::tmem_ld_32x32(t_lane + 256 + 32 * g, v);
+    ptx::tmem_ld_wait();
+    if (kDq) {
+      if (row < a.N) store_row32(a.dq + (long long)b * a.dq_bs + (long long)row * a.dq_ld + h * kHd + 32 * g, v, a.scale);
+    } else {
+      if (row < a.N) store_row32(a.dv + (long long)b * a.dv_bs + (long long)row * a.dv_ld + h * kHd + 32 * g, v, 1.f);
+      ptx::tmem_ld_32x32(t_lane + 320 + 32 * g, v);
+      ptx::tmem_ld_wait();
+      if (row < a.N) store_row32(a.dk + (long long)b * a.dk_bs + (long long)row * a.dk_ld + h * kHd + 32 * g, v, a.scale);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+// ---- host side ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// (d, token, head, clip) view with a [64 x 128 x 1 x 1] SWIZZLE_128B box
+static int make_map(CUtensorMap* m, const void* ptr, long long ld, long long bs, int B, int H, int N, const char* name) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled entry point not available");
+    return T4S_ERR_CUDA;
+  }
+  if (!ptr || (reinterpret_cast<uintptr_t>(ptr) & 15) || (ld % 8) || (bs % 8) || ld < (long long)H * kHd || bs <= 0) {
+    set_error("t4s_attn: %s needs a 16-byte aligned base, pitches that are multiples of 8 elements and ld >= heads*64 (ld=%lld, bs=%lld)",
+              name, ld, bs);
+    return T4S_ERR_ARG;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)kHd, (cuuint64_t)N, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)(ld * 2), (cuuint64_t)(kHd * 2), (cuuint64_t)(bs * 2)};
+  cuuint32_t box[4] = {(cuuint32_t)kHd, (cuuint32_t)kTile, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult rc = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(%s) failed with CUresult %d (N=%d H=%d B=%d ld=%lld bs=%lld)", name, (int)rc, N, H, B, ld, bs);
+    return T4S_ERR_CUDA;
+  }
+  return T4S_OK;
+}
+
+static int check_common(const T4sAttn* p) {
+  T4S_REQUIRE(p, "t4s_attn: null descriptor");
+  T4S_REQUIRE(p->head_dim == kHd, "t4s_attn: head_dim must be 64 (got %d)", p->head_dim);
+  T4S_REQUIRE(p->batch > 0 && p->heads > 0 && p->tokens > 0, "t4s_attn: batch, heads and tokens must be positive");
+  T4S_REQUIRE(p->batch <= 65535 && p->heads <= 65535, "t4s_attn: batch / heads exceed the grid limits");
+  T4S_REQUIRE(p->q && p->k && p->v && p->o && p->lse, "t4s_attn: q, k, v, o and lse are required");
+  T4S_REQUIRE(!(reinterpret_cast<uintptr_t>(p->o) & 15) && !(p->o_ld % 8) && !(p->o_bs % 8), "t4s_attn: o must be 16-byte aligned with pitches % 8 == 0");
+  return T4S_OK;
+}
+
+static void fill_args(Args& a, const T4sAttn* p) {
+  a.N = p->tokens;
+  a.n_tiles = (p->tokens + kTile - 1) / kTile;
+  a.Nl = a.n_tiles * kTile;
+  a.H = p->heads;
+  a.scale = p->scale;
+  a.sl2 = p->scale * 1.4426950408889634f;
+  a.o = reinterpret_cast<__nv_bfloat16*>(p->o);
+  a.o_ld = p->o_ld;
+  a.o_bs = p->o_bs;
+  a.lse = p->lse;
+  a.delta = nullptr;
+  a.dq = a.dk = a.dv = nullptr;
+  a.dq_ld = a.dq_bs = a.dk_ld = a.dk_bs = a.dv_ld = a.dv_bs = 0;
+}
+
+}  // namespace attn
+}  // namespace t4s
+
+extern "C" int64_t t4s_attn_padded_len(int tokens) {
+  return (int64_t)((tokens + t4s::attn::kTile - 1) / t4s::attn::kTile) * t4s::attn::kTile;
+}
+
+extern "C" int t4s_attn_fwd(const T4sAttn* p, void* stream) {
+  using namespace t4s::attn;
+  int rc = check_common(p);
+  if (rc) return rc;
+  CUtensorMap tq, tk, tv;
+  if ((rc = make_map(&tq, p->q, p->q_ld, p->q_bs, p->batch, p->heads, p->tokens, "q"))) return rc;
+  if ((rc = make_map(&tk, p->k, p->k_ld, p->k_bs, p->batch, p->heads, p->tokens, "k"))) return rc;
+  if ((rc = make_map(&tv, p->v, p->v_ld, p->v_bs, p->batch, p->heads, p->tokens, "v"))) return rc;
+  Args a;
+  fill_args(a, p);
+  T4S_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmem));
+  dim3 grid(a.n_tiles, p->heads, p->batch);
+  attn_fwd_kernel<<<grid, fwd::kThreads, fwd::kSmem, t4s::as_stream(stream)>>>(tq, tk, tv, a);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+extern "C" int t4s_attn_bwd(const T4sAttnBwd* p, void* stream) {
+  using namespace t4s::attn;
+  T4S_REQUIRE(p, "t4s_attn_bwd: null descriptor");
+  const T4sAttn* f = &p->fwd;
+  int rc = check_common(f);
+  if (rc) return rc;
+  T4S_REQUIRE(p->d_o && p->delta && p->dq && p->dk && p->dv, "t4s_attn_bwd: d_o, delta, dq, dk and dv are required");
+  for (const void* ptr : {(const void*)p->dq, (const void*)p->dk, (const void*)p->dv})
+    T4S_REQUIRE(!(reinterpret_cast<uintptr_t>(ptr) & 15), "t4s_attn_bwd: dq / dk / dv must be 16-byte aligned");
+  T4S_REQUIRE(!(p->dq_ld % 8) && !(p->dq_bs % 8) && !(p->dk_ld % 8) && !(p->dk_bs % 8) && !(p->dv_ld % 8) && !(p->dv_bs % 8),
+              "t4s_attn_bwd: gradient pitches must be multiples of 8 elements");
+  CUtensorMap tq, tk, tv, tdo;
+  if ((rc = make_map(&tq, f->q, f->q_ld, f->q_bs, f->batch, f->heads, f->tokens, "q"))) return rc;
+  if ((rc = make_map(&tk, f->k, f->k_ld, f->k_bs, f->batch, f->heads, f->tokens, "k"))) return rc;
+  if ((rc = make_map(&tv, f->v, f->v_ld, f->v_bs, f->batch, f->heads, f->tokens, "v"))) return rc;
+  if ((rc = make_map(&tdo, p->d_o, p->do_ld, p->do_bs, f->batch, f->heads, f->tokens, "d_o"))) return rc;
+  Args a;
+  fill_args(a, f);
+  a.delta = p->delta;
+  a.dq = reinterpret_cast<__nv_bfloat16*>(p->dq); a.dq_ld = p->dq_ld; a.dq_bs = p->dq_bs;
+  a.dk = reinterpret_cast<__nv_bfloat16*>(p->dk); a.dk_ld = p->dk_ld; a.dk_bs = p->dk_bs;
+  a.dv = reinterpret_cast<__nv_bfloat16*>(p->dv); a.dv_ld = p->dv_ld; a.dv_bs = p->dv_bs;
+  cudaStream_t st = t4s::as_stream(stream);
+  {
+    const long long warps = (long long)f->batch * a.Nl;
+    const int threads = 256;
+    const long long blocks = (warps * 32 + threads - 1) / threads;
+    attn_delta_kernel<<<(unsigned)blocks, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(f->o), f->o_ld, f->o_bs,
+                                                            reinterpret_cast<const __nv_bfloat16*>(p->d_o), p->do_ld, p->do_bs,
+                                                            p->delta, f->batch, f->heads, f->tokens, a.Nl);
+    T4S_LAUNCH_CHECK();
+  }
+  dim3 grid(a.n_tiles, f->heads, f->batch);
+  T4S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
+  attn_bwd_kernel<false><<<grid, bwd::kThreads, bwd::kSmem, st>>>(tq, tk, tv, tdo, a);
+  T4S_LAUNCH_CHECK();
+  T4S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
+  attn_bwd_kernel<true><<<grid, bwd::kThreads, bwd::kSmem, st>>>(tq, tk, tv, tdo, a);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}

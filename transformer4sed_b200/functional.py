@@ -374,7 +374,77 @@ class _Attention(torch.autograd.Function):
         return dqkv, None
 
 
+def _attn_desc(qkv, o, lse, B, N, D, H, scale):
+    a = _lib.Attn()
+    a.batch, a.heads, a.tokens, a.head_dim, a.scale = B, H, N, D // H, scale
+    es = qkv.element_size()
+    base = qkv.data_ptr()
+    a.q, a.k, a.v = base, base + D * es, base + 2 * D * es
+    a.q_ld = a.k_ld = a.v_ld = 3 * D
+    a.q_bs = a.k_bs = a.v_bs = N * 3 * D
+    a.o, a.o_ld, a.o_bs = o.data_ptr(), D, N * D
+    a.lse = lse.data_ptr()
+    return a
+
+
+class _FlashAttention(torch.autograd.Function):
+    """Fused tcgen05 attention (csrc/attn.cu): no [B, H, N, N] tensor is materialised; bf16 mode, head_dim 64."""
+
+    @staticmethod
+    def forward(ctx, qkv, H):
+        _lib.ensure_device(qkv)
+        qkv = qkv.contiguous()
+        B, N, D3 = qkv.shape
+        D = D3 // 3
+        dev = qkv.device
+        lib = _lib.load()
+        Nl = lib.t4s_attn_padded_len(N)
+        with torch.cuda.device(dev):
+            o = torch.empty(B, N, D, dtype=qkv.dtype, device=dev)
+            lse = torch.empty(B, H, Nl, dtype=torch.float32, device=dev)
+            a = _attn_desc(qkv, o, lse, B, N, D, H, (D // H) ** -0.5)
+            _lib_call("t4s_attn_fwd", ctypes.byref(a), _st())
+        ctx.save_for_backward(qkv, o, lse)
+        ctx.H = H
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, o, lse = ctx.saved_tensors
+        H = ctx.H
+        B, N, D3 = qkv.shape
+        D = D3 // 3
+        dev = qkv.device
+        do = do.contiguous()
+        if do.dtype != qkv.dtype:
+            do = convert(do, torch.empty(do.shape, dtype=qkv.dtype, device=dev))
+        with torch.cuda.device(dev):
+            dqkv = torch.empty_like(qkv)
+            delta = torch.empty_like(lse)
+            g = _lib.AttnBwd()
+            g.fwd = _attn_desc(qkv, o, lse, B, N, D, H, (D // H) ** -0.5)
+            g.d_o, g.do_ld, g.do_bs = do.data_ptr(), D, N * D
+            g.delta = delta.data_ptr()
+            es = dqkv.element_size()
+            g.dq, g.dk, g.dv = dqkv.data_ptr(), dqkv.data_ptr() + D * es, dqkv.data_ptr() + 2 * D * es
+            g.dq_ld = g.dk_ld = g.dv_ld = 3 * D
+            g.dq_bs = g.dk_bs = g.dv_bs = N * 3 * D
+            _lib_call("t4s_attn_bwd", ctypes.byref(g), _st())
+        return dqkv, None
+
+
+_FUSED_ATTN = True
+
+
+def set_fused_attention(flag: bool):
+    """Debug / A-B switch: False routes bf16 attention through the unfused GEMM + softmax kernels."""
+    global _FUSED_ATTN
+    _FUSED_ATTN = bool(flag)
+
+
 def attention(qkv, num_heads):
+    if _FUSED_ATTN and qkv.dtype == torch.bfloat16 and qkv.shape[-1] // 3 // num_heads == 64:
+        return _FlashAttention.apply(qkv, num_heads)
     return _Attention.apply(qkv, num_heads)
 
 
