@@ -227,24 +227,12 @@ def run_ours(args):
 
 
 def instrumented_step(train_step, wav_dev, ext, ops, B):
-    """One extra step with every C-ABI launch group bracketed by CUDA events on the launching stream."""
+    """One extra step with every C-ABI launch bracketed by CUDA events on the launching stream (never the timed region)."""
     from transformer4sed_b200 import _lib
     pk, pk_src = peaks()
-    recs = []
-    orig_gemm = ops.gemm
-    orig_check = _lib.check
-
-    def gemm_timed(A, Bop, C, M, N, K, nb1=1, nb2=1, **kw):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        orig_gemm(A, Bop, C, M, N, K, nb1=nb1, nb2=nb2, **kw)
-        e.record()
-        recs.append(("gemm", s, e, 2.0 * M * N * K * nb1 * nb2))
-
-    ops.gemm = gemm_timed
-    import transformer4sed_b200.functional as F
-    F.ops.gemm = gemm_timed
+    prof = _lib.LaunchProfiler()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _lib.profiler = prof
     try:
         torch.cuda.synchronize()
         t0.record()
@@ -252,12 +240,26 @@ def instrumented_step(train_step, wav_dev, ext, ops, B):
         t1.record()
         torch.cuda.synchronize()
     finally:
-        ops.gemm = orig_gemm
-        F.ops.gemm = orig_gemm
-        _lib.check = orig_check
-    gemm_ms = sum(s.elapsed_time(e) for _, s, e, _ in recs)
-    gemm_flops = sum(f for *_, f in recs)
+        _lib.profiler = None
     step_ms = t0.elapsed_time(t1)
+    gemm_ms = gemm_flops = 0.0
+    n_gemm = 0
+    attn_ms = 0.0
+    for name, key, s, e in prof.records:
+        if name == "t4s_gemm":
+            M, N, K, nb = key[:4]
+            gemm_ms += s.elapsed_time(e)
+            gemm_flops += 2.0 * M * N * K * nb
+            n_gemm += 1
+        elif name in ("t4s_attn_fwd", "t4s_attn_bwd"):
+            attn_ms += s.elapsed_time(e)
+    summary = prof.summary()
+    try:
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/step_breakdown.json", "w") as f:
+            json.dump({"step_ms": step_ms, "ops": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in summary.items()}}, f, indent=1)
+    except OSError:
+        pass
     # front end alone, L2 flushed between iterations
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=wav_dev.device)
     ts = []
@@ -273,12 +275,13 @@ def instrumented_step(train_step, wav_dev, ext, ops, B):
     mel_bytes = B * (4 * N_SAMPLES + 4 * 128 * 1000)
     roof = {"bound": "tensor", "kernel": "t4s::gemm::gemm_kernel (tcgen05, all GEMM launches of one step)", "achieved": gemm_flops / gemm_ms / 1e9,
             "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": gemm_flops / gemm_ms / 1e9 / pk["bf16_tflops_sustained"], "traffic": None,
-            "launches": len(recs), "gemm_ms_per_step": gemm_ms, "share_of_step": gemm_ms / step_ms, "peak_source": pk_src + " (sustained bf16)",
+            "launches": n_gemm, "gemm_ms_per_step": gemm_ms, "share_of_step": gemm_ms / step_ms, "peak_source": pk_src + " (sustained bf16)",
             "how": "CUDA events around every t4s_gemm launch of one extra instrumented step; flops = 2MNK per launch"}
     mel_roof = {"bound": "hbm", "kernel": "t4s::mel::mel_kernel (+peak kernel)", "achieved": mel_bytes / mel_ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": mel_bytes / mel_ms / 1e6 / pk["hbm_gbs"], "traffic": None, "ms": mel_ms, "clips_per_s": B / mel_ms * 1e3,
                 "algorithmic_bytes_per_clip": 4 * N_SAMPLES + 4 * 128 * 1000, "peak_source": pk_src}
-    return roof, mel_roof, {"step_instrumented": step_ms, "gemm": gemm_ms, "front_end": mel_ms, "other": step_ms - gemm_ms - mel_ms}
+    return roof, mel_roof, {"step_instrumented": step_ms, "gemm": gemm_ms, "fused_attention": attn_ms, "front_end": mel_ms,
+                            "other": step_ms - gemm_ms - attn_ms - mel_ms}
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -39,12 +39,25 @@ def bench_gemm(res):
             y = torch.empty(M, N, device="cuda", dtype=dtype)
             f = lambda: ops.gemm(ops.Op(x, M, K), ops.Op(w, N, K), ops.Out(y, N), M, N, K)  # noqa: E731
             med, best = timeit(f, flush=flush)
+            if name != "square8k":
+                bias = torch.randn(N, device="cuda")
+                aux = torch.empty_like(y)
+                resid = torch.randn(M, N, device="cuda").to(dtype)
+                fe = {"bias": lambda: ops.gemm(ops.Op(x, M, K), ops.Op(w, N, K), ops.Out(y, N), M, N, K, bias=bias),
+                      "bias_gelu_aux": lambda: ops.gemm(ops.Op(x, M, K), ops.Op(w, N, K), ops.Out(y, N), M, N, K, bias=bias,
+                                                        aux=ops.Out(aux, N), act=ops.ACT_GELU),
+                      "bias_res": lambda: ops.gemm(ops.Op(x, M, K), ops.Op(w, N, K), ops.Out(y, N), M, N, K, bias=bias,
+                                                   residual=ops.Out(resid, N))}
+                extra = {k: timeit(v, flush=flush)[0] for k, v in fe.items()}
+                del aux, resid
+            else:
+                extra = {}
             ref = lambda: torch.matmul(x, w.t(), out=y)  # noqa: E731
             torch.backends.cuda.matmul.allow_tf32 = True
             rmed, rbest = timeit(ref, flush=flush)
             fl = 2.0 * M * N * K
             res.append(dict(kernel="gemm", name=name, dtype=str(dtype), M=M, N=N, K=K, ms=med, tflops=fl / med / 1e9,
-                            best_tflops=fl / best / 1e9, cublas_ms=rmed, cublas_tflops=fl / rmed / 1e9))
+                            best_tflops=fl / best / 1e9, cublas_ms=rmed, cublas_tflops=fl / rmed / 1e9, epilogue_ms=extra))
             print(res[-1], flush=True)
             del x, w, y
 

@@ -150,6 +150,35 @@ def exported_symbols():
     return sorted(set(re.findall(r"\b(t4s_[a-z0-9_]+)\s*\(", hdr)))
 
 
+class LaunchProfiler:
+    """Brackets every C-ABI call with CUDA events on the launching stream (bench.py's instrumented step).
+    `records` = [(name, key, start_event, end_event)]; keys carry GEMM shapes so time can be grouped per op."""
+
+    def __init__(self):
+        self.records = []
+
+    def timed(self, name, key, fn):
+        import torch
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        rc = fn()
+        e.record()
+        self.records.append((name, key, s, e))
+        return rc
+
+    def summary(self):
+        agg = {}
+        for name, key, s, e in self.records:
+            k = name if key is None else f"{name}{key}"
+            a = agg.setdefault(k, [0, 0.0])
+            a[0] += 1
+            a[1] += s.elapsed_time(e)
+        return dict(sorted(agg.items(), key=lambda kv: -kv[1][1]))
+
+
+profiler = None  # set to a LaunchProfiler to time every launch (never inside a timed benchmark region)
+
+
 def check(rc, what=""):
     if rc != 0:
         msg = load().t4s_last_error().decode(errors="replace")

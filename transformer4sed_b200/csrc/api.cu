@@ -20,6 +20,14 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return T4S_ERR_CUDA;
 }
 
+void ensure_context() {
+  static thread_local bool done = false;
+  if (!done) {
+    cudaFree(nullptr);
+    done = true;
+  }
+}
+
 int sm_count() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;

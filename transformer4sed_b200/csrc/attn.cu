@@ -589,6 +589,7 @@ static EncodeTiledFn get_encode() {
 
 // (d, token, head, clip) view with a [64 x 128 x 1 x 1] SWIZZLE_128B box
 static int make_map(CUtensorMap* m, const void* ptr, long long ld, long long bs, int B, int H, int N, const char* name) {
+  ensure_context();
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");

@@ -11,6 +11,9 @@ namespace t4s {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 int sm_count();
+// Bind the primary context to the calling thread (autograd worker threads may not have one yet): driver entry points
+// such as cuTensorMapEncodeTiled fail with CUDA_ERROR_INVALID_CONTEXT otherwise.
+void ensure_context();
 
 #define T4S_CUDA(expr)                                                        \
   do {                                                                        \

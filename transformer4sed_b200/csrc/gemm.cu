@@ -6,8 +6,11 @@
 //   warp 0    TMA producer: 4-D tensor maps (k, row, batch1, batch2), SWIZZLE_128B boxes -> NS-stage smem ring
 //   warp 1    MMA issuer:   one lane issues tcgen05.mma (M=128, N=BN, K=32 B per instruction), commits to mbarriers
 //   warp 2    TMEM allocator (2 x BN fp32 columns: accumulator double buffer, epilogue overlaps the next mainloop)
-//   warps 4-7 epilogue: tcgen05.ld 32x32b -> registers -> per-warp smem transpose -> bias / GELU / residual ->
-//             coalesced 16-byte stores (row-predicated, so ragged M/N tiles and TMA zero-fill compose)
+//   warps 4-11 epilogue: two warps per TMEM lane quarter, each draining half of the tile's columns in 32-column chunks:
+//             tcgen05.ld 32x32b (next chunk in flight while this one is processed) -> bias / GELU / residual in registers ->
+//             each thread stores 64 (bf16) or 128 (fp32) contiguous bytes of its own row with 16-byte accesses; the
+//             accumulator buffer is handed back to the MMA warp as soon as its last chunk is in registers.
+//             Row / column predicates make ragged M/N tiles and TMA zero-fill compose.
 // bf16 inputs use kind::f16, fp32 inputs use kind::tf32 (tensor map type TFLOAT32 rounds on load).
 #include <algorithm>
 
@@ -18,15 +21,14 @@ namespace t4s {
 namespace gemm {
 
 constexpr int kBM = 128;
-constexpr int kThreads = 256;
-constexpr int kEpiStride = 36;  // floats; 16-byte accesses are conflict-free both ways
-constexpr int kEpiBytesPerWarp = 32 * kEpiStride * 4;
+constexpr int kThreads = 384;
+constexpr int kEpiWarps = 8;
 
 struct MatArg {
   void* ptr;
   long long ld, s1, s2;
   int dtype;
-  int vec;  // 16-byte (fp32) / 8-byte (bf16) vector access is legal
+  int vec;  // 16-byte accesses are legal at every (row, column % 8 == 0) position
 };
 
 struct Args {
@@ -38,6 +40,7 @@ struct Args {
   long long total_tiles;
   MatArg C, aux, res;
   const float* bias;
+  int bias_vec;  // bias base is 16-byte aligned
   float alpha;
   int act;
 };
@@ -49,65 +52,130 @@ struct Cfg {
   static constexpr int kStage = kStageA + kStageB;
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmem = 1024 /*align slack*/ + kStages * kStage + 4 * kEpiBytesPerWarp + 256 /*barriers*/;
+  static constexpr int kSmem = 1024 /*align slack*/ + kStages * kStage + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// x * Phi(x) with erfc from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 on Phi, i.e. far below bf16 resolution): 2 MUFU + ~12 FP32
+// instructions instead of erff's ~30, which made the fc1 epilogue the bottleneck.  Used only when the output is bf16.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float half_erfc = 0.5f * poly * t * e;           // 0.5 * erfc(|x|/sqrt 2) = Phi(-|x|)
+  return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
+}
 
-__device__ __forceinline__ void store4(const MatArg& m, long long off, int ncols_valid, float4 v) {
+// 32 consecutive columns of one output row, from / to registers.  `nvalid` = columns that exist (may exceed 32).
+__device__ __forceinline__ void store32(const MatArg& m, long long off, int nvalid, const float (&x)[32]) {
   if (m.dtype == T4S_F32) {
     float* p = reinterpret_cast<float*>(m.ptr) + off;
-    if (m.vec && ncols_valid >= 4) {
-      *reinterpret_cast<float4*>(p) = v;
+    if (m.vec && nvalid >= 32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(p)[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
     } else {
-      if (ncols_valid > 0) p[0] = v.x;
-      if (ncols_valid > 1) p[1] = v.y;
-      if (ncols_valid > 2) p[2] = v.z;
-      if (ncols_valid > 3) p[3] = v.w;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) p[i] = x[i];
     }
   } else {
     __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(m.ptr) + off;
-    if (m.vec && ncols_valid >= 4) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-      uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&lo);
-      u.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(p) = u;
+    if (m.vec && nvalid >= 32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        uint4 u;
+        __nv_bfloat162 t;
+        t = __floats2bfloat162_rn(x[8 * i], x[8 * i + 1]);     u.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(x[8 * i + 2], x[8 * i + 3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(x[8 * i + 4], x[8 * i + 5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+        t = __floats2bfloat162_rn(x[8 * i + 6], x[8 * i + 7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+        reinterpret_cast<uint4*>(p)[i] = u;
+      }
     } else {
-      if (ncols_valid > 0) p[0] = __float2bfloat16_rn(v.x);
-      if (ncols_valid > 1) p[1] = __float2bfloat16_rn(v.y);
-      if (ncols_valid > 2) p[2] = __float2bfloat16_rn(v.z);
-      if (ncols_valid > 3) p[3] = __float2bfloat16_rn(v.w);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) p[i] = __float2bfloat16_rn(x[i]);
     }
   }
 }
 
-__device__ __forceinline__ float4 load4(const MatArg& m, long long off, int ncols_valid) {
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ void add32(const MatArg& m, long long off, int nvalid, float (&x)[32]) {
   if (m.dtype == T4S_F32) {
     const float* p = reinterpret_cast<const float*>(m.ptr) + off;
-    if (m.vec && ncols_valid >= 4) {
-      v = *reinterpret_cast<const float4*>(p);
+    if (m.vec && nvalid >= 32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = reinterpret_cast<const float4*>(p)[i];
+        x[4 * i] += v.x; x[4 * i + 1] += v.y; x[4 * i + 2] += v.z; x[4 * i + 3] += v.w;
+      }
     } else {
-      if (ncols_valid > 0) v.x = p[0];
-      if (ncols_valid > 1) v.y = p[1];
-      if (ncols_valid > 2) v.z = p[2];
-      if (ncols_valid > 3) v.w = p[3];
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) x[i] += p[i];
     }
   } else {
     const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(m.ptr) + off;
-    if (m.vec && ncols_valid >= 4) {
-      uint2 u = *reinterpret_cast<const uint2*>(p);
-      __nv_bfloat162 lo = *reinterpret_cast<__nv_bfloat162*>(&u.x), hi = *reinterpret_cast<__nv_bfloat162*>(&u.y);
-      v = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+    if (m.vec && nvalid >= 32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = reinterpret_cast<const uint4*>(p)[i];
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          x[8 * i + 2 * j] += f.x;
+          x[8 * i + 2 * j + 1] += f.y;
+        }
+      }
     } else {
-      if (ncols_valid > 0) v.x = __bfloat162float(p[0]);
-      if (ncols_valid > 1) v.y = __bfloat162float(p[1]);
-      if (ncols_valid > 2) v.z = __bfloat162float(p[2]);
-      if (ncols_valid > 3) v.w = __bfloat162float(p[3]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < nvalid) x[i] += __bfloat162float(p[i]);
     }
   }
-  return v;
+}
+
+// One 32-column chunk of the epilogue for the row this thread owns.
+__device__ __forceinline__ void epilogue_chunk(const Args& a, const uint32_t (&v)[32], int grow, int gcol, long long c_row,
+                                               long long x_row, long long r_row) {
+  const int nvalid = a.N - gcol;
+  if (grow >= a.M || nvalid <= 0) return;
+  float x[32];
+  if (a.bias) {
+    if (a.bias_vec && nvalid >= 32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + gcol) + i);
+        x[4 * i] = fmaf(a.alpha, __uint_as_float(v[4 * i]), b4.x);
+        x[4 * i + 1] = fmaf(a.alpha, __uint_as_float(v[4 * i + 1]), b4.y);
+        x[4 * i + 2] = fmaf(a.alpha, __uint_as_float(v[4 * i + 2]), b4.z);
+        x[4 * i + 3] = fmaf(a.alpha, __uint_as_float(v[4 * i + 3]), b4.w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = fmaf(a.alpha, __uint_as_float(v[i]), i < nvalid ? __ldg(a.bias + gcol + i) : 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = a.alpha * __uint_as_float(v[i]);
+  }
+  if (a.aux.ptr) store32(a.aux, x_row + gcol, nvalid, x);
+  if (a.act == T4S_ACT_GELU) {
+    if (a.C.dtype == T4S_BF16) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = gelu_fast(x[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = gelu_erf(x[i]);
+    }
+  }
+  if (a.res.ptr) add32(a.res, r_row + gcol, nvalid, x);
+  store32(a.C, c_row + gcol, nvalid, x);
 }
 
 template <int BN, bool kTf32, bool kAMn, bool kBMn>
@@ -122,8 +190,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   unsigned char* sA = smem;
   unsigned char* sB = smem + C::kStages * C::kStageA;
-  float* sEpi = reinterpret_cast<float*>(smem + C::kStages * C::kStage);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStage + 4 * kEpiBytesPerWarp);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStage);
   uint64_t* full = bars;
   uint64_t* empty = bars + C::kStages;
   uint64_t* tfull = bars + 2 * C::kStages;
@@ -144,7 +211,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], 4);
+      ptx::mbar_init(&tempty[i], kEpiWarps);
     }
     ptx::fence_barrier_init();
   }
@@ -237,10 +304,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
-    const int q = warp - 4;  // TMEM lane quarter this warp may access
-    float* st = sEpi + q * 32 * kEpiStride;
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int half = (warp - 4) >> 2;  // which half of the tile's columns this warp drains
+    constexpr int kHalfCols = BN / 2;
+    constexpr int kChunks = kHalfCols / 32;
     uint32_t ai = 0;
-    const int rsub = lane >> 3, c4 = (lane & 7) * 4;
     for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ai) {
       const int zs = (int)(tile / tiles_per_batch);
       const int r = (int)(tile - (long long)zs * tiles_per_batch);
@@ -250,65 +318,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int z1 = z % a.nb1, z2 = z / a.nb1;
       const int as = ai & 1;
       const uint32_t aph = (ai >> 1) & 1;
+      const int grow = m0 + q * 32 + lane;
+      const long long c_row = (long long)z1 * a.C.s1 + (long long)z2 * a.C.s2 + (long long)sp * a.c_split + (long long)grow * a.C.ld;
+      const long long x_row = (long long)z1 * a.aux.s1 + (long long)z2 * a.aux.s2 + (long long)grow * a.aux.ld;
+      const long long r_row = (long long)z1 * a.res.s1 + (long long)z2 * a.res.s2 + (long long)grow * a.res.ld;
+      const int col_base = n0 + half * kHalfCols;
       ptx::mbar_wait(&tfull[as], aph);
       ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-      const long long c_base = (long long)z1 * a.C.s1 + (long long)z2 * a.C.s2 + (long long)sp * a.c_split;
-      const long long x_base = (long long)z1 * a.aux.s1 + (long long)z2 * a.aux.s2;
-      const long long r_base = (long long)z1 * a.res.s1 + (long long)z2 * a.res.s2;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= a.N) break;  // warp-uniform
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_row + c0, v);
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * kHalfCols;
+      uint32_t va[32], vb[32];
+      ptx::tmem_ld_32x32(t_row, va);
+#pragma unroll
+      for (int c = 0; c < kChunks; ++c) {
         ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(st + lane * kEpiStride + 4 * j) =
-              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                          __uint_as_float(v[4 * j + 3]));
-        __syncwarp();
-        const int gcol = n0 + c0 + c4;
-        const int nvalid = a.N - gcol;  // may be <= 0
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.bias && nvalid > 0) {
-          b4.x = a.bias[gcol];
-          if (nvalid > 1) b4.y = a.bias[gcol + 1];
-          if (nvalid > 2) b4.z = a.bias[gcol + 2];
-          if (nvalid > 3) b4.w = a.bias[gcol + 3];
+        if (c + 1 < kChunks) {
+          if (c & 1) ptx::tmem_ld_32x32(t_row + 32 * (c + 1), va);
+          else ptx::tmem_ld_32x32(t_row + 32 * (c + 1), vb);
+        } else {
+          // the whole half-tile is in registers: hand the accumulator buffer back before the global stores
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&tempty[as]);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = rsub + 4 * i;
-          const int grow = m0 + q * 32 + row;
-          float4 x = *reinterpret_cast<const float4*>(st + row * kEpiStride + c4);
-          if (grow < a.M && nvalid > 0) {
-            x.x = fmaf(a.alpha, x.x, b4.x);
-            x.y = fmaf(a.alpha, x.y, b4.y);
-            x.z = fmaf(a.alpha, x.z, b4.z);
-            x.w = fmaf(a.alpha, x.w, b4.w);
-            if (a.aux.ptr) store4(a.aux, x_base + (long long)grow * a.aux.ld + gcol, nvalid, x);
-            if (a.act == T4S_ACT_GELU) {
-              x.x = gelu_erf(x.x);
-              x.y = gelu_erf(x.y);
-              x.z = gelu_erf(x.z);
-              x.w = gelu_erf(x.w);
-            }
-            if (a.res.ptr) {
-              float4 rr = load4(a.res, r_base + (long long)grow * a.res.ld + gcol, nvalid);
-              x.x += rr.x;
-              x.y += rr.y;
-              x.z += rr.z;
-              x.w += rr.w;
-            }
-            store4(a.C, c_base + (long long)grow * a.C.ld + gcol, nvalid, x);
-          }
-        }
-        __syncwarp();
+        if (c & 1) epilogue_chunk(a, vb, grow, col_base + 32 * c, c_row, x_row, r_row);
+        else epilogue_chunk(a, va, grow, col_base + 32 * c, c_row, x_row, r_row);
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty[as]);
     }
   }
 
@@ -341,6 +375,7 @@ static EncodeTiledFn get_encode() {
 static int make_map(CUtensorMap* m, const T4sOperand& op, int K, int esize, bool tf32, int box_k, int box_rows, const char* name) {
   const bool mn = op.mn_major != 0;
   const long long inner = mn ? op.rows : K, outer = mn ? K : op.rows;  // inner = contiguous dimension
+  ensure_context();
   EncodeTiledFn enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled entry point not available");
@@ -381,8 +416,8 @@ static MatArg mat_arg(const T4sMatrix& m) {
   o.s1 = m.stride1;
   o.s2 = m.stride2;
   o.dtype = m.dtype;
-  const int align = m.dtype == T4S_F32 ? 16 : 8;
-  o.vec = m.ptr && !(reinterpret_cast<uintptr_t>(m.ptr) % align) && !(m.ld % 4) && !(m.stride1 % 4) && !(m.stride2 % 4);
+  const int q = m.dtype == T4S_F32 ? 4 : 8;  // elements per 16 bytes
+  o.vec = m.ptr && !(reinterpret_cast<uintptr_t>(m.ptr) % 16) && !(m.ld % q) && !(m.stride1 % q) && !(m.stride2 % q);
   return o;
 }
 
@@ -434,6 +469,7 @@ extern "C" int t4s_gemm(const T4sGemm* g, void* stream) {
                   (!a.b_b2 || g->B.nb2 == g->nb2), "t4s_gemm: operand batch extents must be 1 or match nb1/nb2");
   a.C = mat_arg(g->C); a.aux = mat_arg(g->aux); a.res = mat_arg(g->residual);
   a.bias = g->bias; a.alpha = g->alpha; a.act = g->act;
+  a.bias_vec = g->bias && !(reinterpret_cast<uintptr_t>(g->bias) & 15);
   a.split_k = g->split_k > 1 ? g->split_k : 1;
   a.c_split = g->c_split_stride;
   T4S_REQUIRE(a.split_k == 1 || (g->c_split_stride > 0 && !g->bias && !g->residual.ptr && !g->aux.ptr && g->act == T4S_ACT_NONE),

@@ -34,7 +34,11 @@ def act_dtype():
 
 
 def _lib_call(name, *args):
-    _lib.check(getattr(_lib.load(), name)(*args), name)
+    fn = getattr(_lib.load(), name)
+    if _lib.profiler is not None:
+        _lib.check(_lib.profiler.timed(name, None, lambda: fn(*args)), name)
+    else:
+        _lib.check(fn(*args), name)
 
 
 def _st():

@@ -69,7 +69,12 @@ def gemm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, bias=None, aux: Out = None
     g.bias = ctypes.c_void_p(bias.data_ptr()) if bias is not None else ctypes.c_void_p(0)
     g.alpha, g.act = float(alpha), act
     with torch.cuda.device(A.t.device):
-        _lib.check(_lib.load().t4s_gemm(ctypes.byref(g), _lib.stream_ptr()), "t4s_gemm")
+        if _lib.profiler is not None:
+            key = (M, N, K, nb1 * nb2, "T" if A.mn_major else "N", "T" if B.mn_major else "N", split_k)
+            rc = _lib.profiler.timed("t4s_gemm", key, lambda: _lib.load().t4s_gemm(ctypes.byref(g), _lib.stream_ptr()))
+        else:
+            rc = _lib.load().t4s_gemm(ctypes.byref(g), _lib.stream_ptr())
+        _lib.check(rc, "t4s_gemm")
 
 
 def reduce_splits(ws, splits, n, out, accumulate=False):
