@@ -184,6 +184,37 @@ int64_t t4s_attn_padded_len(int tokens);
 int t4s_attn_fwd(const T4sAttn* a, void* stream);
 int t4s_attn_bwd(const T4sAttnBwd* a, void* stream);
 
+/* ---- K5: fused Transformer-XL relative-position attention (csrc/attn_rel.cu) -----------------------------------
+ * Replaces transformerXL.py:299-593 (RelPositionMultiheadAttention core: AC + rel_shift(BD) -> softmax -> . v) and
+ * rel_shift (:254-297) forward and backward:  score[i, j] = (qu_i . k_j + qv_i . pos[T-1-i+j]) * scale with
+ * qu = q + pos_bias_u, qv = q + pos_bias_v, pos = linear_pos(pos_emb) [2T-1, heads*64] (row k <-> relative position T-1-k).
+ * Layout rules as for t4s_attn_*.  The backward writes dqu = scale * dS K, dk = scale * dS^T qu, dv = P^T dO and streams
+ * dS back to position coordinates: dbd [B, H, T, dbd_ld] (bf16), row i receives dS[i, :] at columns T-1-i .. 2T-2-i; every
+ * other column is left untouched (the caller keeps the buffer zero outside that band, e.g. by zeroing it once), so
+ * d(qv) = scale * dbd . pos and d(pos) = scale * sum_b dbd^T . qv are plain GEMMs. */
+typedef struct {
+  int batch, heads, tokens, head_dim;
+  float scale;
+  const void* qu; int64_t qu_ld, qu_bs;
+  const void* qv; int64_t qv_ld, qv_bs;
+  const void* k;  int64_t k_ld, k_bs;
+  const void* v;  int64_t v_ld, v_bs;
+  const void* pos; int64_t pos_ld;
+  void* o;        int64_t o_ld, o_bs;
+  float* lse;
+} T4sRelAttn;
+typedef struct {
+  T4sRelAttn fwd;
+  const void* d_o; int64_t do_ld, do_bs;
+  float* delta;
+  void* dqu; int64_t dqu_ld, dqu_bs;
+  void* dk;  int64_t dk_ld, dk_bs;
+  void* dv;  int64_t dv_ld, dv_bs;
+  void* dbd; int64_t dbd_ld;
+} T4sRelAttnBwd;
+int t4s_relattn_fwd(const T4sRelAttn* a, void* stream);
+int t4s_relattn_bwd(const T4sRelAttnBwd* a, void* stream);
+
 /* ---- layout / glue kernels (csrc/misc.cu) -------------------------------------------------------------------
  * passt.py:302-315 (patch conv as im2col + GEMM), :503-519,:560-569 (positional tables, cls/dist tokens),
  * passt_sed.py:199-218 (frequency mean-pool), :23-34,:258-259 (pad + linear interpolation). */

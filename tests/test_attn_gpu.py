@@ -88,3 +88,47 @@ def test_attention_abi_rejects_bad_arguments():
     a.batch, a.heads, a.tokens, a.head_dim = 1, 1, 16, 32
     assert lib.t4s_attn_fwd(ctypes.byref(a), None) != 0
     assert b"head_dim" in lib.t4s_last_error()
+
+
+def _rel_ref(qkv, p, u, v, H):
+    B, T, D3 = qkv.shape
+    D = D3 // 3
+    hd = D // H
+    q, k, val = qkv.view(B, T, 3, H, hd).permute(2, 0, 3, 1, 4)
+    pp = p.view(2 * T - 1, H, hd).permute(1, 2, 0)
+    ac = (q + u[None, :, None, :]) @ k.transpose(-1, -2)
+    bd = (q + v[None, :, None, :]) @ pp
+    idx = (T - 1 - torch.arange(T, device="cuda").unsqueeze(1)) + torch.arange(T, device="cuda").unsqueeze(0)
+    bd = bd.gather(-1, idx.expand(B, H, T, T))          # rel_shift: out[i, j] = bd[i, T-1-i+j]  (transformerXL.py:254-297)
+    a = ((ac + bd) * hd ** -0.5).softmax(-1)
+    return (a @ val).transpose(1, 2).reshape(B, T, D)
+
+
+@pytest.mark.parametrize("B,T,H", [(1, 128, 1), (1, 37, 3), (2, 200, 2), (3, 385, 2), (2, 1000, 12)])
+def test_fused_relpos_attention_matches_reference(B, T, H):
+    """csrc/attn_rel.cu (t4s_relattn_fwd / t4s_relattn_bwd + the two position-gradient GEMMs) vs float64 PyTorch."""
+    from transformer4sed_b200 import functional as F
+    F.set_precision("bf16")
+    D = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(T * 3 + H)
+    mk = lambda *s, sc=1.0: torch.randn(*s, generator=g, device="cuda") * sc  # noqa: E731
+    qkv = mk(B, T, 3 * D, sc=0.6).to(torch.bfloat16).requires_grad_(True)
+    p = mk(2 * T - 1, D, sc=0.5).to(torch.bfloat16).requires_grad_(True)
+    u, v = mk(H, 64, sc=0.3).requires_grad_(True), mk(H, 64, sc=0.3).requires_grad_(True)
+    w = mk(B, T, D).to(torch.bfloat16)
+    for rep in range(2):   # twice: the dBD band buffer is reused across calls
+        for t in (qkv, p, u, v):
+            t.grad = None
+        o = F.relpos_attention(qkv, p, u, v, H)
+        o.backward(w)
+    ins = [t.detach().double().requires_grad_(True) for t in (qkv, p, u, v)]
+    o_ref = _rel_ref(*ins, H)
+    o_ref.backward(w.double())
+    assert _rel(o, o_ref) < 1.5e-2
+    D_ = D
+    for name, ours, ref in (("dq", qkv.grad[..., :D_], ins[0].grad[..., :D_]), ("dk", qkv.grad[..., D_:2 * D_], ins[0].grad[..., D_:2 * D_]),
+                            ("dv", qkv.grad[..., 2 * D_:], ins[0].grad[..., 2 * D_:]), ("dpos", p.grad, ins[1].grad),
+                            ("du", u.grad, ins[2].grad), ("dvb", v.grad, ins[3].grad)):
+        assert torch.isfinite(ours.float()).all(), name
+        e = _rel(ours, ref)
+        assert e < 3e-2, f"{name}: rel err {e:.3e}"

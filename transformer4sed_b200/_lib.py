@@ -58,6 +58,25 @@ class AttnBwd(ctypes.Structure):
                 ("dv", c_void_p), ("dv_ld", ctypes.c_int64), ("dv_bs", ctypes.c_int64)]
 
 
+class RelAttn(ctypes.Structure):
+    _fields_ = [("batch", c_int), ("heads", c_int), ("tokens", c_int), ("head_dim", c_int), ("scale", c_float),
+                ("qu", c_void_p), ("qu_ld", ctypes.c_int64), ("qu_bs", ctypes.c_int64),
+                ("qv", c_void_p), ("qv_ld", ctypes.c_int64), ("qv_bs", ctypes.c_int64),
+                ("k", c_void_p), ("k_ld", ctypes.c_int64), ("k_bs", ctypes.c_int64),
+                ("v", c_void_p), ("v_ld", ctypes.c_int64), ("v_bs", ctypes.c_int64),
+                ("pos", c_void_p), ("pos_ld", ctypes.c_int64),
+                ("o", c_void_p), ("o_ld", ctypes.c_int64), ("o_bs", ctypes.c_int64),
+                ("lse", c_void_p)]
+
+
+class RelAttnBwd(ctypes.Structure):
+    _fields_ = [("fwd", RelAttn), ("d_o", c_void_p), ("do_ld", ctypes.c_int64), ("do_bs", ctypes.c_int64), ("delta", c_void_p),
+                ("dqu", c_void_p), ("dqu_ld", ctypes.c_int64), ("dqu_bs", ctypes.c_int64),
+                ("dk", c_void_p), ("dk_ld", ctypes.c_int64), ("dk_bs", ctypes.c_int64),
+                ("dv", c_void_p), ("dv_ld", ctypes.c_int64), ("dv_bs", ctypes.c_int64),
+                ("dbd", c_void_p), ("dbd_ld", ctypes.c_int64)]
+
+
 def _declare(lib):
     P, I, Z, F, L = c_void_p, c_int, c_size_t, c_float, ctypes.c_int64
     sigs = {
@@ -79,6 +98,8 @@ def _declare(lib):
         "t4s_attn_padded_len": (L, [I]),
         "t4s_attn_fwd": (I, [ctypes.POINTER(Attn), P]),
         "t4s_attn_bwd": (I, [ctypes.POINTER(AttnBwd), P]),
+        "t4s_relattn_fwd": (I, [ctypes.POINTER(RelAttn), P]),
+        "t4s_relattn_bwd": (I, [ctypes.POINTER(RelAttnBwd), P]),
         "t4s_split_tf32": (I, [ctypes.POINTER(Operand), I, P, L, I, P]),
         "t4s_layernorm_fwd": (I, [P, P, P, P, P, P, L, I, F, F, I, L, L, P]),
         "t4s_layernorm_bwd_workspace": (Z, [L, I]),

@@ -1,0 +1,641 @@
+// K5: fused Transformer-XL relative-position attention (transformerXL.py:299-593, rel_shift :254-297), forward and backward.
+//
+//   score[i, j] = ((q_i + u) . k_j + (q_i + v) . p[T-1-i+j]) * scale          p = linear_pos(pos_emb)  [2T-1, H*64]
+//
+// The [T, 2T-1] position-score matrix and its rel_shift never exist in memory.  Per 128 x 128 score tile (queries i0.., keys j0..)
+// the tensor core computes, next to AC = QU K^T, the product BD = QV Pw^T against the 256-row window Pw = p[T-128-i0+j0 ...] that
+// holds every position row the tile can reference (TMA zero-fills the rows that fall outside the table); the shift is then a
+// per-row skew, BD_shifted[r, c] = BD[r, 127 - r + c], applied by the softmax warps on the way out of TMEM: each thread (= query
+// row) parks 64 accumulator columns in a private, bank-conflict-free shared-memory row and reads them back at its own offset.
+//
+//   forward    as attn.cu's forward (online softmax, P in shared memory, O folded in registers); the shifted scores are written
+//              back to TMEM (tcgen05.st) by the max pass so the exponential pass is unchanged.  One CTA per SM (512 TMEM columns).
+//   backward   two kernels, both with thread = query row: dQ (CTA = query tile, loops over key tiles) accumulates
+//              d(q+u) = scale dS K in TMEM and streams dS, un-shifted back to position coordinates, into dBD: every warp stages
+//              its 32 dS rows in shared memory and writes them out with coalesced 4-byte stores, a funnel shift absorbing the odd
+//              element offsets (TMA tile stores cannot: they need 16-byte aligned inner coordinates).  The [T, 2T-1] gradient is
+//              consumed by two plain GEMMs: d(q+v) = dBD p, dp = sum_b dBD^T (q+v);
+//              dK/dV (CTA = key tile, loops over query tiles) consumes the P / dS tiles transposed in place as MN-major A
+//              operands.  P is recomputed from lse (no max pass); dP reuses the S columns of TMEM once P is in registers.
+#include "attn_common.cuh"
+
+namespace t4s {
+namespace attn {
+namespace rel {
+
+constexpr int kThreads = 192;          // warps 0-3 softmax (thread = query row), 4 TMA producer, 5 MMA issuer
+constexpr int kPwBytes = 256 * 128;    // position window: 256 rows x 64 bf16
+constexpr int kWarpScratch = 8704;     // per softmax warp: 32 skew rows x 66 floats (8448 B) / 32 dBD staging rows x 256 B
+constexpr int kScrRow = 66;            // floats; lanes l read at 65 l + const -> conflict free, 8-byte stores conflict free
+constexpr int kStageRow = 256;         // bytes (dense rows of 128 bf16)
+constexpr uint32_t kIdescBD = ptx::umma_idesc(1, 128, 256, 0, 0);
+constexpr uint32_t kIdescAmn = ptx::umma_idesc(1, 128, 64, 1, 1);  // A and B MN-major
+
+struct RelArgs {
+  Args a;
+  __nv_bfloat16* dqu; long long dqu_ld, dqu_bs;
+  __nv_bfloat16* dbd; long long dbd_ld;
+};
+
+// bd[cc] = BD[r][127 - r + c0 + cc] for this thread's row r = 32 w + l; t_bd = TMEM address of BD column 0 (lane quarter applied)
+__device__ __forceinline__ void skew_chunk(uint32_t t_bd, float* scr, int w, int l, int c0, float (&bd)[32]) {
+  const int wb = 96 - 32 * w + c0;  // first of the 64 columns this warp's rows can reference for this chunk
+  uint32_t x0[32], x1[32];
+  ptx::tmem_ld_32x32(t_bd + wb, x0);
+  ptx::tmem_ld_32x32(t_bd + wb + 32, x1);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    *reinterpret_cast<uint2*>(scr + 2 * k) = make_uint2(x0[2 * k], x0[2 * k + 1]);
+    *reinterpret_cast<uint2*>(scr + 32 + 2 * k) = make_uint2(x1[2 * k], x1[2 * k + 1]);
+  }
+  const volatile float* rd = scr + (31 - l);
+#pragma unroll
+  for (int cc = 0; cc < 32; ++cc) bd[cc] = rd[cc];
+}
+
+// D[128 x 64] (+)= A^T . B with A = a [128 (K) x 128 (M)] K-major-written tile consumed MN-major (two 64-wide M blocks 16 KB
+// apart) and B = [128 rows (K) x 64] tile consumed MN-major.
+__device__ __forceinline__ void mma_k128_amn(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, bool accumulate) {
+  const uint64_t adesc = ptx::umma_desc_sw128(a_addr, kTileBytes, 1024), bdesc = ptx::umma_desc_sw128(b_addr, 8192, 1024);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ptx::mma_f16(d_tmem, adesc + 128 * k, bdesc + 128 * k, kIdescAmn, (accumulate || k > 0) ? 1u : 0u);
+}
+
+// ======================================================================================================
+// forward
+// ======================================================================================================
+namespace fwd {
+constexpr int oQU = 0, oQV = oQU + kTileBytes, oK = oQV + kTileBytes, oV = oK + 2 * kTileBytes, oPw = oV + 2 * kTileBytes,
+              oP = oPw + kPwBytes, oScr = oP + kPBytes, oBar = oScr + 4 * kWarpScratch;
+constexpr int kSmem = oBar + 128;
+constexpr int kTmemCols = 512;  // S: [0,128)  BD: [128,384)  O: [384,448), [448,512)
+enum { bQFull = 0, bKvFull = 1, bKvEmpty = 3, bPwFull = 5, bPwEmpty = 6, bSFull = 7, bSFree = 8, bPFull = 9, bOFull = 10, bOFree = 12,
+       bCount = 14 };
+}  // namespace fwd
+
+__global__ void __launch_bounds__(kThreads, 1)
+relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_constant__ CUtensorMap tmQV,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmPos, const Args a) {
+  using namespace fwd;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = a.n_tiles;
+
+  if (threadIdx.x == 0) {
+    if (ptx::smem_u32(smem) & 1023u) {
+      printf("t4s relattn_fwd: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    ptx::mbar_init(&bars[bQFull], 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars[bKvFull + i], 1);
+      ptx::mbar_init(&bars[bKvEmpty + i], 1);
+      ptx::mbar_init(&bars[bOFull + i], 1);
+      ptx::mbar_init(&bars[bOFree + i], 4);
+    }
+    ptx::mbar_init(&bars[bPwFull], 1);
+    ptx::mbar_init(&bars[bPwEmpty], 1);
+    ptx::mbar_init(&bars[bSFull], 1);
+    ptx::mbar_init(&bars[bSFree], 4);
+    ptx::mbar_init(&bars[bPFull], 4);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tmap(&tmQU);
+    ptx::prefetch_tmap(&tmQV);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+    ptx::prefetch_tmap(&tmPos);
+  }
+  if (warp == 5) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(&bars[bQFull], 2 * kTileBytes);
+      ptx::tma_load_4d(smem + oQU, &tmQU, &bars[bQFull], 0, q0, h, b);
+      ptx::tma_load_4d(smem + oQV, &tmQV, &bars[bQFull], 0, q0, h, b);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1;
+        ptx::mbar_wait(&bars[bKvEmpty + s], ((j >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bars[bKvFull + s], 2 * kTileBytes);
+        ptx::tma_load_4d(smem + oK + s * kTileBytes, &tmK, &bars[bKvFull + s], 0, j * kTile, h, b);
+        ptx::tma_load_4d(smem + oV + s * kTileBytes, &tmV, &bars[bKvFull + s], 0, j * kTile, h, b);
+        ptx::mbar_wait(&bars[bPwEmpty], (j & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&bars[bPwFull], kPwBytes);
+        ptx::tma_load_4d(smem + oPw, &tmPos, &bars[bPwFull], 0, a.N - kTile - q0 + j * kTile, h, 0);
+      }
+    }
+  } else if (warp == 5) {
+    const uint32_t sQU = ptx::smem_u32(smem + oQU), sQV = ptx::smem_u32(smem + oQV), sK = ptx::smem_u32(smem + oK),
+                   sV = ptx::smem_u32(smem + oV), sPw = ptx::smem_u32(smem + oPw), sP = ptx::smem_u32(smem + oP);
+    ptx::mbar_wait(&bars[bQFull], 0);
+    ptx::mbar_wait(&bars[bKvFull + 0], 0);
+    ptx::mbar_wait(&bars[bPwFull], 0);
+    ptx::tc_fence_after();
+    if (lane == 0) {
+      mma_k64(tmem, sQU, sK, kIdescS, false);
+      mma_k64(tmem + 128, sQV, sPw, kIdescBD, false);
+      ptx::tc_commit(&bars[bPwEmpty]);
+      ptx::tc_commit(&bars[bSFull]);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j & 1;
+      if (j + 1 < n_tiles) {
+        ptx::mbar_wait(&bars[bKvFull + (s ^ 1)], ((j + 1) >> 1) & 1);
+        ptx::mbar_wait(&bars[bPwFull], (j + 1) & 1);
+        ptx::mbar_wait(&bars[bSFree], j & 1);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          mma_k64(tmem, sQU, sK + (s ^ 1) * kTileBytes, kIdescS, false);
+          mma_k64(tmem + 128, sQV, sPw, kIdescBD, false);
+          ptx::tc_commit(&bars[bPwEmpty]);
+          ptx::tc_commit(&bars[bSFull]);
+        }
+        __syncwarp();
+      }
+      ptx::mbar_wait(&bars[bPFull], j & 1);
+      ptx::mbar_wait(&bars[bOFree + s], ((j >> 1) & 1) ^ 1);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        mma_k128_mn(tmem + 384 + 64 * s, sP, sV + s * kTileBytes, kIdescPV, false);
+        ptx::tc_commit(&bars[bKvEmpty + s]);
+        ptx::tc_commit(&bars[bOFull + s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int r = warp * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    float* scr = reinterpret_cast<float*>(smem + oScr + warp * kWarpScratch) + lane * kScrRow;
+    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    const float sl2 = a.sl2;
+
+    auto fold = [&](int jj) {
+      const int s = jj & 1;
+      ptx::mbar_wait(&bars[bOFull + s], (jj >> 1) & 1);
+      ptx::tc_fence_after();
+      uint32_t v0[32], v1[32];
+      ptx::tmem_ld_32x32(t_lane + 384 + 64 * s, v0);
+      ptx::tmem_ld_32x32(t_lane + 384 + 64 * s + 32, v1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[bOFree + s]);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(v0[i]));
+        acc[32 + i] = fmaf(acc[32 + i], alpha_prev, __uint_as_float(v1[i]));
+      }
+    };
+
+    for (int j = 0; j < n_tiles; ++j) {
+      const int nvalid = a.N - j * kTile;
+      const bool full = nvalid >= kTile;
+      ptx::mbar_wait(&bars[bSFull], j & 1);
+      ptx::tc_fence_after();
+      // pass 1: shifted scores = AC + skew(BD), written back over AC; running max
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float bd[32];
+        skew_chunk(t_lane + 128, scr, warp, lane, 32 * c, bd);
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float sc = __uint_as_float(v[i]) + bd[i];
+          v[i] = __float_as_uint(sc);
+          if (full || 32 * c + i < nvalid) mx = fmaxf(mx, sc);
+        }
+        ptx::tmem_st_32x32(t_lane + 32 * c, v);
+      }
+      ptx::tmem_st_wait();
+      const float m_new = fmaxf(m, mx);
+      const float alpha = ex2((m - m_new) * sl2);
+      const float mneg = -m_new * sl2;
+      if (j > 0) fold(j - 1);
+      // pass 2: exponentials, row sum, P tile
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
+        ptx::tmem_ld_wait();
+        if (c == 3) {
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars[bSFree]);
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, mneg));
+          float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, mneg));
+          if (!full) {
+            if (32 * c + 2 * i >= nvalid) p0 = 0.f;
+            if (32 * c + 2 * i + 1 >= nvalid) p1 = 0.f;
+          }
+          rs += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
+        }
+        store_row_chunk(smem + oP, r, 32 * c, pk);
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[bPFull]);
+      l = fmaf(l, alpha, rs);
+      m = m_new;
+      alpha_prev = alpha;
+    }
+    fold(n_tiles - 1);
+    const int row = q0 + r;
+    const float inv = 1.f / l;
+    a.lse[((long long)b * a.H + h) * a.Nl + row] = fmaf(m, sl2, log2f(l));
+    if (row < a.N) store_row64(a.o + (long long)b * a.o_bs + (long long)row * a.o_ld + h * kHd, acc, inv);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+// ======================================================================================================
+// backward
+// ======================================================================================================
+namespace bwd {
+// operand region (112 KB): dQ  kernel: resident [QU][QV][dO], streamed [K][V][Pw]
+//                          dKV kernel: resident [K][V],       streamed [QU][QV][dO][Pw]
+constexpr int oOps = 0, oP = oOps + 7 * kTileBytes, oDs = oP + kPBytes, oScr = oDs + kPBytes, oBar = oScr + 4 * kWarpScratch;
+constexpr int kSmem = oBar + 128;
+constexpr int kTmemCols = 512;  // S / dP: [0,128)  BD: [128,384)  acc0: [384,448)  acc1: [448,512)
+enum { bResFull = 0, bStrFull = 1, bStrEmpty = 2, bSFull = 3, bPReady = 4, bDpFull = 5, bDsFull = 6, bFin = 7, bAccFull = 8, bCount = 9 };
+}  // namespace bwd
+
+template <bool kDq>
+__global__ void __launch_bounds__(kThreads, 1)
+relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_constant__ CUtensorMap tmQV,
+                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                   const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmPos, const RelArgs ra) {
+  using namespace bwd;
+  const Args& a = ra.a;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
+  const int n_tiles = a.n_tiles;
+  const long long stat_base = ((long long)b * a.H + h) * a.Nl;
+  // operand tiles
+  unsigned char* sQU = smem + oOps + (kDq ? 0 : 2) * kTileBytes;
+  unsigned char* sQV = smem + oOps + (kDq ? 1 : 3) * kTileBytes;
+  unsigned char* sDO = smem + oOps + (kDq ? 2 : 4) * kTileBytes;
+  unsigned char* sK = smem + oOps + (kDq ? 3 : 0) * kTileBytes;
+  unsigned char* sV = smem + oOps + (kDq ? 4 : 1) * kTileBytes;
+  unsigned char* sPw = smem + oOps + 5 * kTileBytes;
+
+  if (threadIdx.x == 0) {
+    if (ptx::smem_u32(smem) & 1023u) {
+      printf("t4s relattn_bwd: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    ptx::mbar_init(&bars[bResFull], 1);
+    ptx::mbar_init(&bars[bStrFull], 1);
+    ptx::mbar_init(&bars[bStrEmpty], 1);
+    ptx::mbar_init(&bars[bSFull], 1);
+    ptx::mbar_init(&bars[bPReady], 4);
+    ptx::mbar_init(&bars[bDpFull], 1);
+    ptx::mbar_init(&bars[bDsFull], 4);
+    ptx::mbar_init(&bars[bFin], 1);
+    ptx::mbar_init(&bars[bAccFull], 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4 && lane == 0) {
+    ptx::prefetch_tmap(&tmQU);
+    ptx::prefetch_tmap(&tmQV);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+    ptx::prefetch_tmap(&tmDO);
+    ptx::prefetch_tmap(&tmPos);
+  }
+  if (warp == 5) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 4) {
+    // ---------------- TMA producer ----------------
+    if (lane == 0) {
+      if (kDq) {
+        ptx::mbar_arrive_expect_tx(&bars[bResFull], 3 * kTileBytes);
+        ptx::tma_load_4d(sQU, &tmQU, &bars[bResFull], 0, t0, h, b);
+        ptx::tma_load_4d(sQV, &tmQV, &bars[bResFull], 0, t0, h, b);
+        ptx::tma_load_4d(sDO, &tmDO, &bars[bResFull], 0, t0, h, b);
+      } else {
+        ptx::mbar_arrive_expect_tx(&bars[bResFull], 2 * kTileBytes);
+        ptx::tma_load_4d(sK, &tmK, &bars[bResFull], 0, t0, h, b);
+        ptx::tma_load_4d(sV, &tmV, &bars[bResFull], 0, t0, h, b);
+      }
+      for (int t = 0; t < n_tiles; ++t) {
+        ptx::mbar_wait(&bars[bStrEmpty], (t & 1) ^ 1);
+        const int i0 = kDq ? t0 : t * kTile, j0 = kDq ? t * kTile : t0;
+        if (kDq) {
+          ptx::mbar_arrive_expect_tx(&bars[bStrFull], 2 * kTileBytes + kPwBytes);
+          ptx::tma_load_4d(sK, &tmK, &bars[bStrFull], 0, j0, h, b);
+          ptx::tma_load_4d(sV, &tmV, &bars[bStrFull], 0, j0, h, b);
+        } else {
+          ptx::mbar_arrive_expect_tx(&bars[bStrFull], 3 * kTileBytes + kPwBytes);
+          ptx::tma_load_4d(sQU, &tmQU, &bars[bStrFull], 0, i0, h, b);
+          ptx::tma_load_4d(sQV, &tmQV, &bars[bStrFull], 0, i0, h, b);
+          ptx::tma_load_4d(sDO, &tmDO, &bars[bStrFull], 0, i0, h, b);
+        }
+        ptx::tma_load_4d(sPw, &tmPos, &bars[bStrFull], 0, a.N - kTile - i0 + j0, h, 0);
+      }
+    }
+  } else if (warp == 5) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t uQU = ptx::smem_u32(sQU), uQV = ptx::smem_u32(sQV), uDO = ptx::smem_u32(sDO), uK = ptx::smem_u32(sK),
+                   uV = ptx::smem_u32(sV), uPw = ptx::smem_u32(sPw), uP = ptx::smem_u32(smem + oP), uDs = ptx::smem_u32(smem + oDs);
+    ptx::mbar_wait(&bars[bResFull], 0);
+    for (int t = 0; t < n_tiles; ++t) {
+      ptx::mbar_wait(&bars[bStrFull], t & 1);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        mma_k64(tmem, uQU, uK, kIdescS, false);          // AC = (q+u) k^T
+        mma_k64(tmem + 128, uQV, uPw, kIdescBD, false);  // BD = (q+v) Pw^T
+        ptx::tc_commit(&bars[bSFull]);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&bars[bPReady], t & 1);             // P is in registers: the S columns are free
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        mma_k64(tmem, uDO, uV, kIdescS, false);          // dP = dO v^T
+        ptx::tc_commit(&bars[bDpFull]);
+      }
+      __syncwarp();
+      ptx::mbar_wait(&bars[bDsFull], t & 1);             // P / dS tiles are in shared memory
+      ptx::tc_fence_after();
+      if (lane == 0) {
+        if (kDq) {
+          mma_k128_mn(tmem + 384, uDs, uK, kIdescPV, t > 0);   // d(q+u) += dS K
+        } else {
+          mma_k128_amn(tmem + 384, uP, uDO, t > 0);            // dV += P^T dO
+          mma_k128_amn(tmem + 448, uDs, uQU, t > 0);           // dK += dS^T (q+u)
+        }
+        ptx::tc_commit(&bars[bStrEmpty]);
+        ptx::tc_commit(&bars[bFin]);
+        if (t == n_tiles - 1) ptx::tc_commit(&bars[bAccFull]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ---------------- softmax warps: thread = query row ----------------
+    const int r = warp * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    unsigned char* wscr = smem + oScr + warp * kWarpScratch;
+    float* scr = reinterpret_cast<float*>(wscr) + lane * kScrRow;
+    unsigned char* stage_row = wscr + lane * kStageRow;
+    const float sl2 = a.sl2;
+    float my_lse = 0.f, my_delta = 0.f;
+    if (kDq) {
+      my_lse = a.lse[stat_base + t0 + r];
+      my_delta = a.delta[stat_base + t0 + r];
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+      const int i0 = kDq ? t0 : t * kTile, j0 = kDq ? t * kTile : t0;
+      if (!kDq) {
+        my_lse = a.lse[stat_base + i0 + r];
+        my_delta = a.delta[stat_base + i0 + r];
+      }
+      const int nvalid = a.N - j0;  // key columns that exist
+      const bool full = nvalid >= kTile;
+      ptx::mbar_wait(&bars[bSFull], t & 1);
+      ptx::tc_fence_after();
+      ptx::mbar_wait(&bars[bFin], (t & 1) ^ 1);  // previous step's MMAs have finished with the P / dS tiles
+      // phase A: P = exp2((AC + shift(BD)) * c - lse), kept packed in registers (and in shared memory for P^T dO)
+      uint32_t pk[4][16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float bd[32];
+        skew_chunk(t_lane + 128, scr, warp, lane, 32 * c, bd);
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float p0 = ex2(fmaf(__uint_as_float(v[2 * i]) + bd[2 * i], sl2, -my_lse));
+          float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]) + bd[2 * i + 1], sl2, -my_lse));
+          if (!full) {
+            if (32 * c + 2 * i >= nvalid) p0 = 0.f;
+            if (32 * c + 2 * i + 1 >= nvalid) p1 = 0.f;
+          }
+          pk[c][i] = pack_bf16(p0, p1);
+        }
+        if (!kDq) store_row_chunk(smem + oP, r, 32 * c, pk[c]);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[bPReady]);
+      // phase B: dS = P (dP - delta)
+      ptx::mbar_wait(&bars[bDpFull], t & 1);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
+        ptx::tmem_ld_wait();
+        uint32_t pd[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[c][i]));
+          pd[i] = pack_bf16(p.x * (__uint_as_float(v[2 * i]) - my_delta), p.y * (__uint_as_float(v[2 * i + 1]) - my_delta));
+        }
+        store_row_chunk(smem + oDs, r, 32 * c, pd);
+        if (kDq) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(stage_row + c * 64 + q * 16) = make_uint4(pd[4 * q], pd[4 * q + 1], pd[4 * q + 2], pd[4 * q + 3]);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[bDsFull]);
+      if (kDq) {
+        // dBD[b, h, i, T-1-i+j0 + e] <- dS[i, j0 + e]: this warp's 32 staged rows, 64 destination words per row
+        const uint32_t* st32 = reinterpret_cast<const uint32_t*>(wscr);
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+          const int i = i0 + warp * 32 + rr;
+          if (i >= a.N) break;
+          const int x0 = a.N - 1 - i + j0;
+          __nv_bfloat16* drow = ra.dbd + (((long long)b * a.H + h) * a.N + i) * ra.dbd_ld + x0;
+          const int par = x0 & 1;  // rows start 16-byte aligned, so the word alignment of the destination is the parity of x0
+          const uint32_t* srow = st32 + rr * (kStageRow / 4);
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const int w = lane + 32 * hh;
+            const int e = par + 2 * w;  // first source element of destination word w
+            const uint32_t val = __funnelshift_r(srow[w], srow[w + 1], 16 * par);
+            if (e + 1 < nvalid) *reinterpret_cast<uint32_t*>(drow + e) = val;
+            else if (e < nvalid) *reinterpret_cast<unsigned short*>(drow + e) = (unsigned short)(val & 0xffffu);
+          }
+          if (par && lane == 0) *reinterpret_cast<unsigned short*>(drow) = (unsigned short)(srow[0] & 0xffffu);
+        }
+        __syncwarp();
+      }
+    }
+    // ---- accumulators ----
+    ptx::mbar_wait(&bars[bAccFull], 0);
+    ptx::tc_fence_after();
+    const int row = t0 + r;
+    uint32_t v0[32], v1[32];
+    ptx::tmem_ld_32x32(t_lane + 384, v0);
+    ptx::tmem_ld_32x32(t_lane + 416, v1);
+    ptx::tmem_ld_wait();
+    if (kDq) {
+      if (row < a.N) {
+        __nv_bfloat16* dst = ra.dqu + (long long)b * ra.dqu_bs + (long long)row * ra.dqu_ld + h * kHd;
+        store_row32(dst, v0, a.scale);
+        store_row32(dst + 32, v1, a.scale);
+      }
+    } else {
+      if (row < a.N) {
+        __nv_bfloat16* dst = a.dv + (long long)b * a.dv_bs + (long long)row * a.dv_ld + h * kHd;
+        store_row32(dst, v0, 1.f);
+        store_row32(dst + 32, v1, 1.f);
+      }
+      ptx::tmem_ld_32x32(t_lane + 448, v0);
+      ptx::tmem_ld_32x32(t_lane + 480, v1);
+      ptx::tmem_ld_wait();
+      if (row < a.N) {
+        __nv_bfloat16* dst = a.dk + (long long)b * a.dk_bs + (long long)row * a.dk_ld + h * kHd;
+        store_row32(dst, v0, a.scale);
+        store_row32(dst + 32, v1, a.scale);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+static int check_rel(const T4sRelAttn* p) {
+  T4S_REQUIRE(p, "t4s_relattn: null descriptor");
+  T4S_REQUIRE(p->head_dim == kHd, "t4s_relattn: head_dim must be 64 (got %d)", p->head_dim);
+  T4S_REQUIRE(p->batch > 0 && p->heads > 0 && p->tokens > 0, "t4s_relattn: batch, heads and tokens must be positive");
+  T4S_REQUIRE(p->batch <= 65535 && p->heads <= 65535, "t4s_relattn: batch / heads exceed the grid limits");
+  T4S_REQUIRE(p->qu && p->qv && p->k && p->v && p->pos && p->o && p->lse, "t4s_relattn: qu, qv, k, v, pos, o and lse are required");
+  T4S_REQUIRE(!(reinterpret_cast<uintptr_t>(p->o) & 15) && !(p->o_ld % 8) && !(p->o_bs % 8), "t4s_relattn: o must be 16-byte aligned with pitches % 8 == 0");
+  return T4S_OK;
+}
+
+static void fill_rel_args(Args& a, const T4sRelAttn* p) {
+  a.N = p->tokens;
+  a.n_tiles = (p->tokens + kTile - 1) / kTile;
+  a.Nl = a.n_tiles * kTile;
+  a.H = p->heads;
+  a.scale = p->scale;
+  a.sl2 = p->scale * 1.4426950408889634f;
+  a.o = reinterpret_cast<__nv_bfloat16*>(p->o);
+  a.o_ld = p->o_ld;
+  a.o_bs = p->o_bs;
+  a.lse = p->lse;
+  a.delta = nullptr;
+  a.dq = a.dk = a.dv = nullptr;
+  a.dq_ld = a.dq_bs = a.dk_ld = a.dk_bs = a.dv_ld = a.dv_bs = 0;
+}
+
+}  // namespace rel
+}  // namespace attn
+}  // namespace t4s
+
+extern "C" int t4s_relattn_fwd(const T4sRelAttn* p, void* stream) {
+  using namespace t4s::attn;
+  using namespace t4s::attn::rel;
+  int rc = check_rel(p);
+  if (rc) return rc;
+  const int B = p->batch, H = p->heads, T = p->tokens;
+  CUtensorMap tqu, tqv, tk, tv, tpos;
+  if ((rc = make_map(&tqu, p->qu, p->qu_ld, p->qu_bs, B, H, T, "qu"))) return rc;
+  if ((rc = make_map(&tqv, p->qv, p->qv_ld, p->qv_bs, B, H, T, "qv"))) return rc;
+  if ((rc = make_map(&tk, p->k, p->k_ld, p->k_bs, B, H, T, "k"))) return rc;
+  if ((rc = make_map(&tv, p->v, p->v_ld, p->v_bs, B, H, T, "v"))) return rc;
+  if ((rc = make_map(&tpos, p->pos, p->pos_ld, p->pos_ld * (2LL * T - 1), 1, H, 2 * T - 1, "pos", 256))) return rc;
+  Args a;
+  fill_rel_args(a, p);
+  T4S_CUDA(cudaFuncSetAttribute(relattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmem));
+  dim3 grid(a.n_tiles, H, B);
+  relattn_fwd_kernel<<<grid, kThreads, fwd::kSmem, t4s::as_stream(stream)>>>(tqu, tqv, tk, tv, tpos, a);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+extern "C" int t4s_relattn_bwd(const T4sRelAttnBwd* p, void* stream) {
+  using namespace t4s::attn;
+  using namespace t4s::attn::rel;
+  T4S_REQUIRE(p, "t4s_relattn_bwd: null descriptor");
+  const T4sRelAttn* f = &p->fwd;
+  int rc = check_rel(f);
+  if (rc) return rc;
+  T4S_REQUIRE(p->d_o && p->delta && p->dqu && p->dk && p->dv && p->dbd, "t4s_relattn_bwd: d_o, delta, dqu, dk, dv and dbd are required");
+  for (const void* ptr : {(const void*)p->dqu, (const void*)p->dk, (const void*)p->dv})
+    T4S_REQUIRE(!(reinterpret_cast<uintptr_t>(ptr) & 15), "t4s_relattn_bwd: dqu / dk / dv must be 16-byte aligned");
+  T4S_REQUIRE(!(p->dqu_ld % 8) && !(p->dqu_bs % 8) && !(p->dk_ld % 8) && !(p->dk_bs % 8) && !(p->dv_ld % 8) && !(p->dv_bs % 8),
+              "t4s_relattn_bwd: gradient pitches must be multiples of 8 elements");
+  const int B = f->batch, H = f->heads, T = f->tokens;
+  CUtensorMap tqu, tqv, tk, tv, tdo, tpos;
+  if ((rc = make_map(&tqu, f->qu, f->qu_ld, f->qu_bs, B, H, T, "qu"))) return rc;
+  if ((rc = make_map(&tqv, f->qv, f->qv_ld, f->qv_bs, B, H, T, "qv"))) return rc;
+  if ((rc = make_map(&tk, f->k, f->k_ld, f->k_bs, B, H, T, "k"))) return rc;
+  if ((rc = make_map(&tv, f->v, f->v_ld, f->v_bs, B, H, T, "v"))) return rc;
+  if ((rc = make_map(&tdo, p->d_o, p->do_ld, p->do_bs, B, H, T, "d_o"))) return rc;
+  if ((rc = make_map(&tpos, f->pos, f->pos_ld, f->pos_ld * (2LL * T - 1), 1, H, 2 * T - 1, "pos", 256))) return rc;
+  T4S_REQUIRE(!(reinterpret_cast<uintptr_t>(p->dbd) & 15) && !(p->dbd_ld % 8) && p->dbd_ld >= 2LL * T - 1,
+              "t4s_relattn_bwd: dbd needs a 16-byte aligned base and a row pitch >= 2T-1 that is a multiple of 8 elements");
+  RelArgs ra;
+  fill_rel_args(ra.a, f);
+  ra.a.delta = p->delta;
+  ra.a.dk = reinterpret_cast<__nv_bfloat16*>(p->dk); ra.a.dk_ld = p->dk_ld; ra.a.dk_bs = p->dk_bs;
+  ra.a.dv = reinterpret_cast<__nv_bfloat16*>(p->dv); ra.a.dv_ld = p->dv_ld; ra.a.dv_bs = p->dv_bs;
+  ra.dqu = reinterpret_cast<__nv_bfloat16*>(p->dqu); ra.dqu_ld = p->dqu_ld; ra.dqu_bs = p->dqu_bs;
+  ra.dbd = reinterpret_cast<__nv_bfloat16*>(p->dbd); ra.dbd_ld = p->dbd_ld;
+  cudaStream_t st = t4s::as_stream(stream);
+  rc = launch_delta(f->o, f->o_ld, f->o_bs, p->d_o, p->do_ld, p->do_bs, p->delta, B, H, T, ra.a.Nl, st);
+  if (rc) return rc;
+  dim3 grid(ra.a.n_tiles, H, B);
+  T4S_CUDA(cudaFuncSetAttribute(relattn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
+  relattn_bwd_kernel<true><<<grid, kThreads, bwd::kSmem, st>>>(tqu, tqv, tk, tv, tdo, tpos, ra);
+  T4S_LAUNCH_CHECK();
+  T4S_CUDA(cudaFuncSetAttribute(relattn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
+  relattn_bwd_kernel<false><<<grid, kThreads, bwd::kSmem, st>>>(tqu, tqv, tk, tv, tdo, tpos, ra);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}

@@ -16,6 +16,7 @@ from . import _lib, ops
 from .ops import Op, Out
 
 _MODE = "bf16"
+_FUSED_ATTN = True
 
 
 def set_precision(mode: str):
@@ -437,9 +438,6 @@ class _FlashAttention(torch.autograd.Function):
         return dqkv, None
 
 
-_FUSED_ATTN = True
-
-
 def set_fused_attention(flag: bool):
     """Debug / A-B switch: False routes bf16 attention through the unfused GEMM + softmax kernels."""
     global _FUSED_ATTN
@@ -541,7 +539,117 @@ class _RelPosAttention(torch.autograd.Function):
         return dqkv, dp_lin, du, dv, None
 
 
+_dbd_cache = {}
+
+
+def _dbd_buffer(B, H, T, Lp, dev):
+    """Position-coordinate score gradient [B, H, T, Lp] (bf16).  The fused backward only ever writes the band
+    T-1-i <= x <= 2T-2-i of row i, so the buffer is zeroed once and then reused by every layer and step."""
+    key = (B, H, T, Lp, str(dev))
+    t = _dbd_cache.get(key)
+    if t is None:
+        _dbd_cache.clear()
+        t = torch.zeros(B, H, T, Lp, dtype=torch.bfloat16, device=dev)
+        _dbd_cache[key] = t
+    return t
+
+
+def _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, scale):
+    a = _lib.RelAttn()
+    a.batch, a.heads, a.tokens, a.head_dim, a.scale = B, H, T, D // H, scale
+    es = qkv.element_size()
+    a.qu, a.qu_ld, a.qu_bs = qu.data_ptr(), D, T * D
+    a.qv, a.qv_ld, a.qv_bs = qv.data_ptr(), D, T * D
+    a.k, a.v = qkv.data_ptr() + D * es, qkv.data_ptr() + 2 * D * es
+    a.k_ld = a.v_ld = 3 * D
+    a.k_bs = a.v_bs = T * 3 * D
+    a.pos, a.pos_ld = p_lin.data_ptr(), p_lin.stride(0)
+    a.o, a.o_ld, a.o_bs = o.data_ptr(), D, T * D
+    a.lse = lse.data_ptr()
+    return a
+
+
+class _FlashRelPosAttention(torch.autograd.Function):
+    """Fused tcgen05 Transformer-XL attention (csrc/attn_rel.cu): AC, the position scores and their rel_shift live in
+    TMEM / shared memory only.  bf16 mode, head_dim 64."""
+
+    @staticmethod
+    def forward(ctx, qkv, p_lin, u, v, H):
+        _lib.ensure_device(qkv)
+        qkv = qkv.contiguous()
+        p_lin = p_lin.contiguous()
+        B, T, D3 = qkv.shape
+        D = D3 // 3
+        dt, dev = qkv.dtype, qkv.device
+        code = ops.dtype_code(dt)
+        lib = _lib.load()
+        Nl = lib.t4s_attn_padded_len(T)
+        with torch.cuda.device(dev):
+            qu = torch.empty(B, T, D, dtype=dt, device=dev)
+            qv = torch.empty(B, T, D, dtype=dt, device=dev)
+            _lib_call("t4s_add_rowvec", _p(qkv), 3 * D, _p(u.detach().reshape(-1)), _p(qu), B * T, D, 1.0, code, _st())
+            _lib_call("t4s_add_rowvec", _p(qkv), 3 * D, _p(v.detach().reshape(-1)), _p(qv), B * T, D, 1.0, code, _st())
+            o = torch.empty(B, T, D, dtype=dt, device=dev)
+            lse = torch.empty(B, H, Nl, dtype=torch.float32, device=dev)
+            a = _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, (D // H) ** -0.5)
+            _lib_call("t4s_relattn_fwd", ctypes.byref(a), _st())
+        ctx.save_for_backward(qkv, p_lin, u, v, qu, qv, o, lse)
+        ctx.H = H
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        qkv, p_lin, u, v, qu, qv, o, lse = ctx.saved_tensors
+        H = ctx.H
+        B, T, D3 = qkv.shape
+        D = D3 // 3
+        hd = D // H
+        L = 2 * T - 1
+        Lp = _pad8(L)
+        scale = hd ** -0.5
+        dt, dev = qkv.dtype, qkv.device
+        code = ops.dtype_code(dt)
+        do = do.contiguous()
+        if do.dtype != dt:
+            do = convert(do, torch.empty(do.shape, dtype=dt, device=dev))
+        with torch.cuda.device(dev):
+            dqkv = torch.empty_like(qkv)
+            dqu = torch.empty(B, T, D, dtype=dt, device=dev)
+            delta = torch.empty_like(lse)
+            dBD = _dbd_buffer(B, H, T, Lp, dev)
+            g = _lib.RelAttnBwd()
+            g.fwd = _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, scale)
+            g.d_o, g.do_ld, g.do_bs = do.data_ptr(), D, T * D
+            g.delta = delta.data_ptr()
+            es = dqkv.element_size()
+            g.dqu, g.dqu_ld, g.dqu_bs = dqu.data_ptr(), D, T * D
+            g.dk, g.dv = dqkv.data_ptr() + D * es, dqkv.data_ptr() + 2 * D * es
+            g.dk_ld = g.dv_ld = 3 * D
+            g.dk_bs = g.dv_bs = T * 3 * D
+            g.dbd, g.dbd_ld = dBD.data_ptr(), Lp
+            _lib_call("t4s_relattn_bwd", ctypes.byref(g), _st())
+            bm = dict(nb1=H, stride1=T * Lp, nb2=B, stride2=H * T * Lp)
+            # d(q+v) = scale dBD p ; dp = scale sum_b dBD^T (q+v)
+            dqv = torch.empty(B, T, D, dtype=dt, device=dev)
+            mm(Op(dBD, T, Lp, 0, **bm), Op(p_lin, hd, D, 0, nb1=H, stride1=hd, mn_major=True), Out(dqv, D, 0, hd, T * D), T, hd, L, nb1=H, nb2=B,
+               alpha=scale)
+            dp_lin = None
+            if ctx.needs_input_grad[1]:
+                ws = torch.empty(B, L, D, dtype=torch.float32, device=dev)
+                mm(Op(dBD, L, Lp, 0, mn_major=True, **bm), _tok_heads(qv, B, T, D, H, mn=True), Out(ws, D, 0, hd, L * D), L, hd, T, nb1=H, nb2=B,
+                   alpha=scale)
+                dp32 = torch.empty(L, D, dtype=torch.float32, device=dev)
+                ops.reduce_splits(ws, B, L * D, dp32)
+                dp_lin = convert(dp32, torch.empty(L, D, dtype=dt, device=dev))
+            _lib_call("t4s_add2", _p(dqu), D, _p(dqv), D, _p(dqkv), 3 * D, B * T, D, 1.0, 1.0, code, _st())
+            du = colsum(dqu.reshape(B * T, D)).reshape(u.shape) if ctx.needs_input_grad[2] else None
+            dv = colsum(dqv.reshape(B * T, D)).reshape(v.shape) if ctx.needs_input_grad[3] else None
+        return dqkv, dp_lin, du, dv, None
+
+
 def relpos_attention(qkv, p_lin, pos_bias_u, pos_bias_v, num_heads):
+    if _FUSED_ATTN and qkv.dtype == torch.bfloat16 and qkv.shape[-1] // 3 // num_heads == 64:
+        return _FlashRelPosAttention.apply(qkv, p_lin, pos_bias_u, pos_bias_v, num_heads)
     return _RelPosAttention.apply(qkv, p_lin, pos_bias_u, pos_bias_v, num_heads)
 
 
