@@ -171,6 +171,8 @@ typedef struct {
   const void* v; int64_t v_ld, v_bs;
   void* o;       int64_t o_ld, o_bs;
   float* lse;
+  float* o32;    /* optional [B, N, heads*64] fp32 copy of o (un-rounded): when given, the backward forms
+                    delta = rowsum(dO * o32) from it so that sum_j dS[i, j] cancels to fp32 rather than bf16 accuracy */
 } T4sAttn;
 typedef struct {
   T4sAttn fwd;          /* q, k, v, o, lse as given to / produced by t4s_attn_fwd */
@@ -202,6 +204,7 @@ typedef struct {
   const void* pos; int64_t pos_ld;
   void* o;        int64_t o_ld, o_bs;
   float* lse;
+  float* o32;     /* optional, as in T4sAttn */
 } T4sRelAttn;
 typedef struct {
   T4sRelAttn fwd;

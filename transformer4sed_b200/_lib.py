@@ -48,7 +48,7 @@ class Attn(ctypes.Structure):
                 ("k", c_void_p), ("k_ld", ctypes.c_int64), ("k_bs", ctypes.c_int64),
                 ("v", c_void_p), ("v_ld", ctypes.c_int64), ("v_bs", ctypes.c_int64),
                 ("o", c_void_p), ("o_ld", ctypes.c_int64), ("o_bs", ctypes.c_int64),
-                ("lse", c_void_p)]
+                ("lse", c_void_p), ("o32", c_void_p)]
 
 
 class AttnBwd(ctypes.Structure):
@@ -66,7 +66,7 @@ class RelAttn(ctypes.Structure):
                 ("v", c_void_p), ("v_ld", ctypes.c_int64), ("v_bs", ctypes.c_int64),
                 ("pos", c_void_p), ("pos_ld", ctypes.c_int64),
                 ("o", c_void_p), ("o_ld", ctypes.c_int64), ("o_bs", ctypes.c_int64),
-                ("lse", c_void_p)]
+                ("lse", c_void_p), ("o32", c_void_p)]
 
 
 class RelAttnBwd(ctypes.Structure):

@@ -213,7 +213,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row = q0 + r;
     const float inv = 1.f / l;
     a.lse[((long long)b * a.H + h) * a.Nl + row] = fmaf(m, sl2, log2f(l));
-    if (row < a.N) store_row64(a.o + (long long)b * a.o_bs + (long long)row * a.o_ld + h * kHd, acc, inv);
+    if (row < a.N) {
+      store_row64(a.o + (long long)b * a.o_bs + (long long)row * a.o_ld + h * kHd, acc, inv);
+      if (a.o32) store_row64_f32(a.o32 + ((long long)b * a.N + row) * ((long long)a.H * kHd) + h * kHd, acc, inv);
+    }
   }
 
   ptx::tc_fence_before();
@@ -227,7 +230,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // ======================================================================================================
 // backward: delta = rowsum(dO * O)
 // ======================================================================================================
-__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long o_ld, long long o_bs,
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long o_ld, long long o_bs, const float* __restrict__ o32,
                                   const __nv_bfloat16* __restrict__ d_o, long long do_ld, long long do_bs,
                                   float* __restrict__ delta, int B, int H, int N, int Nl) {
   const long long wg = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -245,14 +248,23 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long
     const int c = c0 + lane;
     float s = 0.f;
     if (c < chunks) {
-      const uint4 x = reinterpret_cast<const uint4*>(op)[c], y = reinterpret_cast<const uint4*>(dp)[c];
-      const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&x);
+      const uint4 y = reinterpret_cast<const uint4*>(dp)[c];
       const __nv_bfloat162* yp = reinterpret_cast<const __nv_bfloat162*>(&y);
+      if (o32) {
+        const float4* xp = reinterpret_cast<const float4*>(o32 + ((long long)b * N + n) * ((long long)H * kHd)) + 2 * c;
+        const float4 x0 = xp[0], x1 = xp[1];
+        const float2 y0 = __bfloat1622float2(yp[0]), y1 = __bfloat1622float2(yp[1]), y2 = __bfloat1622float2(yp[2]),
+                     y3 = __bfloat1622float2(yp[3]);
+        s = x0.x * y0.x + x0.y * y0.y + x0.z * y1.x + x0.w * y1.y + x1.x * y2.x + x1.y * y2.y + x1.z * y3.x + x1.w * y3.y;
+      } else {
+        const uint4 x = reinterpret_cast<const uint4*>(op)[c];
+        const __nv_bfloat162* xp = reinterpret_cast<const __nv_bfloat162*>(&x);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 xf = __bfloat1622float2(xp[i]), yf = __bfloat1622float2(yp[i]);
-        s = fmaf(xf.x, yf.x, s);
-        s = fmaf(xf.y, yf.y, s);
+        for (int i = 0; i < 4; ++i) {
+          const float2 xf = __bfloat1622float2(xp[i]), yf = __bfloat1622float2(yp[i]);
+          s = fmaf(xf.x, yf.x, s);
+          s = fmaf(xf.y, yf.y, s);
+        }
       }
     }
     s += __shfl_xor_sync(0xffffffffu, s, 1);
@@ -525,12 +537,12 @@ int make_map(CUtensorMap* m, const void* ptr, long long ld, long long bs, int B,
   return T4S_OK;
 }
 
-int launch_delta(const void* o, long long o_ld, long long o_bs, const void* d_o, long long do_ld, long long do_bs, float* delta, int B,
+int launch_delta(const void* o, long long o_ld, long long o_bs, const float* o32, const void* d_o, long long do_ld, long long do_bs, float* delta, int B,
                  int H, int N, int Nl, cudaStream_t st) {
   const long long warps = (long long)B * Nl;
   const int threads = 256;
   const long long blocks = (warps * 32 + threads - 1) / threads;
-  attn_delta_kernel<<<(unsigned)blocks, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(o), o_ld, o_bs,
+  attn_delta_kernel<<<(unsigned)blocks, threads, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(o), o_ld, o_bs, o32,
                                                           reinterpret_cast<const __nv_bfloat16*>(d_o), do_ld, do_bs, delta, B, H, N, Nl);
   T4S_LAUNCH_CHECK();
   return T4S_OK;
@@ -557,6 +569,7 @@ static void fill_args(Args& a, const T4sAttn* p) {
   a.o_ld = p->o_ld;
   a.o_bs = p->o_bs;
   a.lse = p->lse;
+  a.o32 = p->o32;
   a.delta = nullptr;
   a.dq = a.dk = a.dv = nullptr;
   a.dq_ld = a.dq_bs = a.dk_ld = a.dk_bs = a.dv_ld = a.dv_bs = 0;
@@ -609,7 +622,7 @@ extern "C" int t4s_attn_bwd(const T4sAttnBwd* p, void* stream) {
   a.dk = reinterpret_cast<__nv_bfloat16*>(p->dk); a.dk_ld = p->dk_ld; a.dk_bs = p->dk_bs;
   a.dv = reinterpret_cast<__nv_bfloat16*>(p->dv); a.dv_ld = p->dv_ld; a.dv_bs = p->dv_bs;
   cudaStream_t st = t4s::as_stream(stream);
-  if ((rc = launch_delta(f->o, f->o_ld, f->o_bs, p->d_o, p->do_ld, p->do_bs, p->delta, f->batch, f->heads, f->tokens, a.Nl, st))) return rc;
+  if ((rc = launch_delta(f->o, f->o_ld, f->o_bs, f->o32, p->d_o, p->do_ld, p->do_bs, p->delta, f->batch, f->heads, f->tokens, a.Nl, st))) return rc;
   dim3 grid(a.n_tiles, f->heads, f->batch);
   T4S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
   attn_bwd_kernel<false><<<grid, bwd::kThreads, bwd::kSmem, st>>>(tq, tk, tv, tdo, a);

@@ -60,6 +60,7 @@ struct Args {
   float scale;
   __nv_bfloat16* o;  long long o_ld, o_bs;
   float* lse;        // [B, H, Nl], log2 units
+  float* o32;        // optional fp32 copy of o, [B, N, H*64] contiguous
   const float* delta;
   __nv_bfloat16* dq; long long dq_ld, dq_bs;
   __nv_bfloat16* dk; long long dk_ld, dk_bs;
@@ -76,6 +77,11 @@ __device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const float (&v)
     u.w = pack_bf16(v[8 * q + 6] * mul, v[8 * q + 7] * mul);
     reinterpret_cast<uint4*>(dst)[q] = u;
   }
+}
+__device__ __forceinline__ void store_row64_f32(float* dst, const float (&v)[64], float mul) {
+#pragma unroll
+  for (int q = 0; q < 16; ++q)
+    reinterpret_cast<float4*>(dst)[q] = make_float4(v[4 * q] * mul, v[4 * q + 1] * mul, v[4 * q + 2] * mul, v[4 * q + 3] * mul);
 }
 __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (&v)[32], float mul) {
 #pragma unroll
@@ -96,7 +102,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode();
 // (d, token, head, clip) bf16 view with a [64 x box_rows x 1 x 1] SWIZZLE_128B box
 // delta[b, h, n] = sum_d dO * O (0 for the padded rows n >= N)
-int launch_delta(const void* o, long long o_ld, long long o_bs, const void* d_o, long long do_ld, long long do_bs, float* delta, int B,
+int launch_delta(const void* o, long long o_ld, long long o_bs, const float* o32, const void* d_o, long long do_ld, long long do_bs, float* delta, int B,
                  int H, int N, int Nl, cudaStream_t st);
 int make_map(CUtensorMap* m, const void* ptr, long long ld, long long bs, int B, int H, int N, const char* name, int box_rows = kTile);
 

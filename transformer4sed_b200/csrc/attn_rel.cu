@@ -268,7 +268,10 @@ relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
     const int row = q0 + r;
     const float inv = 1.f / l;
     a.lse[((long long)b * a.H + h) * a.Nl + row] = fmaf(m, sl2, log2f(l));
-    if (row < a.N) store_row64(a.o + (long long)b * a.o_bs + (long long)row * a.o_ld + h * kHd, acc, inv);
+    if (row < a.N) {
+      store_row64(a.o + (long long)b * a.o_bs + (long long)row * a.o_ld + h * kHd, acc, inv);
+      if (a.o32) store_row64_f32(a.o32 + ((long long)b * a.N + row) * ((long long)a.H * kHd) + h * kHd, acc, inv);
+    }
   }
 
   ptx::tc_fence_before();
@@ -568,6 +571,7 @@ static void fill_rel_args(Args& a, const T4sRelAttn* p) {
   a.o_ld = p->o_ld;
   a.o_bs = p->o_bs;
   a.lse = p->lse;
+  a.o32 = p->o32;
   a.delta = nullptr;
   a.dq = a.dk = a.dv = nullptr;
   a.dq_ld = a.dq_bs = a.dk_ld = a.dk_bs = a.dv_ld = a.dv_bs = 0;
@@ -628,7 +632,7 @@ extern "C" int t4s_relattn_bwd(const T4sRelAttnBwd* p, void* stream) {
   ra.dqu = reinterpret_cast<__nv_bfloat16*>(p->dqu); ra.dqu_ld = p->dqu_ld; ra.dqu_bs = p->dqu_bs;
   ra.dbd = reinterpret_cast<__nv_bfloat16*>(p->dbd); ra.dbd_ld = p->dbd_ld;
   cudaStream_t st = t4s::as_stream(stream);
-  rc = launch_delta(f->o, f->o_ld, f->o_bs, p->d_o, p->do_ld, p->do_bs, p->delta, B, H, T, ra.a.Nl, st);
+  rc = launch_delta(f->o, f->o_ld, f->o_bs, f->o32, p->d_o, p->do_ld, p->do_bs, p->delta, B, H, T, ra.a.Nl, st);
   if (rc) return rc;
   dim3 grid(ra.a.n_tiles, H, B);
   T4S_CUDA(cudaFuncSetAttribute(relattn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));

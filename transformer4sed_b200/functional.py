@@ -379,7 +379,7 @@ class _Attention(torch.autograd.Function):
         return dqkv, None
 
 
-def _attn_desc(qkv, o, lse, B, N, D, H, scale):
+def _attn_desc(qkv, o, lse, B, N, D, H, scale, o32=None):
     a = _lib.Attn()
     a.batch, a.heads, a.tokens, a.head_dim, a.scale = B, H, N, D // H, scale
     es = qkv.element_size()
@@ -389,6 +389,7 @@ def _attn_desc(qkv, o, lse, B, N, D, H, scale):
     a.q_bs = a.k_bs = a.v_bs = N * 3 * D
     a.o, a.o_ld, a.o_bs = o.data_ptr(), D, N * D
     a.lse = lse.data_ptr()
+    a.o32 = o32.data_ptr() if o32 is not None else None
     return a
 
 
@@ -407,15 +408,17 @@ class _FlashAttention(torch.autograd.Function):
         with torch.cuda.device(dev):
             o = torch.empty(B, N, D, dtype=qkv.dtype, device=dev)
             lse = torch.empty(B, H, Nl, dtype=torch.float32, device=dev)
-            a = _attn_desc(qkv, o, lse, B, N, D, H, (D // H) ** -0.5)
+            # un-rounded copy of o for the backward's delta (kept only when a backward can follow)
+            o32 = torch.empty(B, N, D, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+            a = _attn_desc(qkv, o, lse, B, N, D, H, (D // H) ** -0.5, o32)
             _lib_call("t4s_attn_fwd", ctypes.byref(a), _st())
-        ctx.save_for_backward(qkv, o, lse)
+        ctx.save_for_backward(qkv, o, lse, o32)
         ctx.H = H
         return o
 
     @staticmethod
     def backward(ctx, do):
-        qkv, o, lse = ctx.saved_tensors
+        qkv, o, lse, o32 = ctx.saved_tensors
         H = ctx.H
         B, N, D3 = qkv.shape
         D = D3 // 3
@@ -427,7 +430,7 @@ class _FlashAttention(torch.autograd.Function):
             dqkv = torch.empty_like(qkv)
             delta = torch.empty_like(lse)
             g = _lib.AttnBwd()
-            g.fwd = _attn_desc(qkv, o, lse, B, N, D, H, (D // H) ** -0.5)
+            g.fwd = _attn_desc(qkv, o, lse, B, N, D, H, (D // H) ** -0.5, o32)
             g.d_o, g.do_ld, g.do_bs = do.data_ptr(), D, N * D
             g.delta = delta.data_ptr()
             es = dqkv.element_size()
@@ -554,7 +557,7 @@ def _dbd_buffer(B, H, T, Lp, dev):
     return t
 
 
-def _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, scale):
+def _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, scale, o32=None):
     a = _lib.RelAttn()
     a.batch, a.heads, a.tokens, a.head_dim, a.scale = B, H, T, D // H, scale
     es = qkv.element_size()
@@ -566,6 +569,7 @@ def _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, scale):
     a.pos, a.pos_ld = p_lin.data_ptr(), p_lin.stride(0)
     a.o, a.o_ld, a.o_bs = o.data_ptr(), D, T * D
     a.lse = lse.data_ptr()
+    a.o32 = o32.data_ptr() if o32 is not None else None
     return a
 
 
@@ -591,15 +595,16 @@ class _FlashRelPosAttention(torch.autograd.Function):
             _lib_call("t4s_add_rowvec", _p(qkv), 3 * D, _p(v.detach().reshape(-1)), _p(qv), B * T, D, 1.0, code, _st())
             o = torch.empty(B, T, D, dtype=dt, device=dev)
             lse = torch.empty(B, H, Nl, dtype=torch.float32, device=dev)
-            a = _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, (D // H) ** -0.5)
+            o32 = torch.empty(B, T, D, dtype=torch.float32, device=dev) if any(ctx.needs_input_grad[:4]) else None
+            a = _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, (D // H) ** -0.5, o32)
             _lib_call("t4s_relattn_fwd", ctypes.byref(a), _st())
-        ctx.save_for_backward(qkv, p_lin, u, v, qu, qv, o, lse)
+        ctx.save_for_backward(qkv, p_lin, u, v, qu, qv, o, lse, o32)
         ctx.H = H
         return o
 
     @staticmethod
     def backward(ctx, do):
-        qkv, p_lin, u, v, qu, qv, o, lse = ctx.saved_tensors
+        qkv, p_lin, u, v, qu, qv, o, lse, o32 = ctx.saved_tensors
         H = ctx.H
         B, T, D3 = qkv.shape
         D = D3 // 3
@@ -618,7 +623,7 @@ class _FlashRelPosAttention(torch.autograd.Function):
             delta = torch.empty_like(lse)
             dBD = _dbd_buffer(B, H, T, Lp, dev)
             g = _lib.RelAttnBwd()
-            g.fwd = _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, scale)
+            g.fwd = _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, scale, o32)
             g.d_o, g.do_ld, g.do_bs = do.data_ptr(), D, T * D
             g.delta = delta.data_ptr()
             es = dqkv.element_size()
