@@ -99,6 +99,9 @@ typedef struct {
 
 #define T4S_ACT_NONE 0
 #define T4S_ACT_GELU 1
+/* backward of GELU fused into a dgrad GEMM: C = (alpha * acc + bias) * gelu'(residual), `residual` holding the saved
+ * pre-activation (it is multiplied in, not added) */
+#define T4S_ACT_GELU_GRAD 2
 
 typedef struct {
   int M, N, K;

@@ -74,6 +74,40 @@ def test_linear_gelu_residual(mode):
              lambda x, w, b, r: torch.nn.functional.gelu(torch.nn.functional.linear(x, w, b)) + r, [x, w, b, r], mode, tol(mode))
 
 
+@pytest.mark.parametrize("M1,M2,K,Hd", [(3, 100, 192, 264), (2, 333, 768, 3072)])
+def test_mlp_fused_gelu_backward(mode, M1, M2, K, Hd):
+    """timm Mlp + residual as one node: gelu' is applied inside the fc2 dgrad GEMM epilogue (T4S_ACT_GELU_GRAD)."""
+    F = _F()
+    x, r = rnd(M1, M2, K, seed=21, grad=True), rnd(M1, M2, K, seed=22, grad=True)
+    w1, b1 = rnd(Hd, K, seed=23, scale=K ** -0.5, grad=True), rnd(Hd, seed=24, scale=0.2, grad=True)
+    w2, b2 = rnd(K, Hd, seed=25, scale=Hd ** -0.5, grad=True), rnd(K, seed=26, scale=0.2, grad=True)
+    tf = torch.nn.functional
+    run_pair(lambda x, w1, b1, w2, b2, r: F.mlp(F.to_act(x), w1, b1, w2, b2, residual=F.to_act(r)),
+             lambda x, w1, b1, w2, b2, r: tf.linear(tf.gelu(tf.linear(x, w1, b1)), w2, b2) + r, [x, w1, b1, w2, b2, r], mode,
+             tol(mode, strict=5e-5))  # two chained K <= 3072 contractions; the contract itself is 1e-3
+
+
+@pytest.mark.parametrize("rows,cols", [(5000, 768), (4097, 3072), (777, 10), (64, 2304)])
+def test_colsum_strips(rows, cols):
+    """bias-gradient column sums (two-stage, deterministic) for bf16 and fp32 inputs, vector and scalar paths."""
+    F = _F()
+    for dt, t in ((torch.float32, 1e-5), (torch.bfloat16, 1e-5)):
+        x = rnd(rows, cols, seed=31).to(dt)
+        out = F.colsum(x)
+        ref = x.double().sum(0)
+        check(f"colsum {dt}", out, ref, t)
+        assert torch.equal(out, F.colsum(x))
+
+
+def test_layer_norm_wide_rows_bf16_fast_path():
+    """C = 768, many rows: exercises the 16-byte bf16 LayerNorm backward and the partial-sum reduction."""
+    F = _F()
+    F.set_precision("bf16")
+    x, g, b = rnd(4, 1190, 768, seed=41, grad=True), (1 + 0.1 * rnd(768, seed=42)).requires_grad_(True), rnd(768, seed=43, scale=0.1, grad=True)
+    run_pair(lambda x, g, b: F.layer_norm(F.to_act(x), g, b, 1e-6, skip=2),
+             lambda x, g, b: torch.nn.functional.layer_norm(x[:, 2:], (768,), g, b, 1e-6), [x, g, b], "bf16", 2e-2)
+
+
 def test_linear_narrow_head_fp32_out(mode):
     F = _F()
     x, w, b = rnd(2, 500, 192, seed=5, grad=True), rnd(10, 192, seed=6, scale=0.1, grad=True), rnd(10, seed=7, grad=True)

@@ -60,7 +60,8 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // instructions instead of erff's ~30, which made the fc1 epilogue the bottleneck.  Used only when the output is bf16.
 __device__ __forceinline__ float gelu_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
@@ -69,6 +70,25 @@ __device__ __forceinline__ float gelu_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
   const float half_erfc = 0.5f * poly * t * e;           // 0.5 * erfc(|x|/sqrt 2) = Phi(-|x|)
   return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
+}
+
+// d/dx [x Phi(x)] = Phi(x) + x phi(x), same erfc approximation (shares the exponential)
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float half_erfc = 0.5f * poly * t * e;
+  const float cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
+  return fmaf(x * 0.3989422804014327f, e, cdf);
+}
+__device__ __forceinline__ float gelu_grad_erf(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
 }
 
 // 32 consecutive columns of one output row, from / to registers.  `nvalid` = columns that exist (may exceed 32).
@@ -100,6 +120,40 @@ __device__ __forceinline__ void store32(const MatArg& m, long long off, int nval
 #pragma unroll
       for (int i = 0; i < 32; ++i)
         if (i < nvalid) p[i] = __float2bfloat16_rn(x[i]);
+    }
+  }
+}
+
+__device__ __forceinline__ void load32(const MatArg& m, long long off, int nvalid, float (&x)[32]) {
+  if (m.dtype == T4S_F32) {
+    const float* p = reinterpret_cast<const float*>(m.ptr) + off;
+    if (m.vec && nvalid >= 32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = reinterpret_cast<const float4*>(p)[i];
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = i < nvalid ? p[i] : 0.f;
+    }
+  } else {
+    const __nv_bfloat16* p = reinterpret_cast<const __nv_bfloat16*>(m.ptr) + off;
+    if (m.vec && nvalid >= 32) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint4 u = reinterpret_cast<const uint4*>(p)[i];
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(h[j]);
+          x[8 * i + 2 * j] = f.x;
+          x[8 * i + 2 * j + 1] = f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = i < nvalid ? __bfloat162float(p[i]) : 0.f;
     }
   }
 }
@@ -174,7 +228,19 @@ __device__ __forceinline__ void epilogue_chunk(const Args& a, const uint32_t (&v
       for (int i = 0; i < 32; ++i) x[i] = gelu_erf(x[i]);
     }
   }
-  if (a.res.ptr) add32(a.res, r_row + gcol, nvalid, x);
+  if (a.act == T4S_ACT_GELU_GRAD) {
+    float h[32];
+    load32(a.res, r_row + gcol, nvalid, h);
+    if (a.C.dtype == T4S_BF16) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] *= gelu_grad_fast(h[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] *= gelu_grad_erf(h[i]);
+    }
+  } else if (a.res.ptr) {
+    add32(a.res, r_row + gcol, nvalid, x);
+  }
   store32(a.C, c_row + gcol, nvalid, x);
 }
 
@@ -472,6 +538,7 @@ extern "C" int t4s_gemm(const T4sGemm* g, void* stream) {
   a.bias_vec = g->bias && !(reinterpret_cast<uintptr_t>(g->bias) & 15);
   a.split_k = g->split_k > 1 ? g->split_k : 1;
   a.c_split = g->c_split_stride;
+  T4S_REQUIRE(g->act != T4S_ACT_GELU_GRAD || g->residual.ptr, "t4s_gemm: T4S_ACT_GELU_GRAD needs the pre-activation in `residual`");
   T4S_REQUIRE(a.split_k == 1 || (g->c_split_stride > 0 && !g->bias && !g->residual.ptr && !g->aux.ptr && g->act == T4S_ACT_NONE),
               "t4s_gemm: split_k needs c_split_stride and a plain epilogue");
   cudaStream_t st = t4s::as_stream(stream);

@@ -170,6 +170,210 @@ __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ 
   }
 }
 
+
+// bf16 fast path of the LayerNorm backward (cols % 8 == 0, cols <= 1024): 16-byte loads, the row stays packed in registers
+// (converted twice instead of held as fp32) so that two blocks fit per SM, per-lane dgamma / dbeta accumulators.
+constexpr int kLnMaxC8 = 4;  // 16-byte chunks per lane -> cols <= 1024
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+  return u;
+}
+
+template <int kC8>
+__global__ void __launch_bounds__(kThreads, 2)
+ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                   const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dx_add,
+                   __nv_bfloat16* __restrict__ dx, float* __restrict__ part /*[grid][2][cols]*/, long long rows, int cols,
+                   float in_scale, long long n_inner, long long bstride) {
+  extern __shared__ float s_part[];  // [kWarpsPerBlock][2][cols]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + warp;
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const int nc = cols >> 3;
+  float ag[kC8][8], ab[kC8][8];
+#pragma unroll
+  for (int i = 0; i < kC8; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ag[i][e] = ab[i][e] = 0.f;
+  const float inv_cols = 1.0f / (float)cols;
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const long long xoff = (r / n_inner) * bstride + (r % n_inner) * cols;
+    const uint4* xr = reinterpret_cast<const uint4*>(x + xoff);
+    const uint4* dyr = reinterpret_cast<const uint4*>(dy + r * cols);
+    uint4 xp[kC8], dp[kC8];
+#pragma unroll
+    for (int i = 0; i < kC8; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nc) {
+        xp[i] = xr[c];
+        dp[i] = dyr[c];
+      }
+    }
+    const float mu = mean[r], rs = rstd[r];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kC8; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nc) {
+        float xv[8], dv[8];
+        unpack8(xp[i], xv);
+        unpack8(dp[i], dv);
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + 8 * c), g1 = *reinterpret_cast<const float4*>(gamma + 8 * c + 4);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (xv[e] * in_scale - mu) * rs, gd = dv[e] * g[e];
+          s1 += gd;
+          s2 = fmaf(gd, xh, s2);
+          ag[i][e] = fmaf(dv[e], xh, ag[i][e]);
+          ab[i][e] += dv[e];
+        }
+      }
+    }
+    const float m1 = warp_sum(s1) * inv_cols, m2 = warp_sum(s2) * inv_cols;
+    const float k = rs * in_scale;
+    uint4* dxr = reinterpret_cast<uint4*>(dx + xoff);
+#pragma unroll
+    for (int i = 0; i < kC8; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nc) {
+        float xv[8], dv[8], o[8];
+        unpack8(xp[i], xv);
+        unpack8(dp[i], dv);
+        const float4 g0 = *reinterpret_cast<const float4*>(gamma + 8 * c), g1 = *reinterpret_cast<const float4*>(gamma + 8 * c + 4);
+        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float xh = (xv[e] * in_scale - mu) * rs;
+          o[e] = k * (dv[e] * g[e] - m1 - xh * m2);
+        }
+        if (dx_add) {
+          float av[8];
+          unpack8(reinterpret_cast<const uint4*>(dx_add + xoff)[c], av);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] += av[e];
+        }
+        dxr[c] = pack8(o);
+      }
+    }
+  }
+  if (part) {
+    float* sp = s_part + warp * 2 * cols;
+#pragma unroll
+    for (int i = 0; i < kC8; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nc) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          sp[8 * c + e] = ag[i][e];
+          sp[cols + 8 * c + e] = ab[i][e];
+        }
+      }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 2 * cols; j += kThreads) {
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < kWarpsPerBlock; ++w) acc += s_part[w * 2 * cols + j];
+      part[(size_t)blockIdx.x * 2 * cols + j] = acc;
+    }
+  }
+}
+
+// out0[j] (+)= sum_p part[p * stride + j] for j < n0;  out1[j - n0] likewise for n0 <= j < n0 + n1.
+// Block = 32 columns x 8 partial-sum lanes (deterministic: fixed order inside a lane, fixed tree across lanes).
+__global__ void __launch_bounds__(256) reduce_parts_kernel(const float* __restrict__ part, int nparts, long long stride, int n0, int n1,
+                                                           float* __restrict__ out0, float* __restrict__ out1, int accumulate) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (j < n0 + n1) {
+    int p = ty;
+    for (; p + 24 < nparts; p += 32) {
+      const float a = part[(size_t)p * stride + j], b = part[(size_t)(p + 8) * stride + j], c = part[(size_t)(p + 16) * stride + j],
+                  d = part[(size_t)(p + 24) * stride + j];
+      acc += (a + b) + (c + d);
+    }
+    for (; p < nparts; p += 8) acc += part[(size_t)p * stride + j];
+  }
+  sm[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < n0 + n1) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][tx];
+    float* o = j < n0 ? out0 + j : out1 + (j - n0);
+    *o = (accumulate ? *o : 0.f) + t;
+  }
+}
+
+// Column sums, stage 1 (bf16 / fp32, 16-byte loads): block = 32 lanes x 8 warps; a lane owns 8 (bf16) or 4 (fp32) adjacent
+// columns, the 8 warps walk interleaved rows of the block's strip with 4 loads in flight, then combine through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_strip_kernel(const T* __restrict__ x, long long rows, int cols, long long ld,
+                                                           float* __restrict__ part, int rows_per_block) {
+  constexpr int kE = 16 / sizeof(T);
+  __shared__ float sm[8][32 * kE + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + lane) * kE;
+  const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float acc[kE];
+#pragma unroll
+  for (int e = 0; e < kE; ++e) acc[e] = 0.f;
+  if (c < cols) {
+    auto add = [&](const uint4& u) {
+      if (sizeof(T) == 2) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 t = __bfloat1622float2(h[i]);
+          acc[(2 * i) % kE] += t.x;
+          acc[(2 * i + 1) % kE] += t.y;
+        }
+      } else {
+        const float* f = reinterpret_cast<const float*>(&u);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i % kE] += f[i];
+      }
+    };
+    long long r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      const uint4 a = *reinterpret_cast<const uint4*>(x + r * ld + c), b = *reinterpret_cast<const uint4*>(x + (r + 8) * ld + c),
+                  d = *reinterpret_cast<const uint4*>(x + (r + 16) * ld + c), e = *reinterpret_cast<const uint4*>(x + (r + 24) * ld + c);
+      add(a); add(b); add(d); add(e);
+    }
+    for (; r < r1; r += 8) add(*reinterpret_cast<const uint4*>(x + r * ld + c));
+  }
+#pragma unroll
+  for (int e = 0; e < kE; ++e) sm[warp][lane * kE + e] = acc[e];
+  __syncthreads();
+  for (int j = threadIdx.x; j < 32 * kE; j += 256) {
+    const int col = blockIdx.x * 32 * kE + j;
+    if (col < cols) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += sm[w][j];
+      part[(size_t)blockIdx.y * cols + col] = t;
+    }
+  }
+}
+
 // out[j] (+)= sum_p part[p * stride + j]
 __global__ void reduce_rows_kernel(const float* __restrict__ part, int nparts, long long stride, int n, float* __restrict__ out,
                                    int accumulate) {
@@ -360,48 +564,81 @@ int t4s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   if (want_params) T4S_REQUIRE(ws && ws_bytes >= (size_t)grid * 2 * cols * sizeof(float), "t4s_layernorm_bwd: workspace too small");
   const size_t smem = want_params ? (size_t)kWarpsPerBlock * 2 * cols * sizeof(float) : 0;
   cudaStream_t st = t4s::as_stream(stream);
-  T4S_DISPATCH_DTYPE(dtype, {
-    if (smem > 48 * 1024) T4S_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ln_bwd_kernel<T><<<grid, kThreads, smem, st>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma, mean, rstd,
-                                                   static_cast<const T*>(dx_add), static_cast<T*>(dx), want_params ? ws : nullptr,
-                                                   rows, cols, in_scale, n_inner, x_bstride);
-  });
+  const bool fast = dtype == T4S_BF16 && cols % 8 == 0 && cols <= 256 * kLnMaxC8 && x_bstride % 8 == 0 &&
+                    !((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
+                       reinterpret_cast<uintptr_t>(dx_add) | reinterpret_cast<uintptr_t>(gamma)) & 15);
+  if (fast) {
+    using B16 = __nv_bfloat16;
+    auto launch = [&](auto kern) -> int {
+      if (smem > 48 * 1024) T4S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, kThreads, smem, st>>>(static_cast<const B16*>(dy), static_cast<const B16*>(x), gamma, mean, rstd,
+                                         static_cast<const B16*>(dx_add), static_cast<B16*>(dx), want_params ? ws : nullptr, rows, cols,
+                                         in_scale, n_inner, x_bstride);
+      return T4S_OK;
+    };
+    int rc;
+    if (cols <= 256) rc = launch(ln_bwd_bf16_kernel<1>);
+    else if (cols <= 512) rc = launch(ln_bwd_bf16_kernel<2>);
+    else if (cols <= 768) rc = launch(ln_bwd_bf16_kernel<3>);
+    else rc = launch(ln_bwd_bf16_kernel<4>);
+    if (rc) return rc;
+  } else {
+    T4S_DISPATCH_DTYPE(dtype, {
+      if (smem > 48 * 1024) T4S_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ln_bwd_kernel<T><<<grid, kThreads, smem, st>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma, mean, rstd,
+                                                     static_cast<const T*>(dx_add), static_cast<T*>(dx), want_params ? ws : nullptr,
+                                                     rows, cols, in_scale, n_inner, x_bstride);
+    });
+  }
   T4S_LAUNCH_CHECK();
   if (want_params) {
-    if (dgamma) {
-      reduce_rows_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws, grid, 2LL * cols, cols, dgamma, 0);
+    if (dgamma && dbeta) {
+      reduce_parts_kernel<<<(2 * cols + 31) / 32, 256, 0, st>>>(ws, grid, 2LL * cols, cols, cols, dgamma, dbeta, 0);
       T4S_LAUNCH_CHECK();
-    }
-    if (dbeta) {
-      reduce_rows_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws + cols, grid, 2LL * cols, cols, dbeta, 0);
+    } else if (dgamma) {
+      reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(ws, grid, 2LL * cols, cols, 0, dgamma, nullptr, 0);
+      T4S_LAUNCH_CHECK();
+    } else {
+      reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(ws + cols, grid, 2LL * cols, cols, 0, dbeta, nullptr, 0);
       T4S_LAUNCH_CHECK();
     }
   }
   return T4S_OK;
 }
 
+static int colsum_parts(int64_t rows, int cols, int elems_per_lane) {
+  // enough blocks for ~4 per SM, each strip at least 64 rows
+  const long long col_blocks = (cols + 32 * elems_per_lane - 1) / (32 * elems_per_lane);
+  const long long want = std::max<long long>(1, (4LL * t4s::sm_count() + col_blocks - 1) / col_blocks);
+  return (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, want));
+}
+
 size_t t4s_colsum_workspace(int64_t rows, int cols) {
-  const int parts = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, 4L * t4s::sm_count()));
+  // sized for the most finely split variant (fp32 lanes own 4 columns; the scalar fallback uses the same count)
+  const int parts = std::max(colsum_parts(rows, cols, 4), colsum_parts(rows, cols, 8));
   return (size_t)parts * cols * sizeof(float);
 }
 
 int t4s_colsum(const void* x, int dtype, int64_t rows, int cols, int64_t ld, float* ws, size_t ws_bytes, float* out, int accumulate,
                void* stream) {
   T4S_REQUIRE(x && out && ws && rows > 0 && cols > 0, "t4s_colsum: bad arguments");
-  const bool vec = cols % 4 == 0 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
-  const int parts = (int)std::max<long long>(1, std::min<long long>((rows + 63) / 64, 4L * t4s::sm_count()));
+  T4S_REQUIRE(dtype == T4S_F32 || dtype == T4S_BF16, "t4s_colsum: bad dtype");
+  const int kE = dtype == T4S_F32 ? 4 : 8;
+  const bool vec = cols % kE == 0 && ld % kE == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  const int parts = colsum_parts(rows, cols, vec ? kE : 4);
   T4S_REQUIRE(ws_bytes >= (size_t)parts * cols * sizeof(float), "t4s_colsum: workspace too small");
   const int rpb = (int)((rows + parts - 1) / parts);
+  const int nparts = (int)((rows + rpb - 1) / rpb);
   cudaStream_t st = t4s::as_stream(stream);
   if (vec) {
-    dim3 grid((cols + 1023) / 1024, parts);
-    T4S_DISPATCH_DTYPE(dtype, (colsum_partial_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), rows, cols, ld, ws, rpb)));
+    dim3 grid((cols + 32 * kE - 1) / (32 * kE), nparts);
+    T4S_DISPATCH_DTYPE(dtype, (colsum_strip_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), rows, cols, ld, ws, rpb)));
   } else {
-    dim3 grid((cols + 255) / 256, parts);
+    dim3 grid((cols + 255) / 256, nparts);
     T4S_DISPATCH_DTYPE(dtype, (colsum_partial_scalar_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), rows, cols, ld, ws, rpb)));
   }
   T4S_LAUNCH_CHECK();
-  reduce_rows_kernel<<<(cols + 255) / 256, 256, 0, st>>>(ws, (int)((rows + rpb - 1) / rpb), cols, cols, out, accumulate);
+  reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(ws, nparts, cols, cols, 0, out, nullptr, accumulate);
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }

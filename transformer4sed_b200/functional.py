@@ -255,6 +255,69 @@ def linear(x, w, b=None, residual=None, act=ops.ACT_NONE, out_dtype=None):
     return _Linear.apply(x, w, b, residual, act, out_dtype)
 
 
+class _Mlp(torch.autograd.Function):
+    """y = fc2(gelu(fc1(x))) + residual (timm Mlp, passt.py:270-276) as one autograd node: the backward applies gelu' inside the
+    epilogue of the fc2 dgrad GEMM (T4S_ACT_GELU_GRAD), so the hidden-size gradient is written once and never re-read by an
+    element-wise kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, residual):
+        _lib.ensure_device(x)
+        shp = x.shape
+        K = shp[-1]
+        x2 = x.reshape(-1, K)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        M, Hd, N = x2.shape[0], w1.shape[0], w2.shape[0]
+        w1q, w2q = cast_weight(w1), cast_weight(w2)
+        dt, dev = x.dtype, x.device
+        with torch.cuda.device(dev):
+            h = torch.empty(M, Hd, dtype=dt, device=dev)
+            pre = torch.empty(M, Hd, dtype=dt, device=dev)
+            mm(Op(x2, M, x2.stride(0)), Op(w1q, Hd, w1q.stride(0)), Out(h, Hd), M, Hd, K, bias=b1.detach(), aux=Out(pre, Hd), act=ops.ACT_GELU)
+            y = torch.empty(M, N, dtype=dt, device=dev)
+            res2 = residual.reshape(M, N) if residual is not None else None
+            mm(Op(h, M, Hd), Op(w2q, N, w2q.stride(0)), Out(y, N), M, N, Hd, bias=b2.detach(),
+               residual=Out(res2, res2.stride(0)) if res2 is not None else None)
+        ctx.save_for_backward(x2, w1, w2, pre, h)
+        ctx.in_shape = shp
+        ctx.has_res = residual is not None
+        return y.reshape(*shp[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w1, w2, pre, h = ctx.saved_tensors
+        M, K = x2.shape
+        Hd, N = w1.shape[0], w2.shape[0]
+        dev = x2.device
+        dy2 = dy.reshape(M, N)
+        if dy2.stride(-1) != 1:
+            dy2 = dy2.contiguous()
+        ng = ctx.needs_input_grad
+        with torch.cuda.device(dev):
+            if dy2.dtype != x2.dtype:
+                dy2 = convert(dy2, torch.empty(M, N, dtype=x2.dtype, device=dev))
+            w1q, w2q = cast_weight(w1), cast_weight(w2)
+            dpre = torch.empty(M, Hd, dtype=x2.dtype, device=dev)
+            mm(Op(dy2, M, dy2.stride(0)), Op(w2q, Hd, w2q.stride(0), mn_major=True), Out(dpre, Hd), M, Hd, N, residual=Out(pre, Hd),
+               act=ops.ACT_GELU_GRAD)
+            dw2 = weight_grad(dy2, h, N, Hd) if ng[3] else None
+            db2 = colsum(dy2) if ng[4] else None
+            dx = None
+            if ng[0]:
+                dx = torch.empty(M, K, dtype=x2.dtype, device=dev)
+                mm(Op(dpre, M, Hd), Op(w1q, K, w1q.stride(0), mn_major=True), Out(dx, K), M, K, Hd)
+                dx = dx.reshape(ctx.in_shape)
+            dw1 = weight_grad(dpre, x2, Hd, K) if ng[1] else None
+            db1 = colsum(dpre) if ng[2] else None
+        d_res = dy if ctx.has_res else None
+        return dx, dw1, db1, dw2, db2, d_res
+
+
+def mlp(x, w1, b1, w2, b2, residual=None):
+    return _Mlp.apply(x, w1, b1, w2, b2, residual)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # LayerNorm over the last dim of x [B, n, C], optionally skipping the first `skip` tokens of every clip
 # ------------------------------------------------------------------------------------------------------------------

@@ -11,7 +11,7 @@ from . import _lib
 from ._lib import Gemm, Matrix, Operand
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU = 0, 1
+ACT_NONE, ACT_GELU, ACT_GELU_GRAD = 0, 1, 2
 
 
 def dtype_code(dt):

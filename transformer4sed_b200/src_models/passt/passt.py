@@ -40,8 +40,7 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x, residual=None):
-        h = F.linear(x, self.fc1.weight, self.fc1.bias, act=ops.ACT_GELU)
-        return F.linear(h, self.fc2.weight, self.fc2.bias, residual=residual)
+        return F.mlp(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias, residual=residual)
 
 
 class PatchEmbed(nn.Module):
