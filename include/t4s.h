@@ -247,6 +247,37 @@ int t4s_add2(const void* x, int64_t ldx, const void* y, int64_t ldy, void* out, 
              int dtype, void* stream);
 int t4s_convert(const void* in, int in_dtype, void* out, int out_dtype, size_t n, void* stream);
 
+/* ---- sliding-window global-local fusion and MLM frame masking (csrc/window.cu) -------------------------------------------
+ * src/models/encoder_slide_window.py:16-36 + src/models/passt/passt_win.py:23-41: the reference loops over 11 (train teacher) or
+ * 17 (validation) time windows in Python, one backbone pass each.  Here every window is one more sequence of ONE backbone pass:
+ * t4s_patch_im2col_windows gathers the patches of all windows (out [(w, b, f, t), patch*patch]; `width` is the row pitch of the
+ * full image, starts[w] the first mel frame of window w; `starts` is a HOST array), and t4s_window_overlap_add_* averages the
+ * per-window frame embeddings back onto the clip's time axis (out[b,t] = mean over covering windows, 0 where none covers). */
+#define T4S_MAX_WINDOWS 64
+int t4s_patch_im2col_windows(const void* img, int img_dtype, void* out, int out_dtype, int batch, int height, int width, const int* starts,
+                             int n_windows, int patch, int stride, int f_dim, int t_dim, void* stream);
+typedef struct {
+  void* ptr;            /* frame 0 of clip 0 of this window: [batch][frames][dim] with clips batch_stride elements apart */
+  int64_t batch_stride;
+  int out_start;        /* output frame the window's frame 0 lands on (round(w_left * scale), encoder_slide_window.py:31) */
+  int frames;           /* frames of this window; those past the end of the output are dropped (zero gradient) */
+} T4sWindowSegment;
+/* segs: HOST array of n_windows entries (<= T4S_MAX_WINDOWS). */
+int t4s_window_overlap_add_fwd(const T4sWindowSegment* segs, int n_windows, void* out, int dtype, int batch, int frames, int dim, void* stream);
+/* writes the gradient of every window through segs[w].ptr */
+int t4s_window_overlap_add_bwd(const void* dout, const T4sWindowSegment* segs, int n_windows, int dtype, int batch, int frames, int dim,
+                               void* stream);
+/* src/models/transformer/mask.py:62-82 (MlmModule.setence_mask): out[r] = kind[r]==1 ? token : kind[r]==2 ? x[src[r]] : x[r]
+ * (kind: 0 keep / "self", 1 mask token, 2 random other frame of the un-masked sequence).  The backward routes dout back to
+ * x (including the copied-from rows, summed in ascending row order: deterministic) and to the mask token.
+ * copy_rows: the n_copy_rows row indices with kind == 2, ascending (device).  dx or d_token may be NULL. */
+#define T4S_MASK_GRAD_BLOCKS 64
+int t4s_mask_rows_fwd(const void* x, const float* token, const unsigned char* kind, const int64_t* src, void* out, int64_t rows, int dim,
+                      int dtype, void* stream);
+size_t t4s_mask_rows_bwd_workspace(int64_t rows, int dim);
+int t4s_mask_rows_bwd(const void* dout, const unsigned char* kind, const int64_t* src, const int64_t* copy_rows, int n_copy_rows, void* dx,
+                      float* d_token, float* ws, size_t ws_bytes, int64_t rows, int dim, int dtype, void* stream);
+
 /* ---- K6/K7: heads and losses (csrc/head.cu) ------------------------------------------------------------------
  * passt_sed.py:285-296 (sigmoid, pad mask, linear-softmax pool), pooling.py:37-51 (AttentionPooling),
  * recipes/desed/finetune/train.py:166-178 (BCE / MSE), recipes/desed/mlm/mlm_passt/train.py:36-38 (masked MSE). */

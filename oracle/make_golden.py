@@ -139,6 +139,35 @@ def golden_model(tag, kw, seed, batch):
     print(f"matsed_{tag}.npz loss={loss.item():.6f}", "strong range", strong.min().item(), strong.max().item())
 
 
+def golden_window(tag, kw, seed, batch):
+    """Sliding-window global-local fusion (passt_sed.py:266-271, encoder_slide_window.py, passt_win.py): validation kwargs
+    (eval, win [512,31], temp 0.5: 17 windows, the last one 504 frames -> 49 patches) and the teacher's training kwargs
+    (train mode, win [512,49]: 11 windows, each drawing a random time-table offset from the global CPU RNG)."""
+    net, sd = build_ref(kw, seed)
+    ext = net.get_feature_extractor().eval()
+    wav = synth.synth_wav(batch, 320000, seed=seed + 1)
+    mel = ext.normalize(ext(wav))
+    hooks = {}
+    net.slide_window_layer.register_forward_hook(lambda m, i, o: hooks.__setitem__("x_local", o))
+    net.eval()
+    with torch.no_grad():
+        s_val, w_val, _ = net(mel, encoder_win=True, mix_rate=0.5, win_param=[512, 31], temp_w=0.5)
+    local_val = hooks["x_local"]
+    net.train()
+    torch.manual_seed(seed + 7)
+    with torch.no_grad():
+        s_tr, w_tr, _ = net(mel, encoder_win=True, mix_rate=0.5, win_param=[512, 49], temp_w=1)
+    local_tr = hooks["x_local"]
+    torch.manual_seed(seed + 7)
+    offs = [torch.randint(1 + 99 - 50, (1,)).item() for _ in range(11)]   # passt.py:508, one draw per window
+    out = dict(wav_ck=checksum(wav), mel_ck=checksum(mel),
+               strong_val=f32(s_val), weak_val=f32(w_val), local_val=f32(local_val[:, ::4, ::4]),
+               strong_train=f32(s_tr), weak_train=f32(w_tr), local_train=f32(local_tr[:, ::4, ::4]),
+               train_offsets=np.array(offs, dtype=np.int32), train_seed=np.array(seed + 7))
+    np.savez_compressed(os.path.join(OUT, f"matsed_window_{tag}.npz"), **out)
+    print(f"matsed_window_{tag}.npz", offs, "strong_val range", s_val.min().item(), s_val.max().item())
+
+
 def golden_mlm(tag, kw, seed, batch):
     """MAT-SED pre-train forward (mlm=True): needs the synthetic PaSST checkpoint on disk."""
     import tempfile
@@ -211,7 +240,7 @@ if __name__ == "__main__":
     base = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_adapter=True, decoder="transformerXL",
                 decoder_layer_num=3, decoder_pos_emd_len=1000, mlm=False)  # config/mat-sed/base/finetune2.yaml:53-62
     pre = dict(base, mlm=True, mlm_dict=dict(strategy="block", block_width=10, mask_rate=0.75, out_dim=768))  # pretrain.yaml:39-52
-    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "mlm"]
+    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm"]
     if "frontend" in which:
         golden_frontend()
         golden_frontend_16k()
@@ -221,6 +250,8 @@ if __name__ == "__main__":
         golden_model("small", small, seed=3, batch=2)
     if "base" in which:
         golden_model("base", base, seed=4, batch=1)
+    if "window" in which:
+        golden_window("base", base, seed=8, batch=1)   # out_dim is hard-wired to 768 upstream (encoder_slide_window.py:10)
     if "mlm" in which:
         golden_mlm("base", pre, seed=6, batch=2)  # B>1: upstream masking is a silent no-op
         golden_mlm("base", pre, seed=6, batch=1)  # B=1: reshape is a view, masking applies

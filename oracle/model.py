@@ -21,14 +21,15 @@ def linear(x, sd, prefix, bias=True):
 # ------------------------------------------------------------------------------------------------
 # PaSST backbone  (reference src/models/passt/passt.py)
 # ------------------------------------------------------------------------------------------------
-def patch_embed_tokens(mel, sd, p="backbone."):
+def patch_embed_tokens(mel, sd, p="backbone.", t_offset=0):
     """mel [B,128,T] -> tokens [B, 2+F*Tp, D]; patch conv (:302-315) + time/freq pos (:503-519) +
     cls/dist tokens (:560-569).  Eval path: time pos-embed cropped from offset 0 (:511), or the
-    patch grid cropped to the table's 99 columns (:515)."""
+    patch grid cropped to the table's 99 columns (:515).  `t_offset` injects the train-mode random
+    crop offset of the time table (:506-509)."""
     x = F.conv2d(mel.unsqueeze(1), sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"], stride=10)
     tpos = sd[p + "time_new_pos_embed"]
     if x.shape[-1] < tpos.shape[-1]:
-        tpos = tpos[:, :, :, :x.shape[-1]]
+        tpos = tpos[:, :, :, t_offset:t_offset + x.shape[-1]]
     else:
         x = x[:, :, :, :tpos.shape[-1]]
     x = x + tpos + sd[p + "freq_new_pos_embed"]
@@ -61,9 +62,9 @@ def vit_block(x, sd, p, num_heads, eps=1e-6):
     return x
 
 
-def passt_backbone(mel, sd, depth=12, num_heads=12, feature_layer=10, p="backbone."):
+def passt_backbone(mel, sd, depth=12, num_heads=12, feature_layer=10, p="backbone.", t_offset=0):
     """passt.py:492-583.  Returns (layer{feature_layer}_out [B,N,D], final-norm tokens [B,N,D], F, T')."""
-    x, Fd, Td = patch_embed_tokens(mel, sd, p)
+    x, Fd, Td = patch_embed_tokens(mel, sd, p, t_offset)
     feat = None
     for k in range(depth):
         x = vit_block(x, sd, f"{p}blocks.{k}.", num_heads)
@@ -217,12 +218,48 @@ def apply_mask(x, mask_id, probs, rand_idx, mask_token, style=(0.8, 0.1, 0.1), s
     return out.reshape(B, T, C)
 
 
+def window_starts(input_len, win_param):
+    """encoder_slide_window.py:29-30: [(w_left, w_right)] of the Python loop."""
+    win, step = win_param
+    return [(w, min(w + win, input_len)) for w in range(0, input_len + step - win, step)]
+
+
+def slide_window_embed(mel, sd, win_param, emb_len, feature_layer=10, f_pool_mode="mean_pool", ratio=10, t_offsets=None):
+    """EncoderSlideWindow.__call__ (encoder_slide_window.py:16-36) with PasstWithSlide.encode (passt_win.py:23-41): one
+    backbone pass per window, x`ratio` linear interpolation WITHOUT the last-frame pad, overlap-add mean, nan -> 0.
+    `t_offsets[i]` injects window i's train-mode time-table offset (passt.py:506-509); None = eval (0)."""
+    B, _, L = mel.shape
+    scale = emb_len / L
+    emb = acc = None
+    for i, (w_left, w_right) in enumerate(window_starts(L, win_param)):
+        feat, _, Fd, Td = passt_backbone(mel[:, :, w_left:w_right], sd, feature_layer=feature_layer,
+                                         t_offset=0 if t_offsets is None else t_offsets[i])
+        out = f_pool(feat, sd, Fd, Td, f_pool_mode)
+        if ratio != 1:
+            out = F.interpolate(out.transpose(1, 2), scale_factor=ratio, mode="linear").transpose(1, 2)
+        if emb is None:
+            emb = torch.zeros(B, emb_len, out.shape[-1], dtype=out.dtype)
+            acc = torch.zeros_like(emb)
+        out_left = round(w_left * scale)
+        out_right = int(min(emb_len, out_left + out.shape[1]))
+        emb[:, out_left:out_right] = emb[:, out_left:out_right] + out
+        acc[:, out_left:out_right] += 1
+    emb = emb / acc
+    return torch.where(torch.isnan(emb), torch.zeros_like(emb), emb)
+
+
 def mat_sed_forward(mel, sd, decoder_layers=3, feature_layer=10, f_pool_mode="mean_pool", decode_ratio=10,
-                    temp_w=1.0, pad_mask=None, mlm=False, decoder_input_override=None, stages=None):
-    """PaSST_SED.forward (passt_sed.py:242-296), encoder_win=False.  Returns (strong, weak, other) or
-    (pred, other) in MLM mode.  `stages` (dict) receives intermediate tensors when given."""
+                    temp_w=1.0, pad_mask=None, mlm=False, decoder_input_override=None, stages=None,
+                    encoder_win=False, mix_rate=0.5, win_param=(512, 49), win_t_offsets=None):
+    """PaSST_SED.forward (passt_sed.py:242-296).  Returns (strong, weak, other) or (pred, other) in MLM mode.
+    `stages` (dict) receives intermediate tensors when given.  encoder_win: sliding-window fusion (:266-271)."""
     feat, frame, Fd, Td = passt_backbone(mel, sd, feature_layer=feature_layer)
     x = pad_interpolate(f_pool(feat, sd, Fd, Td, f_pool_mode), decode_ratio)
+    if encoder_win:
+        x_local = slide_window_embed(mel, sd, win_param, x.shape[1], feature_layer, f_pool_mode, decode_ratio, win_t_offsets)
+        if stages is not None:
+            stages.update(x_global=x, x_local=x_local)
+        x = mix_rate * x_local + (1 - mix_rate) * x
     other = {"frame_before_mask": x}
     dec_in = x if decoder_input_override is None else decoder_input_override(x, other)
     y = txl_decoder(dec_in, sd, decoder_layers)

@@ -32,5 +32,11 @@ if "gemm" in which:
     ops.gemm(ops.Op(x, M, 768), ops.Op(w1, 3072, 768), ops.Out(y, 3072), M, 3072, 768, bias=bias)                       # plain + bias
     ops.gemm(ops.Op(x, M, 768), ops.Op(w1, 3072, 768), ops.Out(y, 3072), M, 3072, 768, bias=bias, aux=ops.Out(aux, 3072),
              act=ops.ACT_GELU)                                                                                         # fc1 forward
+if "mel" in which:
+    from transformer4sed_b200.src_models.passt.passt_feature_extraction import PasstFeatureExtractor
+    ext = PasstFeatureExtractor(n_mels=128, sr=32000, win_length=800, hopsize=320, n_fft=1024, htk=False, fmin=0.0, fmax=None,
+                                fmin_aug_range=10, fmax_aug_range=2000).cuda().eval()
+    wav = torch.randn(B, 320000, generator=g, device="cuda") * 0.1
+    ext.logmel(wav)
 torch.cuda.synchronize()
 print("done")

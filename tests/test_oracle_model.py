@@ -108,3 +108,27 @@ def test_ops(golden):
     np.testing.assert_allclose(checksum(xin), g["txl_in_ck"], rtol=1e-12)
     out = M.txl_decoder(xin, sd, 2, num_heads=4, p="")
     np.testing.assert_allclose(out.numpy(), g["txl_out"], rtol=1e-4, atol=1e-5)
+
+
+def test_sliding_window(golden):
+    """Oracle sliding-window fusion (encoder_slide_window.py + passt_win.py) vs the unmodified reference: validation kwargs
+    (eval, [512, 31], temp 0.5) and the teacher's training kwargs (train mode, [512, 49], recorded RNG offsets)."""
+    g = golden("matsed_window_base.npz")
+    seed = 8
+    sd = _sd(schema.mat_sed_shapes(), seed)
+    wav = synth.synth_wav(1, 320000, seed=seed + 1)
+    np.testing.assert_allclose(checksum(wav), g["wav_ck"], rtol=1e-12)
+    mel = F.passt_logmel(wav)
+    assert [b - a for a, b in M.window_starts(1000, (512, 31))][-2:] == [512, 504] and len(M.window_starts(1000, (512, 31))) == 17
+    assert len(M.window_starts(1000, (512, 49))) == 11
+    with torch.no_grad():
+        st = {}
+        s, w, _ = M.mat_sed_forward(mel, sd, encoder_win=True, win_param=(512, 31), temp_w=0.5, stages=st)
+        np.testing.assert_allclose(st["x_local"][:, ::4, ::4].numpy(), g["local_val"], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(s.numpy(), g["strong_val"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(w.numpy(), g["weak_val"], rtol=1e-4, atol=1e-6)
+        st = {}
+        s, w, _ = M.mat_sed_forward(mel, sd, encoder_win=True, win_param=(512, 49), win_t_offsets=[int(v) for v in g["train_offsets"]], stages=st)
+        np.testing.assert_allclose(st["x_local"][:, ::4, ::4].numpy(), g["local_train"], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(s.numpy(), g["strong_train"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(w.numpy(), g["weak_train"], rtol=1e-4, atol=1e-6)

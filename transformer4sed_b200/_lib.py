@@ -77,6 +77,10 @@ class RelAttnBwd(ctypes.Structure):
                 ("dbd", c_void_p), ("dbd_ld", ctypes.c_int64)]
 
 
+class WindowSegment(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("batch_stride", ctypes.c_int64), ("out_start", c_int), ("frames", c_int)]
+
+
 def _declare(lib):
     P, I, Z, F, L = c_void_p, c_int, c_size_t, c_float, ctypes.c_int64
     sigs = {
@@ -113,6 +117,12 @@ def _declare(lib):
         "t4s_relpos_softmax_bwd": (I, [P, P, P, L, I, L, L, L, I, P]),
         "t4s_patch_im2col": (I, [P, I, P, I, I, I, I, I, I, I, I, P]),
         "t4s_add2": (I, [P, L, P, L, P, L, L, I, F, F, I, P]),
+        "t4s_patch_im2col_windows": (I, [P, I, P, I, I, I, I, ctypes.POINTER(c_int), I, I, I, I, I, P]),
+        "t4s_window_overlap_add_fwd": (I, [ctypes.POINTER(WindowSegment), I, P, I, I, I, I, P]),
+        "t4s_window_overlap_add_bwd": (I, [P, ctypes.POINTER(WindowSegment), I, I, I, I, I, P]),
+        "t4s_mask_rows_fwd": (I, [P, P, P, P, P, L, I, I, P]),
+        "t4s_mask_rows_bwd_workspace": (Z, [L, I]),
+        "t4s_mask_rows_bwd": (I, [P, P, P, P, I, P, P, P, Z, L, I, I, P]),
         "t4s_patch_posbias": (I, [P, P, P, I, I, I, I, I, P]),
         "t4s_cls_dist_tokens": (I, [P, I, P, P, P, I, L, I, P]),
         "t4s_patch_small_grads": (I, [P, I, P, P, P, P, P, P, P, I, L, I, I, I, I, I, P]),

@@ -744,67 +744,104 @@ def rel_pos_table(T, d_model, device, dtype):
 # Patch embedding + positional tables + cls/dist tokens          reference: passt.py:302-315, 496-569
 # ------------------------------------------------------------------------------------------------------------------
 class _PatchEmbed(torch.autograd.Function):
+    """`windows` = None (whole image, one positional offset) or (starts, t_dim, t_offsets): every time window
+    [start, start + (t_dim-1)*stride + patch) of the image becomes one sequence; output rows are window-major
+    [(w, b), n_tok, D] (sliding-window fusion, reference encoder_slide_window.py:29-33)."""
+
     @staticmethod
-    def forward(ctx, mel, conv_w, conv_b, time_pos, freq_pos, cls, dist, new_pos, stride, t_offset):
+    def forward(ctx, mel, conv_w, conv_b, time_pos, freq_pos, cls, dist, new_pos, stride, t_offset, windows):
         _lib.ensure_device(mel)
         mel = mel.contiguous()
         B, Hh, W = mel.shape
         D, _, P, _ = conv_w.shape
         F = (Hh - P) // stride + 1
-        Tp_full = (W - P) // stride + 1
         Tt = time_pos.shape[-1]
-        Tp = min(Tp_full, Tt)          # a longer grid is cropped to the table (passt.py:515)
+        if windows is None:
+            Tp_full = (W - P) // stride + 1
+            Tp = min(Tp_full, Tt)          # a longer grid is cropped to the table (passt.py:515)
+            starts, offsets = None, [int(t_offset)]
+        else:
+            starts, Tp, offsets = [int(v) for v in windows[0]], int(windows[1]), [int(v) for v in windows[2]]
+            if Tp > Tt or len(offsets) != len(starts):
+                raise _lib.T4sError("patch_embed: bad window specification")
+        nW = len(offsets)
         dt, dev = act_dtype(), mel.device
         n_tok = 2 + F * Tp
+        PP = P * P
         with torch.cuda.device(dev):
-            A = torch.empty(B * F * Tp, P * P, dtype=dt, device=dev)
-            _lib_call("t4s_patch_im2col", _p(mel), ops.dtype_code(mel.dtype), _p(A), ops.dtype_code(dt), B, Hh, W, P, stride, F, Tp, _st())
-            pos = torch.empty(F * Tp, D, dtype=torch.float32, device=dev)
-            _lib_call("t4s_patch_posbias", _p(time_pos.detach()), _p(freq_pos.detach()), _p(pos), D, F, Tp, Tt, t_offset, _st())
-            x = torch.empty(B, n_tok, D, dtype=dt, device=dev)
-            w2 = cast_weight(conv_w).reshape(D, P * P)
-            mm(Op(A, F * Tp, P * P, 0, nb1=B, stride1=F * Tp * P * P), Op(w2, D, P * P), Out(x, D, 2 * D, n_tok * D), F * Tp, D, P * P, nb1=B,
-               bias=conv_b.detach(), residual=Out(pos, D, 0, 0))
-            _lib_call("t4s_cls_dist_tokens", _p(x), ops.dtype_code(dt), _p(cls.detach()), _p(dist.detach()), _p(new_pos.detach()), B, n_tok * D, D,
-                      _st())
+            A = torch.empty(nW * B * F * Tp, PP, dtype=dt, device=dev)
+            if starts is None:
+                _lib_call("t4s_patch_im2col", _p(mel), ops.dtype_code(mel.dtype), _p(A), ops.dtype_code(dt), B, Hh, W, P, stride, F, Tp, _st())
+            else:
+                arr = (ctypes.c_int * nW)(*starts)
+                _lib_call("t4s_patch_im2col_windows", _p(mel), ops.dtype_code(mel.dtype), _p(A), ops.dtype_code(dt), B, Hh, W, arr, nW, P, stride,
+                          F, Tp, _st())
+            same = all(o == offsets[0] for o in offsets)
+            n_pos = 1 if same else nW
+            pos = torch.empty(n_pos, F * Tp, D, dtype=torch.float32, device=dev)
+            for i in range(n_pos):
+                _lib_call("t4s_patch_posbias", _p(time_pos.detach()), _p(freq_pos.detach()), ctypes.c_void_p(pos.data_ptr() + i * F * Tp * D * 4),
+                          D, F, Tp, Tt, offsets[i], _st())
+            x = torch.empty(nW * B, n_tok, D, dtype=dt, device=dev)
+            w2 = cast_weight(conv_w).reshape(D, PP)
+            mm(Op(A, F * Tp, PP, 0, nb1=B, stride1=F * Tp * PP, nb2=nW, stride2=B * F * Tp * PP), Op(w2, D, PP),
+               Out(x, D, 2 * D, n_tok * D, B * n_tok * D), F * Tp, D, PP, nb1=B, nb2=nW, bias=conv_b.detach(),
+               residual=Out(pos, D, 0, 0, 0 if same else F * Tp * D))
+            _lib_call("t4s_cls_dist_tokens", _p(x), ops.dtype_code(dt), _p(cls.detach()), _p(dist.detach()), _p(new_pos.detach()), nW * B,
+                      n_tok * D, D, _st())
         ctx.save_for_backward(A, conv_w)
-        ctx.cfg = (B, F, Tp, Tt, t_offset, D, P, n_tok, time_pos.shape, freq_pos.shape, cls.shape, new_pos.shape)
+        ctx.cfg = (B, F, Tp, Tt, offsets, D, P, n_tok, time_pos.shape, freq_pos.shape, cls.shape, new_pos.shape)
         return x
 
     @staticmethod
     def backward(ctx, dx):
         A, conv_w = ctx.saved_tensors
-        B, F, Tp, Tt, t_offset, D, P, n_tok, tshape, fshape, cshape, nshape = ctx.cfg
+        B, F, Tp, Tt, offsets, D, P, n_tok, tshape, fshape, cshape, nshape = ctx.cfg
+        nW = len(offsets)
         dev = dx.device
         dx = dx.contiguous()
         if dx.dtype != A.dtype:
             dx = convert(dx, torch.empty(dx.shape, dtype=A.dtype, device=dev))
         ng = ctx.needs_input_grad
+        PP = P * P
         with torch.cuda.device(dev):
             f32 = dict(dtype=torch.float32, device=dev)
             tmp = torch.empty(n_tok * D, **f32)
-            d_time = torch.empty(tshape, **f32) if ng[3] else None
-            d_freq = torch.empty(fshape, **f32) if ng[4] else None
-            d_bias = torch.empty(D, **f32) if ng[2] else None
-            d_cls = torch.empty(cshape, **f32) if ng[5] else None
-            d_dist = torch.empty(cshape, **f32) if ng[6] else None
-            d_new = torch.empty(nshape, **f32) if ng[7] else None
-            if any(g is not None for g in (d_time, d_freq, d_bias, d_cls, d_dist, d_new)):
-                _lib_call("t4s_patch_small_grads", _p(dx), ops.dtype_code(dx.dtype), _p(tmp), _p(d_time), _p(d_freq), _p(d_bias), _p(d_cls),
-                          _p(d_dist), _p(d_new), B, n_tok * D, D, F, Tp, Tt, t_offset, _st())
+            shapes = (tshape if ng[3] else None, fshape if ng[4] else None, (D,) if ng[2] else None, cshape if ng[5] else None,
+                      cshape if ng[6] else None, nshape if ng[7] else None)
+            same = all(o == offsets[0] for o in offsets)
+            groups = 1 if same else nW            # windows sharing a positional offset reduce together (batch = all their clips)
+            parts = [torch.empty((groups,) + tuple(sh), **f32) if sh is not None else None for sh in shapes]
+            if any(g is not None for g in parts):
+                per = nW * B // groups
+                es = dx.element_size()
+                for i in range(groups):
+                    ptrs = [ctypes.c_void_p(g.data_ptr() + i * g[0].numel() * 4) if g is not None else ctypes.c_void_p(0) for g in parts]
+                    _lib_call("t4s_patch_small_grads", ctypes.c_void_p(dx.data_ptr() + i * per * n_tok * D * es), ops.dtype_code(dx.dtype), _p(tmp),
+                              ptrs[0], ptrs[1], ptrs[2], ptrs[3], ptrs[4], ptrs[5], per, n_tok * D, D, F, Tp, Tt, offsets[i], _st())
+            outs = []
+            for g in parts:
+                if g is None or groups == 1:
+                    outs.append(g[0] if g is not None else None)
+                else:
+                    o = torch.empty(g.shape[1:], **f32)
+                    ops.reduce_splits(g, groups, o.numel(), o)
+                    outs.append(o)
+            d_time, d_freq, d_bias, d_cls, d_dist, d_new = outs
             dw = None
             if ng[1]:
-                ws = torch.empty(B, D, P * P, **f32)
-                mm(Op(dx, D, D, 2 * D, nb1=B, stride1=n_tok * D, mn_major=True), Op(A, P * P, P * P, 0, nb1=B, stride1=F * Tp * P * P, mn_major=True),
-                   Out(ws, P * P, 0, D * P * P), D, P * P, F * Tp, nb1=B)
-                dw = torch.empty(D, P * P, **f32)
-                ops.reduce_splits(ws, B, D * P * P, dw)
+                nb = nW * B
+                ws = torch.empty(nb, D, PP, **f32)
+                mm(Op(dx, D, D, 2 * D, nb1=nb, stride1=n_tok * D, mn_major=True), Op(A, PP, PP, 0, nb1=nb, stride1=F * Tp * PP, mn_major=True),
+                   Out(ws, PP, 0, D * PP), D, PP, F * Tp, nb1=nb)
+                dw = torch.empty(D, PP, **f32)
+                ops.reduce_splits(ws, nb, D * PP, dw)
                 dw = dw.reshape(conv_w.shape)
-        return None, dw, d_bias, d_time, d_freq, d_cls, d_dist, d_new, None, None
+        return None, dw, d_bias, d_time, d_freq, d_cls, d_dist, d_new, None, None, None
 
 
-def patch_embed(mel, conv_w, conv_b, time_pos, freq_pos, cls, dist, new_pos, stride=10, t_offset=0):
-    return _PatchEmbed.apply(mel, conv_w, conv_b, time_pos, freq_pos, cls, dist, new_pos, stride, t_offset)
+def patch_embed(mel, conv_w, conv_b, time_pos, freq_pos, cls, dist, new_pos, stride=10, t_offset=0, windows=None):
+    return _PatchEmbed.apply(mel, conv_w, conv_b, time_pos, freq_pos, cls, dist, new_pos, stride, t_offset, windows)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -861,6 +898,138 @@ class _PadInterp(torch.autograd.Function):
 def pad_interpolate(x, ratio, pad=True):
     """(optionally repeat the last frame, then) linear interpolation x ratio along time, align_corners=False."""
     return _PadInterp.apply(x, int(ratio), int(bool(pad)))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# sliding-window overlap-add mean, global/local blend            reference: encoder_slide_window.py:24-36, passt_sed.py:266-271
+# ------------------------------------------------------------------------------------------------------------------
+def _segments(groups, B, C):
+    """groups: [(tensor [n_w*B, L, C] window-major, out_starts [n_w])] -> ctypes array of T4sWindowSegment."""
+    segs = []
+    for t, starts in groups:
+        L = t.shape[1]
+        es = t.element_size()
+        for i, st in enumerate(starts):
+            segs.append(_lib.WindowSegment(ctypes.c_void_p(t.data_ptr() + i * B * L * C * es), L * C, int(st), L))
+    return (_lib.WindowSegment * len(segs))(*segs), len(segs)
+
+
+class _OverlapAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, frames, B, spec, *locals_):
+        _lib.ensure_device(locals_[0])
+        locals_ = [t.contiguous() for t in locals_]
+        C = locals_[0].shape[-1]
+        dt, dev = locals_[0].dtype, locals_[0].device
+        segs, n = _segments(list(zip(locals_, spec)), B, C)
+        out = torch.empty(B, frames, C, dtype=dt, device=dev)
+        with torch.cuda.device(dev):
+            _lib_call("t4s_window_overlap_add_fwd", segs, n, _p(out), ops.dtype_code(dt), B, frames, C, _st())
+        ctx.cfg = (frames, B, spec, [t.shape for t in locals_], dt)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        frames, B, spec, shapes, dt = ctx.cfg
+        dev = dout.device
+        dout = dout.contiguous()
+        if dout.dtype != dt:
+            dout = convert(dout, torch.empty(dout.shape, dtype=dt, device=dev))
+        C = dout.shape[-1]
+        grads = [torch.empty(sh, dtype=dt, device=dev) for sh in shapes]
+        segs, n = _segments(list(zip(grads, spec)), B, C)
+        with torch.cuda.device(dev):
+            _lib_call("t4s_window_overlap_add_bwd", _p(dout), segs, n, ops.dtype_code(dt), B, frames, C, _st())
+        return (None, None, None) + tuple(grads)
+
+
+def window_overlap_add(groups, batch, frames):
+    """groups: list of (local [n_w*batch, L, C] window-major, out_starts list) -> [batch, frames, C]: mean over the windows
+    covering each frame, 0 where none does."""
+    spec = tuple(tuple(int(v) for v in st) for _, st in groups)
+    return _OverlapAdd.apply(int(frames), int(batch), spec, *[t for t, _ in groups])
+
+
+class _Lerp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, w):
+        _lib.ensure_device(a)
+        a, b = a.contiguous(), b.contiguous()
+        if b.dtype != a.dtype:
+            b = convert(b, torch.empty(b.shape, dtype=a.dtype, device=a.device))
+        C = a.shape[-1]
+        out = torch.empty_like(a)
+        with torch.cuda.device(a.device):
+            _lib_call("t4s_add2", _p(a), C, _p(b), C, _p(out), C, a.numel() // C, C, 1.0 - w, w, ops.dtype_code(a.dtype), _st())
+        ctx.w = w
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        C = dout.shape[-1]
+        code = ops.dtype_code(dout.dtype)
+        da = db = None
+        with torch.cuda.device(dout.device):
+            if ctx.needs_input_grad[0]:
+                da = torch.empty_like(dout)
+                _lib_call("t4s_add_rowvec", _p(dout), C, ctypes.c_void_p(0), _p(da), dout.numel() // C, C, 1.0 - ctx.w, code, _st())
+            if ctx.needs_input_grad[1]:
+                db = torch.empty_like(dout)
+                _lib_call("t4s_add_rowvec", _p(dout), C, ctypes.c_void_p(0), _p(db), dout.numel() // C, C, ctx.w, code, _st())
+        return da, db, None
+
+
+def lerp(a, b, w):
+    """(1 - w) * a + w * b   (mix_rate blend of the global and the sliding-window embeddings, passt_sed.py:271)."""
+    return _Lerp.apply(a, b, float(w))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# MLM frame replacement                                           reference: transformer/mask.py:62-82
+# ------------------------------------------------------------------------------------------------------------------
+class _MaskRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, token, kind, src):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        rows = x.numel() // C
+        tok = token.detach().reshape(-1).float().contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib_call("t4s_mask_rows_fwd", _p(x), _p(tok), _p(kind), _p(src), _p(out), rows, C, ops.dtype_code(x.dtype), _st())
+        ctx.save_for_backward(kind, src)
+        ctx.cfg = (rows, C, token.shape, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        kind, src = ctx.saved_tensors
+        rows, C, tshape, dt = ctx.cfg
+        dev = dout.device
+        dout = dout.contiguous()
+        if dout.dtype != dt:
+            dout = convert(dout, torch.empty(dout.shape, dtype=dt, device=dev))
+        lib = _lib.load()
+        copy_rows = torch.nonzero(kind == 2).reshape(-1)  # index bookkeeping (ascending); the arithmetic is in the kernel
+        with torch.cuda.device(dev):
+            dx = torch.empty_like(dout) if ctx.needs_input_grad[0] else None
+            dtok = torch.empty(C, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+            nbytes = lib.t4s_mask_rows_bwd_workspace(rows, C)
+            ws = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+            _lib_call("t4s_mask_rows_bwd", _p(dout), _p(kind), _p(src), _p(copy_rows), copy_rows.numel(), _p(dx), _p(dtok), _p(ws), nbytes, rows,
+                      C, ops.dtype_code(dt), _st())
+        return dx, (dtok.reshape(tshape) if dtok is not None else None), None, None
+
+
+def mask_rows(token_seq, mask_token, mask_mask, random_mask, random_indices):
+    """token_seq [B, T, C]; rows (flattened b*T + t) in `mask_mask` become the mask token, rows in `random_mask` become a copy of
+    row random_indices[k] (k-th selected row) of the ORIGINAL sequence, all other rows pass through."""
+    kind = mask_mask.to(torch.uint8) + 2 * random_mask.to(torch.uint8)
+    src = torch.zeros(kind.numel(), dtype=torch.int64, device=kind.device)
+    src[random_mask] = random_indices.to(torch.int64)
+    return _MaskRows.apply(token_seq, mask_token, kind.contiguous(), src)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -148,12 +148,18 @@ class PaSST(nn.Module):
         return {'new_pos_embed', 'freq_new_pos_embed', 'time_new_pos_embed', 'cls_token', 'dist_token'}
 
     # ---- token-major fast path used by PaSST_SED ---------------------------------------------------------------
-    def forward_tokens(self, mel, feature_layers=()):
+    def forward_tokens(self, mel, feature_layers=(), windows=None):
         """mel [B, n_mels, T] -> (dict {layer k: tokens [B, N, D] after block k}, final-norm tokens [B, N, D], f_dim, t_dim).
         Token-major tensors, no transposes, only the requested layers are kept (the reference materialises 12 fp32
-        transposed copies, passt.py:574-576)."""
+        transposed copies, passt.py:574-576).
+
+        `windows` = (starts, width): instead of the whole image, every crop mel[:, :, s:s+width] (s in starts) is embedded as its
+        own sequence and all of them ride through the blocks as ONE batch, window-major [(w, b), N_w, D] -- the batched form
+        of the reference's per-window backbone calls (encoder_slide_window.py:29-33)."""
         pe = self.patch_embed
         H, W = mel.shape[-2], mel.shape[-1]
+        if windows is not None:
+            W = int(windows[1])
         if not (H == pe.img_size[0] and W == pe.img_size[1]) and W not in getattr(self, "_warned", ()):
             warnings.warn(f"Input image size ({H}*{W}) doesn't match model ({pe.img_size[0]}*{pe.img_size[1]}).")
             self._warned = getattr(self, "_warned", ()) + (W,)
@@ -161,13 +167,22 @@ class PaSST(nn.Module):
         f_dim = (H - P) // S + 1
         t_full = (W - P) // S + 1
         t_table = self.time_new_pos_embed.shape[-1]
-        toffset = 0
-        if t_full < t_table and self.training:
-            toffset = torch.randint(1 + t_table - t_full, (1,)).item()  # same draw as the reference (passt.py:508)
         t_dim = min(t_full, t_table)
+
+        def draw():
+            if t_full < t_table and self.training:
+                return torch.randint(1 + t_table - t_full, (1,)).item()  # same draw as the reference (passt.py:508)
+            return 0
+
+        spec, toffset = None, 0
+        if windows is None:
+            toffset = draw()
+        else:
+            starts = [int(v) for v in windows[0]]
+            spec = (starts, t_dim, [draw() for _ in starts])    # one draw per window, in window order, like the reference loop
         x = F.patch_embed(mel, pe.proj.weight, pe.proj.bias, self.time_new_pos_embed.reshape(self.embed_dim, t_table),
                           self.freq_new_pos_embed.reshape(self.embed_dim, f_dim), self.cls_token.reshape(-1),
-                          self.dist_token.reshape(-1), self.new_pos_embed.reshape(2, -1), stride=S, t_offset=toffset)
+                          self.dist_token.reshape(-1), self.new_pos_embed.reshape(2, -1), stride=S, t_offset=toffset, windows=spec)
         feats = {}
         for k, block in enumerate(self.blocks):
             x = block(x)

@@ -20,17 +20,19 @@ class MlmModule:
     def setence_mask(self, token_seq, mask_token, apply=True):
         B, T, C = token_seq.shape
         dev = token_seq.device
-        mask_id_seq = self.get_mask_id_seq(B, T, dev)
+        rng_dev = self.device if self.device is not None else dev   # the reference draws on `self.device` (mask.py:71,79,88,96)
+        mask_id_seq = self.get_mask_id_seq(B, T, rng_dev)
         mask_id_flat = mask_id_seq.view(-1)
-        probs = torch.rand(B * T, device=dev)
+        probs = torch.rand(B * T, device=rng_dev)
         mask_mask = mask_id_flat & (probs < self.mask_style["mask_token"])
         random_mask = mask_id_flat & (probs >= self.mask_style["mask_token"]) & (
             probs < self.mask_style["mask_token"] + self.mask_style["random"])
-        random_indices = torch.randint(0, B * T, (int(random_mask.sum().item()),), device=dev)
+        random_indices = torch.randint(0, B * T, (int(random_mask.sum().item()),), device=rng_dev)
+        mask_id_seq = mask_id_seq.to(dev)
         if not apply:
             return token_seq, mask_id_seq
         from ... import functional as F
-        return F.mask_rows(token_seq, mask_token, mask_mask, random_mask, random_indices), mask_id_seq
+        return F.mask_rows(token_seq, mask_token, mask_mask.to(dev), random_mask.to(dev), random_indices.to(dev)), mask_id_seq
 
     def get_mask_id_seq(self, batch_len, seq_len, device=None):
         if self.strategy == "random":
