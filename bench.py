@@ -254,10 +254,20 @@ def instrumented_step(train_step, wav_dev, ext, ops, B):
         elif name in ("t4s_attn_fwd", "t4s_attn_bwd"):
             attn_ms += s.elapsed_time(e)
     summary = prof.summary()
+    shapes = {}
+    for name, key, s, e in prof.records:
+        if name == "t4s_gemm":
+            M, N, K, nb = key[:4]
+            a = shapes.setdefault(str(key), [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += s.elapsed_time(e)
+            a[2] += 2.0 * M * N * K * nb
     try:
         os.makedirs("gpurun_out", exist_ok=True)
-        with open("gpurun_out/step_breakdown.json", "w") as f:
-            json.dump({"step_ms": step_ms, "ops": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in summary.items()}}, f, indent=1)
+        with open(os.environ.get("T4S_BREAKDOWN", "gpurun_out/step_breakdown.json"), "w") as f:
+            json.dump({"step_ms": step_ms, "ops": {k: {"launches": v[0], "ms": round(v[1], 4)} for k, v in summary.items()},
+                       "gemm_tflops": {k: {"launches": v[0], "ms": round(v[1], 4), "tflops": round(v[2] / v[1] / 1e9, 1)}
+                                       for k, v in sorted(shapes.items(), key=lambda kv: -kv[1][1])}}, f, indent=1)
     except OSError:
         pass
     # front end alone, L2 flushed between iterations

@@ -15,7 +15,7 @@ if [ "${T4S_REF:-0}" = "1" ]; then
   tail -c 1500 gpurun_out/bench_ref_${TAG}.json
 fi
 if [ "${T4S_NCU_LIST:-0}" = "1" ]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv \
+  T4S_BREAKDOWN=/dev/null timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_${TAG}.csv \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_list_${TAG}.log 2>&1
   echo "ncu list rc=$?"
 fi

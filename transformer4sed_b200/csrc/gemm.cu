@@ -54,39 +54,57 @@ struct Cfg {
   static constexpr int kStages = (BN == 256) ? 4 : 6;
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmem = 1024 /*align slack*/ + kStages * kStage + 256 /*barriers*/;
+  // staged epilogue: per epilogue warp two 2 KB SWIZZLE_64B boxes (32 rows x 32 bf16) for TMA tile stores
+  static constexpr int kStageOff = kStages * kStage + 512;
+  static constexpr int kSmemStaged = 1024 + kStageOff + kEpiWarps * 2 * 2048;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-// x * Phi(x) with erfc from Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7 on Phi, i.e. far below bf16 resolution): 2 MUFU + ~12 FP32
-// instructions instead of erff's ~30, which made the fc1 epilogue the bottleneck.  Used only when the output is bf16.
-__device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-  const float half_erfc = 0.5f * poly * t * e;           // 0.5 * erfc(|x|/sqrt 2) = Phi(-|x|)
-  return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
+// ---- bf16-output GELU / GELU' on packed fp32 pairs (FFMA2 / FMUL2 / FADD2: two lanes per issue slot) ---------------------------
+// Phi(-a) = exp2(-q(a)), q a degree-5 polynomial fitted to -log2(Phi(-a)) on [0, 6.5] (monotone beyond it): |error| of
+// x*Phi(x) < 7e-7 absolute and < 3.3e-3 of the value down to x = -4, i.e. below bf16 resolution.  One MUFU and 4.5 issue slots
+// per element; the Abramowitz-Stegun erfc it replaces cost 2 MUFU + ~15 slots and made the fc1 / fc2-dgrad epilogues the
+// bottleneck of those GEMMs (tensor pipe 30 % active).  Used only when the output is bf16; fp32 outputs keep erff.
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ float ex2f(float x) { float e; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x)); return e; }
+#define T4S_K2(c) pack2(c, c)
+// -q(a) - shift: exp2 of it is Phi(-a) * 2^-shift
+__device__ __forceinline__ uint64_t neg_log2_tail(uint64_t a, float c0) {
+  uint64_t q = fma2(a, T4S_K2(-4.73970344e-04f), T4S_K2(7.08921017e-03f));
+  q = fma2(q, a, T4S_K2(-5.18392308e-02f));
+  q = fma2(q, a, T4S_K2(-4.59979016e-01f));
+  q = fma2(q, a, T4S_K2(-1.15079439e+00f));
+  return fma2(q, a, T4S_K2(c0));
 }
-
-// d/dx [x Phi(x)] = Phi(x) + x phi(x), same erfc approximation (shares the exponential)
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
-  const float half_erfc = 0.5f * poly * t * e;
-  const float cdf = x >= 0.f ? 1.0f - half_erfc : half_erfc;
-  return fmaf(x * 0.3989422804014327f, e, cdf);
+// x Phi(x) = relu(x) - a Phi(-a),  a = |x|
+__device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
+  const uint64_t a = pack2(fabsf(x0), fabsf(x1)), na = pack2(-fabsf(x0), -fabsf(x1)), x = pack2(x0, x1);
+  float q0, q1;
+  unpack2(neg_log2_tail(a, -1.00003661e+00f + 1.0f), q0, q1);   // exp2 -> 2 Phi(-a)
+  const uint64_t e = pack2(ex2f(q0), ex2f(q1));
+  const uint64_t y = mul2(fma2(na, e, add2(x, a)), T4S_K2(0.5f));
+  unpack2(y, x0, x1);
+}
+// d/dx [x Phi(x)] = Phi(x) + x phi(x);  Phi(x) = 0.5 + copysign(0.5 - Phi(-a), x).  Multiplies g in place.
+__device__ __forceinline__ void gelu_grad_fast2(float h0, float h1, float& g0, float& g1) {
+  const uint64_t a = pack2(fabsf(h0), fabsf(h1)), x = pack2(h0, h1);
+  float q0, q1;
+  unpack2(neg_log2_tail(a, -1.00003661e+00f), q0, q1);
+  const uint64_t tail = pack2(ex2f(q0), ex2f(q1));                 // Phi(-a)
+  float u0, u1;
+  unpack2(fma2(tail, T4S_K2(-1.0f), T4S_K2(0.5f)), u0, u1);        // 0.5 - Phi(-a) >= 0
+  u0 = __uint_as_float(__float_as_uint(u0) | (__float_as_uint(h0) & 0x80000000u));
+  u1 = __uint_as_float(__float_as_uint(u1) | (__float_as_uint(h1) & 0x80000000u));
+  const uint64_t cdf = add2(pack2(u0, u1), T4S_K2(0.5f));
+  float w0, w1;
+  unpack2(mul2(mul2(a, T4S_K2(-0.72134752044448170f)), a), w0, w1);   // -a^2 / 2 in log2 units
+  const uint64_t pdf = pack2(ex2f(w0), ex2f(w1));
+  const uint64_t d = fma2(mul2(x, T4S_K2(0.3989422804014327f)), pdf, cdf);
+  unpack2(mul2(pack2(g0, g1), d), g0, g1);
 }
 __device__ __forceinline__ float gelu_grad_erf(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.3989422804014327f * __expf(-0.5f * x * x);
@@ -223,7 +241,7 @@ __device__ __forceinline__ void epilogue_chunk(const Args& a, const uint32_t (&v
   if (a.act == T4S_ACT_GELU) {
     if (a.C.dtype == T4S_BF16) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] = gelu_fast(x[i]);
+      for (int i = 0; i < 32; i += 2) gelu_fast2(x[i], x[i + 1]);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] = gelu_erf(x[i]);
@@ -234,7 +252,7 @@ __device__ __forceinline__ void epilogue_chunk(const Args& a, const uint32_t (&v
     load32(a.res, r_row + gcol, nvalid, h);
     if (a.C.dtype == T4S_BF16) {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) x[i] *= gelu_grad_fast(h[i]);
+      for (int i = 0; i < 32; i += 2) gelu_grad_fast2(h[i], h[i + 1], x[i], x[i + 1]);
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) x[i] *= gelu_grad_erf(h[i]);
@@ -243,6 +261,80 @@ __device__ __forceinline__ void epilogue_chunk(const Args& a, const uint32_t (&v
     add32(a.res, r_row + gcol, nvalid, x);
   }
   store32(a.C, c_row + gcol, nvalid, x);
+}
+
+// Staged variant of epilogue_chunk for bf16 outputs: the 32 x 32 chunk of a warp is written to a SWIZZLE_64B shared-memory box
+// (16-byte stores, conflict free) and leaves through ONE TMA tile store, instead of 4 STG.128 per thread that each touch 32
+// different rows (32 L1 wavefronts per instruction: with two outputs the fc1 epilogue needed more LSU cycles than the tile's
+// MMAs).  Ragged edges are clipped by the tensor map.  `seq` alternates the warp's two staging boxes; lane 0 owns the bulk groups.
+__device__ __forceinline__ void stage_store(const CUtensorMap* map, unsigned char* boxes, uint32_t& seq, int lane, const float (&x)[32],
+                                            int gcol, int row0, int z1, int z2) {
+  unsigned char* box = boxes + (seq & 1) * 2048;
+  ++seq;
+  if (lane == 0) ptx::bulk_wait_read_1();   // the store that last used this box has drained it
+  __syncwarp();
+  uint4* dst = reinterpret_cast<uint4*>(box + lane * 64);
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 u;
+    __nv_bfloat162 t;
+    t = __floats2bfloat162_rn(x[8 * i], x[8 * i + 1]);     u.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(x[8 * i + 2], x[8 * i + 3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(x[8 * i + 4], x[8 * i + 5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __floats2bfloat162_rn(x[8 * i + 6], x[8 * i + 7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+    dst[i ^ sw] = u;
+  }
+  ptx::fence_proxy_async();
+  __syncwarp();
+  if (lane == 0) {
+    ptx::tma_store_4d(map, box, gcol, row0, z1, z2);
+    ptx::bulk_commit();
+  }
+}
+
+// warp-uniform control flow (every lane stages its row; rows / columns outside the matrix are clipped by the TMA store)
+__device__ __forceinline__ void epilogue_chunk_staged(const Args& a, const CUtensorMap* mapC, const CUtensorMap* mapX, unsigned char* boxes,
+                                                      uint32_t& seq, int lane, const uint32_t (&v)[32], int row0, int gcol, long long r_row,
+                                                      int z1, int z2) {
+  const int nvalid = a.N - gcol;
+  if (row0 >= a.M || nvalid <= 0) return;
+  const bool row_ok = row0 + lane < a.M;
+  float x[32];
+  if (a.bias) {
+    if (a.bias_vec && nvalid >= 32) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + gcol) + i);
+        x[4 * i] = fmaf(a.alpha, __uint_as_float(v[4 * i]), b4.x);
+        x[4 * i + 1] = fmaf(a.alpha, __uint_as_float(v[4 * i + 1]), b4.y);
+        x[4 * i + 2] = fmaf(a.alpha, __uint_as_float(v[4 * i + 2]), b4.z);
+        x[4 * i + 3] = fmaf(a.alpha, __uint_as_float(v[4 * i + 3]), b4.w);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = fmaf(a.alpha, __uint_as_float(v[i]), i < nvalid ? __ldg(a.bias + gcol + i) : 0.f);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] = a.alpha * __uint_as_float(v[i]);
+  }
+  if (a.aux.ptr) stage_store(mapX, boxes, seq, lane, x, gcol, row0, z1, z2);
+  if (a.act == T4S_ACT_GELU) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) gelu_fast2(x[i], x[i + 1]);
+  }
+  if (a.act == T4S_ACT_GELU_GRAD) {
+    float h[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) h[i] = 0.f;
+    if (row_ok) load32(a.res, r_row + gcol, nvalid, h);
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) gelu_grad_fast2(h[i], h[i + 1], x[i], x[i + 1]);
+  } else if (a.res.ptr) {
+    if (row_ok) add32(a.res, r_row + gcol, nvalid, x);
+  }
+  stage_store(mapC, boxes, seq, lane, x, gcol, row0, z1, z2);
 }
 
 // Tile r of a batch -> (m tile, n tile).  Tiles that run concurrently (148 consecutive indices) form a compact
@@ -256,9 +348,10 @@ __device__ __forceinline__ void tile_coords(const Args& a, int r, int& tm, int& 
   tn = g * a.group_n + (rem - tm * width);
 }
 
-template <int BN, bool kTf32, bool kAMn, bool kBMn>
+template <int BN, bool kTf32, bool kAMn, bool kBMn, bool kStaged>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Args a) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+            const __grid_constant__ CUtensorMap tmX, const Args a) {
   using C = Cfg<BN>;
   constexpr int kBK = kTf32 ? 32 : 64;   // K elements per pipeline stage
   constexpr int kRowEl = kTf32 ? 32 : 64; // elements per 128-byte swizzle row
@@ -281,6 +374,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    if (kStaged) {
+      ptx::prefetch_tmap(&tmC);
+      if (a.aux.ptr) ptx::prefetch_tmap(&tmX);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -388,6 +485,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = (warp - 4) >> 2;  // which half of the tile's columns this warp drains
     constexpr int kHalfCols = BN / 2;
     constexpr int kChunks = kHalfCols / 32;
+    unsigned char* boxes = smem + C::kStageOff + (warp - 4) * 4096;   // staged epilogue only
+    uint32_t seq = 0;
     uint32_t ai = 0;
     for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ai) {
       const int zs = (int)(tile / tiles_per_batch);
@@ -422,10 +521,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(&tempty[as]);
         }
-        if (c & 1) epilogue_chunk(a, vb, grow, col_base + 32 * c, c_row, x_row, r_row);
-        else epilogue_chunk(a, va, grow, col_base + 32 * c, c_row, x_row, r_row);
+        if (kStaged) {
+          if (c & 1) epilogue_chunk_staged(a, &tmC, &tmX, boxes, seq, lane, vb, m0 + q * 32, col_base + 32 * c, r_row, z1, z2);
+          else epilogue_chunk_staged(a, &tmC, &tmX, boxes, seq, lane, va, m0 + q * 32, col_base + 32 * c, r_row, z1, z2);
+        } else {
+          if (c & 1) epilogue_chunk(a, vb, grow, col_base + 32 * c, c_row, x_row, r_row);
+          else epilogue_chunk(a, va, grow, col_base + 32 * c, c_row, x_row, r_row);
+        }
       }
     }
+    if (kStaged && lane == 0) ptx::bulk_wait_all();   // the staging boxes must outlive the last stores
   }
 
   ptx::tc_fence_before();
@@ -503,8 +608,25 @@ static MatArg mat_arg(const T4sMatrix& m) {
   return o;
 }
 
+// 4-D store map (col, row, b1, b2) over a bf16 output, box 32 x 32, SWIZZLE_64B.  Returns false when the matrix cannot be
+// described (alignment / strides): the caller then uses the register-direct epilogue.
+static bool make_store_map(CUtensorMap* m, const T4sMatrix& c, int M, int N, int nb1, int nb2) {
+  if (!c.ptr || c.dtype != T4S_BF16 || (reinterpret_cast<uintptr_t>(c.ptr) & 15) || (c.ld * 2) % 16 || c.ld < N) return false;
+  const long long s1 = nb1 > 1 ? c.stride1 : c.ld, s2 = nb2 > 1 ? c.stride2 : c.ld;
+  if (s1 <= 0 || s2 <= 0 || (s1 * 2) % 16 || (s2 * 2) % 16) return false;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  ensure_context();
+  cuuint64_t dims[4] = {(cuuint64_t)N, (cuuint64_t)M, (cuuint64_t)nb1, (cuuint64_t)nb2};
+  cuuint64_t strides[3] = {(cuuint64_t)(c.ld * 2), (cuuint64_t)(s1 * 2), (cuuint64_t)(s2 * 2)};
+  cuuint32_t box[4] = {32, 32, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, c.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int BN, bool kTf32, bool kAMn, bool kBMn>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, Args& a, cudaStream_t st) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, const CUtensorMap* tmX, Args& a, cudaStream_t st) {
   a.tiles_m = (a.M + kBM - 1) / kBM;
   a.tiles_n = (a.N + BN - 1) / BN;
   a.group_n = std::min(a.tiles_n, 16);
@@ -518,9 +640,18 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, Args& a, cudaS
   }
   a.total_tiles = (long long)a.tiles_m * a.tiles_n * a.nb1 * a.nb2 * a.split_k;
   const int grid = (int)std::min<long long>(a.total_tiles, sm_count());
-  auto kern = gemm_kernel<BN, kTf32, kAMn, kBMn>;
+  if constexpr (!kTf32) {
+    if (tmC) {
+      auto kern = gemm_kernel<BN, kTf32, kAMn, kBMn, true>;
+      T4S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemStaged));
+      kern<<<grid, kThreads, Cfg<BN>::kSmemStaged, st>>>(tmA, tmB, *tmC, tmX ? *tmX : *tmC, a);
+      T4S_LAUNCH_CHECK();
+      return T4S_OK;
+    }
+  }
+  auto kern = gemm_kernel<BN, kTf32, kAMn, kBMn, false>;
   T4S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
-  kern<<<grid, kThreads, Cfg<BN>::kSmem, st>>>(tmA, tmB, a);
+  kern<<<grid, kThreads, Cfg<BN>::kSmem, st>>>(tmA, tmB, tmA, tmA, a);
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }
@@ -559,12 +690,21 @@ extern "C" int t4s_gemm(const T4sGemm* g, void* stream) {
   T4S_REQUIRE(a.split_k == 1 || (g->c_split_stride > 0 && !g->bias && !g->residual.ptr && !g->aux.ptr && g->act == T4S_ACT_NONE),
               "t4s_gemm: split_k needs c_split_stride and a plain epilogue");
   cudaStream_t st = t4s::as_stream(stream);
+  // bf16 outputs of un-split GEMMs leave through TMA tile stores (staged epilogue) whenever the layout allows it
+  CUtensorMap tmCs, tmXs;
+  const CUtensorMap *pC = nullptr, *pX = nullptr;
+  if (!tf32 && a.split_k == 1 && g->M >= 32 && make_store_map(&tmCs, g->C, g->M, g->N, g->nb1, g->nb2) &&
+      (!g->aux.ptr || make_store_map(&tmXs, g->aux, g->M, g->N, g->nb1, g->nb2)) &&
+      !(g->aux.ptr && g->residual.ptr)) {
+    pC = &tmCs;
+    pX = g->aux.ptr ? &tmXs : nullptr;
+  }
   const int variant = (tf32 ? 4 : 0) | (g->A.mn_major ? 2 : 0) | (g->B.mn_major ? 1 : 0);
 #define T4S_GEMM_CASE(V, TF, AM, BM_)                                         \
   case V:                                                                     \
-    if (BN == 256) return launch<256, TF, AM, BM_>(tmA, tmB, a, st);          \
-    if (BN == 128) return launch<128, TF, AM, BM_>(tmA, tmB, a, st);          \
-    return launch<64, TF, AM, BM_>(tmA, tmB, a, st);
+    if (BN == 256) return launch<256, TF, AM, BM_>(tmA, tmB, pC, pX, a, st);  \
+    if (BN == 128) return launch<128, TF, AM, BM_>(tmA, tmB, pC, pX, a, st);  \
+    return launch<64, TF, AM, BM_>(tmA, tmB, pC, pX, a, st);
   switch (variant) {
     T4S_GEMM_CASE(0, false, false, false)
     T4S_GEMM_CASE(1, false, false, true)

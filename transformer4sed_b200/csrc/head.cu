@@ -242,6 +242,222 @@ __global__ void __launch_bounds__(256) attnpool_bwd_kernel(const T* __restrict__
   }
 }
 
+
+// ---- vectorised, head-split variant (the AT branch: 64 items x 1188 keys would otherwise occupy 64 of the 148 SMs) -------------
+// Block = (item, head group); heads are independent, so no cross-block merge is needed.  16-byte loads along the channel
+// dimension; lanes that share a head reduce by shuffles; keys are strided over the warps and the per-warp partial sums are
+// combined through shared memory in warp order (deterministic).
+template <typename T> struct PoolVec;
+template <> struct PoolVec<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 v = __bfloat1622float2(h[i]); f[2 * i] = v.x; f[2 * i + 1] = v.y; }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint4 r;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = r;
+  }
+};
+template <> struct PoolVec<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float (&f)[4]) {
+    const float4 r = *reinterpret_cast<const float4*>(p);
+    f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&f)[4]) { *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]); }
+};
+constexpr int kPoolMaxChunks = 6;   // 16-byte chunks per lane: head-group width <= 32 * 6 chunks
+
+// s_out[h_local][j] = vec_h . m[j, h] for the block's heads; `off` selects k (0) or v (C) inside the [k | v] rows
+template <typename T>
+__device__ __forceinline__ void pool_scores(const T* __restrict__ kvb, int off, int c0, int Cb, int hd, int K, int C, const float* s_vec,
+                                            float* s_out) {
+  using V = PoolVec<T>;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const int nch = Cb / V::N, group = hd / V::N;   // lanes per head (power of two <= 32)
+  for (int j = warp; j < K; j += nw) {
+    const T* row = kvb + (long long)j * 2 * C + off + c0;
+    for (int v0 = 0; v0 < nch; v0 += 32) {
+      const int v = v0 + lane;
+      float acc = 0.f;
+      if (v < nch) {
+        float f[V::N];
+        V::load(row + v * V::N, f);
+#pragma unroll
+        for (int e = 0; e < V::N; ++e) acc += f[e] * s_vec[v * V::N + e];
+      }
+      for (int o = group >> 1; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (v < nch && (lane & (group - 1)) == 0) s_out[(v / group) * K + j] = acc;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) attnpool_fwd_vec_kernel(const T* __restrict__ kv, const float* __restrict__ q, T* __restrict__ ctx,
+                                                               float* __restrict__ probs, int K, int C, int H, long long item_stride, int hsplit) {
+  using V = PoolVec<T>;
+  extern __shared__ float sm[];
+  const int bp = blockIdx.x / hsplit, hs = blockIdx.x % hsplit;
+  const int hd = C / H, Hb = H / hsplit, Cb = Hb * hd, c0 = hs * Cb, nw = blockDim.x >> 5;
+  float* s_p = sm;                 // [Hb][K]
+  float* s_q = s_p + Hb * K;       // [Cb]
+  float* s_part = s_q + Cb;        // [nw][Cb]
+  const T* kvb = kv + (long long)bp * item_stride;
+  for (int c = threadIdx.x; c < Cb; c += blockDim.x) s_q[c] = q[c0 + c];
+  __syncthreads();
+  pool_scores<T>(kvb, 0, c0, Cb, hd, K, C, s_q, s_p);
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int h = warp; h < Hb; h += nw) {
+    float mx = -INFINITY;
+    for (int j = lane; j < K; j += 32) mx = fmaxf(mx, s_p[h * K + j]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < K; j += 32) {
+      const float e = __expf(s_p[h * K + j] - mx);
+      s_p[h * K + j] = e;
+      sum += e;
+    }
+    const float inv = 1.0f / warp_sum(sum);
+    for (int j = lane; j < K; j += 32) {
+      const float p = s_p[h * K + j] * inv;
+      s_p[h * K + j] = p;
+      if (probs) probs[((long long)bp * H + hs * Hb + h) * K + j] = p;
+    }
+  }
+  __syncthreads();
+  const int nch = Cb / V::N;
+  float acc[kPoolMaxChunks][V::N];
+#pragma unroll
+  for (int i = 0; i < kPoolMaxChunks; ++i)
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) acc[i][e] = 0.f;
+  for (int j = warp; j < K; j += nw) {
+    const T* row = kvb + (long long)j * 2 * C + C + c0;
+#pragma unroll
+    for (int i = 0; i < kPoolMaxChunks; ++i) {
+      const int v = i * 32 + lane;
+      if (v < nch) {
+        float f[V::N];
+        V::load(row + v * V::N, f);
+        const float p = s_p[((v * V::N) / hd) * K + j];
+#pragma unroll
+        for (int e = 0; e < V::N; ++e) acc[i][e] += p * f[e];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kPoolMaxChunks; ++i) {
+    const int v = i * 32 + lane;
+    if (v < nch)
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) s_part[warp * Cb + v * V::N + e] = acc[i][e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cb; c += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += s_part[w * Cb + c];
+    ctx[(long long)bp * C + c0 + c] = from_f32<T>(t);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) attnpool_bwd_vec_kernel(const T* __restrict__ kv, const float* __restrict__ q, const float* __restrict__ probs,
+                                                               const T* __restrict__ dctx, T* __restrict__ dkv, float* __restrict__ dq_part,
+                                                               int K, int C, int H, long long item_stride, int hsplit) {
+  using V = PoolVec<T>;
+  extern __shared__ float sm[];
+  const int bp = blockIdx.x / hsplit, hs = blockIdx.x % hsplit;
+  const int hd = C / H, Hb = H / hsplit, Cb = Hb * hd, c0 = hs * Cb, nw = blockDim.x >> 5;
+  float* s_ds = sm;                // [Hb][K]: dp, then ds
+  float* s_pr = s_ds + Hb * K;     // [Hb][K]: probabilities of this head group
+  float* s_q = s_pr + Hb * K;      // [Cb]
+  float* s_dc = s_q + Cb;          // [Cb]
+  float* s_part = s_dc + Cb;       // [nw][Cb]
+  const T* kvb = kv + (long long)bp * item_stride;
+  T* dkvb = dkv + (long long)bp * item_stride;
+  const float* pb = probs + ((long long)bp * H + hs * Hb) * K;
+  for (int c = threadIdx.x; c < Cb; c += blockDim.x) {
+    s_q[c] = q[c0 + c];
+    s_dc[c] = to_f32<T>(dctx[(long long)bp * C + c0 + c]);
+  }
+  for (int i = threadIdx.x; i < Hb * K; i += blockDim.x) s_pr[i] = pb[i];
+  __syncthreads();
+  pool_scores<T>(kvb, C, c0, Cb, hd, K, C, s_dc, s_ds);   // dp[h][j] = dctx_h . v[j, h]
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int h = warp; h < Hb; h += nw) {
+    float dot = 0.f;
+    for (int j = lane; j < K; j += 32) dot += s_pr[h * K + j] * s_ds[h * K + j];
+    dot = warp_sum(dot);
+    for (int j = lane; j < K; j += 32) s_ds[h * K + j] = s_pr[h * K + j] * (s_ds[h * K + j] - dot);
+  }
+  __syncthreads();
+  const int nch = Cb / V::N;
+  float acc[kPoolMaxChunks][V::N];
+#pragma unroll
+  for (int i = 0; i < kPoolMaxChunks; ++i)
+#pragma unroll
+    for (int e = 0; e < V::N; ++e) acc[i][e] = 0.f;
+  for (int j = warp; j < K; j += nw) {
+    const long long ro = (long long)j * 2 * C + c0;
+#pragma unroll
+    for (int i = 0; i < kPoolMaxChunks; ++i) {
+      const int v = i * 32 + lane;
+      if (v < nch) {
+        const int c = v * V::N, h = c / hd;
+        const float ds = s_ds[h * K + j], p = s_pr[h * K + j];
+        float f[V::N], dk[V::N], dv[V::N];
+        V::load(kvb + ro + c, f);
+#pragma unroll
+        for (int e = 0; e < V::N; ++e) {
+          acc[i][e] += ds * f[e];
+          dk[e] = ds * s_q[c + e];
+          dv[e] = p * s_dc[c + e];
+        }
+        V::store(dkvb + ro + c, dk);
+        V::store(dkvb + ro + C + c, dv);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kPoolMaxChunks; ++i) {
+    const int v = i * 32 + lane;
+    if (v < nch)
+#pragma unroll
+      for (int e = 0; e < V::N; ++e) s_part[warp * Cb + v * V::N + e] = acc[i][e];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < Cb; c += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += s_part[w * Cb + c];
+    dq_part[(long long)bp * C + c0 + c] = t;
+  }
+}
+
+// Head groups per item for the vectorised kernels, or 0 when the shape needs the generic kernel.
+static int pool_hsplit(int items, int K, int C, int H, int dtype, const void* kv, const void* other, long long item_stride) {
+  const int vec = dtype == T4S_BF16 ? 8 : 4, hd = C / H, group = hd / vec;
+  if (hd % vec || group < 1 || group > 32 || (group & (group - 1))) return 0;
+  if (((uintptr_t)kv | (uintptr_t)other) % 16 || item_stride % vec || (2LL * C) % vec) return 0;
+  int best = 0;
+  for (int s = 1; s <= H; ++s) {
+    if (H % s) continue;
+    const int Cb = (H / s) * hd;
+    if (Cb / vec > 32 * kPoolMaxChunks) continue;
+    if (best && Cb / vec < 24) break;   // keep at least 24 of the 32 lanes busy
+    best = s;
+    if ((long long)items * s >= 2LL * sm_count()) break;
+  }
+  return best;
+}
+
 static int grid_for(long long n, int threads = 256) {
   return (int)std::max<long long>(1, std::min<long long>((n + threads - 1) / threads, (long long)sm_count() * 8));
 }
@@ -335,9 +551,25 @@ int t4s_attnpool_fwd(const void* kv, const float* q, void* ctx, float* probs, in
                      int dtype, void* stream) {
   if (item_stride <= 0) item_stride = (int64_t)keys * 2 * dim;
   T4S_REQUIRE(kv && q && ctx && items > 0 && keys > 0 && heads > 0 && dim % heads == 0, "t4s_attnpool_fwd: bad arguments");
+  cudaStream_t st = t4s::as_stream(stream);
+  if (const int hsplit = pool_hsplit(items, keys, dim, heads, dtype, kv, ctx, item_stride)) {
+    const int Hb = heads / hsplit, Cb = Hb * (dim / heads);
+    const size_t vsmem = ((size_t)Hb * keys + Cb + 8 * (size_t)Cb) * sizeof(float);
+    if (vsmem <= 200 * 1024) {
+      if (dtype == T4S_F32) {
+        T4S_CUDA(cudaFuncSetAttribute(attnpool_fwd_vec_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+        attnpool_fwd_vec_kernel<float><<<items * hsplit, 256, vsmem, st>>>((const float*)kv, q, (float*)ctx, probs, keys, dim, heads, item_stride, hsplit);
+      } else {
+        T4S_CUDA(cudaFuncSetAttribute(attnpool_fwd_vec_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+        attnpool_fwd_vec_kernel<__nv_bfloat16><<<items * hsplit, 256, vsmem, st>>>((const __nv_bfloat16*)kv, q, (__nv_bfloat16*)ctx, probs, keys, dim,
+                                                                                  heads, item_stride, hsplit);
+      }
+      T4S_LAUNCH_CHECK();
+      return T4S_OK;
+    }
+  }
   const size_t smem = ((size_t)heads * keys + dim) * sizeof(float);
   T4S_REQUIRE(smem <= 200 * 1024, "t4s_attnpool_fwd: heads*keys too large for shared memory");
-  cudaStream_t st = t4s::as_stream(stream);
   if (dtype == T4S_F32) {
     T4S_CUDA(cudaFuncSetAttribute(attnpool_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attnpool_fwd_kernel<float><<<items, 256, smem, st>>>((const float*)kv, q, (float*)ctx, probs, keys, dim, heads, item_stride);
@@ -353,9 +585,26 @@ int t4s_attnpool_bwd(const void* kv, const float* q, const float* probs, const v
                      int dim, int heads, int64_t item_stride, int dtype, void* stream) {
   if (item_stride <= 0) item_stride = (int64_t)keys * 2 * dim;
   T4S_REQUIRE(kv && q && probs && dctx && dkv && dq_part && items > 0 && keys > 0 && heads > 0 && dim % heads == 0, "t4s_attnpool_bwd: bad arguments");
+  cudaStream_t st = t4s::as_stream(stream);
+  if (const int hsplit = pool_hsplit(items, keys, dim, heads, dtype, kv, dkv, item_stride)) {
+    const int Hb = heads / hsplit, Cb = Hb * (dim / heads);
+    const size_t vsmem = (2 * (size_t)Hb * keys + 2 * Cb + 8 * (size_t)Cb) * sizeof(float);
+    if (vsmem <= 200 * 1024 && (uintptr_t)dctx % 16 == 0) {
+      if (dtype == T4S_F32) {
+        T4S_CUDA(cudaFuncSetAttribute(attnpool_bwd_vec_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+        attnpool_bwd_vec_kernel<float><<<items * hsplit, 256, vsmem, st>>>((const float*)kv, q, probs, (const float*)dctx, (float*)dkv, dq_part, keys,
+                                                                          dim, heads, item_stride, hsplit);
+      } else {
+        T4S_CUDA(cudaFuncSetAttribute(attnpool_bwd_vec_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+        attnpool_bwd_vec_kernel<__nv_bfloat16><<<items * hsplit, 256, vsmem, st>>>((const __nv_bfloat16*)kv, q, probs, (const __nv_bfloat16*)dctx,
+                                                                                  (__nv_bfloat16*)dkv, dq_part, keys, dim, heads, item_stride, hsplit);
+      }
+      T4S_LAUNCH_CHECK();
+      return T4S_OK;
+    }
+  }
   const size_t smem = ((size_t)heads * keys + 2 * dim) * sizeof(float);
   T4S_REQUIRE(smem <= 200 * 1024, "t4s_attnpool_bwd: heads*keys too large for shared memory");
-  cudaStream_t st = t4s::as_stream(stream);
   if (dtype == T4S_F32) {
     T4S_CUDA(cudaFuncSetAttribute(attnpool_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attnpool_bwd_kernel<float><<<items, 256, smem, st>>>((const float*)kv, q, probs, (const float*)dctx, (float*)dkv, dq_part, keys, dim, heads, item_stride);

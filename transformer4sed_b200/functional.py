@@ -373,6 +373,59 @@ def layer_norm(x, gamma, beta, eps=1e-5, in_scale=1.0, skip=0):
     return _LayerNorm.apply(x, gamma, beta, float(eps), float(in_scale), int(skip))
 
 
+class _LayerNormRes(torch.autograd.Function):
+    """Pre-norm residual fan-out as ONE node: (y, x_res) = (LN(x), x).  The sub-layer consumes y and adds x_res back in its GEMM
+    epilogue; in the backward the gradient of the residual branch is added inside the LayerNorm-backward kernel (`dx_add`), so
+    autograd never launches an element-wise add for the fan-out of x (24 adds of [B, N, D] per MAT-SED step)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        rows = x.numel() // C
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib_call("t4s_layernorm_fwd", _p(x), _p(gamma.detach()), _p(beta.detach()), _p(y), _p(mean), _p(rstd), rows, C, eps, 1.0,
+                      ops.dtype_code(x.dtype), 0, 0, _st())
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.cfg = (rows, C)
+        return y, x
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        rows, C = ctx.cfg
+        dev = x.device
+        if dy is None:
+            return dres, None, None, None
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = convert(dy, torch.empty(dy.shape, dtype=x.dtype, device=dev))
+        if dres is not None:
+            dres = dres.contiguous()
+            if dres.dtype != x.dtype:
+                dres = convert(dres, torch.empty(dres.shape, dtype=x.dtype, device=dev))
+        lib = _lib.load()
+        with torch.cuda.device(dev):
+            dx = torch.empty_like(x)
+            want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+            dg = torch.empty(C, dtype=torch.float32, device=dev) if want else None
+            db = torch.empty(C, dtype=torch.float32, device=dev) if want else None
+            nbytes = lib.t4s_layernorm_bwd_workspace(rows, C) if want else 0
+            ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
+            _lib_call("t4s_layernorm_bwd", _p(dy), _p(x), _p(gamma.detach()), _p(mean), _p(rstd), _p(dres), _p(dx), _p(dg), _p(db), _p(ws),
+                      nbytes, rows, C, 1.0, ops.dtype_code(x.dtype), 0, 0, _st())
+        return dx, dg, db, None
+
+
+def layer_norm_res(x, gamma, beta, eps=1e-5):
+    """(LN(x), x): use the second output as the residual operand of the sub-layer that consumes the first."""
+    return _LayerNormRes.apply(x, gamma, beta, float(eps))
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Multi-head self-attention on a fused qkv buffer [B, N, 3*D]      reference: passt.py:330-341
 # ------------------------------------------------------------------------------------------------------------------

@@ -92,9 +92,10 @@ class Block(nn.Module):
 
     def forward(self, x, att_mask=None):
         # x = x + attn(norm1(x)); x = x + mlp(norm2(x))   (passt.py:360-363); residual adds ride in the GEMM epilogues
-        x = self.attn(F.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps), att_mask, residual=x)
-        x = self.mlp(F.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps), residual=x)
-        return x
+        y, res = F.layer_norm_res(x, self.norm1.weight, self.norm1.bias, self.norm1.eps)
+        x = self.attn(y, att_mask, residual=res)
+        y, res = F.layer_norm_res(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        return self.mlp(y, residual=res)
 
 
 class PaSST(nn.Module):

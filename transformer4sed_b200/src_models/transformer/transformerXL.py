@@ -85,5 +85,5 @@ class TransformerXL(nn.Module):
             raise NotImplementedError("decoder_win_len attention masks are unused by the shipped configs")
         x = F.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, in_scale=in_scale)
         x = self.attn(x, pos_emb, residual=x)           # residual from the NORMALISED input (upstream semantics)
-        x = self.mlp(F.layer_norm(x, self.norm2.weight, self.norm2.bias, self.norm2.eps), residual=x)
-        return x
+        y, res = F.layer_norm_res(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
+        return self.mlp(y, residual=res)
