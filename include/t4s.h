@@ -278,6 +278,40 @@ size_t t4s_mask_rows_bwd_workspace(int64_t rows, int dim);
 int t4s_mask_rows_bwd(const void* dout, const unsigned char* kind, const int64_t* src, const int64_t* copy_rows, int n_copy_rows, void* dx,
                       float* d_token, float* ws, size_t ws_bytes, int64_t rows, int dim, int dtype, void* stream);
 
+/* ---- PMAM / DASM CNN branch and heads (csrc/cnn.cu) -----------------------------------------------------------------------
+ * src/models/cnn/base.py:33-113 (CNN: Conv2d 3x3 -> BatchNorm2d(eps 1e-3, momentum .99) -> ContextGating -> Dropout -> AvgPool2d),
+ * src/models/cnn_transformer/passt_cnn.py:52-62 (merge with the transformer features), recipes/desed/pmam/train.py:82-87 (prototype
+ * head).  Activations are channels-last [B, H, W, C]; the convolutions and the gating Linear run as t4s_gemm on [pixels, channels]. */
+/* col [(b,h,w), k_padded]: column (ky*3+kx)*C + c = in[b, h+ky-1, w+kx-1, c] (0 outside); in is addressed by element strides
+ * (channel stride 1), so a [B, F, T] mel image can be read as [B, T, F, 1] in place. */
+int t4s_im2col3x3(const void* in, int in_dtype, int64_t stride_b, int64_t stride_h, int64_t stride_w, void* col, int col_dtype, int batch,
+                  int height, int width, int channels, int k_padded, void* stream);
+int t4s_col2im3x3(const void* dcol, void* din, int dtype, int batch, int height, int width, int channels, int k_padded, void* stream);
+size_t t4s_chan_stats_workspace(int64_t rows, int channels);
+/* x, y [rows, channels]; training != 0: batch statistics (+ running-statistics update when the pointers are given), else running
+ * statistics.  mean / rstd [channels] are outputs (kept for the backward). */
+int t4s_batchnorm_fwd(const void* x, void* y, int dtype, int64_t rows, int channels, const float* gamma, const float* beta, float* running_mean,
+                      float* running_var, float eps, float momentum, int training, float* mean, float* rstd, float* ws, size_t ws_bytes,
+                      void* stream);
+int t4s_batchnorm_bwd(const void* dy, const void* x, int dtype, int64_t rows, int channels, const float* gamma, const float* mean, const float* rstd,
+                      int training, void* dx, float* dgamma, float* dbeta, float* ws, size_t ws_bytes, void* stream);
+/* ContextGating product with optional inverted dropout: out = y * sigmoid(lin) * keep(seed, i) / (1 - p) */
+int t4s_gate_fwd(const void* y, const void* lin, void* out, size_t n, float dropout_p, uint64_t seed, int dtype, void* stream);
+int t4s_gate_bwd(const void* dout, const void* y, const void* lin, void* dy, void* dlin, size_t n, float dropout_p, uint64_t seed, int dtype,
+                 void* stream);
+int t4s_avgpool_fwd(const void* x, void* out, int dtype, int batch, int height, int width, int channels, int pool_h, int pool_w, void* stream);
+int t4s_avgpool_bwd(const void* dout, void* dx, int dtype, int batch, int height, int width, int channels, int pool_h, int pool_w, void* stream);
+/* out = a + w[0] * b (w: learnable scalar in device memory); backward: db = w dout (optional), dw = <dout, b>; ws: T4S_SCALE_ADD_BLOCKS floats */
+#define T4S_SCALE_ADD_BLOCKS 256
+int t4s_scale_add_fwd(const void* a, const void* b, const float* w, void* out, size_t n, int dtype, void* stream);
+int t4s_scale_add_bwd(const void* dout, const void* b, const float* w, void* db, float* dw, float* ws, size_t n, int dtype, void* stream);
+/* y = x / max(||x||_2, 1e-12) per row (F.normalize); inv_norm [rows] kept for the backward */
+int t4s_l2norm_fwd(const void* x, void* y, float* inv_norm, int64_t rows, int cols, int dtype, void* stream);
+int t4s_l2norm_bwd(const void* dy, const void* y, const float* inv_norm, void* dx, int64_t rows, int cols, int dtype, void* stream);
+/* p = sigmoid((leaky_relu(s, slope) * 2 - 1) / temperature) */
+int t4s_proto_act_fwd(const float* s, float* p, size_t n, float slope, float temperature, void* stream);
+int t4s_proto_act_bwd(const float* s, const float* p, const float* dp, float* ds, size_t n, float slope, float temperature, void* stream);
+
 /* ---- K6/K7: heads and losses (csrc/head.cu) ------------------------------------------------------------------
  * passt_sed.py:285-296 (sigmoid, pad mask, linear-softmax pool), pooling.py:37-51 (AttentionPooling),
  * recipes/desed/finetune/train.py:166-178 (BCE / MSE), recipes/desed/mlm/mlm_passt/train.py:36-38 (masked MSE). */

@@ -168,6 +168,69 @@ def golden_window(tag, kw, seed, batch):
     print(f"matsed_window_{tag}.npz", offs, "strong_val range", s_val.min().item(), s_val.max().item())
 
 
+def golden_pmam(seed, batch):
+    """PMAM post-pre-training model (config/pmam/post_pretrain.yaml:48-79): PaSST + LoRA, CNN branch, attention f_pool, TXL d=384,
+    MLM head; prototype head + masked BCE of recipes/desed/pmam/train.py:82-112.  (a) eval-mode forward, (b) train-mode
+    forward + backward with conv_dropout = 0 (torch's dropout stream cannot be replayed by another implementation)."""
+    import tempfile
+    import yaml
+    from src.models.cnn_transformer.passt_cnn import PaSST_CNN
+    from src.models.passt.passt import PaSST
+    cfg = yaml.safe_load(open("/root/reference/config/pmam/post_pretrain.yaml"))["PaSST_CNN"]["init_kwargs"]
+    cfg["cnn_param"]["conv_dropout"] = 0.0
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "pretrained_model"))
+        os.chdir(d)
+        try:
+            bb = PaSST(u_patchout=0, s_patchout_t=0, s_patchout_f=0, img_size=(128, 998), patch_size=16, stride=10, in_chans=1,
+                       num_classes=527, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True, distilled=True)
+            torch.save(bb.state_dict(), "pretrained_model/passt-s-f128-p16-s10-ap.476-swa.pt")
+            net = PaSST_CNN(**cfg)
+        finally:
+            os.chdir(cwd)
+    sd = synth_state = synth.synth_state_dict_like(net, seed)
+    net.load_state_dict(sd, strict=True)
+    ext = net.get_feature_extractor().eval()
+    wav = synth.synth_wav(batch, 320000, seed=seed + 1)
+    mel = ext.normalize(ext(wav))
+    protos = torch.nn.functional.normalize(synth.synth_tensor(seed, "prototypes", (30, 768)), dim=-1)
+    labels = synth.synth_strong_labels(batch, 30, 1000, seed + 2)
+    weak_labels = (labels.sum(-1) >= 1).float()
+    dec_in = {}
+    net.decoder.register_forward_pre_hook(lambda m, i: dec_in.__setitem__("x", i[0]))
+
+    def predict(logit):
+        logit = torch.nn.functional.normalize(logit, dim=-1) @ protos.T
+        return torch.sigmoid((torch.nn.functional.leaky_relu(logit, negative_slope=0.2) * 2 - 1) / 0.1)
+
+    out = dict(wav_ck=checksum(wav), mel_ck=checksum(mel), trainable=np.array(sorted(n for n, p in net.named_parameters() if p.requires_grad)),
+               sd_keys=np.array(sorted(sd.keys())),
+               sd_ck=checksum(torch.cat([v.flatten().float() for k, v in sorted(sd.items()) if torch.is_floating_point(v)])))
+    net.eval()     # LoRA merges B A into the weights on eval (lora/layers.py:124-141)
+    torch.manual_seed(seed + 3)
+    with torch.no_grad():
+        pred, other = net(mel)
+    out.update(eval_pred=f32(pred[:, ::8, ::4]), eval_at=f32(other["at_out"]), eval_mask=np.packbits(other["mask_id_seq"].numpy()),
+               eval_fbm=f32(other["frame_before_mask"][:, ::8, ::4]), eval_dec_in=f32(dec_in["x"][:, ::8, ::4]),
+               eval_strong=f32(predict(pred)[:, ::8]))
+    net.train()
+    torch.manual_seed(seed + 4)
+    pred, other = net(mel)
+    m = other["mask_id_seq"]
+    strong = predict(pred)
+    bce = torch.nn.BCELoss()
+    loss = bce(strong[m], labels.transpose(1, 2)[m]) + 0.5 * bce(other["at_out"], weak_labels)
+    loss.backward()
+    gn, gnorm, ghead = grads_summary(net)
+    bn = {k: f32(v) for k, v in net.state_dict().items() if "running_" in k and ("batchnorm0" in k or "batchnorm9" in k)}
+    out.update(train_pred=f32(pred[:, ::8, ::4]), train_at=f32(other["at_out"]), train_mask=np.packbits(m.numpy()),
+               train_loss=np.array(loss.item()), grad_names=gn, grad_norms=gnorm, grad_heads=ghead,
+               train_dec_in=f32(dec_in["x"][:, ::8, ::4]), **{"bn_" + k: v for k, v in bn.items()})
+    np.savez_compressed(os.path.join(OUT, "pmam_base.npz"), **out)
+    print(f"pmam_base.npz loss={loss.item():.6f} masked={m.float().mean().item():.3f} trainable={len(out['trainable'])} grads={len(gn)}")
+
+
 def golden_mlm(tag, kw, seed, batch):
     """MAT-SED pre-train forward (mlm=True): needs the synthetic PaSST checkpoint on disk."""
     import tempfile
@@ -240,7 +303,7 @@ if __name__ == "__main__":
     base = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_adapter=True, decoder="transformerXL",
                 decoder_layer_num=3, decoder_pos_emd_len=1000, mlm=False)  # config/mat-sed/base/finetune2.yaml:53-62
     pre = dict(base, mlm=True, mlm_dict=dict(strategy="block", block_width=10, mask_rate=0.75, out_dim=768))  # pretrain.yaml:39-52
-    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm"]
+    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm", "pmam"]
     if "frontend" in which:
         golden_frontend()
         golden_frontend_16k()
@@ -252,6 +315,8 @@ if __name__ == "__main__":
         golden_model("base", base, seed=4, batch=1)
     if "window" in which:
         golden_window("base", base, seed=8, batch=1)   # out_dim is hard-wired to 768 upstream (encoder_slide_window.py:10)
+    if "pmam" in which:
+        golden_pmam(seed=10, batch=2)
     if "mlm" in which:
         golden_mlm("base", pre, seed=6, batch=2)  # B>1: upstream masking is a silent no-op
         golden_mlm("base", pre, seed=6, batch=1)  # B=1: reshape is a view, masking applies

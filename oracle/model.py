@@ -14,8 +14,16 @@ def layer_norm(x, sd, prefix, eps):
     return F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], eps)
 
 
+LORA_SCALING = 1.0 / 8.0   # lora_alpha / r of the shipped PMAM / DASM configs (config/pmam/post_pretrain.yaml:61-63)
+
+
 def linear(x, sd, prefix, bias=True):
-    return F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"] if bias else None)
+    """nn.Linear, or lora.Linear when the state dict carries lora_A / lora_B for this layer (lora/layers.py:143-153, un-merged:
+    W x + (x A^T B^T) * alpha / r)."""
+    y = F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"] if bias else None)
+    if prefix + ".lora_A" in sd:
+        y = y + (x @ sd[prefix + ".lora_A"].transpose(0, 1) @ sd[prefix + ".lora_B"].transpose(0, 1)) * LORA_SCALING
+    return y
 
 
 # ------------------------------------------------------------------------------------------------
@@ -271,6 +279,48 @@ def mat_sed_forward(mel, sd, decoder_layers=3, feature_layer=10, f_pool_mode="me
         return mlm_head(y, sd), other
     strong, weak = sed_head(y, sd, temp_w, pad_mask)
     return strong, weak, other
+
+
+# ------------------------------------------------------------------------------------------------
+# PMAM: CNN branch, PaSST_CNN forward, prototype head
+# ------------------------------------------------------------------------------------------------
+def cnn_forward(x, sd, nb_filters, pooling, training=False, p="cnn.cnn.", new_stats=None):
+    """cnn/base.py:33-113 with activation 'cg' (ContextGating :19-30), BatchNorm2d(eps 1e-3, momentum .99), AvgPool2d; dropout
+    is not applied (parity runs use eval mode or conv_dropout=0).  x [B, 1, T, F].  `new_stats` (dict) receives the running
+    statistics a training-mode pass leaves behind."""
+    for i in range(len(nb_filters)):
+        x = F.conv2d(x, sd[f"{p}conv{i}.weight"], sd[f"{p}conv{i}.bias"], padding=1)
+        rm, rv = sd[f"{p}batchnorm{i}.running_mean"].clone(), sd[f"{p}batchnorm{i}.running_var"].clone()
+        x = F.batch_norm(x, rm, rv, sd[f"{p}batchnorm{i}.weight"], sd[f"{p}batchnorm{i}.bias"], training, 0.99, 0.001)
+        if new_stats is not None:
+            new_stats[f"{p}batchnorm{i}.running_mean"], new_stats[f"{p}batchnorm{i}.running_var"] = rm, rv
+        lin = F.linear(x.permute(0, 2, 3, 1), sd[f"{p}cg{i}.linear.weight"], sd[f"{p}cg{i}.linear.bias"]).permute(0, 3, 1, 2)
+        x = x * torch.sigmoid(lin)
+        x = F.avg_pool2d(x, tuple(pooling[i]))
+    return x
+
+
+def passt_cnn_forward(mel, sd, nb_filters, pooling, decoder_layers=3, feature_layer=10, f_pool_mode="attention", decode_ratio=10,
+                      training=False, decoder_input_override=None, stages=None, new_stats=None):
+    """PaSST_CNN.forward (cnn_transformer/passt_cnn.py:32-70), mlm=True, encoder_win=False -> (pred [B,T,out_dim], other)."""
+    feat, frame, Fd, Td = passt_backbone(mel, sd, feature_layer=feature_layer)
+    x = pad_interpolate(f_pool(feat, sd, Fd, Td, f_pool_mode), decode_ratio)
+    cnn_feat = cnn_forward(mel.transpose(1, 2).unsqueeze(1), sd, nb_filters, pooling, training, new_stats=new_stats)
+    cnn_feat = F.interpolate(cnn_feat.squeeze(-1), size=x.shape[1], mode="linear").transpose(1, 2)
+    x = linear(x, sd, "transformer_projector") + sd["merge_weight"] * linear(cnn_feat, sd, "cnn_projector")
+    other = {"frame_before_mask": x}
+    dec_in = x if decoder_input_override is None else decoder_input_override(x, other)
+    y = txl_decoder(dec_in, sd, decoder_layers)
+    other["at_out"] = at_branch(frame, sd)
+    if stages is not None:
+        stages.update(cnn_feat=cnn_feat, frame_before_mask=x, decoder_in=dec_in, decoder_out=y)
+    return mlm_head(y, sd), other
+
+
+def prototype_predict(logit, prototypes, temperature=0.1):
+    """recipes/desed/pmam/train.py:82-87."""
+    s = F.normalize(logit, dim=-1) @ prototypes.T
+    return torch.sigmoid((F.leaky_relu(s, negative_slope=0.2) * 2 - 1) / temperature)
 
 
 def bce(p, y):

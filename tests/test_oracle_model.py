@@ -132,3 +132,60 @@ def test_sliding_window(golden):
         np.testing.assert_allclose(st["x_local"][:, ::4, ::4].numpy(), g["local_train"], rtol=2e-4, atol=2e-5)
         np.testing.assert_allclose(s.numpy(), g["strong_train"], rtol=1e-4, atol=1e-6)
         np.testing.assert_allclose(w.numpy(), g["weak_train"], rtol=1e-4, atol=1e-6)
+
+
+def _pmam_mask(seed, batch):
+    """Replay MlmModule's CPU draws (mask.py:62-100) for config/pmam/post_pretrain.yaml: block masking, rate .8, style (.9, .05, .05)."""
+    torch.manual_seed(seed)
+    noise = torch.rand(batch, 100)
+    mask = M.block_mask_from_noise(noise, 0.8, 10, 1000)
+    probs = torch.rand(batch * 1000)
+    n_rand = int((mask.view(-1) & (probs >= 0.9) & (probs < 0.95)).sum())
+    rand_idx = torch.randint(0, batch * 1000, (n_rand,))
+    return mask, probs, rand_idx
+
+
+def test_pmam_passt_cnn(golden):
+    """Oracle PaSST_CNN (PaSST + LoRA, CNN branch, attention f_pool, TXL d=384, MLM + prototype head) vs the unmodified reference:
+    eval-mode forward, and train-mode forward + loss + gradients of every trainable tensor (conv_dropout = 0)."""
+    g = golden("pmam_base.npz")
+    seed, batch = 10, 2
+    shapes = schema.passt_cnn_shapes()
+    assert sorted(shapes) == [k for k in g["sd_keys"] if not str(k).endswith("num_batches_tracked")]
+    sd = _sd(shapes, seed)
+    np.testing.assert_allclose(checksum(torch.cat([v.flatten() for _, v in sorted(sd.items())])), g["sd_ck"], rtol=1e-12)
+    trainable = set(str(k) for k in g["trainable"])
+    for k, v in sd.items():
+        v.requires_grad_(k in trainable)
+    wav = synth.synth_wav(batch, 320000, seed=seed + 1)
+    mel = F.passt_logmel(wav)
+    np.testing.assert_allclose(checksum(mel), g["mel_ck"], rtol=1e-9)
+    protos = torch.nn.functional.normalize(synth.synth_tensor(seed, "prototypes", (30, 768)), dim=-1)
+    labels = synth.synth_strong_labels(batch, 30, 1000, seed + 2)
+    weak_labels = (labels.sum(-1) >= 1).float()
+
+    def run(mask_seed, training, tag):
+        mask, probs, ridx = _pmam_mask(mask_seed, batch)
+        assert (np.packbits(mask.numpy()) == g[f"{tag}_mask"]).all()
+        st, stats = {}, {}
+        pred, other = M.passt_cnn_forward(mel, sd, schema.PMAM_FILTERS, schema.PMAM_POOLING, training=training, stages=st, new_stats=stats,
+                                          decoder_input_override=lambda x, o: M.apply_mask(x, mask, probs, ridx, sd["mask_token"], style=(0.9, 0.05, 0.05)))
+        np.testing.assert_allclose(st["decoder_in"][:, ::8, ::4].detach().numpy(), g[f"{tag}_dec_in"], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(pred[:, ::8, ::4].detach().numpy(), g[f"{tag}_pred"], rtol=1e-3, atol=1e-3)
+        np.testing.assert_allclose(other["at_out"].detach().numpy(), g[f"{tag}_at"], rtol=1e-4, atol=1e-6)
+        return pred, other, mask, stats
+
+    with torch.no_grad():
+        pred, other, _, _ = run(seed + 3, False, "eval")
+        np.testing.assert_allclose(M.prototype_predict(pred, protos)[:, ::8].numpy(), g["eval_strong"], rtol=1e-3, atol=2e-4)
+    pred, other, mask, stats = run(seed + 4, True, "train")
+    strong = M.prototype_predict(pred, protos)
+    loss = M.bce(strong[mask], labels.transpose(1, 2)[mask]) + 0.5 * M.bce(other["at_out"], weak_labels)
+    np.testing.assert_allclose(loss.item(), g["train_loss"], rtol=1e-4)
+    for k in ("cnn.cnn.batchnorm0.running_mean", "cnn.cnn.batchnorm9.running_var"):
+        np.testing.assert_allclose(stats[k].numpy(), g["bn_" + k], rtol=1e-4, atol=1e-6)
+    loss.backward()
+    assert sorted(str(n) for n in g["grad_names"]) == sorted(k for k in trainable if sd[k].grad is not None)
+    for name, norm, head in zip(g["grad_names"], g["grad_norms"], g["grad_heads"]):
+        gr = sd[str(name)].grad
+        np.testing.assert_allclose(gr.double().norm().item(), norm, rtol=5e-3, atol=1e-7, err_msg=str(name))

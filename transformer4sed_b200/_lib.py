@@ -123,6 +123,21 @@ def _declare(lib):
         "t4s_mask_rows_fwd": (I, [P, P, P, P, P, L, I, I, P]),
         "t4s_mask_rows_bwd_workspace": (Z, [L, I]),
         "t4s_mask_rows_bwd": (I, [P, P, P, P, I, P, P, P, Z, L, I, I, P]),
+        "t4s_im2col3x3": (I, [P, I, L, L, L, P, I, I, I, I, I, I, P]),
+        "t4s_col2im3x3": (I, [P, P, I, I, I, I, I, I, P]),
+        "t4s_chan_stats_workspace": (Z, [L, I]),
+        "t4s_batchnorm_fwd": (I, [P, P, I, L, I, P, P, P, P, F, F, I, P, P, P, Z, P]),
+        "t4s_batchnorm_bwd": (I, [P, P, I, L, I, P, P, P, I, P, P, P, P, Z, P]),
+        "t4s_gate_fwd": (I, [P, P, P, Z, F, ctypes.c_uint64, I, P]),
+        "t4s_gate_bwd": (I, [P, P, P, P, P, Z, F, ctypes.c_uint64, I, P]),
+        "t4s_avgpool_fwd": (I, [P, P, I, I, I, I, I, I, I, P]),
+        "t4s_avgpool_bwd": (I, [P, P, I, I, I, I, I, I, I, P]),
+        "t4s_scale_add_fwd": (I, [P, P, P, P, Z, I, P]),
+        "t4s_scale_add_bwd": (I, [P, P, P, P, P, P, Z, I, P]),
+        "t4s_l2norm_fwd": (I, [P, P, P, L, I, I, P]),
+        "t4s_l2norm_bwd": (I, [P, P, P, P, L, I, I, P]),
+        "t4s_proto_act_fwd": (I, [P, P, Z, F, F, P]),
+        "t4s_proto_act_bwd": (I, [P, P, P, P, Z, F, F, P]),
         "t4s_patch_posbias": (I, [P, P, P, I, I, I, I, I, P]),
         "t4s_cls_dist_tokens": (I, [P, I, P, P, P, I, L, I, P]),
         "t4s_patch_small_grads": (I, [P, I, P, P, P, P, P, P, P, I, L, I, I, I, I, I, P]),

@@ -293,6 +293,13 @@ __device__ __forceinline__ void stage_store(const CUtensorMap* map, unsigned cha
   }
 }
 
+// Pull the 64 bytes of this thread's residual row that chunk `gcol` will read into L2 ahead of time (the direct per-row loads
+// are latency-bound otherwise: each one is a DRAM round trip inside the chunk's critical path).
+__device__ __forceinline__ void prefetch_res(const Args& a, long long r_row, int gcol, bool row_ok) {
+  if (a.res.ptr && a.res.dtype == T4S_BF16 && row_ok && gcol < a.N)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const __nv_bfloat16*>(a.res.ptr) + r_row + gcol));
+}
+
 // warp-uniform control flow (every lane stages its row; rows / columns outside the matrix are clipped by the TMA store)
 __device__ __forceinline__ void epilogue_chunk_staged(const Args& a, const CUtensorMap* mapC, const CUtensorMap* mapX, unsigned char* boxes,
                                                       uint32_t& seq, int lane, const uint32_t (&v)[32], int row0, int gcol, long long r_row,
@@ -504,6 +511,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const long long x_row = (long long)z1 * a.aux.s1 + (long long)z2 * a.aux.s2 + (long long)grow * a.aux.ld;
       const long long r_row = (long long)z1 * a.res.s1 + (long long)z2 * a.res.s2 + (long long)grow * a.res.ld;
       const int col_base = n0 + half * kHalfCols;
+      if (kStaged) prefetch_res(a, r_row, col_base, grow < a.M);
       ptx::mbar_wait(&tfull[as], aph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * kHalfCols;
@@ -515,6 +523,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (c + 1 < kChunks) {
           if (c & 1) ptx::tmem_ld_32x32(t_row + 32 * (c + 1), va);
           else ptx::tmem_ld_32x32(t_row + 32 * (c + 1), vb);
+          if (kStaged) prefetch_res(a, r_row, col_base + 32 * (c + 1), grow < a.M);
         } else {
           // the whole half-tile is in registers: hand the accumulator buffer back before the global stores
           ptx::tc_fence_before();

@@ -13,6 +13,14 @@ _MIRRORS = {
     "src.models.passt.passt_sed": "transformer4sed_b200.src_models.passt.passt_sed",
     "src.models.transformer.transformerXL": "transformer4sed_b200.src_models.transformer.transformerXL",
     "src.models.transformer.mask": "transformer4sed_b200.src_models.transformer.mask",
+    "src.models.encoder_slide_window": "transformer4sed_b200.src_models.encoder_slide_window",
+    "src.models.passt.passt_win": "transformer4sed_b200.src_models.passt.passt_win",
+    "src.models.passt.passt_lora": "transformer4sed_b200.src_models.passt.passt_lora",
+    "src.models.lora": "transformer4sed_b200.src_models.lora",
+    "src.models.lora.layers": "transformer4sed_b200.src_models.lora.layers",
+    "src.models.cnn": "transformer4sed_b200.src_models.cnn",
+    "src.models.cnn.base": "transformer4sed_b200.src_models.cnn.base",
+    "src.models.cnn_transformer.passt_cnn": "transformer4sed_b200.src_models.cnn_transformer.passt_cnn",
 }
 
 

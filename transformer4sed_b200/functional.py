@@ -1086,6 +1086,365 @@ def mask_rows(token_seq, mask_token, mask_mask, random_mask, random_indices):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# CNN branch (PMAM / DASM), channels-last                        reference: cnn/base.py:33-113, passt_cnn.py:52-62
+# ------------------------------------------------------------------------------------------------------------------
+class _Im2col3x3(torch.autograd.Function):
+    """x [B, H, W, C] (channels-last) -> col [B*H*W, pad8(9C)].  `mel_layout`: x is the mel image [B, F, T], read in place as the
+    [B, T, F, 1] tensor the reference builds with transpose + unsqueeze (passt_cnn.py:53); it gets no gradient."""
+
+    @staticmethod
+    def forward(ctx, x, mel_layout):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        if mel_layout:
+            B, Fq, T = x.shape
+            H, W, C = T, Fq, 1
+            sb, sh, sw = Fq * T, 1, T
+        else:
+            B, H, W, C = x.shape
+            sb, sh, sw = H * W * C, W * C, C
+        Kp = _pad8(9 * C)
+        dt = act_dtype()
+        col = torch.empty(B * H * W, Kp, dtype=dt, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib_call("t4s_im2col3x3", _p(x), ops.dtype_code(x.dtype), sb, sh, sw, _p(col), ops.dtype_code(dt), B, H, W, C, Kp, _st())
+        ctx.cfg = (B, H, W, C, Kp, mel_layout, x.dtype)
+        return col
+
+    @staticmethod
+    def backward(ctx, dcol):
+        B, H, W, C, Kp, mel_layout, xdt = ctx.cfg
+        if mel_layout or not ctx.needs_input_grad[0]:
+            return None, None
+        dcol = dcol.contiguous()
+        din = torch.empty(B, H, W, C, dtype=dcol.dtype, device=dcol.device)
+        with torch.cuda.device(dcol.device):
+            _lib_call("t4s_col2im3x3", _p(dcol), _p(din), ops.dtype_code(dcol.dtype), B, H, W, C, Kp, _st())
+        return (din if din.dtype == xdt else cast(din, xdt)), None
+
+
+def conv3x3(x, weight, bias, mel_layout=False):
+    """Conv2d(C_in, C_out, 3, stride 1, padding 1) on channels-last x [B, H, W, C_in] -> [B, H, W, C_out] (im2col + tcgen05 GEMM)."""
+    col = _Im2col3x3.apply(x, mel_layout)
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    w2 = weight.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin)
+    if col.shape[1] != 9 * Cin:
+        w2 = torch.nn.functional.pad(w2, (0, col.shape[1] - 9 * Cin))   # zero columns matching the zero-padded im2col rows
+    y = linear(col, w2.contiguous(), bias)
+    if mel_layout:
+        B, Fq, T = x.shape
+        return y.reshape(B, T, Fq, Cout)
+    return y.reshape(x.shape[0], x.shape[1], x.shape[2], Cout)
+
+
+class _BatchNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, training):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        rows = x.numel() // C
+        dev = x.device
+        lib = _lib.load()
+        y = torch.empty_like(x)
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        rstd = torch.empty(C, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nbytes = lib.t4s_chan_stats_workspace(rows, C)
+            ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
+            _lib_call("t4s_batchnorm_fwd", _p(x), _p(y), ops.dtype_code(x.dtype), rows, C, _p(gamma.detach()), _p(beta.detach()), _p(running_mean),
+                      _p(running_var), eps, momentum, int(training), _p(mean), _p(rstd), _p(ws), nbytes, _st())
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.training = bool(training)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        C = x.shape[-1]
+        rows = x.numel() // C
+        dev = x.device
+        dy = dy.contiguous()
+        if dy.dtype != x.dtype:
+            dy = convert(dy, torch.empty(dy.shape, dtype=x.dtype, device=dev))
+        lib = _lib.load()
+        dx = torch.empty_like(x)
+        dg = torch.empty(C, dtype=torch.float32, device=dev)
+        db = torch.empty(C, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            nbytes = lib.t4s_chan_stats_workspace(rows, C)
+            ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
+            _lib_call("t4s_batchnorm_bwd", _p(dy), _p(x), ops.dtype_code(x.dtype), rows, C, _p(gamma.detach()), _p(mean), _p(rstd),
+                      int(ctx.training), _p(dx), _p(dg), _p(db), _p(ws), nbytes, _st())
+        return dx, dg, db, None, None, None, None, None
+
+
+def batch_norm(x, gamma, beta, running_mean, running_var, eps, momentum, training):
+    """BatchNorm2d over the last (channel) dim of a channels-last tensor; updates the running buffers in training mode."""
+    return _BatchNorm.apply(x, gamma, beta, running_mean, running_var, float(eps), float(momentum), bool(training))
+
+
+class _Gate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, lin, p, seed):
+        _lib.ensure_device(y)
+        y, lin = y.contiguous(), lin.contiguous()
+        out = torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            _lib_call("t4s_gate_fwd", _p(y), _p(lin), _p(out), y.numel(), p, seed, ops.dtype_code(y.dtype), _st())
+        ctx.save_for_backward(y, lin)
+        ctx.cfg = (p, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, lin = ctx.saved_tensors
+        p, seed = ctx.cfg
+        dout = dout.contiguous()
+        if dout.dtype != y.dtype:
+            dout = convert(dout, torch.empty(dout.shape, dtype=y.dtype, device=y.device))
+        dy, dlin = torch.empty_like(y), torch.empty_like(y)
+        with torch.cuda.device(y.device):
+            _lib_call("t4s_gate_bwd", _p(dout), _p(y), _p(lin), _p(dy), _p(dlin), y.numel(), p, seed, ops.dtype_code(y.dtype), _st())
+        return dy, dlin, None, None
+
+
+_dropout_calls = 0
+
+
+def context_gate(y, lin, dropout_p=0.0):
+    """y * sigmoid(lin) (ContextGating, cnn/base.py:19-30) followed by inverted dropout with rate `dropout_p` (0 = none).  The
+    keep mask is a counter-based hash of (torch.initial_seed(), call index, element index): reproducible, not torch's stream."""
+    global _dropout_calls
+    seed = 0
+    if dropout_p > 0:
+        _dropout_calls += 1
+        seed = (torch.initial_seed() * 1000003 + _dropout_calls) & 0xFFFFFFFFFFFFFFFF
+    return _Gate.apply(y, lin, float(dropout_p), seed)
+
+
+class _AvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ph, pw):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        B, H, W, C = x.shape
+        out = torch.empty(B, H // ph, W // pw, C, dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib_call("t4s_avgpool_fwd", _p(x), _p(out), ops.dtype_code(x.dtype), B, H, W, C, ph, pw, _st())
+        ctx.cfg = (B, H, W, C, ph, pw)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        B, H, W, C, ph, pw = ctx.cfg
+        dout = dout.contiguous()
+        dx = torch.empty(B, H, W, C, dtype=dout.dtype, device=dout.device)
+        with torch.cuda.device(dout.device):
+            _lib_call("t4s_avgpool_bwd", _p(dout), _p(dx), ops.dtype_code(dout.dtype), B, H, W, C, ph, pw, _st())
+        return dx, None, None
+
+
+def avg_pool(x, ph, pw):
+    """AvgPool2d((ph, pw)) on channels-last x [B, H, W, C]."""
+    if ph == 1 and pw == 1:
+        return x
+    return _AvgPool.apply(x, int(ph), int(pw))
+
+
+class _ScaleAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, w):
+        _lib.ensure_device(a)
+        a, b = a.contiguous(), b.contiguous()
+        if b.dtype != a.dtype:
+            b = convert(b, torch.empty(b.shape, dtype=a.dtype, device=a.device))
+        w32 = w.detach().reshape(-1).float().contiguous()
+        out = torch.empty_like(a)
+        with torch.cuda.device(a.device):
+            _lib_call("t4s_scale_add_fwd", _p(a), _p(b), _p(w32), _p(out), a.numel(), ops.dtype_code(a.dtype), _st())
+        ctx.save_for_backward(b, w32)
+        ctx.wshape = w.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        b, w32 = ctx.saved_tensors
+        dev = b.device
+        dout = dout.contiguous()
+        if dout.dtype != b.dtype:
+            dout = convert(dout, torch.empty(dout.shape, dtype=b.dtype, device=dev))
+        db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
+        dw = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = torch.empty(256, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib_call("t4s_scale_add_bwd", _p(dout), _p(b), _p(w32), _p(db), _p(dw), _p(ws), b.numel(), ops.dtype_code(b.dtype), _st())
+        return (dout if ctx.needs_input_grad[0] else None), db, (dw.reshape(ctx.wshape) if ctx.needs_input_grad[2] else None)
+
+
+def scale_add(a, b, w):
+    """a + w * b with w a one-element tensor (learnable merge weight, passt_cnn.py:60-61); no host sync."""
+    return _ScaleAdd.apply(a, b, w)
+
+
+class _L2Norm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        rows = x.numel() // C
+        y = torch.empty_like(x)
+        inv = torch.empty(rows, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib_call("t4s_l2norm_fwd", _p(x), _p(y), _p(inv), rows, C, ops.dtype_code(x.dtype), _st())
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        dy = dy.contiguous()
+        if dy.dtype != y.dtype:
+            dy = convert(dy, torch.empty(dy.shape, dtype=y.dtype, device=y.device))
+        dx = torch.empty_like(y)
+        C = y.shape[-1]
+        with torch.cuda.device(y.device):
+            _lib_call("t4s_l2norm_bwd", _p(dy), _p(y), _p(inv), _p(dx), y.numel() // C, C, ops.dtype_code(y.dtype), _st())
+        return dx
+
+
+def l2_normalize(x):
+    """F.normalize(x, dim=-1)."""
+    return _L2Norm.apply(x)
+
+
+class _ProtoAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s, slope, temperature):
+        _lib.ensure_device(s)
+        s = s.contiguous().float()
+        p = torch.empty_like(s)
+        with torch.cuda.device(s.device):
+            _lib_call("t4s_proto_act_fwd", _p(s), _p(p), s.numel(), slope, temperature, _st())
+        ctx.save_for_backward(s, p)
+        ctx.cfg = (slope, temperature)
+        return p
+
+    @staticmethod
+    def backward(ctx, dp):
+        s, p = ctx.saved_tensors
+        slope, temperature = ctx.cfg
+        dp = dp.contiguous().float()
+        ds = torch.empty_like(s)
+        with torch.cuda.device(s.device):
+            _lib_call("t4s_proto_act_bwd", _p(s), _p(p), _p(dp), _p(ds), s.numel(), slope, temperature, _st())
+        return ds, None, None
+
+
+def prototype_predict(logit, prototypes, temperature=0.1, slope=0.2):
+    """PMAM prototype head (recipes/desed/pmam/train.py:82-87): sigmoid((leaky_relu(cos-sim to the prototypes, 0.2) * 2 - 1) / T).
+    logit [B, T, C], prototypes [K, C] (already L2-normalised GMM means) -> [B, T, K] fp32."""
+    z = l2_normalize(logit)
+    sim = linear(z, prototypes, None, out_dtype=torch.float32)
+    return _ProtoAct.apply(sim, float(slope), float(temperature))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# LoRA linear                                                    reference: src/models/lora/layers.py:87-153
+# ------------------------------------------------------------------------------------------------------------------
+def invalidate_weight_cache(w):
+    """Forget the cached bf16 copy of `w` (needed after in-place `.data` edits, which do not bump the version counter)."""
+    _wcache.pop(id(w), None)
+    shadow = getattr(w, "_t4s_shadow", None)
+    if shadow is not None:      # parameter-arena bf16 shadow: refresh it in place
+        convert(w.detach(), shadow)
+
+
+class _LoraLinear(torch.autograd.Function):
+    """y = act(x (W + s B A)^T + b) + residual.  Forward: the rank-r update is folded into an effective weight (one small GEMM), so
+    the token GEMM is the ordinary one with its fused epilogue.  Backward: dx through the effective weight; dA, dB through the
+    low-rank factors only (u = dh B, t = x A^T, both [tokens, r]) -- no [N, K] weight-gradient GEMM unless W itself trains."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, A, B, scaling, residual, act):
+        _lib.ensure_device(x)
+        shp = x.shape
+        K = shp[-1]
+        x2 = x.reshape(-1, K)
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        M, N, r = x2.shape[0], w.shape[0], A.shape[0]
+        dt, dev = x.dtype, x.device
+        with torch.cuda.device(dev):
+            Aq, Bq = to_plain(A, dt), to_plain(B, dt)
+            weff = torch.empty(N, K, dtype=dt, device=dev)
+            wq = cast_weight(w)
+            # W_eff = W + s * B A:  [N, r] x [K, r]^T with A consumed MN-major (A is [r, K])
+            mm(Op(Bq, N, r), Op(Aq, K, K, mn_major=True), Out(weff, K), N, K, r, alpha=scaling, residual=Out(wq, wq.stride(0)))
+            y = torch.empty(M, N, dtype=dt, device=dev)
+            aux = torch.empty(M, N, dtype=dt, device=dev) if act == ops.ACT_GELU else None
+            res2 = residual.reshape(M, N) if residual is not None else None
+            mm(Op(x2, M, x2.stride(0)), Op(weff, N, K), Out(y, N), M, N, K, bias=b.detach() if b is not None else None,
+               aux=Out(aux, N) if aux is not None else None, residual=Out(res2, res2.stride(0)) if res2 is not None else None, act=act)
+        ctx.save_for_backward(x2, w, A, B, aux, weff)
+        ctx.cfg = (scaling, act, shp, b is not None, residual is not None)
+        return y.reshape(*shp[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, A, B, aux, weff = ctx.saved_tensors
+        scaling, act, shp, has_bias, has_res = ctx.cfg
+        M, K = x2.shape
+        N, r = w.shape[0], A.shape[0]
+        dt, dev = x2.dtype, x2.device
+        dy2 = dy.reshape(M, N)
+        if dy2.stride(-1) != 1:
+            dy2 = dy2.contiguous()
+        ng = ctx.needs_input_grad
+        with torch.cuda.device(dev):
+            if dy2.dtype != dt:
+                dy2 = convert(dy2, torch.empty(M, N, dtype=dt, device=dev))
+            if act == ops.ACT_GELU:
+                dh = torch.empty(M, N, dtype=dt, device=dev)
+                _lib_call("t4s_gelu_bwd", _p(dy2), _p(aux), _p(dh), M * N, ops.dtype_code(dt), _st())
+            else:
+                dh = dy2
+            dx = dw = db = dA = dB = None
+            if ng[0]:
+                dx = torch.empty(M, K, dtype=dt, device=dev)
+                mm(Op(dh, M, dh.stride(0)), Op(weff, K, K, mn_major=True), Out(dx, K), M, K, N)
+                dx = dx.reshape(shp)
+            if ng[1]:
+                dw = weight_grad(dh, x2, N, K)
+            if has_bias and ng[2]:
+                db = colsum(dh)
+            if ng[3] or ng[4]:
+                Aq, Bq = to_plain(A, dt), to_plain(B, dt)
+                rp = _pad8(r)
+                if ng[3]:
+                    u = torch.zeros(M, rp, dtype=dt, device=dev) if rp != r else torch.empty(M, rp, dtype=dt, device=dev)
+                    mm(Op(dh, M, dh.stride(0)), Op(Bq, r, r, mn_major=True), Out(u, rp), M, r, N, alpha=scaling)   # u = s dh B
+                    dA = weight_grad(u[:, :r], x2, r, K)                                                          # dA = u^T x
+                if ng[4]:
+                    t = torch.zeros(M, rp, dtype=dt, device=dev) if rp != r else torch.empty(M, rp, dtype=dt, device=dev)
+                    mm(Op(x2, M, x2.stride(0)), Op(Aq, r, K), Out(t, rp), M, r, K, alpha=scaling)                  # t = s x A^T
+                    dB = weight_grad(dh, t[:, :r], N, r)                                                          # dB = dh^T t
+        d_res = dy if has_res else None
+        return dx, dw, db, dA, dB, None, d_res, None
+
+
+def to_plain(p, dtype):
+    """Small parameter -> contiguous tensor of the activation dtype (no caching: LoRA factors change every step)."""
+    p = p.detach().contiguous()
+    return p if p.dtype == dtype else convert(p, torch.empty(p.shape, dtype=dtype, device=p.device))
+
+
+def lora_linear(x, w, b, lora_A, lora_B, scaling, residual=None, act=ops.ACT_NONE):
+    return _LoraLinear.apply(x, w, b, lora_A, lora_B, float(scaling), residual, act)
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # heads and losses
 # ------------------------------------------------------------------------------------------------------------------
 class _SedPool(torch.autograd.Function):

@@ -84,3 +84,43 @@ def mat_sed_shapes(embed_dim=768, decoder_dim=768, decoder_layer_num=3, class_nu
         d.update(attention_pooling_shapes("at_adpater.0.", embed_dim))
         _lin(d, "at_adpater.1", class_num, embed_dim)
     return d
+
+
+def cnn_shapes(nb_filters, n_in_channel=1, prefix="cnn.cnn."):
+    """reference src/models/cnn/base.py:62-103 (activation 'cg', BatchNorm): conv{i}, batchnorm{i} (+ running stats), cg{i}.linear."""
+    d = {}
+    for i, n_out in enumerate(nb_filters):
+        n_in = n_in_channel if i == 0 else nb_filters[i - 1]
+        d[f"{prefix}conv{i}.weight"] = (n_out, n_in, 3, 3)
+        d[f"{prefix}conv{i}.bias"] = (n_out,)
+        for k in ("weight", "bias", "running_mean", "running_var"):
+            d[f"{prefix}batchnorm{i}.{k}"] = (n_out,)
+        _lin(d, f"{prefix}cg{i}.linear", n_out, n_out)
+    return d
+
+
+def add_lora(d, r=8, prefix="backbone."):
+    """reference src/models/passt/passt_lora.py: every block Linear and both heads carry lora_A [r, in] / lora_B [out, r]."""
+    for k in [k for k in d if k.startswith(prefix) and k.endswith(".weight") and len(d[k]) == 2 and
+              any(t in k for t in (".attn.qkv.", ".attn.proj.", ".mlp.fc1.", ".mlp.fc2.", "head.1.", "head_dist."))]:
+        n_out, n_in = d[k]
+        d[k[:-len("weight")] + "lora_A"] = (r, n_in)
+        d[k[:-len("weight")] + "lora_B"] = (n_out, r)
+    return d
+
+
+PMAM_FILTERS = (16, 16, 32, 32, 64, 64, 128, 128, 256, 384)
+PMAM_POOLING = ((2, 2), (1, 1), (2, 2), (1, 1), (1, 2), (1, 2), (1, 2), (1, 2), (1, 2), (1, 1))
+
+
+def passt_cnn_shapes(embed_dim=768, decoder_dim=384, decoder_layer_num=3, class_num=30, f_pool="attention", mlm=True, lora_r=8,
+                     nb_filters=PMAM_FILTERS):
+    """reference src/models/cnn_transformer/passt_cnn.py:9-19 on top of PaSST_SED (config/pmam/post_pretrain.yaml:48-79)."""
+    d = mat_sed_shapes(embed_dim, decoder_dim, decoder_layer_num, class_num, True, f_pool, mlm, 768)
+    if lora_r:
+        add_lora(d, lora_r)
+    d.update(cnn_shapes(nb_filters))
+    _lin(d, "cnn_projector", decoder_dim, nb_filters[-1])
+    d["merge_weight"] = (1,)
+    _lin(d, "transformer_projector", decoder_dim, embed_dim)
+    return d

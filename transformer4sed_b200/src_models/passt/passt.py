@@ -123,15 +123,22 @@ class PaSST(nn.Module):
         self.time_new_pos_embed = nn.Parameter(torch.zeros(1, embed_dim, 1, self.patch_embed.grid_size[1]))
         self.pos_drop = nn.Dropout(p=drop_rate)
         self.blocks = nn.Sequential(*[
-            Block(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, drop=drop_rate,
-                  attn_drop=attn_drop_rate, drop_path=0., norm_layer=norm_layer, act_layer=act_layer) for _ in range(depth)])
+            self.make_block(dim=embed_dim, num_heads=num_heads, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, drop=drop_rate,
+                            attn_drop=attn_drop_rate, drop_path=0., norm_layer=norm_layer, act_layer=act_layer) for _ in range(depth)])
         self.norm = norm_layer(embed_dim)
         self.pre_logits = nn.Identity()
         # classification heads are unused by the SED path but kept so that PaSST checkpoints load with strict=True
         self.head = nn.Sequential(nn.LayerNorm(self.num_features),
-                                  nn.Linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity())
-        self.head_dist = nn.Linear(self.embed_dim, self.num_classes) if num_classes > 0 else nn.Identity()
+                                  self.make_head_linear(self.num_features, num_classes) if num_classes > 0 else nn.Identity())
+        self.head_dist = self.make_head_linear(self.embed_dim, self.num_classes) if num_classes > 0 else nn.Identity()
         self.init_weights(weight_init)
+
+    # construction hooks (passt_lora.PaSST swaps in LoRA layers)
+    def make_block(self, **kw):
+        return Block(**kw)
+
+    def make_head_linear(self, in_features, out_features):
+        return nn.Linear(in_features, out_features)
 
     def init_weights(self, mode=''):
         for p in (self.new_pos_embed, self.freq_new_pos_embed, self.time_new_pos_embed, self.dist_token, self.cls_token):

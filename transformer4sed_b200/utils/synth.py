@@ -49,7 +49,15 @@ def synth_tensor(seed: int, name: str, shape, kind: str = None) -> torch.Tensor:
 
 def synth_state_dict(shapes: dict, seed: int) -> dict:
     """``shapes``: {key: shape}.  Returns {key: fp32 tensor}."""
-    return {k: synth_tensor(seed, k, s) for k, s in sorted(shapes.items())}
+    out = {}
+    for k, s in sorted(shapes.items()):
+        if k.endswith("running_var"):        # same rules as synth_state_dict_like
+            out[k] = 0.5 + torch.rand(tuple(s), generator=_gen(seed, k))
+        elif k.endswith("running_mean"):
+            out[k] = 0.1 * torch.randn(tuple(s), generator=_gen(seed, k))
+        else:
+            out[k] = synth_tensor(seed, k, s)
+    return out
 
 
 def synth_state_dict_like(module: torch.nn.Module, seed: int) -> dict:
