@@ -335,6 +335,18 @@ int t4s_attnpool_fwd(const void* kv, const float* q, void* ctx, float* probs, in
 int t4s_attnpool_bwd(const void* kv, const float* q, const float* probs, const void* dctx, void* dkv, float* dq_part, int items, int keys,
                      int dim, int heads, int64_t item_stride, int dtype, void* stream);
 
+/* ---- DASM open-vocabulary head (csrc/head.cu, csrc/cnn.cu) ----------------------------------------------------------------------
+ * src/models/detect_any_sound/detect_any_sound.py:376-388: strong[b,k,t] = clamp(sigmoid(score[b,t,k]/temp) * at_out[b,k], 1e-7, 1)
+ * (padded frames forced to 0 before the clamp), weak = clamp(sum_t p^2 / sum_t p, 1e-7, 1).  score is the query x frame GEMM output. */
+int t4s_query_pool_fwd(const float* score, const float* at_out, const unsigned char* pad_mask, float temp, float* strong, float* weak, int batch,
+                       int frames, int queries, void* stream);
+int t4s_query_pool_bwd(const float* score, const float* at_out, const float* strong, const float* dstrong, const float* dweak,
+                       const unsigned char* pad_mask, float temp, float* dscore, float* dat, int batch, int frames, int queries, void* stream);
+/* boolean attn_mask of nn.MultiheadAttention (at_adapter.py:28-31, tgt_mask): s[(b,h,q), c] = -inf where mask[q, c] != 0 */
+int t4s_mask_scores(void* s, const unsigned char* mask, int64_t rows, int cols, int64_t ld, int n_queries, int dtype, void* stream);
+/* inverted dropout with a counter-based mask (seed, element index); the backward is the same call on the gradient */
+int t4s_dropout(const void* x, void* out, size_t n, float dropout_p, uint64_t seed, int dtype, void* stream);
+
 /* ---- K9: parameter-side kernels of a training step (csrc/optim.cu) ------------------------------------------------
  * torch.optim.AdamW semantics (recipes/desed/setting.py:254-258) over a flat fp32 arena; `bf16_shadow` (optional) receives the
  * updated weights as bf16 GEMM operands in the same pass; `grad_scale` folds the 1/world_size of the gradient all-reduce. */

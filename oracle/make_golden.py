@@ -231,6 +231,64 @@ def golden_pmam(seed, batch):
     print(f"pmam_base.npz loss={loss.item():.6f} masked={m.float().mean().item():.3f} trainable={len(out['trainable'])} grads={len(gn)}")
 
 
+DASM_KW = dict(
+    cnn_param=dict(n_in_channel=1, activation="cg", conv_dropout=0.0, kernel_size=[3] * 10, padding=[1] * 10, stride=[1] * 10,
+                   nb_filters=[16, 16, 32, 32, 64, 64, 128, 128, 256, 384],
+                   pooling=[[2, 2], [1, 1], [2, 2], [1, 1], [1, 2], [1, 2], [1, 2], [1, 2], [1, 2], [1, 1]]),
+    backbone_param=dict(embed_dim=768, passt_feature_layer=10, pretrain_model_path=None, lora_config=dict(r=8, lora_alpha=1, requires_grad_pretrain=False)),
+    at_param=dict(at_decoder_layer=2, query_projector=True, query_dim=768, out_type="sigmoid", query=None),
+    mlm_dict=None, backbone_upsample_ratio=10, decoder_dim=384, num_heads=12, decoder="transformerXL", decoder_layer_num=3,
+    decoder_pos_emd_len=1000, decoder_expand_rate=1, class_num=407)   # SURVEY §3.5 / §8d config 5 (upstream training YAML unreleased)
+
+
+def golden_dasm(seed, batch, K=407):
+    """DASM open-vocabulary detection: K external query embeddings (temp_w = 4 keeps the sigmoid of the synthetic-weight scores,
+    mean -7.6 / std 2.6, out of saturation; the shipped default 0.1 would clamp every output to 1e-7).  (a) eval-mode forward (with and without a boolean tgt_mask
+    and a pad mask); (b) train-mode (BatchNorm batch statistics, un-merged LoRA) forward + backward with every dropout set to 0
+    (nn.TransformerDecoderLayer defaults to 0.1; torch's dropout stream cannot be replayed by another implementation)."""
+    from src.models.detect_any_sound.detect_any_sound import DASM
+    import copy
+    net = DASM(**copy.deepcopy(DASM_KW))
+    sd = synth.synth_state_dict_like(net, seed)
+    net.load_state_dict(sd, strict=True)
+    ext = net.get_feature_extractor().eval()
+    wav = synth.synth_wav(batch, 320000, seed=seed + 1)
+    mel = ext.normalize(ext(wav))
+    query = torch.nn.functional.normalize(synth.synth_tensor(seed, "queries", (K, 768)), dim=-1) * 3.0
+    g = torch.Generator().manual_seed(seed + 5)
+    tgt_mask = torch.rand(K, K, generator=g) < 0.3
+    tgt_mask.fill_diagonal_(False)
+    pad_mask = torch.zeros(batch, 1000, dtype=torch.bool)
+    pad_mask[-1, 900:] = True
+    labels = synth.synth_strong_labels(batch, K, 1000, seed + 2)
+    weak_labels = (labels.sum(-1) >= 1).float()
+    out = dict(wav_ck=checksum(wav), mel_ck=checksum(mel), query_ck=checksum(query), tgt_mask=np.packbits(tgt_mask.numpy()),
+               sd_keys=np.array(sorted(sd.keys())), trainable=np.array(sorted(n for n, p in net.named_parameters() if p.requires_grad)),
+               sd_ck=checksum(torch.cat([v.flatten().float() for k, v in sorted(sd.items()) if torch.is_floating_point(v)])))
+    net.eval()
+    with torch.no_grad():
+        s, w, o = net(mel, temp_w=4.0, query=query.clone())
+        out.update(eval_strong=f32(s[:, ::3, ::4]), eval_weak=f32(w), eval_at=f32(o["at_out"]), eval_argmax=s.argmax(dim=1).numpy().astype(np.int16))
+        s, w, o = net(mel, temp_w=4.0, pad_mask=pad_mask, query=query.clone(), tgt_mask=tgt_mask)
+        out.update(evalm_strong=f32(s[:, ::3, ::4]), evalm_weak=f32(w), evalm_at=f32(o["at_out"]))
+    net.train()
+    for m in net.modules():
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+        if isinstance(m, torch.nn.MultiheadAttention):
+            m.dropout = 0.0
+    s, w, o = net(mel, temp_w=4.0, query=query.clone())
+    bce = torch.nn.BCELoss()
+    loss = bce(s, labels) + 0.5 * bce(w, weak_labels) + 0.5 * bce(o["at_out"], weak_labels)
+    loss.backward()
+    gn, gnorm, ghead = grads_summary(net)
+    out.update(train_strong=f32(s[:, ::3, ::4]), train_weak=f32(w), train_at=f32(o["at_out"]), train_loss=np.array(loss.item()),
+               grad_names=gn, grad_norms=gnorm, grad_heads=ghead)
+    np.savez_compressed(os.path.join(OUT, "dasm_base.npz"), **out)
+    print(f"dasm_base.npz loss={loss.item():.6f} strong range {s.min().item():.3g} {s.max().item():.3g} at range {o['at_out'].min().item():.3g} "
+          f"{o['at_out'].max().item():.3g} grads={len(gn)}")
+
+
 def golden_mlm(tag, kw, seed, batch):
     """MAT-SED pre-train forward (mlm=True): needs the synthetic PaSST checkpoint on disk."""
     import tempfile
@@ -303,7 +361,7 @@ if __name__ == "__main__":
     base = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_adapter=True, decoder="transformerXL",
                 decoder_layer_num=3, decoder_pos_emd_len=1000, mlm=False)  # config/mat-sed/base/finetune2.yaml:53-62
     pre = dict(base, mlm=True, mlm_dict=dict(strategy="block", block_width=10, mask_rate=0.75, out_dim=768))  # pretrain.yaml:39-52
-    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm", "pmam"]
+    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm", "pmam", "dasm"]
     if "frontend" in which:
         golden_frontend()
         golden_frontend_16k()
@@ -317,6 +375,8 @@ if __name__ == "__main__":
         golden_window("base", base, seed=8, batch=1)   # out_dim is hard-wired to 768 upstream (encoder_slide_window.py:10)
     if "pmam" in which:
         golden_pmam(seed=10, batch=2)
+    if "dasm" in which:
+        golden_dasm(seed=12, batch=2)
     if "mlm" in which:
         golden_mlm("base", pre, seed=6, batch=2)  # B>1: upstream masking is a silent no-op
         golden_mlm("base", pre, seed=6, batch=1)  # B=1: reshape is a view, masking applies

@@ -323,6 +323,75 @@ def prototype_predict(logit, prototypes, temperature=0.1):
     return torch.sigmoid((F.leaky_relu(s, negative_slope=0.2) * 2 - 1) / temperature)
 
 
+# ------------------------------------------------------------------------------------------------
+# DASM: query-based open-vocabulary detection  (reference src/models/detect_any_sound/)
+# ------------------------------------------------------------------------------------------------
+def mha(q_in, kv_in, sd, p, num_heads, attn_mask=None):
+    """nn.MultiheadAttention(batch_first=True) forward, eval mode (no dropout): packed in_proj, scaled dot-product with an optional
+    boolean attn_mask [Nq, Nk] (True = masked out), out_proj."""
+    B, Nq, D = q_in.shape
+    Nk, hd = kv_in.shape[1], D // num_heads
+    w, b = sd[p + "in_proj_weight"], sd[p + "in_proj_bias"]
+    q = F.linear(q_in, w[:D], b[:D]).reshape(B, Nq, num_heads, hd).transpose(1, 2)
+    k = F.linear(kv_in, w[D:2 * D], b[D:2 * D]).reshape(B, Nk, num_heads, hd).transpose(1, 2)
+    v = F.linear(kv_in, w[2 * D:], b[2 * D:]).reshape(B, Nk, num_heads, hd).transpose(1, 2)
+    s = (q * hd ** -0.5) @ k.transpose(-2, -1)
+    if attn_mask is not None:
+        s = s.masked_fill(attn_mask, float("-inf"))
+    o = (s.softmax(dim=-1) @ v).transpose(1, 2).reshape(B, Nq, D)
+    return F.linear(o, sd[p + "out_proj.weight"], sd[p + "out_proj.bias"])
+
+
+def at_decoder(queries, memory, sd, n_layers, num_heads, tgt_mask=None, p="at_decoder.decoder.layers."):
+    """at_adapter.py:7-50: nn.TransformerDecoder of post-norm layers that cross-attend FIRST (:28-31), GELU FFN, eps 1e-5."""
+    x = queries
+    for i in range(n_layers):
+        q = f"{p}{i}."
+        x = layer_norm(x + mha(x, memory, sd, q + "multihead_attn.", num_heads), sd, q + "norm1", 1e-5)
+        x = layer_norm(x + mha(x, x, sd, q + "self_attn.", num_heads, tgt_mask), sd, q + "norm2", 1e-5)
+        x = layer_norm(x + linear(F.gelu(linear(x, sd, q + "linear1")), sd, q + "linear2"), sd, q + "norm3", 1e-5)
+    return x
+
+
+def mlp_head(x, sd, p, n_layers):
+    """detect_any_sound.py:404-416 (`MLP`): Linear (+GELU) x n."""
+    for i in range(n_layers):
+        x = linear(x, sd, f"{p}layers.{i}")
+        if i < n_layers - 1:
+            x = F.gelu(x)
+    return x
+
+
+def dasm_forward(mel, query, sd, nb_filters, pooling, at_layers=2, decoder_layers=3, num_heads=12, feature_layer=10, ratio=10, temp_w=0.1,
+                 pad_mask=None, tgt_mask=None, training=False, stages=None):
+    """DASM.forward (detect_any_sound.py:304-389): query_projector given, out_type 'sigmoid', no MLM.  query [K, query_dim]."""
+    feat, frame, Fd, Td = passt_backbone(mel, sd, feature_layer=feature_layer)
+    # f_pool (:242-254): norm_before_pool on the patch tokens, attention pooling (6 heads) over frequency
+    y = layer_norm(feat[:, 2:], sd, "norm_before_pool", 1e-5)
+    B, _, C = y.shape
+    y = y.reshape(B, Fd, Td, C).transpose(1, 2).reshape(B * Td, Fd, C)
+    x = pad_interpolate(mha_pool(y, sd, "f_pool_module.", 6).reshape(B, Td, C), ratio)
+    cnn_feat = cnn_forward(mel.transpose(1, 2).unsqueeze(1), sd, nb_filters, pooling, training)
+    cnn_feat = F.interpolate(cnn_feat.squeeze(-1), size=x.shape[1], mode="linear").transpose(1, 2)
+    x = linear(x, sd, "transformer_projector") + sd["merge_weight"] * linear(cnn_feat, sd, "cnn_projector")
+    x = layer_norm(x, sd, "norm_after_merge", 1e-5)
+    at_feat = linear(frame[:, 2:], sd, "at_projector")
+    q = F.gelu(linear(query, sd, "query_projector.0"))
+    mask_feat = at_decoder(q.expand(B, -1, -1), at_feat, sd, at_layers, num_heads, tgt_mask)
+    at_out = torch.sigmoid(mlp_head(mask_feat, sd, "at_head.", 2).squeeze(-1))
+    xd = linear(txl_decoder(x, sd, decoder_layers, num_heads, p="sed_decoder."), sd, "sed_head")
+    emb = mlp_head(mask_feat, sd, "mask_embedding_layer.", 3)
+    score = torch.einsum("bqc,bct->bqt", emb, xd.transpose(1, 2)).transpose(1, 2)          # [B, T, K]
+    sed = torch.sigmoid(score / temp_w) * at_out.unsqueeze(1)
+    if pad_mask is not None:
+        sed = sed.masked_fill(pad_mask.unsqueeze(-1), 0.0)
+    sed = torch.clamp(sed, 1e-7, 1.0)
+    weak = torch.clamp((sed * sed).sum(dim=1) / sed.sum(dim=1), 1e-7, 1.0)
+    if stages is not None:
+        stages.update(x_merged=x, mask_feat=mask_feat, score=score)
+    return sed.transpose(1, 2), weak, {"at_out": at_out}
+
+
 def bce(p, y):
     """torch.nn.BCELoss semantics (log clamped at -100), mean reduction (finetune/train.py:166-173)."""
     return -(y * torch.clamp(p.log(), min=-100.0) + (1 - y) * torch.clamp((1 - p).log(), min=-100.0)).mean()

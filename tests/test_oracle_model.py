@@ -189,3 +189,48 @@ def test_pmam_passt_cnn(golden):
     for name, norm, head in zip(g["grad_names"], g["grad_norms"], g["grad_heads"]):
         gr = sd[str(name)].grad
         np.testing.assert_allclose(gr.double().norm().item(), norm, rtol=5e-3, atol=1e-7, err_msg=str(name))
+
+
+def test_dasm(golden):
+    """Oracle DASM (query projector, cross-attention-first decoder with boolean tgt_mask, query x frame scores, sigmoid * at_out) vs
+    the unmodified reference: eval forward (plain / masked), train-mode forward + loss + gradients (dropouts 0)."""
+    g = golden("dasm_base.npz")
+    seed, batch, K = 12, 2, 407
+    shapes = schema.dasm_shapes()
+    assert sorted(shapes) == [k for k in g["sd_keys"] if not str(k).endswith("num_batches_tracked")]
+    sd = _sd(shapes, seed)
+    np.testing.assert_allclose(checksum(torch.cat([v.flatten() for _, v in sorted(sd.items())])), g["sd_ck"], rtol=1e-12)
+    trainable = set(str(k) for k in g["trainable"])
+    for k, v in sd.items():
+        v.requires_grad_(k in trainable)
+    wav = synth.synth_wav(batch, 320000, seed=seed + 1)
+    mel = F.passt_logmel(wav)
+    query = torch.nn.functional.normalize(synth.synth_tensor(seed, "queries", (K, 768)), dim=-1) * 3.0
+    np.testing.assert_allclose(checksum(query), g["query_ck"], rtol=1e-12)
+    tgt_mask = torch.from_numpy(np.unpackbits(g["tgt_mask"])[:K * K].astype(bool)).view(K, K)
+    pad = torch.zeros(batch, 1000, dtype=torch.bool)
+    pad[-1, 900:] = True
+    kw = dict(nb_filters=schema.PMAM_FILTERS, pooling=schema.PMAM_POOLING, temp_w=4.0)
+    with torch.no_grad():
+        s, w, o = M.dasm_forward(mel, query, sd, **kw)
+        np.testing.assert_allclose(s[:, ::3, ::4].numpy(), g["eval_strong"], rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(w.numpy(), g["eval_weak"], rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(o["at_out"].numpy(), g["eval_at"], rtol=1e-4, atol=1e-6)
+        assert (s.argmax(dim=1).numpy() == g["eval_argmax"]).mean() > 0.999
+        s, w, o = M.dasm_forward(mel, query, sd, pad_mask=pad, tgt_mask=tgt_mask, **kw)
+        np.testing.assert_allclose(s[:, ::3, ::4].numpy(), g["evalm_strong"], rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(w.numpy(), g["evalm_weak"], rtol=1e-3, atol=1e-6)
+        np.testing.assert_allclose(o["at_out"].numpy(), g["evalm_at"], rtol=1e-4, atol=1e-6)
+    labels = synth.synth_strong_labels(batch, K, 1000, seed + 2)
+    weak_labels = (labels.sum(-1) >= 1).float()
+    s, w, o = M.dasm_forward(mel, query, sd, training=True, **kw)
+    np.testing.assert_allclose(s[:, ::3, ::4].detach().numpy(), g["train_strong"], rtol=1e-3, atol=1e-6)
+    loss = M.bce(s, labels) + 0.5 * M.bce(w, weak_labels) + 0.5 * M.bce(o["at_out"], weak_labels)
+    np.testing.assert_allclose(loss.item(), g["train_loss"], rtol=1e-4)
+    loss.backward()
+    for name, norm, head in zip(g["grad_names"], g["grad_norms"], g["grad_heads"]):
+        gr = sd[str(name)].grad
+        assert gr is not None, name
+        if str(name).startswith("cnn.cnn.conv") and str(name).endswith(".bias"):
+            continue    # zero gradient in front of a training-mode BatchNorm (rounding noise only)
+        np.testing.assert_allclose(gr.double().norm().item(), norm, rtol=5e-3, atol=1e-9, err_msg=str(name))

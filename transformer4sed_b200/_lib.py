@@ -138,6 +138,10 @@ def _declare(lib):
         "t4s_l2norm_bwd": (I, [P, P, P, P, L, I, I, P]),
         "t4s_proto_act_fwd": (I, [P, P, Z, F, F, P]),
         "t4s_proto_act_bwd": (I, [P, P, P, P, Z, F, F, P]),
+        "t4s_query_pool_fwd": (I, [P, P, P, F, P, P, I, I, I, P]),
+        "t4s_query_pool_bwd": (I, [P, P, P, P, P, P, F, P, P, I, I, I, P]),
+        "t4s_mask_scores": (I, [P, P, L, I, L, I, I, P]),
+        "t4s_dropout": (I, [P, P, Z, F, ctypes.c_uint64, I, P]),
         "t4s_patch_posbias": (I, [P, P, P, I, I, I, I, I, P]),
         "t4s_cls_dist_tokens": (I, [P, I, P, P, P, I, L, I, P]),
         "t4s_patch_small_grads": (I, [P, I, P, P, P, P, P, P, P, I, L, I, I, I, I, I, P]),

@@ -199,6 +199,13 @@ __global__ void gate_bwd_kernel(const T* __restrict__ dout, const T* __restrict_
   }
 }
 
+// plain inverted dropout (the DASM tagging decoder's nn.TransformerDecoderLayer dropouts); its own backward with the same seed
+template <typename T>
+__global__ void dropout_kernel(const T* __restrict__ x, T* __restrict__ out, long long n, float p, uint64_t seed) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = from_f32<T>(to_f32<T>(x[i]) * keep_scale(seed, i, p));
+}
+
 // ---- AvgPool2d((ph, pw)) on [B, H, W, C] -> [B, H/ph, W/pw, C] -----------------------------------------------------------------
 template <typename T>
 __global__ void avgpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ out, int B, int H, int W, int C, int ph, int pw) {
@@ -433,6 +440,14 @@ int t4s_gate_bwd(const void* dout, const void* y, const void* lin, void* dy, voi
   T4S_DISPATCH_DTYPE(dtype, (gate_bwd_kernel<T><<<grid_for((long long)n), 256, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(dout), static_cast<const T*>(y), static_cast<const T*>(lin), static_cast<T*>(dy),
                                 static_cast<T*>(dlin), (long long)n, dropout_p, seed)));
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_dropout(const void* x, void* out, size_t n, float dropout_p, uint64_t seed, int dtype, void* stream) {
+  T4S_REQUIRE(x && out && dropout_p >= 0.f && dropout_p < 1.f, "t4s_dropout: bad arguments");
+  T4S_DISPATCH_DTYPE(dtype, (dropout_kernel<T><<<grid_for((long long)n), 256, 0, t4s::as_stream(stream)>>>(static_cast<const T*>(x), static_cast<T*>(out),
+                                                                                                          (long long)n, dropout_p, seed)));
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }

@@ -458,6 +458,73 @@ static int pool_hsplit(int items, int K, int C, int H, int dtype, const void* kv
   return best;
 }
 
+
+// ---- DASM (detect_any_sound.py:376-388): p = clamp(sigmoid(score / temp) * at_out, 1e-7, 1) with padded frames forced to 0 first,
+// weak = clamp(sum p^2 / sum p, 1e-7, 1).  score [B, T, K] fp32 (query x frame GEMM), at_out [B, K]; strong [B, K, T].  Block = (b, k).
+__global__ void query_pool_fwd_kernel(const float* __restrict__ score, const float* __restrict__ at_out, const unsigned char* __restrict__ pad_mask,
+                                      float inv_temp, float* __restrict__ strong, float* __restrict__ weak, int T, int K) {
+  __shared__ float s_red[32];
+  const int b = blockIdx.x / K, k = blockIdx.x % K;
+  const float at = at_out[blockIdx.x];
+  float s1 = 0.f, s2 = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    float v = at / (1.0f + expf(-score[((long long)b * T + t) * K + k] * inv_temp));
+    if (pad_mask && pad_mask[(long long)b * T + t]) v = 0.f;
+    const float p = fminf(fmaxf(v, 1e-7f), 1.0f);
+    strong[((long long)b * K + k) * T + t] = p;
+    s1 += p;
+    s2 += p * p;
+  }
+  s1 = block_sum(s1, s_red);
+  s2 = block_sum(s2, s_red);
+  if (threadIdx.x == 0) weak[blockIdx.x] = fminf(fmaxf(s2 / s1, 1e-7f), 1.0f);
+}
+// dscore[b,t,k] and the fixed-order partial of dat[b,k]; clamp passes gradient only inside [1e-7, 1]
+__global__ void query_pool_bwd_kernel(const float* __restrict__ score, const float* __restrict__ at_out, const float* __restrict__ strong,
+                                      const float* __restrict__ dstrong, const float* __restrict__ dweak, const unsigned char* __restrict__ pad_mask,
+                                      float inv_temp, float* __restrict__ dscore, float* __restrict__ dat, int T, int K) {
+  __shared__ float s_red[32];
+  const int b = blockIdx.x / K, k = blockIdx.x % K;
+  const float at = at_out[blockIdx.x];
+  const float* p_row = strong + ((long long)b * K + k) * T;
+  float s1 = 0.f, s2 = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const float p = p_row[t];
+    s1 += p;
+    s2 += p * p;
+  }
+  s1 = block_sum(s1, s_red);
+  s2 = block_sum(s2, s_red);
+  const float w = s2 / s1;
+  float gw = dweak ? dweak[blockIdx.x] : 0.f;
+  if (!(w >= 1e-7f && w <= 1.0f)) gw = 0.f;
+  float acc = 0.f;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const long long si = ((long long)b * T + t) * K + k;
+    const float sig = 1.0f / (1.0f + expf(-score[si] * inv_temp));
+    const float v = (pad_mask && pad_mask[(long long)b * T + t]) ? 0.f : at * sig;
+    const float p = p_row[t];
+    float g = (dstrong ? dstrong[((long long)b * K + k) * T + t] : 0.f) + gw * (2.f * p * s1 - s2) / (s1 * s1);
+    if (!(v >= 1e-7f && v <= 1.0f)) g = 0.f;
+    dscore[si] = g * at * sig * (1.f - sig) * inv_temp;
+    acc += g * sig;
+  }
+  acc = block_sum(acc, s_red);
+  if (threadIdx.x == 0) dat[blockIdx.x] = acc;
+}
+
+// attention scores s [rows, ld] (rows = (b, h, q) with q fastest): entries whose mask[q, c] is set become -inf (boolean attn_mask of
+// nn.MultiheadAttention: True = not allowed to attend)
+template <typename T>
+__global__ void mask_scores_kernel(T* __restrict__ s, const unsigned char* __restrict__ mask, long long rows, int cols, long long ld, int nq) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    const int c = (int)(i - r * cols);
+    if (mask[(r % nq) * cols + c]) s[r * ld + c] = from_f32<T>(-INFINITY);
+  }
+}
+
 static int grid_for(long long n, int threads = 256) {
   return (int)std::max<long long>(1, std::min<long long>((n + threads - 1) / threads, (long long)sm_count() * 8));
 }
@@ -543,6 +610,34 @@ int t4s_mse_bwd(const void* a, const void* b, const unsigned char* row_mask, int
   if (dtype == T4S_F32) mse_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, row_mask, rows, cols, grad_out, fwd_out, (float*)da, (float*)db);
   else if (dtype == T4S_BF16) mse_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, row_mask, rows, cols, grad_out, fwd_out, (__nv_bfloat16*)da, (__nv_bfloat16*)db);
   else { t4s::set_error("t4s_mse_bwd: bad dtype"); return T4S_ERR_ARG; }
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_query_pool_fwd(const float* score, const float* at_out, const unsigned char* pad_mask, float temp, float* strong, float* weak, int batch,
+                        int frames, int queries, void* stream) {
+  T4S_REQUIRE(score && at_out && strong && weak && batch > 0 && frames > 0 && queries > 0 && temp != 0.f, "t4s_query_pool_fwd: bad arguments");
+  query_pool_fwd_kernel<<<batch * queries, 256, 0, t4s::as_stream(stream)>>>(score, at_out, pad_mask, 1.0f / temp, strong, weak, frames, queries);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_query_pool_bwd(const float* score, const float* at_out, const float* strong, const float* dstrong, const float* dweak,
+                       const unsigned char* pad_mask, float temp, float* dscore, float* dat, int batch, int frames, int queries, void* stream) {
+  T4S_REQUIRE(score && at_out && strong && dscore && dat && temp != 0.f, "t4s_query_pool_bwd: bad arguments");
+  query_pool_bwd_kernel<<<batch * queries, 256, 0, t4s::as_stream(stream)>>>(score, at_out, strong, dstrong, dweak, pad_mask, 1.0f / temp, dscore, dat,
+                                                                            frames, queries);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_mask_scores(void* s, const unsigned char* mask, int64_t rows, int cols, int64_t ld, int n_queries, int dtype, void* stream) {
+  T4S_REQUIRE(s && mask && rows > 0 && cols > 0 && n_queries > 0, "t4s_mask_scores: bad arguments");
+  cudaStream_t st = t4s::as_stream(stream);
+  const int grid = grid_for((long long)rows * cols);
+  if (dtype == T4S_F32) mask_scores_kernel<float><<<grid, 256, 0, st>>>((float*)s, mask, rows, cols, ld, n_queries);
+  else if (dtype == T4S_BF16) mask_scores_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16*)s, mask, rows, cols, ld, n_queries);
+  else { t4s::set_error("t4s_mask_scores: bad dtype"); return T4S_ERR_ARG; }
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }

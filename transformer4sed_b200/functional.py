@@ -1445,6 +1445,228 @@ def lora_linear(x, w, b, lora_A, lora_B, scaling, residual=None, act=ops.ACT_NON
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# DASM: general multi-head attention (separate query / key-value sequences, boolean mask, dropout), query pooling
+# reference: src/models/detect_any_sound/at_adapter.py:7-50 (nn.TransformerDecoderLayer), detect_any_sound.py:376-388
+# ------------------------------------------------------------------------------------------------------------------
+_drop_calls = 0
+
+
+def _next_seed():
+    global _drop_calls
+    _drop_calls += 1
+    return (torch.initial_seed() * 1000003 + 7919 * _drop_calls) & 0xFFFFFFFFFFFFFFFF
+
+
+class _Dropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, seed):
+        _lib.ensure_device(x)
+        x = x.contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib_call("t4s_dropout", _p(x), _p(out), x.numel(), p, seed, ops.dtype_code(x.dtype), _st())
+        ctx.cfg = (p, seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        p, seed = ctx.cfg
+        dout = dout.contiguous()
+        dx = torch.empty_like(dout)
+        with torch.cuda.device(dout.device):
+            _lib_call("t4s_dropout", _p(dout), _p(dx), dout.numel(), p, seed, ops.dtype_code(dout.dtype), _st())
+        return dx, None, None
+
+
+def dropout(x, p, training=True):
+    """Inverted dropout with a counter-based mask (reproducible from torch.initial_seed(); not torch's Philox stream)."""
+    if not training or p <= 0:
+        return x
+    return _Dropout.apply(x, float(p), _next_seed())
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        _lib.ensure_device(a)
+        a, b = a.contiguous(), b.contiguous()
+        C = a.shape[-1]
+        out = torch.empty_like(a)
+        with torch.cuda.device(a.device):
+            _lib_call("t4s_add2", _p(a), C, _p(b), C, _p(out), C, a.numel() // C, C, 1.0, 1.0, ops.dtype_code(a.dtype), _st())
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        return dout, dout
+
+
+def add(a, b):
+    return _Add.apply(a, b)
+
+
+class _CrossAttention(torch.autograd.Function):
+    """softmax(q k^T / sqrt(hd) [masked]) v with q [B, Nq, D] and kv [B, Nk, 2D] (k | v per key): the nn.MultiheadAttention core for
+    Nq != Nk.  Scores live in a [B, H, Nq, pad8(Nk)] buffer (Nq = 407 queries: small); GEMMs read heads in place."""
+
+    @staticmethod
+    def forward(ctx, q, kv, H, mask, drop_p, seed):
+        _lib.ensure_device(q)
+        q, kv = q.contiguous(), kv.contiguous()
+        B, Nq, D = q.shape
+        Nk = kv.shape[1]
+        hd = D // H
+        Np = _pad8(Nk)
+        scale = hd ** -0.5
+        dt, dev = q.dtype, q.device
+        code = ops.dtype_code(dt)
+        with torch.cuda.device(dev):
+            P = torch.empty(B, H, Nq, Np, dtype=dt, device=dev)
+            mm(Op(q, Nq, D, 0, nb1=H, stride1=hd, nb2=B, stride2=Nq * D), Op(kv, Nk, 2 * D, 0, nb1=H, stride1=hd, nb2=B, stride2=Nk * 2 * D),
+               Out(P, Np, 0, Nq * Np, H * Nq * Np), Nq, Nk, hd, nb1=H, nb2=B, alpha=scale)
+            if mask is not None:
+                _lib_call("t4s_mask_scores", _p(P), _p(mask), B * H * Nq, Nk, Np, Nq, code, _st())
+            _lib_call("t4s_softmax_fwd", _p(P), _p(P), B * H * Nq, Nk, Np, Np, code, _st())
+            Pd = P
+            if drop_p > 0:
+                Pd = torch.empty_like(P)
+                _lib_call("t4s_dropout", _p(P), _p(Pd), P.numel(), drop_p, seed, code, _st())
+            o = torch.empty(B, Nq, D, dtype=dt, device=dev)
+            mm(Op(Pd, Nq, Np, 0, nb1=H, stride1=Nq * Np, nb2=B, stride2=H * Nq * Np),
+               Op(kv, hd, 2 * D, D, nb1=H, stride1=hd, nb2=B, stride2=Nk * 2 * D, mn_major=True), Out(o, D, 0, hd, Nq * D), Nq, hd, Nk, nb1=H, nb2=B)
+        ctx.save_for_backward(q, kv, P, Pd if drop_p > 0 else None)
+        ctx.cfg = (H, drop_p, seed)
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, kv, P, Pd = ctx.saved_tensors
+        H, drop_p, seed = ctx.cfg
+        B, Nq, D = q.shape
+        Nk = kv.shape[1]
+        hd = D // H
+        Np = P.shape[-1]
+        scale = hd ** -0.5
+        dt, dev = q.dtype, q.device
+        code = ops.dtype_code(dt)
+        do = do.contiguous()
+        if do.dtype != dt:
+            do = convert(do, torch.empty(do.shape, dtype=dt, device=dev))
+        if Pd is None:
+            Pd = P
+        with torch.cuda.device(dev):
+            dq = torch.empty_like(q)
+            dkv = torch.empty_like(kv)
+            dP = torch.empty(B, H, Nq, Np, dtype=dt, device=dev)
+            pm = dict(nb1=H, stride1=Nq * Np, nb2=B, stride2=H * Nq * Np)
+            kh = dict(nb1=H, stride1=hd, nb2=B, stride2=Nk * 2 * D)
+            qh = dict(nb1=H, stride1=hd, nb2=B, stride2=Nq * D)
+            # dPd = dO V^T ; dV = Pd^T dO
+            mm(Op(do, Nq, D, 0, **qh), Op(kv, Nk, 2 * D, D, **kh), Out(dP, Np, 0, Nq * Np, H * Nq * Np), Nq, Nk, hd, nb1=H, nb2=B)
+            mm(Op(Pd, Nk, Np, 0, mn_major=True, **pm), Op(do, hd, D, 0, mn_major=True, **qh), Out(dkv, 2 * D, D, hd, Nk * 2 * D), Nk, hd, Nq,
+               nb1=H, nb2=B)
+            if drop_p > 0:
+                _lib_call("t4s_dropout", _p(dP), _p(dP), dP.numel(), drop_p, seed, code, _st())
+            _lib_call("t4s_softmax_bwd", _p(P), _p(dP), B * H * Nq, Nk, Np, Np, code, _st())
+            # dQ = scale dS K ; dK = scale dS^T Q
+            mm(Op(dP, Nq, Np, 0, **pm), Op(kv, hd, 2 * D, 0, mn_major=True, **kh), Out(dq, D, 0, hd, Nq * D), Nq, hd, Nk, nb1=H, nb2=B, alpha=scale)
+            mm(Op(dP, Nk, Np, 0, mn_major=True, **pm), Op(q, hd, D, 0, mn_major=True, **qh), Out(dkv, 2 * D, 0, hd, Nk * 2 * D), Nk, hd, Nq,
+               nb1=H, nb2=B, alpha=scale)
+        return dq, dkv, None, None, None, None
+
+
+def multi_head_attention(q_in, kv_in, in_proj_weight, in_proj_bias, out_w, out_b, num_heads, attn_mask=None, dropout_p=0.0, training=False,
+                         residual=None):
+    """nn.MultiheadAttention(batch_first=True)(q_in, kv_in, kv_in, attn_mask=...)[0] (+ residual fused into the out_proj epilogue).
+    attn_mask: boolean [Nq, Nk], True = masked out."""
+    D = q_in.shape[-1]
+    q = linear(q_in, in_proj_weight[:D], in_proj_bias[:D])
+    kv = linear(kv_in, in_proj_weight[D:], in_proj_bias[D:])
+    m = attn_mask.to(torch.uint8).contiguous() if attn_mask is not None else None
+    p = float(dropout_p) if training else 0.0
+    o = _CrossAttention.apply(q, kv, num_heads, m, p, _next_seed() if p > 0 else 0)
+    return linear(o, out_w, out_b, residual=residual)
+
+
+class _QueryPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, score, at_out, temp, pad_mask):
+        _lib.ensure_device(score)
+        score = score.contiguous().float()
+        at_out = at_out.contiguous().float()
+        B, T, K = score.shape
+        strong = torch.empty(B, K, T, dtype=torch.float32, device=score.device)
+        weak = torch.empty(B, K, dtype=torch.float32, device=score.device)
+        pm = pad_mask.to(torch.uint8).contiguous() if pad_mask is not None else None
+        with torch.cuda.device(score.device):
+            _lib_call("t4s_query_pool_fwd", _p(score), _p(at_out), _p(pm), float(temp), _p(strong), _p(weak), B, T, K, _st())
+        ctx.save_for_backward(score, at_out, strong, pm)
+        ctx.temp = float(temp)
+        return strong, weak
+
+    @staticmethod
+    def backward(ctx, dstrong, dweak):
+        score, at_out, strong, pm = ctx.saved_tensors
+        B, T, K = score.shape
+        dscore = torch.empty_like(score)
+        dat = torch.empty_like(at_out)
+        ds = dstrong.contiguous().float() if dstrong is not None else None
+        dw = dweak.contiguous().float() if dweak is not None else None
+        with torch.cuda.device(score.device):
+            _lib_call("t4s_query_pool_bwd", _p(score), _p(at_out), _p(strong), _p(ds), _p(dw), _p(pm), ctx.temp, _p(dscore), _p(dat), B, T, K, _st())
+        return dscore, dat, None, None
+
+
+def query_pool(score, at_out, temp=0.1, pad_mask=None):
+    """score [B, T, K] (frame x query logits), at_out [B, K] -> (strong [B, K, T], weak [B, K]) as DASM's head (:379-388)."""
+    return _QueryPool.apply(score, at_out, temp, pad_mask)
+
+
+class _QueryFrameScore(torch.autograd.Function):
+    """score[b, t, q] = <x[b, t, :], emb[b, q, :]>  (einsum 'bqc,bct->bqt' transposed, detect_any_sound.py:378): one batched GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, emb):
+        _lib.ensure_device(x)
+        x, emb = x.contiguous(), emb.contiguous()
+        if emb.dtype != x.dtype:
+            emb = convert(emb, torch.empty(emb.shape, dtype=x.dtype, device=x.device))
+        B, T, C = x.shape
+        K = emb.shape[1]
+        out = torch.empty(B, T, K, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            mm(Op(x, T, C, 0, nb1=B, stride1=T * C), Op(emb, K, C, 0, nb1=B, stride1=K * C), Out(out, K, 0, T * K), T, K, C, nb1=B)
+        ctx.save_for_backward(x, emb)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, emb = ctx.saved_tensors
+        B, T, C = x.shape
+        K = emb.shape[1]
+        dt, dev = x.dtype, x.device
+        Kp = _pad8(K)
+        with torch.cuda.device(dev):
+            # operand copy of the gradient in the activation dtype with a 16-byte row pitch (K = 407 is not a multiple of 8)
+            d2 = torch.zeros(B, T, Kp, dtype=dt, device=dev)
+            d32 = dout.contiguous().float()
+            tmp = torch.empty(B * T, K, dtype=dt, device=dev)
+            convert(d32, tmp)
+            _lib_call("t4s_add2", _p(tmp), K, _p(tmp), K, _p(d2), Kp, B * T, K, 1.0, 0.0, ops.dtype_code(dt), _st())
+            dx = torch.empty_like(x)
+            demb = torch.empty_like(emb)
+            # dx[b] = d[b] emb[b]  (contract over q);  demb[b] = d[b]^T x[b]  (contract over t)
+            mm(Op(d2, T, Kp, 0, nb1=B, stride1=T * Kp), Op(emb, C, C, 0, nb1=B, stride1=K * C, mn_major=True), Out(dx, C, 0, T * C), T, C, K, nb1=B)
+            mm(Op(d2, K, Kp, 0, nb1=B, stride1=T * Kp, mn_major=True), Op(x, C, C, 0, nb1=B, stride1=T * C, mn_major=True), Out(demb, C, 0, K * C),
+               K, C, T, nb1=B)
+        return dx, demb
+
+
+def query_frame_score(x, emb):
+    return _QueryFrameScore.apply(x, emb)
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # heads and losses
 # ------------------------------------------------------------------------------------------------------------------
 class _SedPool(torch.autograd.Function):

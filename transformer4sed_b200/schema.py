@@ -124,3 +124,42 @@ def passt_cnn_shapes(embed_dim=768, decoder_dim=384, decoder_layer_num=3, class_
     d["merge_weight"] = (1,)
     _lin(d, "transformer_projector", decoder_dim, embed_dim)
     return d
+
+
+def mha_shapes(prefix, dim):
+    d = {prefix + "in_proj_weight": (3 * dim, dim), prefix + "in_proj_bias": (3 * dim,)}
+    _lin(d, prefix + "out_proj", dim, dim)
+    return d
+
+
+def dasm_shapes(embed_dim=768, decoder_dim=384, decoder_layer_num=3, at_layers=2, query_dim=768, num_heads=12, expand=1, lora_r=8,
+                nb_filters=PMAM_FILTERS):
+    """reference src/models/detect_any_sound/detect_any_sound.py:20-232 (query_projector=True, out_type='sigmoid', no MLM, no at_query)."""
+    d = passt_shapes(embed_dim)
+    if lora_r:
+        add_lora(d, lora_r)
+    d.update(cnn_shapes(nb_filters))
+    D = decoder_dim
+    d.update(txl_decoder_shapes(D, decoder_layer_num, num_heads=num_heads, mlp_ratio=expand, prefix="sed_decoder."))
+    for i in range(3):
+        _lin(d, f"mask_embedding_layer.layers.{i}", D, D)
+    _lin(d, "sed_head", D, D)
+    _lin(d, "query_projector.0", D, query_dim)
+    for i in range(at_layers):
+        p = f"at_decoder.decoder.layers.{i}."
+        d.update(mha_shapes(p + "self_attn.", D))
+        d.update(mha_shapes(p + "multihead_attn.", D))
+        _lin(d, p + "linear1", D * expand, D)
+        _lin(d, p + "linear2", D, D * expand)
+        for n in ("norm1", "norm2", "norm3"):
+            _ln(d, p + n, D)
+    _lin(d, "at_head.layers.0", D, D)
+    _lin(d, "at_head.layers.1", 1, D)
+    d.update(attention_pooling_shapes("f_pool_module.", embed_dim))
+    _lin(d, "cnn_projector", D, nb_filters[-1])
+    d["merge_weight"] = (1,)
+    _lin(d, "transformer_projector", D, embed_dim)
+    _lin(d, "at_projector", D, embed_dim)
+    _ln(d, "norm_before_pool", embed_dim)
+    _ln(d, "norm_after_merge", D)
+    return d
