@@ -195,6 +195,9 @@ def run_ours(args):
     roof, mel_roof, breakdown = None, None, None
     if rank == 0:
         roof, mel_roof, breakdown = instrumented_step(train_step, wav_dev, ext, ops, B)
+    elif world > 1:
+        train_step(wav_dev)   # the instrumented step contains the gradient all-reduce: every rank has to take part in it
+        torch.cuda.synchronize()
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_sample(target_seconds=15.0)

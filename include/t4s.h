@@ -44,7 +44,7 @@ int t4s_sm_count(void);
  * and, with T4S_MEL_DCASE flags, src/preprocess/feats_extraction.py:41-57 (setmelspectrogram + take_log).
  */
 typedef struct {
-  int n_fft;        /* 1024 or 2048 */
+  int n_fft;        /* 1024 (PaSST, register FFT) or any other power of two in 256..4096 (shared-memory FFT) */
   int win_length;   /* <= n_fft */
   int hop;
   int n_mels;       /* <= 128 */
@@ -64,12 +64,14 @@ size_t t4s_mel_tables_bytes(int n_fft, int win_length);
 int t4s_mel_tables_init(void* tables, const float* window_host, int n_fft, int win_length, void* stream);
 
 /* Sparse mel basis in CSR-by-row form: row m covers bins [bin_start[m], bin_start[m]+bin_count[m]) with weights
- * weights[w_offset[m] ...].  Every row has <= 32 taps. */
+ * weights[w_offset[m] ...].  n_fft = 1024: every row has <= 32 taps; other n_fft: any span. */
 int t4s_mel_forward(const float* wav, const float* peak, const void* tables,
                     const int* bin_start, const int* bin_count, const int* w_offset, const float* weights, int n_weights,
                     void* out /* [B, n_mels, T] */, int batch, int n_samples, int n_frames,
                     const T4sMelParams* p, void* stream);
 
+/* take_log (src/preprocess/feats_extraction.py:41-44): out = clamp(multiplier * log10(max(in, amin)), lo, hi) */
+int t4s_amp_to_db(const float* in, float* out, size_t n, float multiplier, float amin, float lo, float hi, void* stream);
 /* normalize only: out = (ln(in + 1e-5) + 4.5) / 5  (passt_feature_extraction.py:91-94). */
 int t4s_mel_normalize(const float* in, float* out, size_t n, void* stream);
 

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import checksum
 from oracle import frontend as OF
 from transformer4sed_b200.utils import synth
 
@@ -101,3 +102,31 @@ def test_rejects_cpu_tensor_and_bad_shapes():
         ext.logmel(torch.zeros(1, 32000))
     with pytest.raises(_lib.T4sError):
         ext.logmel(torch.zeros(1, 400).cuda())  # too short for reflect padding
+
+
+def test_dcase16k_front_end(golden):
+    """SURVEY §8 a1': the 16 kHz DCASE-style parametrisation (n_fft = win = 2048, hop 256, hamming, magnitude, HTK mel, dB clamp) on the
+    generic-n_fft kernel vs torchaudio golden vectors of the reference's `setmelspectrogram` + `take_log`, fused and un-fused."""
+    from oracle import frontend as OF
+    from transformer4sed_b200.src_preprocess.feats_extraction import setmelspectrogram, take_log
+    g = golden("frontend_dcase16k.npz")
+    w = synth.synth_wav(2, 48000, seed=21)
+    np.testing.assert_allclose(checksum(w), g["in_ck"], rtol=1e-12)
+    ms = setmelspectrogram(dict(sample_rate=16000, n_window=2048, hop_length=256, f_min=0, f_max=8000, n_mels=128)).cuda()
+    mel = ms(w.cuda())
+    db_fused = ms.logmel(w.cuda())
+    db = take_log(mel)
+    assert db.shape == tuple(g["db"].shape) == (2, 128, 1 + 48000 // 256)
+    assert (db.cpu() - torch.from_numpy(g["db"])).abs().max().item() < 2e-3           # dB units (fp32 FFT noise near the -50 dB floor)
+    assert (db_fused - db).abs().max().item() < 1e-5
+    # full 10 s clips at 16 kHz and a ragged length, against the CPU oracle
+    for n in (160000, 40001):
+        w = synth.synth_wav(3, n, seed=30 + n % 7)
+        ours = ms.logmel(w.cuda()).cpu()
+        ref = OF.dcase_logmel(w)
+        assert ours.shape == ref.shape and (ours - ref).abs().max().item() < 2e-3
+    # another power-of-two frame (n_fft 512) goes through the same kernel
+    ms2 = setmelspectrogram(dict(sample_rate=16000, n_window=512, hop_length=160, f_min=0, f_max=8000, n_mels=64)).cuda()
+    w = synth.synth_wav(2, 32000, seed=33)
+    ref = OF.dcase_logmel(w, n_fft=512, hop=160, n_mels=64)
+    assert (ms2.logmel(w.cuda()).cpu() - ref).abs().max().item() < 2e-3

@@ -319,6 +319,13 @@ static size_t smem_bytes(const T4sMelParams& mp, int n_weights) {
 }
 
 }  // namespace mel
+namespace melg {   // csrc/mel_generic.cu: every other power-of-two n_fft
+bool supported(int n_fft);
+size_t tables_bytes(int n_fft);
+int tables_init(void* tables, const float* window_host, int n_fft, int win_length, cudaStream_t st);
+int forward(const float* wav, const float* peak, const void* tables, const int* bin_start, const int* bin_count, const int* w_offset,
+            const float* weights, int n_weights, void* out, int batch, int n_samples, int n_frames, const T4sMelParams* mp, cudaStream_t st);
+}  // namespace melg
 }  // namespace t4s
 
 extern "C" {
@@ -335,15 +342,19 @@ int t4s_wav_peak(const float* wav, float* peak, int batch, int n_samples, void* 
 }
 
 size_t t4s_mel_tables_bytes(int n_fft, int win_length) {
-  if (n_fft != t4s::mel::kNfft || win_length <= 0 || win_length > n_fft) return 0;
+  if (win_length <= 0 || win_length > n_fft) return 0;
+  if (n_fft != t4s::mel::kNfft) return t4s::melg::supported(n_fft) ? t4s::melg::tables_bytes(n_fft) : 0;
   return t4s::mel::tables_bytes(win_length);
 }
 
 int t4s_mel_tables_init(void* tables, const float* window_host, int n_fft, int win_length, void* stream) {
   T4S_REQUIRE(tables && window_host, "t4s_mel_tables_init: null pointer");
   if (n_fft != t4s::mel::kNfft) {
-    t4s::set_error("t4s_mel_tables_init: n_fft=%d unsupported (only %d)", n_fft, t4s::mel::kNfft);
-    return T4S_ERR_UNSUPPORTED;
+    if (!t4s::melg::supported(n_fft) || win_length <= 0 || win_length > n_fft) {
+      t4s::set_error("t4s_mel_tables_init: n_fft=%d unsupported (powers of two in 256..4096)", n_fft);
+      return T4S_ERR_UNSUPPORTED;
+    }
+    return t4s::melg::tables_init(tables, window_host, n_fft, win_length, t4s::as_stream(stream));
   }
   T4S_REQUIRE(win_length > 0 && win_length <= n_fft && (win_length % 4) == 0, "t4s_mel_tables_init: win_length must be a multiple of 4 and <= n_fft");
   cudaStream_t st = t4s::as_stream(stream);
@@ -362,8 +373,12 @@ int t4s_mel_forward(const float* wav, const float* peak, const void* tables, con
   using namespace t4s::mel;
   T4S_REQUIRE(wav && tables && bin_start && bin_count && w_offset && weights && out && mp, "t4s_mel_forward: null pointer");
   if (mp->n_fft != kNfft) {
-    t4s::set_error("t4s_mel_forward: n_fft=%d unsupported (only %d)", mp->n_fft, kNfft);
-    return T4S_ERR_UNSUPPORTED;
+    if (!t4s::melg::supported(mp->n_fft)) {
+      t4s::set_error("t4s_mel_forward: n_fft=%d unsupported (powers of two in 256..4096)", mp->n_fft);
+      return T4S_ERR_UNSUPPORTED;
+    }
+    return t4s::melg::forward(wav, peak, tables, bin_start, bin_count, w_offset, weights, n_weights, out, batch, n_samples, n_frames, mp,
+                              t4s::as_stream(stream));
   }
   T4S_REQUIRE(mp->win_length > 0 && mp->win_length <= kNfft && mp->win_length % 4 == 0, "t4s_mel_forward: win_length must be a multiple of 4 and <= n_fft");
   T4S_REQUIRE(mp->hop > 0 && mp->hop % 2 == 0, "t4s_mel_forward: hop must be positive and even");
