@@ -38,5 +38,11 @@ if "mel" in which:
                                 fmin_aug_range=10, fmax_aug_range=2000).cuda().eval()
     wav = torch.randn(B, 320000, generator=g, device="cuda") * 0.1
     ext.logmel(wav)
+if "melg" in which:
+    from transformer4sed_b200.src_preprocess.feats_extraction import setmelspectrogram
+    ms = setmelspectrogram(dict(sample_rate=16000, n_window=2048, hop_length=256, f_min=0, f_max=8000, n_mels=128)).cuda()
+    wav = torch.randn(B, 160000, generator=g, device="cuda") * 0.1
+    ms.logmel(wav)
+    ms.logmel(wav)
 torch.cuda.synchronize()
 print("done")

@@ -280,11 +280,13 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long
 namespace bwd {
 constexpr int kThreads = 320;  // warps 0-7 softmax (two column halves), 8 TMA, 9 MMA
 // resident pair (K,V for dKV / Q,dO for dQ), streamed pair x 2 stages, two [128x128] bf16 operand tiles, lse/delta stages
-constexpr int oRes = 0, oStr = oRes + 2 * kTileBytes, oP = oStr + 4 * kTileBytes, oDs = oP + kPBytes, oStat = oDs + kPBytes,
+// The P / dS operand tiles are double-buffered: the softmax warps fill buffer (i+1)&1 while the tensor core still reads buffer i&1
+// for tile i's dV / dK (dQ) products.
+constexpr int oRes = 0, oStr = oRes + 2 * kTileBytes, oP = oStr + 4 * kTileBytes, oDs = oP + 2 * kPBytes, oStat = oDs + 2 * kPBytes,
               oBar = oStat + 2 * 2 * kTile * 4;
 constexpr int kSmem = oBar + 128;
 constexpr int kTmemCols = 512;  // S: [0,128)  dP: [128,256)  acc0: [256,320)  acc1: [320,384)
-enum { bResFull = 0, bStrFull = 1, bStrEmpty = 3, bSFull = 5, bSFree = 6, bPFull = 7, bPFree = 8, bAccFull = 9, bCount = 10 };
+enum { bResFull = 0, bStrFull = 1, bStrEmpty = 3, bSFull = 5, bSFree = 6, bPFull = 7, bPFree = 8 /* +1 */, bAccFull = 10, bCount = 11 };
 }  // namespace bwd
 
 // kDq = false: dK/dV kernel (resident K_j, V_j; streams Q_i, dO_i, lse_i, delta_i; thread = key row)
@@ -316,6 +318,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::mbar_init(&bars[bSFree], 8);
     ptx::mbar_init(&bars[bPFull], 8);
     ptx::mbar_init(&bars[bPFree], 1);
+    ptx::mbar_init(&bars[bPFree + 1], 1);
     ptx::mbar_init(&bars[bAccFull], 1);
     ptx::fence_barrier_init();
   }
@@ -399,14 +402,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tc_fence_after();
       if (lane == 0) {
         const uint32_t cur = str + s * 2 * kTileBytes;
+        const uint32_t pb = sP + s * kPBytes, db = sDs + s * kPBytes;
         if (kDq) {
-          mma_k128_mn(tmem + 256, sDs, cur, kIdescPV, i > 0);                  // dQ += dS K_j
+          mma_k128_mn(tmem + 256, db, cur, kIdescPV, i > 0);                   // dQ += dS K_j
         } else {
-          mma_k128_mn(tmem + 256, sP, cur + kTileBytes, kIdescPV, i > 0);      // dV += P^T dO_i
-          mma_k128_mn(tmem + 320, sDs, cur, kIdescPV, i > 0);                  // dK += dS^T Q_i
+          mma_k128_mn(tmem + 256, pb, cur + kTileBytes, kIdescPV, i > 0);      // dV += P^T dO_i
+          mma_k128_mn(tmem + 320, db, cur, kIdescPV, i > 0);                   // dK += dS^T Q_i
         }
         ptx::tc_commit(&bars[bStrEmpty + s]);
-        ptx::tc_commit(&bars[bPFree]);
+        ptx::tc_commit(&bars[bPFree + s]);
         if (i == n_tiles - 1) ptx::tc_commit(&bars[bAccFull]);
       }
       __syncwarp();
@@ -428,21 +432,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       if (!kDq) ptx::mbar_wait(&bars[bStrFull + s], (i >> 1) & 1);  // lse / delta of this query tile have landed
       ptx::mbar_wait(&bars[bSFull], i & 1);
       ptx::tc_fence_after();
-      ptx::mbar_wait(&bars[bPFree], (i & 1) ^ 1);  // previous tile's MMAs have finished reading the P / dS tiles
+      ptx::mbar_wait(&bars[bPFree + s], ((i >> 1) & 1) ^ 1);  // tile i-2's MMAs have finished reading this P / dS buffer
       const int nvalid = a.N - i * kTile;          // dQ: key columns that exist
       const bool full = nvalid >= kTile;
+      // all four TMEM loads of this thread's 64 columns are issued before the first wait (the exposed tcgen05.ld round trips
+      // were the longest stall of the softmax warps), and S / dP are handed back to the MMA warp right after they land
+      uint32_t vs0[32], vp0[32], vs1[32], vp1[32];
+      ptx::tmem_ld_32x32(t_lane + 64 * g, vs0);
+      ptx::tmem_ld_32x32(t_lane + 128 + 64 * g, vp0);
+      ptx::tmem_ld_32x32(t_lane + 64 * g + 32, vs1);
+      ptx::tmem_ld_32x32(t_lane + 128 + 64 * g + 32, vp1);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[bSFree]);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int col0 = 64 * g + 32 * c;
-        uint32_t vs[32], vp[32];
-        ptx::tmem_ld_32x32(t_lane + col0, vs);
-        ptx::tmem_ld_32x32(t_lane + 128 + col0, vp);
-        ptx::tmem_ld_wait();
-        if (c == 1) {
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bars[bSFree]);
-        }
+        const uint32_t (&vs)[32] = c ? vs1 : vs0;
+        const uint32_t (&vp)[32] = c ? vp1 : vp0;
         uint32_t pp[16], pd[16];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
@@ -468,8 +476,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           pd[2 * q] = pack_bf16(d[0], d[1]);
           pd[2 * q + 1] = pack_bf16(d[2], d[3]);
         }
-        if (!kDq) store_row_chunk(smem + oP, r, col0, pp);
-        store_row_chunk(smem + oDs, r, col0, pd);
+        if (!kDq) store_row_chunk(smem + oP + s * kPBytes, r, col0, pp);
+        store_row_chunk(smem + oDs + s * kPBytes, r, col0, pd);
       }
       ptx::fence_proxy_async();
       __syncwarp();
