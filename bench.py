@@ -287,11 +287,16 @@ def instrumented_step(train_step, wav_dev, ext, ops, B):
     mel_ms = statistics.median(ts)
     mel_bytes = B * (4 * N_SAMPLES + 4 * 128 * 1000)
     roof = {"bound": "tensor", "kernel": "t4s::gemm::gemm_kernel (tcgen05, all GEMM launches of one step)", "achieved": gemm_flops / gemm_ms / 1e9,
-            "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": gemm_flops / gemm_ms / 1e9 / pk["bf16_tflops_sustained"], "traffic": None,
+            "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": gemm_flops / gemm_ms / 1e9 / pk["bf16_tflops_sustained"],
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE captured launch (fc1 shape M=76160 N=3072 K=768, bias epilogue) from the
+            # committed `ncu --set full` capture; algorithmic bytes of that launch: 589.6 MB (profiles/r1j_ncu_full_summary.md)
+            "traffic": 537.2e6, "traffic_note": "bytes per launch of the fc1-shape GEMM (359.4 GFLOP); profiles/r1j_ncu_full_summary.md",
             "launches": n_gemm, "gemm_ms_per_step": gemm_ms, "share_of_step": gemm_ms / step_ms, "peak_source": pk_src + " (sustained bf16)",
             "how": "CUDA events around every t4s_gemm launch of one extra instrumented step; flops = 2MNK per launch"}
     mel_roof = {"bound": "hbm", "kernel": "t4s::mel::mel_kernel (+peak kernel)", "achieved": mel_bytes / mel_ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": mel_bytes / mel_ms / 1e6 / pk["hbm_gbs"], "traffic": None, "ms": mel_ms, "clips_per_s": B / mel_ms * 1e3,
+                "frac": mel_bytes / mel_ms / 1e6 / pk["hbm_gbs"],
+                "traffic": 93.75e6 * B / 64, "traffic_note": "ncu --set full, 64 clips per launch: 82.0 MB read + 11.8 MB written (profiles/r1j_ncu_full_summary.md)",
+                "ms": mel_ms, "clips_per_s": B / mel_ms * 1e3,
                 "algorithmic_bytes_per_clip": 4 * N_SAMPLES + 4 * 128 * 1000, "peak_source": pk_src}
     return roof, mel_roof, {"step_instrumented": step_ms, "gemm": gemm_ms, "fused_attention": attn_ms, "front_end": mel_ms,
                             "other": step_ms - gemm_ms - attn_ms - mel_ms}
