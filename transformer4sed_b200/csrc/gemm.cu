@@ -13,6 +13,7 @@
 //             Row / column predicates make ragged M/N tiles and TMA zero-fill compose.
 // bf16 inputs use kind::f16, fp32 inputs use kind::tf32 (tensor map type TFLOAT32 rounds on load).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "ptx.cuh"
@@ -57,6 +58,11 @@ struct Cfg {
   // staged epilogue: per epilogue warp two 2 KB SWIZZLE_64B boxes (32 rows x 32 bf16) for TMA tile stores
   static constexpr int kStageOff = kStages * kStage + 512;
   static constexpr int kSmemStaged = 1024 + kStageOff + kEpiWarps * 2 * 2048;
+  // CTA-pair mode (cta_group::2, BN = 256): each CTA stages its 128 rows of A and HALF of the B tile (128 of the 256 N rows):
+  // 32 KB per stage instead of 48, i.e. a third less operand traffic from L2 per FLOP and six stages in the same budget
+  static constexpr int kStageB2 = kStageB / 2;
+  static constexpr int kStage2 = kStageA + kStageB2;
+  static constexpr int kStages2 = 6;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -355,25 +361,38 @@ __device__ __forceinline__ void tile_coords(const Args& a, int r, int& tm, int& 
   tn = g * a.group_n + (rem - tm * width);
 }
 
-template <int BN, bool kTf32, bool kAMn, bool kBMn, bool kStaged>
+// kPair: the CTAs of a 2-CTA cluster (one TPC) work on one 256 x BN tile with tcgen05.mma.cta_group::2: CTA rank r owns rows
+// [256 tm + 128 r, +128) of A / C and stages rows [n0 + 128 r, +128) of B; the leader (rank 0) issues the MMAs for both, its
+// `full` barriers collect the TMA bytes of both CTAs, commits are multicast to both CTAs' `empty` / `tfull` barriers, and the
+// peer's epilogue warps hand their accumulator buffer back on the leader's `tempty` barrier.
+template <int BN, bool kTf32, bool kAMn, bool kBMn, bool kStaged, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
             const __grid_constant__ CUtensorMap tmX, const Args a) {
   using C = Cfg<BN>;
+  static_assert(!kPair || (BN == 256 && !kTf32), "pair mode: bf16, BN = 256");
   constexpr int kBK = kTf32 ? 32 : 64;   // K elements per pipeline stage
   constexpr int kRowEl = kTf32 ? 32 : 64; // elements per 128-byte swizzle row
   constexpr int kBoxBytes = kBK * 128;    // one MN-major box: kBK rows (K) x 128 B (M/N)
+  constexpr int kNStages = kPair ? C::kStages2 : C::kStages;
+  constexpr int kStageBytesB = kPair ? C::kStageB2 : C::kStageB;
+  constexpr int kStageBytes = C::kStageA + kStageBytesB;
+  constexpr int kRowsB = kPair ? BN / 2 : BN;      // B rows staged by this CTA
+  constexpr int kTileM = kPair ? 2 * kBM : kBM;    // rows of C per scheduled tile
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = ptx::smem_u32(smem_raw);
   unsigned char* smem = smem_raw + (((raw + 1023u) & ~1023u) - raw);
   unsigned char* sA = smem;
-  unsigned char* sB = smem + C::kStages * C::kStageA;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStage);
+  unsigned char* sB = smem + kNStages * C::kStageA;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kNStages * kStageBytes);
   uint64_t* full = bars;
-  uint64_t* empty = bars + C::kStages;
-  uint64_t* tfull = bars + 2 * C::kStages;
+  uint64_t* empty = bars + kNStages;
+  uint64_t* tfull = bars + 2 * kNStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
+  const long long tile_first = kPair ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
+  const long long tile_step = kPair ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks_all = (a.K + kBK - 1) / kBK;
@@ -387,22 +406,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < kNStages; ++i) {
       ptx::mbar_init(&full[i], 1);
       ptx::mbar_init(&empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull[i], 1);
-      ptx::mbar_init(&tempty[i], kEpiWarps);
+      ptx::mbar_init(&tempty[i], kPair ? 2 * kEpiWarps : kEpiWarps);
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, C::kTmemCols);
-    ptx::tmem_relinquish();
+    if (kPair) {
+      ptx::tmem_alloc2(tmem_slot, C::kTmemCols);
+      ptx::tmem_relinquish2();
+    } else {
+      ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync();
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -412,48 +437,68 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ================= TMA producer =================
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x) {
+      for (long long tile = tile_first; tile < a.total_tiles; tile += tile_step) {
         const int zs = (int)(tile / tiles_per_batch);
         const int r = (int)(tile - (long long)zs * tiles_per_batch);
         int tm, tn;
         tile_coords(a, r, tm, tn);
-        const int m0 = tm * kBM, n0 = tn * BN;
+        const int m0 = tm * kTileM + (int)rank * kBM, n0 = tn * BN + (int)rank * (kPair ? kRowsB : 0);
         const int nbz = a.nb1 * a.nb2;
         const int sp = zs / nbz, z = zs - sp * nbz;
         const int z1 = z % a.nb1, z2 = z / a.nb1;
         const int kb0 = sp * a.kb_per_split, kb1 = min(kblocks_all, kb0 + a.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % C::kStages;
-          const uint32_t ph = (it / C::kStages) & 1;
+          const int s = it % kNStages;
+          const uint32_t ph = (it / kNStages) & 1;
           ptx::mbar_wait(&empty[s], ph ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
           const int az1 = a.a_b1 ? z1 : 0, az2 = a.a_b2 ? z2 : 0, bz1 = a.b_b1 ? z1 : 0, bz2 = a.b_b2 ? z2 : 0;
-          if (kAMn) {
+          if (kPair) {
+            // both CTAs' bytes are counted on the leader's barrier
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full[s], 2 * kStageBytes);
+            const uint32_t bar = ptx::mapa(ptx::smem_u32(&full[s]), 0);
+            if (kAMn) {
 #pragma unroll
-            for (int j = 0; j < kBM / kRowEl; ++j)
-              ptx::tma_load_4d(sA + s * C::kStageA + j * kBoxBytes, &tmA, &full[s], m0 + j * kRowEl, kb * kBK, az1, az2);
-          } else {
-            ptx::tma_load_4d(sA + s * C::kStageA, &tmA, &full[s], kb * kBK, m0, az1, az2);
-          }
-          if (kBMn) {
+              for (int j = 0; j < kBM / kRowEl; ++j)
+                ptx::tma_load_4d_pair(sA + s * C::kStageA + j * kBoxBytes, &tmA, bar, m0 + j * kRowEl, kb * kBK, az1, az2);
+            } else {
+              ptx::tma_load_4d_pair(sA + s * C::kStageA, &tmA, bar, kb * kBK, m0, az1, az2);
+            }
+            if (kBMn) {
 #pragma unroll
-            for (int j = 0; j < BN / kRowEl; ++j)
-              ptx::tma_load_4d(sB + s * C::kStageB + j * kBoxBytes, &tmB, &full[s], n0 + j * kRowEl, kb * kBK, bz1, bz2);
+              for (int j = 0; j < kRowsB / kRowEl; ++j)
+                ptx::tma_load_4d_pair(sB + s * kStageBytesB + j * kBoxBytes, &tmB, bar, n0 + j * kRowEl, kb * kBK, bz1, bz2);
+            } else {
+              ptx::tma_load_4d_pair(sB + s * kStageBytesB, &tmB, bar, kb * kBK, n0, bz1, bz2);
+            }
           } else {
-            ptx::tma_load_4d(sB + s * C::kStageB, &tmB, &full[s], kb * kBK, n0, bz1, bz2);
+            ptx::mbar_arrive_expect_tx(&full[s], C::kStage);
+            if (kAMn) {
+#pragma unroll
+              for (int j = 0; j < kBM / kRowEl; ++j)
+                ptx::tma_load_4d(sA + s * C::kStageA + j * kBoxBytes, &tmA, &full[s], m0 + j * kRowEl, kb * kBK, az1, az2);
+            } else {
+              ptx::tma_load_4d(sA + s * C::kStageA, &tmA, &full[s], kb * kBK, m0, az1, az2);
+            }
+            if (kBMn) {
+#pragma unroll
+              for (int j = 0; j < BN / kRowEl; ++j)
+                ptx::tma_load_4d(sB + s * C::kStageB + j * kBoxBytes, &tmB, &full[s], n0 + j * kRowEl, kb * kBK, bz1, bz2);
+            } else {
+              ptx::tma_load_4d(sB + s * C::kStageB, &tmB, &full[s], kb * kBK, n0, bz1, bz2);
+            }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = ptx::umma_idesc(kTf32 ? 2 : 1, kBM, BN, kAMn ? 1 : 0, kBMn ? 1 : 0);
+  } else if (warp == 1 && rank == 0) {
+    // ================= MMA issuer (pair mode: the leader CTA only) =================
+    constexpr uint32_t idesc = ptx::umma_idesc(kTf32 ? 2 : 1, kTileM, BN, kAMn ? 1 : 0, kBMn ? 1 : 0);
     // per-instruction K step (16 bf16 / 8 tf32 = 32 bytes of K): K-major advances 32 B inside the swizzled row,
     // MN-major advances whole rows (16 or 8 rows of 128 B); in 16-byte descriptor units.
     constexpr uint32_t kStepA = kAMn ? (kTf32 ? 64u : 128u) : 2u;
     constexpr uint32_t kStepB = kBMn ? (kTf32 ? 64u : 128u) : 2u;
     uint32_t it = 0, ai = 0;
-    for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ai) {
+    for (long long tile = tile_first; tile < a.total_tiles; tile += tile_step, ++ai) {
       const int as = ai & 1;
       const uint32_t aph = (ai >> 1) & 1;
       const int sp = (int)(tile / (tiles_per_batch * a.nb1 * a.nb2));
@@ -462,26 +507,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % C::kStages;
-        const uint32_t ph = (it / C::kStages) & 1;
+        const int s = it % kNStages;
+        const uint32_t ph = (it / kNStages) & 1;
         ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
         if (lane == 0) {
           // tf32 MN-major: 32-byte-atom swizzle, 4-row K groups (512 B); everything else: SWIZZLE_128B, 8-row groups
           const uint64_t adesc = ptx::umma_desc_sw128(ptx::smem_u32(sA + s * C::kStageA), kAMn ? kBoxBytes : 16,
                                                       (kAMn && kTf32) ? 512 : 1024, (kAMn && kTf32) ? 1 : 2);
-          const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sB + s * C::kStageB), kBMn ? kBoxBytes : 16,
+          const uint64_t bdesc = ptx::umma_desc_sw128(ptx::smem_u32(sB + s * kStageBytesB), kBMn ? kBoxBytes : 16,
                                                       (kBMn && kTf32) ? 512 : 1024, (kBMn && kTf32) ? 1 : 2);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
-            if (kTf32)
+            if (kPair)
+              ptx::mma_f16_pair(d_tmem, adesc + kStepA * k, bdesc + kStepB * k, idesc, acc);
+            else if (kTf32)
               ptx::mma_tf32(d_tmem, adesc + kStepA * k, bdesc + kStepB * k, idesc, acc);
             else
               ptx::mma_f16(d_tmem, adesc + kStepA * k, bdesc + kStepB * k, idesc, acc);
           }
-          ptx::tc_commit(&empty[s]);                    // frees the smem stage when these MMAs retire
-          if (kb == kb1 - 1) ptx::tc_commit(&tfull[as]);  // accumulator complete
+          if (kPair) {
+            ptx::tc_commit2(&empty[s]);                     // both CTAs' producers may refill the stage
+            if (kb == kb1 - 1) ptx::tc_commit2(&tfull[as]);  // both CTAs' epilogues may drain their half
+          } else {
+            ptx::tc_commit(&empty[s]);                    // frees the smem stage when these MMAs retire
+            if (kb == kb1 - 1) ptx::tc_commit(&tfull[as]);  // accumulator complete
+          }
         }
         __syncwarp();
       }
@@ -495,12 +547,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     unsigned char* boxes = smem + C::kStageOff + (warp - 4) * 4096;   // staged epilogue only
     uint32_t seq = 0;
     uint32_t ai = 0;
-    for (long long tile = blockIdx.x; tile < a.total_tiles; tile += gridDim.x, ++ai) {
+    for (long long tile = tile_first; tile < a.total_tiles; tile += tile_step, ++ai) {
       const int zs = (int)(tile / tiles_per_batch);
       const int r = (int)(tile - (long long)zs * tiles_per_batch);
       int tm, tn;
       tile_coords(a, r, tm, tn);
-      const int m0 = tm * kBM, n0 = tn * BN;
+      const int m0 = tm * kTileM + (int)rank * kBM, n0 = tn * BN;
       const int nbz = a.nb1 * a.nb2;
       const int sp = zs / nbz, z = zs - sp * nbz;
       const int z1 = z % a.nb1, z2 = z / a.nb1;
@@ -528,7 +580,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // the whole half-tile is in registers: hand the accumulator buffer back before the global stores
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&tempty[as]);
+          if (lane == 0) {
+            if (kPair) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tempty[as]), 0));   // the leader's barrier counts both CTAs
+            else ptx::mbar_arrive(&tempty[as]);
+          }
         }
         if (kStaged) {
           if (c & 1) epilogue_chunk_staged(a, &tmC, &tmX, boxes, seq, lane, vb, m0 + q * 32, col_base + 32 * c, r_row, z1, z2);
@@ -543,10 +598,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if (kPair) ptx::cluster_sync();   // the peer's shared memory and barriers stay alive until both CTAs are done
+  else __syncthreads();
   if (warp == 2) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    if (kPair) ptx::tmem_dealloc2(tmem_base, C::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -634,9 +691,35 @@ static bool make_store_map(CUtensorMap* m, const T4sMatrix& c, int M, int N, int
              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <typename Kern>
+static int launch_kernel(Kern kern, int grid, int smem, bool pair, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                         const CUtensorMap& tmC, const CUtensorMap& tmX, const Args& a) {
+  T4S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (!pair) {
+    kern<<<grid, kThreads, smem, st>>>(tmA, tmB, tmC, tmX, a);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    T4S_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmX, a));
+  }
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
 template <int BN, bool kTf32, bool kAMn, bool kBMn>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, const CUtensorMap* tmX, Args& a, cudaStream_t st) {
-  a.tiles_m = (a.M + kBM - 1) / kBM;
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, const CUtensorMap* tmX, Args& a, cudaStream_t st,
+                  bool pair) {
+  a.tiles_m = pair ? (a.M + 2 * kBM - 1) / (2 * kBM) : (a.M + kBM - 1) / kBM;
   a.tiles_n = (a.N + BN - 1) / BN;
   a.group_n = std::min(a.tiles_n, 16);
   const int bk = kTf32 ? 32 : 64;
@@ -649,20 +732,19 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
   }
   a.total_tiles = (long long)a.tiles_m * a.tiles_n * a.nb1 * a.nb2 * a.split_k;
   const int grid = (int)std::min<long long>(a.total_tiles, sm_count());
-  if constexpr (!kTf32) {
-    if (tmC) {
-      auto kern = gemm_kernel<BN, kTf32, kAMn, kBMn, true>;
-      T4S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmemStaged));
-      kern<<<grid, kThreads, Cfg<BN>::kSmemStaged, st>>>(tmA, tmB, *tmC, tmX ? *tmX : *tmC, a);
-      T4S_LAUNCH_CHECK();
-      return T4S_OK;
+  if constexpr (!kTf32 && BN == 256) {
+    if (pair) {
+      const int grid2 = 2 * (int)std::min<long long>(a.total_tiles, sm_count() / 2);   // one CTA pair per TPC
+      if (tmC) return launch_kernel(gemm_kernel<BN, kTf32, kAMn, kBMn, true, true>, grid2, Cfg<BN>::kSmemStaged, true, st, tmA, tmB, *tmC,
+                                    tmX ? *tmX : *tmC, a);
+      return launch_kernel(gemm_kernel<BN, kTf32, kAMn, kBMn, false, true>, grid2, Cfg<BN>::kSmem, true, st, tmA, tmB, tmA, tmA, a);
     }
   }
-  auto kern = gemm_kernel<BN, kTf32, kAMn, kBMn, false>;
-  T4S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem));
-  kern<<<grid, kThreads, Cfg<BN>::kSmem, st>>>(tmA, tmB, tmA, tmA, a);
-  T4S_LAUNCH_CHECK();
-  return T4S_OK;
+  if constexpr (!kTf32) {
+    if (tmC) return launch_kernel(gemm_kernel<BN, kTf32, kAMn, kBMn, true, false>, grid, Cfg<BN>::kSmemStaged, false, st, tmA, tmB, *tmC,
+                                  tmX ? *tmX : *tmC, a);
+  }
+  return launch_kernel(gemm_kernel<BN, kTf32, kAMn, kBMn, false, false>, grid, Cfg<BN>::kSmem, false, st, tmA, tmB, tmA, tmA, a);
 }
 
 }  // namespace gemm
@@ -680,10 +762,13 @@ extern "C" int t4s_gemm(const T4sGemm* g, void* stream) {
   const bool tf32 = g->in_dtype == T4S_F32;
   const int esize = tf32 ? 4 : 2, bk = tf32 ? 32 : 64;
   const int BN = g->N > 128 ? 256 : (g->N > 64 ? 128 : 64);
+  // CTA-pair (cta_group::2) tiles for bf16 GEMMs with full-width N tiles and at least one 256-row tile (T4S_GEMM_PAIR=0 disables)
+  static const bool pair_enabled = [] { const char* e = getenv("T4S_GEMM_PAIR"); return !(e && e[0] == '0'); }();
+  const bool pair = pair_enabled && !tf32 && BN == 256 && g->M >= 256;
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, g->A, g->K, esize, tf32, bk, kBM, "A");
   if (rc) return rc;
-  rc = make_map(&tmB, g->B, g->K, esize, tf32, bk, BN, "B");
+  rc = make_map(&tmB, g->B, g->K, esize, tf32, bk, pair ? BN / 2 : BN, "B");
   if (rc) return rc;
   Args a;
   a.M = g->M; a.N = g->N; a.K = g->K; a.nb1 = g->nb1; a.nb2 = g->nb2;
@@ -709,11 +794,11 @@ extern "C" int t4s_gemm(const T4sGemm* g, void* stream) {
     pX = g->aux.ptr ? &tmXs : nullptr;
   }
   const int variant = (tf32 ? 4 : 0) | (g->A.mn_major ? 2 : 0) | (g->B.mn_major ? 1 : 0);
-#define T4S_GEMM_CASE(V, TF, AM, BM_)                                         \
-  case V:                                                                     \
-    if (BN == 256) return launch<256, TF, AM, BM_>(tmA, tmB, pC, pX, a, st);  \
-    if (BN == 128) return launch<128, TF, AM, BM_>(tmA, tmB, pC, pX, a, st);  \
-    return launch<64, TF, AM, BM_>(tmA, tmB, pC, pX, a, st);
+#define T4S_GEMM_CASE(V, TF, AM, BM_)                                                \
+  case V:                                                                            \
+    if (BN == 256) return launch<256, TF, AM, BM_>(tmA, tmB, pC, pX, a, st, pair);   \
+    if (BN == 128) return launch<128, TF, AM, BM_>(tmA, tmB, pC, pX, a, st, false);  \
+    return launch<64, TF, AM, BM_>(tmA, tmB, pC, pX, a, st, false);
   switch (variant) {
     T4S_GEMM_CASE(0, false, false, false)
     T4S_GEMM_CASE(1, false, false, true)
