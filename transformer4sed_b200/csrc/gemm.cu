@@ -45,6 +45,7 @@ struct Args {
   int bias_vec;  // bias base is 16-byte aligned
   float alpha;
   int act;
+  int res_tma;   // staged epilogue: the residual / pre-activation tile arrives by TMA (tensor map tmR) instead of per-row loads
 };
 
 template <int BN>
@@ -274,10 +275,13 @@ __device__ __forceinline__ void epilogue_chunk(const Args& a, const uint32_t (&v
 // different rows (32 L1 wavefronts per instruction: with two outputs the fc1 epilogue needed more LSU cycles than the tile's
 // MMAs).  Ragged edges are clipped by the tensor map.  `seq` alternates the warp's two staging boxes; lane 0 owns the bulk groups.
 __device__ __forceinline__ void stage_store(const CUtensorMap* map, unsigned char* boxes, uint32_t& seq, int lane, const float (&x)[32],
-                                            int gcol, int row0, int z1, int z2) {
+                                            int gcol, int row0, int z1, int z2, bool single_box) {
   unsigned char* box = boxes + (seq & 1) * 2048;
   ++seq;
-  if (lane == 0) ptx::bulk_wait_read_1();   // the store that last used this box has drained it
+  if (lane == 0) {   // the store that last used this box has drained it
+    if (single_box) ptx::bulk_wait_read_all();
+    else ptx::bulk_wait_read_1();
+  }
   __syncwarp();
   uint4* dst = reinterpret_cast<uint4*>(box + lane * 64);
   const int sw = (lane >> 1) & 3;
@@ -307,9 +311,26 @@ __device__ __forceinline__ void prefetch_res(const Args& a, long long r_row, int
 }
 
 // warp-uniform control flow (every lane stages its row; rows / columns outside the matrix are clipped by the TMA store)
+// 32 bf16 of this lane's row out of a SWIZZLE_64B box filled by a TMA load
+__device__ __forceinline__ void read_box_row(const unsigned char* box, int lane, float (&h)[32]) {
+  const uint4* src = reinterpret_cast<const uint4*>(box + lane * 64);
+  const int sw = (lane >> 1) & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 u = src[i ^ sw];
+    const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(hh[j]);
+      h[8 * i + 2 * j] = f.x;
+      h[8 * i + 2 * j + 1] = f.y;
+    }
+  }
+}
+
 __device__ __forceinline__ void epilogue_chunk_staged(const Args& a, const CUtensorMap* mapC, const CUtensorMap* mapX, unsigned char* boxes,
                                                       uint32_t& seq, int lane, const uint32_t (&v)[32], int row0, int gcol, long long r_row,
-                                                      int z1, int z2) {
+                                                      int z1, int z2, const float (&rtile)[32], bool have_rtile /* residual chunk already in registers */) {
   const int nvalid = a.N - gcol;
   if (row0 >= a.M || nvalid <= 0) return;
   const bool row_ok = row0 + lane < a.M;
@@ -332,22 +353,32 @@ __device__ __forceinline__ void epilogue_chunk_staged(const Args& a, const CUten
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] = a.alpha * __uint_as_float(v[i]);
   }
-  if (a.aux.ptr) stage_store(mapX, boxes, seq, lane, x, gcol, row0, z1, z2);
+  if (a.aux.ptr) stage_store(mapX, boxes, seq, lane, x, gcol, row0, z1, z2, a.res_tma != 0);
   if (a.act == T4S_ACT_GELU) {
 #pragma unroll
     for (int i = 0; i < 32; i += 2) gelu_fast2(x[i], x[i + 1]);
   }
   if (a.act == T4S_ACT_GELU_GRAD) {
-    float h[32];
+    if (have_rtile) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) h[i] = 0.f;
-    if (row_ok) load32(a.res, r_row + gcol, nvalid, h);
+      for (int i = 0; i < 32; i += 2) gelu_grad_fast2(rtile[i], rtile[i + 1], x[i], x[i + 1]);
+    } else {
+      float h[32];
 #pragma unroll
-    for (int i = 0; i < 32; i += 2) gelu_grad_fast2(h[i], h[i + 1], x[i], x[i + 1]);
+      for (int i = 0; i < 32; ++i) h[i] = 0.f;
+      if (row_ok) load32(a.res, r_row + gcol, nvalid, h);
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) gelu_grad_fast2(h[i], h[i + 1], x[i], x[i + 1]);
+    }
   } else if (a.res.ptr) {
-    if (row_ok) add32(a.res, r_row + gcol, nvalid, x);
+    if (have_rtile) {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] += rtile[i];
+    } else if (row_ok) {
+      add32(a.res, r_row + gcol, nvalid, x);
+    }
   }
-  stage_store(mapC, boxes, seq, lane, x, gcol, row0, z1, z2);
+  stage_store(mapC, boxes, seq, lane, x, gcol, row0, z1, z2, a.res_tma != 0);
 }
 
 // Tile r of a batch -> (m tile, n tile).  Tiles that run concurrently (148 consecutive indices) form a compact
@@ -368,7 +399,7 @@ __device__ __forceinline__ void tile_coords(const Args& a, int r, int& tm, int& 
 template <int BN, bool kTf32, bool kAMn, bool kBMn, bool kStaged, bool kPair>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-            const __grid_constant__ CUtensorMap tmX, const Args a) {
+            const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR, const Args a) {
   using C = Cfg<BN>;
   static_assert(!kPair || (BN == 256 && !kTf32), "pair mode: bf16, BN = 256");
   constexpr int kBK = kTf32 ? 32 : 64;   // K elements per pipeline stage
@@ -390,6 +421,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint64_t* tfull = bars + 2 * kNStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rbars = bars + 24;   // one per epilogue warp: residual-tile TMA loads (staged epilogue)
   const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;
   const long long tile_first = kPair ? (long long)(blockIdx.x >> 1) : (long long)blockIdx.x;
   const long long tile_step = kPair ? (long long)(gridDim.x >> 1) : (long long)gridDim.x;
@@ -403,6 +435,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (kStaged) {
       ptx::prefetch_tmap(&tmC);
       if (a.aux.ptr) ptx::prefetch_tmap(&tmX);
+      if (a.res_tma) ptx::prefetch_tmap(&tmR);
     }
   }
   if (warp == 1 && lane == 0) {
@@ -414,6 +447,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       ptx::mbar_init(&tfull[i], 1);
       ptx::mbar_init(&tempty[i], kPair ? 2 * kEpiWarps : kEpiWarps);
     }
+    if (kStaged)
+      for (int i = 0; i < kEpiWarps; ++i) ptx::mbar_init(&rbars[i], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 2) {
@@ -545,7 +580,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     constexpr int kHalfCols = BN / 2;
     constexpr int kChunks = kHalfCols / 32;
     unsigned char* boxes = smem + C::kStageOff + (warp - 4) * 4096;   // staged epilogue only
-    uint32_t seq = 0;
+    // with a TMA-fed residual, box 0 receives the residual chunks and box 1 alone stages the stores (seq stays odd)
+    const bool rtma = kStaged && a.res_tma;
+    uint64_t* rbar = &rbars[warp - 4];
+    uint32_t rph = 0;
+    uint32_t seq = rtma ? 1u : 0u;
     uint32_t ai = 0;
     for (long long tile = tile_first; tile < a.total_tiles; tile += tile_step, ++ai) {
       const int zs = (int)(tile / tiles_per_batch);
@@ -563,7 +602,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const long long x_row = (long long)z1 * a.aux.s1 + (long long)z2 * a.aux.s2 + (long long)grow * a.aux.ld;
       const long long r_row = (long long)z1 * a.res.s1 + (long long)z2 * a.res.s2 + (long long)grow * a.res.ld;
       const int col_base = n0 + half * kHalfCols;
-      if (kStaged) prefetch_res(a, r_row, col_base, grow < a.M);
+      const bool tile_live = m0 + q * 32 < a.M;      // warp-uniform: this warp's 32 rows exist
+      if (rtma) {
+        if (tile_live && col_base < a.N && lane == 0) {
+          ptx::fence_proxy_async();
+          ptx::mbar_arrive_expect_tx(rbar, 2048);
+          ptx::tma_load_4d(boxes, &tmR, rbar, col_base, m0 + q * 32, z1, z2);
+        }
+      } else if (kStaged) {
+        prefetch_res(a, r_row, col_base, grow < a.M);
+      }
       ptx::mbar_wait(&tfull[as], aph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + half * kHalfCols;
@@ -575,7 +623,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (c + 1 < kChunks) {
           if (c & 1) ptx::tmem_ld_32x32(t_row + 32 * (c + 1), va);
           else ptx::tmem_ld_32x32(t_row + 32 * (c + 1), vb);
-          if (kStaged) prefetch_res(a, r_row, col_base + 32 * (c + 1), grow < a.M);
+          if (kStaged && !rtma) prefetch_res(a, r_row, col_base + 32 * (c + 1), grow < a.M);
         } else {
           // the whole half-tile is in registers: hand the accumulator buffer back before the global stores
           ptx::tc_fence_before();
@@ -586,8 +634,25 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
         if (kStaged) {
-          if (c & 1) epilogue_chunk_staged(a, &tmC, &tmX, boxes, seq, lane, vb, m0 + q * 32, col_base + 32 * c, r_row, z1, z2);
-          else epilogue_chunk_staged(a, &tmC, &tmX, boxes, seq, lane, va, m0 + q * 32, col_base + 32 * c, r_row, z1, z2);
+          float rt[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rt[i] = 0.f;
+          const bool chunk_live = tile_live && col_base + 32 * c < a.N;
+          if (rtma && chunk_live) {
+            ptx::mbar_wait(rbar, rph);
+            rph ^= 1;
+            read_box_row(boxes, lane, rt);
+            __syncwarp();
+            if (c + 1 < kChunks && col_base + 32 * (c + 1) < a.N && lane == 0) {   // next chunk's residual lands while this one is processed
+              ptx::fence_proxy_async();
+              ptx::mbar_arrive_expect_tx(rbar, 2048);
+              ptx::tma_load_4d(boxes, &tmR, rbar, col_base + 32 * (c + 1), m0 + q * 32, z1, z2);
+            }
+          }
+          const bool have_rt = rtma && chunk_live;
+          if (c & 1) epilogue_chunk_staged(a, &tmC, &tmX, boxes, seq, lane, vb, m0 + q * 32, col_base + 32 * c, r_row, z1, z2, rt, have_rt);
+          else epilogue_chunk_staged(a, &tmC, &tmX, boxes, seq, lane, va, m0 + q * 32, col_base + 32 * c, r_row, z1, z2, rt, have_rt);
+          if (rtma) seq |= 1u;   // keep using box 1 for the stores
         } else {
           if (c & 1) epilogue_chunk(a, vb, grow, col_base + 32 * c, c_row, x_row, r_row);
           else epilogue_chunk(a, va, grow, col_base + 32 * c, c_row, x_row, r_row);
@@ -693,10 +758,10 @@ static bool make_store_map(CUtensorMap* m, const T4sMatrix& c, int M, int N, int
 
 template <typename Kern>
 static int launch_kernel(Kern kern, int grid, int smem, bool pair, cudaStream_t st, const CUtensorMap& tmA, const CUtensorMap& tmB,
-                         const CUtensorMap& tmC, const CUtensorMap& tmX, const Args& a) {
+                         const CUtensorMap& tmC, const CUtensorMap& tmX, const CUtensorMap& tmR, const Args& a) {
   T4S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   if (!pair) {
-    kern<<<grid, kThreads, smem, st>>>(tmA, tmB, tmC, tmX, a);
+    kern<<<grid, kThreads, smem, st>>>(tmA, tmB, tmC, tmX, tmR, a);
   } else {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
@@ -710,15 +775,15 @@ static int launch_kernel(Kern kern, int grid, int smem, bool pair, cudaStream_t 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    T4S_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmX, a));
+    T4S_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmX, tmR, a));
   }
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }
 
 template <int BN, bool kTf32, bool kAMn, bool kBMn>
-static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, const CUtensorMap* tmX, Args& a, cudaStream_t st,
-                  bool pair) {
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC, const CUtensorMap* tmX, const CUtensorMap* tmR, Args& a,
+                  cudaStream_t st, bool pair) {
   a.tiles_m = pair ? (a.M + 2 * kBM - 1) / (2 * kBM) : (a.M + kBM - 1) / kBM;
   a.tiles_n = (a.N + BN - 1) / BN;
   a.group_n = std::min(a.tiles_n, 16);
@@ -736,15 +801,15 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensor
     if (pair) {
       const int grid2 = 2 * (int)std::min<long long>(a.total_tiles, sm_count() / 2);   // one CTA pair per TPC
       if (tmC) return launch_kernel(gemm_kernel<BN, kTf32, kAMn, kBMn, true, true>, grid2, Cfg<BN>::kSmemStaged, true, st, tmA, tmB, *tmC,
-                                    tmX ? *tmX : *tmC, a);
-      return launch_kernel(gemm_kernel<BN, kTf32, kAMn, kBMn, false, true>, grid2, Cfg<BN>::kSmem, true, st, tmA, tmB, tmA, tmA, a);
+                                    tmX ? *tmX : *tmC, tmR ? *tmR : *tmC, a);
+      return launch_kernel(gemm_kernel<BN, kTf32, kAMn, kBMn, false, true>, grid2, Cfg<BN>::kSmem, true, st, tmA, tmB, tmA, tmA, tmA, a);
     }
   }
   if constexpr (!kTf32) {
     if (tmC) return launch_kernel(gemm_kernel<BN, kTf32, kAMn, kBMn, true, false>, grid, Cfg<BN>::kSmemStaged, false, st, tmA, tmB, *tmC,
-                                  tmX ? *tmX : *tmC, a);
+                                  tmX ? *tmX : *tmC, tmR ? *tmR : *tmC, a);
   }
-  return launch_kernel(gemm_kernel<BN, kTf32, kAMn, kBMn, false, false>, grid, Cfg<BN>::kSmem, false, st, tmA, tmB, tmA, tmA, a);
+  return launch_kernel(gemm_kernel<BN, kTf32, kAMn, kBMn, false, false>, grid, Cfg<BN>::kSmem, false, st, tmA, tmB, tmA, tmA, tmA, a);
 }
 
 }  // namespace gemm
@@ -785,20 +850,28 @@ extern "C" int t4s_gemm(const T4sGemm* g, void* stream) {
               "t4s_gemm: split_k needs c_split_stride and a plain epilogue");
   cudaStream_t st = t4s::as_stream(stream);
   // bf16 outputs of un-split GEMMs leave through TMA tile stores (staged epilogue) whenever the layout allows it
-  CUtensorMap tmCs, tmXs;
-  const CUtensorMap *pC = nullptr, *pX = nullptr;
+  CUtensorMap tmCs, tmXs, tmRs;
+  const CUtensorMap *pC = nullptr, *pX = nullptr, *pR = nullptr;
+  a.res_tma = 0;
   if (!tf32 && a.split_k == 1 && g->M >= 32 && make_store_map(&tmCs, g->C, g->M, g->N, g->nb1, g->nb2) &&
       (!g->aux.ptr || make_store_map(&tmXs, g->aux, g->M, g->N, g->nb1, g->nb2)) &&
       !(g->aux.ptr && g->residual.ptr)) {
     pC = &tmCs;
     pX = g->aux.ptr ? &tmXs : nullptr;
+    // the residual / pre-activation tile rides in by TMA too when it has the layout for it (a stride-0 broadcast does not)
+    static const bool res_tma_enabled = [] { const char* e = getenv("T4S_GEMM_RES_TMA"); return !(e && e[0] == '0'); }();
+    if (res_tma_enabled && g->residual.ptr && (g->nb1 == 1 || g->residual.stride1 > 0) && (g->nb2 == 1 || g->residual.stride2 > 0) &&
+        make_store_map(&tmRs, g->residual, g->M, g->N, g->nb1, g->nb2)) {
+      pR = &tmRs;
+      a.res_tma = 1;
+    }
   }
   const int variant = (tf32 ? 4 : 0) | (g->A.mn_major ? 2 : 0) | (g->B.mn_major ? 1 : 0);
 #define T4S_GEMM_CASE(V, TF, AM, BM_)                                                \
   case V:                                                                            \
-    if (BN == 256) return launch<256, TF, AM, BM_>(tmA, tmB, pC, pX, a, st, pair);   \
-    if (BN == 128) return launch<128, TF, AM, BM_>(tmA, tmB, pC, pX, a, st, false);  \
-    return launch<64, TF, AM, BM_>(tmA, tmB, pC, pX, a, st, false);
+    if (BN == 256) return launch<256, TF, AM, BM_>(tmA, tmB, pC, pX, pR, a, st, pair);   \
+    if (BN == 128) return launch<128, TF, AM, BM_>(tmA, tmB, pC, pX, pR, a, st, false);  \
+    return launch<64, TF, AM, BM_>(tmA, tmB, pC, pX, pR, a, st, false);
   switch (variant) {
     T4S_GEMM_CASE(0, false, false, false)
     T4S_GEMM_CASE(1, false, false, true)
