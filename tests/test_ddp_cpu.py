@@ -73,3 +73,52 @@ def test_shards_cover_batch_without_overlap():
             spans = [shard_for_rank(n, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_sliding_window_placement_matches_reference_loop():
+    """Host logic of the batched sliding window (no GPU): window enumeration, grouping by patch grid and output offsets equal the
+    reference's Python loop (encoder_slide_window.py:26-34) for the shipped train / validation parameters."""
+    from oracle import model as OM
+    from transformer4sed_b200.src_models.encoder_slide_window import EncoderSlideWindow
+
+    class Probe(EncoderSlideWindow):
+        def encode(self, x):
+            raise AssertionError("not used")
+
+        def frames_per_window(self, width):
+            return min((width - 16) // 10 + 1, 99)
+
+    for win in ([512, 49], [512, 31], [512, 29], [1000, 100], [256, 256]):
+        ours = Probe(None, win).window_starts(1000)
+        ref = [(a, b - a) for a, b in OM.window_starts(1000, tuple(win))]
+        assert ours == ref, (win, ours, ref)
+    w31 = Probe(None, [512, 31]).window_starts(1000)
+    assert len(w31) == 17 and w31[-1] == (496, 504) and Probe(None, [512, 31]).frames_per_window(504) == 49
+    w49 = Probe(None, [512, 49]).window_starts(1000)
+    assert len(w49) == 11 and w49[-1] == (490, 510) and Probe(None, [512, 49]).frames_per_window(510) == 50
+    assert Probe(None, [2000, 10]).window_starts(1000) == []      # window longer than the clip + step: no window, embedding is all zeros
+
+
+def test_pmam_dasm_schemas_and_lora_merge_roundtrip_cpu():
+    """State-dict schemas of the PMAM / DASM mirrors match the golden key lists recorded from the reference; LoRA merge / un-merge on
+    eval() / train() is exact bookkeeping (host-side torch ops, no kernel)."""
+    import numpy as np
+    import os
+    import torch
+    from transformer4sed_b200 import schema
+    from transformer4sed_b200.src_models import lora
+    gdir = os.path.join(os.path.dirname(__file__), "golden")
+    for name, shapes in (("pmam_base.npz", schema.passt_cnn_shapes()), ("dasm_base.npz", schema.dasm_shapes())):
+        keys = [str(k) for k in np.load(os.path.join(gdir, name))["sd_keys"] if not str(k).endswith("num_batches_tracked")]
+        assert sorted(shapes) == keys
+    lin = lora.Linear(32, 48, r=8, lora_alpha=1)
+    with torch.no_grad():
+        lin.lora_B.normal_(0, 0.3)
+    w0 = lin.weight.detach().clone()
+    lin.eval()
+    assert lin.merged and torch.allclose(lin.weight, w0 + (lin.lora_B @ lin.lora_A) / 8, atol=1e-7)
+    lin.eval()
+    assert torch.allclose(lin.weight, w0 + (lin.lora_B @ lin.lora_A) / 8, atol=1e-7)     # idempotent
+    lin.train()
+    assert not lin.merged and torch.allclose(lin.weight, w0, atol=1e-6)
+    assert not lin.weight.requires_grad and lin.lora_A.requires_grad
