@@ -186,6 +186,9 @@ typedef struct {
   void* dq; int64_t dq_ld, dq_bs;
   void* dk; int64_t dk_ld, dk_bs;
   void* dv; int64_t dv_ld, dv_bs;
+  float* dq32;          /* optional workspace [B, N, heads*64] fp32.  When given, ONE fused kernel computes dK / dV and adds the dQ tiles
+                           into dq32 with TMA reduce-add (S, P, dS are formed once instead of twice), then dq = scale * dq32 is written;
+                           the fp32 summation order over key tiles is not fixed.  NULL: the deterministic two-kernel backward. */
 } T4sAttnBwd;
 int64_t t4s_attn_padded_len(int tokens);
 int t4s_attn_fwd(const T4sAttn* a, void* stream);

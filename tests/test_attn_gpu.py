@@ -66,18 +66,33 @@ def test_fused_matches_unfused_path():
 
 
 def test_fused_attention_is_deterministic():
+    """Forward, dK and dV are bitwise reproducible in both backward variants.  dQ is bitwise reproducible in the two-kernel backward;
+    the one-kernel backward adds the dQ tiles with TMA reduce-add, so its fp32 summation order over the 10 key tiles is not fixed:
+    there dQ must agree to fp32-reassociation accuracy (far below bf16 resolution) and match the deterministic variant."""
     from transformer4sed_b200 import functional as F
     F.set_precision("bf16")
     g = torch.Generator(device="cuda").manual_seed(9)
     base = torch.randn(2, 1190, 3 * 768, generator=g, device="cuda").to(torch.bfloat16)
     w = torch.randn(2, 1190, 768, generator=g, device="cuda").to(torch.bfloat16)
-    res = []
-    for _ in range(2):
+
+    def run():
         x = base.clone().requires_grad_(True)
         o = F.attention(x, 12)
         o.backward(w)
-        res.append((o.clone(), x.grad.clone()))
-    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+        return o.clone(), x.grad.clone()
+
+    try:
+        F.set_fused_attention_backward(False)
+        a, b = run(), run()
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        F.set_fused_attention_backward(True)
+        c, d = run(), run()
+        assert torch.equal(c[0], d[0]) and torch.equal(c[0], a[0])
+        assert torch.equal(c[1][:, :, 768:], d[1][:, :, 768:]) and torch.equal(c[1][:, :, 768:], a[1][:, :, 768:])   # dK, dV
+        assert _rel(c[1][:, :, :768].float(), d[1][:, :, :768].float()) < 4e-3                                      # dQ: one bf16 ulp at most
+        assert _rel(c[1][:, :, :768].float(), a[1][:, :, :768].float()) < 8e-3
+    finally:
+        F.set_fused_attention_backward(True)
 
 
 def test_attention_abi_rejects_bad_arguments():

@@ -55,7 +55,7 @@ class AttnBwd(ctypes.Structure):
     _fields_ = [("fwd", Attn), ("d_o", c_void_p), ("do_ld", ctypes.c_int64), ("do_bs", ctypes.c_int64), ("delta", c_void_p),
                 ("dq", c_void_p), ("dq_ld", ctypes.c_int64), ("dq_bs", ctypes.c_int64),
                 ("dk", c_void_p), ("dk_ld", ctypes.c_int64), ("dk_bs", ctypes.c_int64),
-                ("dv", c_void_p), ("dv_ld", ctypes.c_int64), ("dv_bs", ctypes.c_int64)]
+                ("dv", c_void_p), ("dv_ld", ctypes.c_int64), ("dv_bs", ctypes.c_int64), ("dq32", c_void_p)]
 
 
 class RelAttn(ctypes.Structure):

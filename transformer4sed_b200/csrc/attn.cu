@@ -17,6 +17,8 @@
 //   tensor pipe stays busy while the exponentials run.
 //
 // Out-of-range rows are handled by TMA zero fill (loads) and row predicates (stores); out-of-range key columns are masked.
+#include <cstdlib>
+
 #include "attn_common.cuh"
 
 namespace t4s {
@@ -280,22 +282,48 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, long long
 namespace bwd {
 constexpr int kThreads = 320;  // warps 0-7 softmax (two column halves), 8 TMA, 9 MMA
 // resident pair (K,V for dKV / Q,dO for dQ), streamed pair x 2 stages, two [128x128] bf16 operand tiles, lse/delta stages
-// The P / dS operand tiles are double-buffered: the softmax warps fill buffer (i+1)&1 while the tensor core still reads buffer i&1
-// for tile i's dV / dK (dQ) products.
+// Modes: 0 = dK/dV kernel, 1 = dQ kernel (the deterministic two-kernel backward), 2 = fused: the dK/dV kernel also forms
+// dQ_i += dS_ij K_j per tile and adds it to an fp32 dQ buffer with TMA reduce-add (cp.reduce.async.bulk.tensor .add), so S, P
+// and dS -- the exponential / softmax work that bounds these kernels -- are computed once instead of twice.
+// P / dS operand tiles: two buffers in modes 0 / 1 (fill i+1 while the tensor core reads i), one in mode 2 (the room goes to
+// the per-warp dQ staging boxes).
+constexpr int kDqBox = 32 * 128;  // per softmax warp: 32 rows x 32 fp32, SWIZZLE_128B
 constexpr int oRes = 0, oStr = oRes + 2 * kTileBytes, oP = oStr + 4 * kTileBytes, oDs = oP + 2 * kPBytes, oStat = oDs + 2 * kPBytes,
               oBar = oStat + 2 * 2 * kTile * 4;
+constexpr int oDsF = oP + kPBytes, oDqF = oDsF + kPBytes;   // fused layout: P, dS single, then 8 dQ boxes (ends below oStat)
+static_assert(oDqF + 8 * kDqBox <= oStat, "fused layout must fit in front of the statistics");
 constexpr int kSmem = oBar + 128;
-constexpr int kTmemCols = 512;  // S: [0,128)  dP: [128,256)  acc0: [256,320)  acc1: [320,384)
-enum { bResFull = 0, bStrFull = 1, bStrEmpty = 3, bSFull = 5, bSFree = 6, bPFull = 7, bPFree = 8 /* +1 */, bAccFull = 10, bCount = 11 };
+constexpr int kTmemCols = 512;  // S: [0,128)  dP: [128,256)  acc0: [256,320)  acc1: [320,384)  dQ tile (fused): [384,448)
+enum { bResFull = 0, bStrFull = 1, bStrEmpty = 3, bSFull = 5, bSFree = 6, bPFull = 7, bPFree = 8 /* +1 */, bAccFull = 10, bDqFull = 11,
+       bDqFree = 12, bCount = 13 };
+constexpr uint32_t kIdescAmn = ptx::umma_idesc(1, 128, 64, 1, 1);  // A and B MN-major
+// D[128 x 64] (+)= A^T . B: A = a [128 (K) x 128 (M)] tile written K-major, consumed MN-major (two 64-wide M blocks 16 KB apart);
+// B = [128 rows (K) x 64] tile consumed MN-major
+__device__ __forceinline__ void mma_k128_amn(uint32_t d_tmem, uint32_t a_addr, uint32_t b_addr, bool accumulate) {
+  const uint64_t adesc = ptx::umma_desc_sw128(a_addr, kTileBytes, 1024), bdesc = ptx::umma_desc_sw128(b_addr, 8192, 1024);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) ptx::mma_f16(d_tmem, adesc + 128 * k, bdesc + 128 * k, kIdescAmn, (accumulate || k > 0) ? 1u : 0u);
+}
+// shared -> global tile reduce-add (fp32), bulk async-group completion; the box is clipped at the tensor bounds
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(ptx::smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 }  // namespace bwd
 
 // kDq = false: dK/dV kernel (resident K_j, V_j; streams Q_i, dO_i, lse_i, delta_i; thread = key row)
 // kDq = true : dQ kernel    (resident Q_i, dO_i; streams K_j, V_j;                  thread = query row)
-template <bool kDq>
+template <int kMode>
 __global__ void __launch_bounds__(bwd::kThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const Args a) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmDQ,
+                const Args a) {
   using namespace bwd;
+  constexpr bool kDq = kMode == 1, kFused = kMode == 2;
+  constexpr int kPBuf = kFused ? 0 : kPBytes;          // stride between the two P / dS buffers (0: single buffer)
+  constexpr int oDsM = kFused ? oDsF : oDs;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
@@ -320,9 +348,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::mbar_init(&bars[bPFree], 1);
     ptx::mbar_init(&bars[bPFree + 1], 1);
     ptx::mbar_init(&bars[bAccFull], 1);
+    ptx::mbar_init(&bars[bDqFull], 1);
+    ptx::mbar_init(&bars[bDqFree], 8);
     ptx::fence_barrier_init();
   }
   if (warp == 8 && lane == 0) {
+    if (kFused) ptx::prefetch_tmap(&tmDQ);
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
@@ -374,7 +405,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else if (warp == 9) {
     // ---------------- MMA issuer ----------------
     const uint32_t r0 = ptx::smem_u32(sRes0), r1 = ptx::smem_u32(sRes1), str = ptx::smem_u32(smem + oStr),
-                   sP = ptx::smem_u32(smem + oP), sDs = ptx::smem_u32(smem + oDs);
+                   sP = ptx::smem_u32(smem + oP), sDs = ptx::smem_u32(smem + oDsM);
     ptx::mbar_wait(&bars[bResFull], 0);
     ptx::mbar_wait(&bars[bStrFull + 0], 0);
     ptx::tc_fence_after();
@@ -402,7 +433,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tc_fence_after();
       if (lane == 0) {
         const uint32_t cur = str + s * 2 * kTileBytes;
-        const uint32_t pb = sP + s * kPBytes, db = sDs + s * kPBytes;
+        const uint32_t pb = sP + s * kPBuf, db = sDs + s * kPBuf;
         if (kDq) {
           mma_k128_mn(tmem + 256, db, cur, kIdescPV, i > 0);                   // dQ += dS K_j
         } else {
@@ -410,7 +441,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mma_k128_mn(tmem + 320, db, cur, kIdescPV, i > 0);                   // dK += dS^T Q_i
         }
         ptx::tc_commit(&bars[bStrEmpty + s]);
-        ptx::tc_commit(&bars[bPFree + s]);
+        if (kFused) {
+          // dQ_i tile = dS_ij K_j (A = the dS^T tile read MN-major, B = the resident K_j): fresh accumulator every tile
+          ptx::mbar_wait(&bars[bDqFree], (i & 1) ^ 1);   // the softmax warps have drained tile i-1's product
+          ptx::tc_fence_after();
+          mma_k128_amn(tmem + 384, db, r0, false);
+          ptx::tc_commit(&bars[bDqFull]);
+        }
+        ptx::tc_commit(&bars[bPFree + (kFused ? 0 : s)]);
         if (i == n_tiles - 1) ptx::tc_commit(&bars[bAccFull]);
       }
       __syncwarp();
@@ -426,13 +464,41 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       my_lse = a.lse[stat_base + t0 + r];
       my_delta = a.delta[stat_base + t0 + r];
     }
+    // fused mode: move query tile `it`'s dQ product (this warp: rows 32 wq.., columns 32 g..) from TMEM to the warp's staging box
+    // and add it to the fp32 dQ buffer with one TMA reduce
+    unsigned char* dq_box = smem + oDqF + warp * kDqBox;
+    auto drain_dq = [&](int it) {
+      ptx::mbar_wait(&bars[bDqFull], it & 1);
+      ptx::tc_fence_after();
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(t_lane + 384 + 32 * g, v);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(&bars[bDqFree]);
+        ptx::bulk_wait_read_all();           // the previous reduce has finished reading the box
+      }
+      __syncwarp();
+      uint4* dst = reinterpret_cast<uint4*>(dq_box + lane * 128);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) dst[q ^ (lane & 7)] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_reduce_add_4d(&tmDQ, dq_box, 32 * g, it * kTile + 32 * wq, h, b);
+        ptx::bulk_commit();
+      }
+    };
     for (int i = 0; i < n_tiles; ++i) {
       const int s = i & 1;
       const float* st = sStat + s * 2 * kTile;
       if (!kDq) ptx::mbar_wait(&bars[bStrFull + s], (i >> 1) & 1);  // lse / delta of this query tile have landed
       ptx::mbar_wait(&bars[bSFull], i & 1);
       ptx::tc_fence_after();
-      ptx::mbar_wait(&bars[bPFree + s], ((i >> 1) & 1) ^ 1);  // tile i-2's MMAs have finished reading this P / dS buffer
+      if (kFused && i > 0) drain_dq(i - 1);
+      // the MMAs that last read this P / dS buffer (tile i-2, or i-1 with a single buffer) have finished
+      ptx::mbar_wait(&bars[bPFree + (kFused ? 0 : s)], kFused ? ((i & 1) ^ 1) : (((i >> 1) & 1) ^ 1));
       const int nvalid = a.N - i * kTile;          // dQ: key columns that exist
       const bool full = nvalid >= kTile;
       // all four TMEM loads of this thread's 64 columns are issued before the first wait (the exposed tcgen05.ld round trips
@@ -476,13 +542,14 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           pd[2 * q] = pack_bf16(d[0], d[1]);
           pd[2 * q + 1] = pack_bf16(d[2], d[3]);
         }
-        if (!kDq) store_row_chunk(smem + oP + s * kPBytes, r, col0, pp);
-        store_row_chunk(smem + oDs + s * kPBytes, r, col0, pd);
+        if (!kDq) store_row_chunk(smem + oP + s * kPBuf, r, col0, pp);
+        store_row_chunk(smem + oDsM + s * kPBuf, r, col0, pd);
       }
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars[bPFull]);
     }
+    if (kFused) drain_dq(n_tiles - 1);
     // ---- write the accumulators: each column half takes 32 of the 64 head-dim columns ----
     ptx::mbar_wait(&bars[bAccFull], 0);
     ptx::tc_fence_after();
@@ -498,6 +565,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tmem_ld_wait();
       if (row < a.N) store_row32(a.dk + (long long)b * a.dk_bs + (long long)row * a.dk_ld + h * kHd + 32 * g, v, a.scale);
     }
+    if (kFused && lane == 0) ptx::bulk_wait_all();   // the staging boxes must outlive the last reduce
   }
 
   ptx::tc_fence_before();
@@ -505,6 +573,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 9) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+// dq[b, n, h*64 + d] (bf16, strided) = scale * dq32[b, n, h*64 + d]   (fused backward: fp32 reduce buffer -> gradient slot)
+__global__ void dq_finish_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dq, long long dq_ld, long long dq_bs, int N, int D,
+                                 float scale, long long total8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const long long e = i * 8;
+    const int d = (int)(e % D);
+    const long long bn = e / D;
+    const int n = (int)(bn % N);
+    const long long b = bn / N;
+    const float4 x = *reinterpret_cast<const float4*>(dq32 + e), y = *reinterpret_cast<const float4*>(dq32 + e + 4);
+    uint4 u;
+    u.x = pack_bf16(x.x * scale, x.y * scale);
+    u.y = pack_bf16(x.z * scale, x.w * scale);
+    u.z = pack_bf16(y.x * scale, y.y * scale);
+    u.w = pack_bf16(y.z * scale, y.w * scale);
+    *reinterpret_cast<uint4*>(dq + b * dq_bs + (long long)n * dq_ld + d) = u;
   }
 }
 
@@ -632,11 +719,38 @@ extern "C" int t4s_attn_bwd(const T4sAttnBwd* p, void* stream) {
   cudaStream_t st = t4s::as_stream(stream);
   if ((rc = launch_delta(f->o, f->o_ld, f->o_bs, f->o32, p->d_o, p->do_ld, p->do_bs, p->delta, f->batch, f->heads, f->tokens, a.Nl, st))) return rc;
   dim3 grid(a.n_tiles, f->heads, f->batch);
-  T4S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
-  attn_bwd_kernel<false><<<grid, bwd::kThreads, bwd::kSmem, st>>>(tq, tk, tv, tdo, a);
+  static const bool fused_enabled = [] { const char* e = getenv("T4S_ATTN_FUSED_BWD"); return !(e && e[0] == '0'); }();
+  if (p->dq32 && fused_enabled) {
+    // one kernel: dK / dV as before, dQ tiles reduce-added (fp32, TMA) into dq32, then scaled and rounded into the dq slot
+    const int D = f->heads * kHd;
+    T4S_REQUIRE(!(reinterpret_cast<uintptr_t>(p->dq32) & 15), "t4s_attn_bwd: dq32 must be 16-byte aligned");
+    CUtensorMap tdq;
+    {
+      t4s::ensure_context();
+      EncodeTiledFn enc = get_encode();
+      T4S_REQUIRE(enc, "cuTensorMapEncodeTiled entry point not available");
+      cuuint64_t dims[4] = {(cuuint64_t)kHd, (cuuint64_t)f->tokens, (cuuint64_t)f->heads, (cuuint64_t)f->batch};
+      cuuint64_t strides[3] = {(cuuint64_t)D * 4, (cuuint64_t)kHd * 4, (cuuint64_t)f->tokens * D * 4};
+      cuuint32_t box[4] = {32, 32, 1, 1}, estr[4] = {1, 1, 1, 1};
+      CUresult cr = enc(&tdq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, p->dq32, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      T4S_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled(dq32) failed with CUresult %d", (int)cr);
+    }
+    T4S_CUDA(cudaMemsetAsync(p->dq32, 0, (size_t)f->batch * f->tokens * D * sizeof(float), st));
+    T4S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
+    attn_bwd_kernel<2><<<grid, bwd::kThreads, bwd::kSmem, st>>>(tq, tk, tv, tdo, tdq, a);
+    T4S_LAUNCH_CHECK();
+    const long long total8 = (long long)f->batch * f->tokens * D / 8;
+    const int fgrid = (int)std::min<long long>((total8 + 255) / 256, (long long)t4s::sm_count() * 16);
+    dq_finish_kernel<<<fgrid, 256, 0, st>>>(p->dq32, a.dq, a.dq_ld, a.dq_bs, f->tokens, D, a.scale, total8);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
+  T4S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
+  attn_bwd_kernel<0><<<grid, bwd::kThreads, bwd::kSmem, st>>>(tq, tk, tv, tdo, tq, a);
   T4S_LAUNCH_CHECK();
-  T4S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
-  attn_bwd_kernel<true><<<grid, bwd::kThreads, bwd::kSmem, st>>>(tq, tk, tv, tdo, a);
+  T4S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
+  attn_bwd_kernel<1><<<grid, bwd::kThreads, bwd::kSmem, st>>>(tq, tk, tv, tdo, tq, a);
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }

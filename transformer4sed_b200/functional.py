@@ -17,6 +17,7 @@ from .ops import Op, Out
 
 _MODE = "bf16"
 _FUSED_ATTN = True
+_FUSED_ATTN_BWD = True   # one-kernel attention backward (dQ via TMA reduce-add); False: deterministic two-kernel backward
 
 
 def set_precision(mode: str):
@@ -553,6 +554,8 @@ class _FlashAttention(torch.autograd.Function):
             g.dq, g.dk, g.dv = dqkv.data_ptr(), dqkv.data_ptr() + D * es, dqkv.data_ptr() + 2 * D * es
             g.dq_ld = g.dk_ld = g.dv_ld = 3 * D
             g.dq_bs = g.dk_bs = g.dv_bs = N * 3 * D
+            dq32 = torch.empty(B, N, D, dtype=torch.float32, device=dev) if _FUSED_ATTN_BWD else None   # zeroed by the call
+            g.dq32 = dq32.data_ptr() if dq32 is not None else None
             _lib_call("t4s_attn_bwd", ctypes.byref(g), _st())
         return dqkv, None
 
@@ -561,6 +564,12 @@ def set_fused_attention(flag: bool):
     """Debug / A-B switch: False routes bf16 attention through the unfused GEMM + softmax kernels."""
     global _FUSED_ATTN
     _FUSED_ATTN = bool(flag)
+
+
+def set_fused_attention_backward(flag: bool):
+    """False selects the deterministic two-kernel attention backward (dQ summed in a fixed order)."""
+    global _FUSED_ATTN_BWD
+    _FUSED_ATTN_BWD = bool(flag)
 
 
 def attention(qkv, num_heads):
