@@ -829,7 +829,10 @@ extern "C" int t4s_gemm(const T4sGemm* g, void* stream) {
   const int BN = g->N > 128 ? 256 : (g->N > 64 ? 128 : 64);
   // CTA-pair (cta_group::2) tiles for bf16 GEMMs with full-width N tiles and at least one 256-row tile (T4S_GEMM_PAIR=0 disables)
   static const bool pair_enabled = [] { const char* e = getenv("T4S_GEMM_PAIR"); return !(e && e[0] == '0'); }();
-  const bool pair = pair_enabled && !tf32 && BN == 256 && g->M >= 256;
+  // Measured on B200: the pair tile pays off when the contraction is deep (wgrad, fc2, the K >= 2304 dgrads: +4..10 %) or the output
+  // narrow; wide-output / short-K products (fc1, qkv, the GELU' dgrad: N >= 2048 with K <= 1024) are epilogue-bound and run ~7 %
+  // faster on single-CTA tiles (ncu: 291 us vs 315 us for M=76160 N=3072 K=768), so those keep them.
+  const bool pair = pair_enabled && !tf32 && BN == 256 && g->M >= 256 && !(g->K <= 1024 && g->N >= 2048);
   CUtensorMap tmA, tmB;
   int rc = make_map(&tmA, g->A, g->K, esize, tf32, bk, kBM, "A");
   if (rc) return rc;
