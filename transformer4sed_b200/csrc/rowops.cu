@@ -3,6 +3,7 @@
 //   relative-position softmax with the Transformer-XL shift folded into the read, column sums (bias / gamma grads),
 //   GELU backward.  All take fp32 or bf16 activations; statistics and parameters are fp32.
 #include <algorithm>
+#include <initializer_list>
 
 #include "common.cuh"
 
@@ -516,6 +517,153 @@ __global__ void __launch_bounds__(kThreads) softmax_bwd_kernel(const T* __restri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// bf16 row softmax with 16-byte accesses (cols % 8 == 0, cols <= 1024; one warp per row, 4 vectors of 8 per lane).
+// The un-fused attention path (head sizes other than 64: the d = 384 PMAM / DASM decoders) spends its time here; the scalar
+// kernels above move 2 bytes per thread per instruction.  kRel: the rel_shift is an unaligned 2-byte offset (T-1-i) into the
+// position-score row, so that row goes through a per-warp shared-memory buffer: aligned 16-byte traffic to global memory,
+// the odd offset is absorbed by 2-byte shared-memory accesses.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kVecMaxV = 4;                 // 8-element vectors per lane  -> cols <= 1024
+constexpr int kRowBuf = 1024 + 16;          // bf16 elements per warp buffer
+
+template <bool kRel>
+__global__ void __launch_bounds__(kThreads) softmax_fwd_bf16_kernel(const __nv_bfloat16* __restrict__ s, const __nv_bfloat16* __restrict__ bd,
+                                                                    __nv_bfloat16* __restrict__ p, long long rows, int cols, long long ld_s,
+                                                                    long long ld_bd, long long ld_p, int T_len) {
+  __shared__ __align__(16) __nv_bfloat16 sbuf[kRel ? kWarpsPerBlock * kRowBuf : 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + warp;
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const int nvec = cols >> 3;
+  __nv_bfloat16* wb = sbuf + (kRel ? warp * kRowBuf : 0);
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const uint4* sr = reinterpret_cast<const uint4*>(s + r * ld_s);
+    int lo = 0;
+    if (kRel) {
+      // stage bd[r, shift .. shift + cols) : aligned vectors [shift/8, (shift + cols + 7)/8)
+      const int shift = T_len - 1 - (int)(r % T_len);
+      const int v0 = shift >> 3, v1 = (shift + cols + 7) >> 3;
+      lo = shift - 8 * v0;
+      const uint4* br = reinterpret_cast<const uint4*>(bd + r * ld_bd);
+      __syncwarp();
+      for (int v = v0 + lane; v < v1; v += 32) reinterpret_cast<uint4*>(wb)[v - v0] = br[v];
+      __syncwarp();
+    }
+    float x[kVecMaxV][8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kVecMaxV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        unpack8(sr[v], x[i]);
+        if (kRel) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) x[i][e] += __bfloat162float(wb[lo + 8 * v + e]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) mx = fmaxf(mx, x[i][e]);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVecMaxV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          x[i][e] = __expf(x[i][e] - mx);
+          sum += x[i][e];
+        }
+      }
+    }
+    const float inv = 1.0f / warp_sum(sum);
+    uint4* pr = reinterpret_cast<uint4*>(p + r * ld_p);
+#pragma unroll
+    for (int i = 0; i < kVecMaxV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) x[i][e] *= inv;
+        pr[v] = pack8(x[i]);
+      }
+    }
+  }
+}
+
+// ds = p * (dp - sum_j p dp), written over dp; kRel also writes the whole shifted position-gradient row dbd[r, 0 .. ld_bd)
+// (ds at columns [shift, shift + cols), zeros elsewhere) with aligned 16-byte stores.
+template <bool kRel>
+__global__ void __launch_bounds__(kThreads) softmax_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ p, __nv_bfloat16* __restrict__ dp,
+                                                                    __nv_bfloat16* __restrict__ dbd, long long rows, int cols, long long ld_p,
+                                                                    long long ld_dp, long long ld_bd, int T_len) {
+  __shared__ __align__(16) __nv_bfloat16 sbuf[kRel ? kWarpsPerBlock * kRowBuf : 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + warp;
+  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const int nvec = cols >> 3;
+  __nv_bfloat16* wb = sbuf + (kRel ? warp * kRowBuf : 0);
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const uint4* pr = reinterpret_cast<const uint4*>(p + r * ld_p);
+    uint4* dr = reinterpret_cast<uint4*>(dp + r * ld_dp);
+    float pv[kVecMaxV][8], dv[kVecMaxV][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVecMaxV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+        unpack8(pr[v], pv[i]);
+        unpack8(dr[v], dv[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dot += pv[i][e] * dv[i][e];
+      }
+    }
+    dot = warp_sum(dot);
+    if (kRel) __syncwarp();
+#pragma unroll
+    for (int i = 0; i < kVecMaxV; ++i) {
+      const int v = lane + 32 * i;
+      if (v < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pv[i][e] *= dv[i][e] - dot;
+        const uint4 o = pack8(pv[i]);
+        dr[v] = o;
+        if (kRel) reinterpret_cast<uint4*>(wb)[v] = o;
+      }
+    }
+    if (kRel) {
+      __syncwarp();
+      const int shift = T_len - 1 - (int)(r % T_len);
+      uint4* br = reinterpret_cast<uint4*>(dbd + r * ld_bd);
+      const int nout = (int)(ld_bd >> 3);
+      for (int v = lane; v < nout; v += 32) {
+        const int c0 = 8 * v - shift;            // source column of element 0
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (c0 > -8 && c0 < cols) {
+          __align__(16) __nv_bfloat16 t[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = c0 + e;
+            t[e] = (c >= 0 && c < cols) ? wb[c] : __float2bfloat16_rn(0.f);
+          }
+          o = *reinterpret_cast<const uint4*>(t);
+        }
+        br[v] = o;
+      }
+    }
+  }
+}
+
+static bool softmax_vec_ok(int dtype, int cols, std::initializer_list<const void*> ptrs, std::initializer_list<long long> lds) {
+  if (dtype != T4S_BF16 || cols % 8 || cols > 8 * 32 * kVecMaxV) return false;
+  for (const void* q : ptrs)
+    if (q && (reinterpret_cast<uintptr_t>(q) & 15)) return false;
+  for (long long l : lds)
+    if (l % 8) return false;
+  return true;
+}
+
 static int grid_for_rows(long long rows) {
   long long blocks = (rows + kWarpsPerBlock - 1) / kWarpsPerBlock;
   return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)sm_count() * 8));
@@ -655,6 +803,12 @@ int t4s_gelu_bwd(const void* dy, const void* h, void* dh, size_t n, int dtype, v
 
 int t4s_softmax_fwd(const void* s, void* p, int64_t rows, int cols, int64_t ld_s, int64_t ld_p, int dtype, void* stream) {
   T4S_REQUIRE(s && p && rows > 0 && cols > 0 && cols <= 32 * kSmMaxE, "t4s_softmax_fwd: cols must be in 1..%d", 32 * kSmMaxE);
+  if (softmax_vec_ok(dtype, cols, {s, (const void*)p}, {(long long)ld_s, (long long)ld_p})) {
+    softmax_fwd_bf16_kernel<false><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(s), nullptr, static_cast<__nv_bfloat16*>(p), rows, cols, ld_s, 0, ld_p, 0);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (softmax_fwd_kernel<T, false><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(s), nullptr, static_cast<T*>(p), rows, cols, ld_s, 0, ld_p, 0)));
   T4S_LAUNCH_CHECK();
@@ -663,6 +817,12 @@ int t4s_softmax_fwd(const void* s, void* p, int64_t rows, int cols, int64_t ld_s
 
 int t4s_softmax_bwd(const void* p, void* dp, int64_t rows, int cols, int64_t ld_p, int64_t ld_dp, int dtype, void* stream) {
   T4S_REQUIRE(p && dp && rows > 0 && cols > 0 && cols <= 32 * kSmMaxE, "t4s_softmax_bwd: cols must be in 1..%d", 32 * kSmMaxE);
+  if (softmax_vec_ok(dtype, cols, {p, dp}, {(long long)ld_p, (long long)ld_dp})) {
+    softmax_bwd_bf16_kernel<false><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(p), static_cast<__nv_bfloat16*>(dp), nullptr, rows, cols, ld_p, ld_dp, 0, 0);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (softmax_bwd_kernel<T, false><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(p), static_cast<T*>(dp), nullptr, rows, cols, ld_p, ld_dp, 0, 0)));
   T4S_LAUNCH_CHECK();
@@ -673,6 +833,13 @@ int t4s_relpos_softmax_fwd(const void* ac, const void* bd, void* p, int64_t rows
                            int64_t ld_p, int dtype, void* stream) {
   T4S_REQUIRE(ac && bd && p && rows > 0 && T_len > 0 && T_len <= 32 * kSmMaxE && rows % T_len == 0 && ld_bd >= 2 * T_len - 1,
               "t4s_relpos_softmax_fwd: bad arguments");
+  if (softmax_vec_ok(dtype, T_len, {ac, bd, p}, {(long long)ld_ac, (long long)ld_bd, (long long)ld_p}) && ld_bd >= ((2 * T_len - 1 + 7) & ~7)) {
+    softmax_fwd_bf16_kernel<true><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(ac), static_cast<const __nv_bfloat16*>(bd), static_cast<__nv_bfloat16*>(p), rows, T_len, ld_ac, ld_bd, ld_p,
+        T_len);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (softmax_fwd_kernel<T, true><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(ac), static_cast<const T*>(bd), static_cast<T*>(p), rows, T_len, ld_ac, ld_bd,
                                 ld_p, T_len)));
@@ -684,6 +851,13 @@ int t4s_relpos_softmax_bwd(const void* p, void* dp, void* dbd, int64_t rows, int
                            int dtype, void* stream) {
   T4S_REQUIRE(p && dp && dbd && rows > 0 && T_len > 0 && T_len <= 32 * kSmMaxE && rows % T_len == 0 && ld_bd >= 2 * T_len - 1,
               "t4s_relpos_softmax_bwd: bad arguments");
+  if (softmax_vec_ok(dtype, T_len, {p, dp, dbd}, {(long long)ld_p, (long long)ld_dp, (long long)ld_bd})) {
+    softmax_bwd_bf16_kernel<true><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(p), static_cast<__nv_bfloat16*>(dp), static_cast<__nv_bfloat16*>(dbd), rows, T_len, ld_p, ld_dp, ld_bd,
+        T_len);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (softmax_bwd_kernel<T, true><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(p), static_cast<T*>(dp), static_cast<T*>(dbd), rows, T_len, ld_p, ld_dp, ld_bd,
                                 T_len)));
