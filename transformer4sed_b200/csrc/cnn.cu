@@ -44,6 +44,59 @@ __global__ void im2col3x3_kernel(const TI* __restrict__ in, long long sb, long l
   }
 }
 
+// 16-byte variant for contiguous channels-last inputs with C % 8 == 0 (bf16) / C % 4 == 0 (fp32): thread = (pixel, tap, vector)
+template <typename T>
+__global__ void im2col3x3_vec_kernel(const T* __restrict__ in, T* __restrict__ col, int B, int H, int W, int C, int Kp) {
+  constexpr int kV = 16 / sizeof(T);
+  const int cv = C / kV;
+  const long long total = (long long)B * H * W * 9 * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * kV;
+    long long t = idx / cv;
+    const int tap = (int)(t % 9);
+    const long long p = t / 9;
+    const int w = (int)(p % W);
+    const long long q = p / W;
+    const int h = (int)(q % H);
+    const long long b = q / H;
+    const int hh = h + tap / 3 - 1, ww = w + tap % 3 - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (hh >= 0 && hh < H && ww >= 0 && ww < W) v = *reinterpret_cast<const uint4*>(in + ((b * H + hh) * W + ww) * C + c);
+    *reinterpret_cast<uint4*>(col + p * Kp + tap * C + c) = v;
+  }
+}
+template <typename T>
+__global__ void col2im3x3_vec_kernel(const T* __restrict__ dcol, T* __restrict__ din, int B, int H, int W, int C, int Kp) {
+  constexpr int kV = 16 / sizeof(T);
+  const int cv = C / kV;
+  const long long total = (long long)B * H * W * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * kV;
+    long long p = idx / cv;
+    const int w = (int)(p % W);
+    const long long q = p / W;
+    const int h = (int)(q % H);
+    const long long b = q / H;
+    float acc[kV];
+#pragma unroll
+    for (int e = 0; e < kV; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int hh = h - (tap / 3 - 1), ww = w - (tap % 3 - 1);
+      if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+        const uint4 u = *reinterpret_cast<const uint4*>(dcol + ((b * H + hh) * W + ww) * Kp + tap * C + c);
+        const T* tv = reinterpret_cast<const T*>(&u);
+#pragma unroll
+        for (int e = 0; e < kV; ++e) acc[e] += to_f32<T>(tv[e]);
+      }
+    }
+    __align__(16) T o[kV];
+#pragma unroll
+    for (int e = 0; e < kV; ++e) o[e] = from_f32<T>(acc[e]);
+    *reinterpret_cast<uint4*>(din + p * C + c) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
 // gradient of the above: din[b, h, w, c] = sum over taps of dcol[(b, h-ky+1, w-kx+1), tap, c]   (contiguous channels-last output)
 template <typename T>
 __global__ void col2im3x3_kernel(const T* __restrict__ dcol, T* __restrict__ din, int B, int H, int W, int C, int Kp) {
@@ -353,6 +406,17 @@ int t4s_im2col3x3(const void* in, int in_dtype, int64_t stride_b, int64_t stride
   T4S_REQUIRE(in && col && batch > 0 && height > 0 && width > 0 && channels > 0 && k_padded >= 9 * channels, "t4s_im2col3x3: bad arguments");
   const long long total = (long long)batch * height * width * 9;
   cudaStream_t st = t4s::as_stream(stream);
+  const int esz = in_dtype == T4S_BF16 ? 2 : 4, kv = 16 / esz;
+  if (in_dtype == col_dtype && channels % kv == 0 && k_padded == 9 * channels && stride_w == channels && stride_h == (int64_t)width * channels &&
+      stride_b == (int64_t)height * width * channels && !((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(col)) & 15)) {
+    const int vgrid = grid_for(total * (channels / kv));
+    if (in_dtype == T4S_BF16)
+      im2col3x3_vec_kernel<__nv_bfloat16><<<vgrid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)col, batch, height, width, channels, k_padded);
+    else
+      im2col3x3_vec_kernel<float><<<vgrid, 256, 0, st>>>((const float*)in, (float*)col, batch, height, width, channels, k_padded);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   const int grid = grid_for(total);
 #define T4S_I2C(TI, TO) im2col3x3_kernel<TI, TO><<<grid, 256, 0, st>>>((const TI*)in, stride_b, stride_h, stride_w, (TO*)col, batch, height, width, channels, k_padded)
   if (in_dtype == T4S_F32 && col_dtype == T4S_F32) T4S_I2C(float, float);
@@ -367,6 +431,13 @@ int t4s_im2col3x3(const void* in, int in_dtype, int64_t stride_b, int64_t stride
 int t4s_col2im3x3(const void* dcol, void* din, int dtype, int batch, int height, int width, int channels, int k_padded, void* stream) {
   T4S_REQUIRE(dcol && din && batch > 0 && k_padded >= 9 * channels, "t4s_col2im3x3: bad arguments");
   const long long total = (long long)batch * height * width * channels;
+  const int kv = dtype == T4S_BF16 ? 8 : 4;
+  if (channels % kv == 0 && k_padded % kv == 0 && !((reinterpret_cast<uintptr_t>(dcol) | reinterpret_cast<uintptr_t>(din)) & 15)) {
+    T4S_DISPATCH_DTYPE(dtype, (col2im3x3_vec_kernel<T><<<grid_for(total / kv), 256, 0, t4s::as_stream(stream)>>>(
+                                  static_cast<const T*>(dcol), static_cast<T*>(din), batch, height, width, channels, k_padded)));
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (col2im3x3_kernel<T><<<grid_for(total), 256, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(dcol), static_cast<T*>(din), batch, height, width, channels, k_padded)));
   T4S_LAUNCH_CHECK();

@@ -1445,6 +1445,9 @@ class _LoraLinear(torch.autograd.Function):
 
 def to_plain(p, dtype):
     """Small parameter -> contiguous tensor of the activation dtype (no caching: LoRA factors change every step)."""
+    shadow = getattr(p, "_t4s_shadow", None)   # bf16 copy kept fresh by the fused AdamW kernel (training.ParamArena)
+    if shadow is not None and shadow.dtype == dtype:
+        return shadow
     p = p.detach().contiguous()
     return p if p.dtype == dtype else convert(p, torch.empty(p.shape, dtype=dtype, device=p.device))
 
