@@ -352,6 +352,17 @@ int t4s_mask_scores(void* s, const unsigned char* mask, int64_t rows, int cols, 
 /* inverted dropout with a counter-based mask (seed, element index); the backward is the same call on the gradient */
 int t4s_dropout(const void* x, void* out, size_t n, float dropout_p, uint64_t seed, int dtype, void* stream);
 
+/* ---- train-loop glue next to the hot path (csrc/aug.cu), fp32 ----------------------------------------------
+ * frame_shift (src/preprocess/data_aug.py:12-31): out[b, r, (t + shifts[b]) mod len] = x[b, r, t]; shifts: DEVICE int32 [batch] */
+int t4s_roll_rows(const float* x, float* out, const int* shifts_dev, int batch, int rows, int len, void* stream);
+/* mixup (data_aug.py:34-91): out[b] = w_self x[b] + w_other x[perm[b]] (perm: DEVICE int64 [batch]), optionally clamped to [0, 1] */
+int t4s_mixup(const float* x, const int64_t* perm_dev, float* out, int batch, int64_t inner, float w_self, float w_other, int clamp01, void* stream);
+/* class-wise median filter of the post-processing (src/postprocess/filter.py:4-36): in / out [batch, length, classes]; class c uses the
+ * odd window window_sizes[c] (HOST array) with replicate padding */
+#define T4S_MEDIAN_MAX_CLASSES 32
+#define T4S_MEDIAN_MAX_WINDOW 255
+int t4s_median_filter(const float* in, float* out, const int* window_sizes, int batch, int length, int classes, void* stream);
+
 /* ---- K9: parameter-side kernels of a training step (csrc/optim.cu) ------------------------------------------------
  * torch.optim.AdamW semantics (recipes/desed/setting.py:254-258) over a flat fp32 arena; `bf16_shadow` (optional) receives the
  * updated weights as bf16 GEMM operands in the same pass; `grad_scale` folds the 1/world_size of the gradient all-reduce. */

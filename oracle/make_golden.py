@@ -289,6 +289,50 @@ def golden_dasm(seed, batch, K=407):
           f"{o['at_out'].max().item():.3g} grads={len(gn)}")
 
 
+def golden_glue():
+    """frame_shift / mixup (src/preprocess/data_aug.py) and median_filter_torch (src/postprocess/filter.py) of the unmodified reference
+    on seeded inputs; the host RNG draws are recorded so other implementations can replay them."""
+    import random
+    from src.postprocess.filter import median_filter_torch
+    from src.preprocess.data_aug import frame_shift, mixup
+    B = 6
+    mel = synth.synth_tensor(31, "glue_mel", (B, 128, 1000))
+    label = (synth.synth_tensor(31, "glue_label", (B, 10, 1000)) > 0.6).float()
+    random.seed(123)
+    fs_mel, fs_label = frame_shift(mel, label, net_pooling=1)
+    random.seed(123)
+    shifts = [int(random.gauss(0, 90)) for _ in range(B)]
+    label4 = (synth.synth_tensor(31, "glue_label4", (B, 10, 250)) > 0.6).float()
+    random.seed(7)
+    fs4_mel, fs4_label = frame_shift(mel, label4, net_pooling=4)
+    random.seed(7)
+    shifts4 = [int(random.gauss(0, 90)) for _ in range(B)]
+    torch.manual_seed(5)
+    np.random.seed(5)
+    mx_mel, mx_label = mixup(mel, label, c=np.random.beta(10, 0.5))          # the call of recipes/desed/finetune/train.py:80
+    torch.manual_seed(5)
+    np.random.seed(5)
+    c = np.random.beta(10, 0.5)
+    perm = torch.randperm(B)
+    torch.manual_seed(6)
+    np.random.seed(6)
+    mh_mel, mh_label = mixup(mel, label, mixup_label_type="hard")
+    torch.manual_seed(6)
+    np.random.seed(6)
+    perm_h = torch.randperm(B)
+    c_h = np.random.beta(0.2, 0.2) * 0.4 + 0.3
+    probs = torch.sigmoid(2.0 * synth.synth_tensor(31, "glue_probs", (4, 1000, 10)))
+    sizes = [int(i / 156 * 1000) for i in [3, 28, 7, 4, 7, 22, 48, 19, 10, 50]][:10]    # train.py:225 with a DESED-style median_window
+    sizes = [max(1, min(k, 101)) for k in sizes]
+    med = median_filter_torch(probs, sizes)
+    out = dict(shifts=np.array(shifts, np.int32), fs_mel=f32(fs_mel[:, ::8, ::5]), fs_label=f32(fs_label), shifts4=np.array(shifts4, np.int32),
+               fs4_mel=f32(fs4_mel[:, ::8, ::5]), fs4_label=f32(fs4_label), c=np.array(c), perm=perm.numpy(), mx_mel=f32(mx_mel[:, ::8, ::5]),
+               mx_label=f32(mx_label), c_h=np.array(c_h), perm_h=perm_h.numpy(), mh_mel=f32(mh_mel[:, ::8, ::5]), mh_label=f32(mh_label),
+               med_sizes=np.array(sizes, np.int32), med=f32(med), mel_ck=checksum(mel), probs_ck=checksum(probs))
+    np.savez_compressed(os.path.join(OUT, "glue.npz"), **out)
+    print("glue.npz shifts", shifts, "c", c, "perm", perm.tolist(), "median sizes", sizes)
+
+
 def golden_mlm(tag, kw, seed, batch):
     """MAT-SED pre-train forward (mlm=True): needs the synthetic PaSST checkpoint on disk."""
     import tempfile
@@ -361,7 +405,7 @@ if __name__ == "__main__":
     base = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_adapter=True, decoder="transformerXL",
                 decoder_layer_num=3, decoder_pos_emd_len=1000, mlm=False)  # config/mat-sed/base/finetune2.yaml:53-62
     pre = dict(base, mlm=True, mlm_dict=dict(strategy="block", block_width=10, mask_rate=0.75, out_dim=768))  # pretrain.yaml:39-52
-    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm", "pmam", "dasm"]
+    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm", "pmam", "dasm", "glue"]
     if "frontend" in which:
         golden_frontend()
         golden_frontend_16k()
@@ -377,6 +421,8 @@ if __name__ == "__main__":
         golden_pmam(seed=10, batch=2)
     if "dasm" in which:
         golden_dasm(seed=12, batch=2)
+    if "glue" in which:
+        golden_glue()
     if "mlm" in which:
         golden_mlm("base", pre, seed=6, batch=2)  # B>1: upstream masking is a silent no-op
         golden_mlm("base", pre, seed=6, batch=1)  # B=1: reshape is a view, masking applies

@@ -23,6 +23,7 @@ _MIRRORS = {
     "src.models.cnn_transformer.passt_cnn": "transformer4sed_b200.src_models.cnn_transformer.passt_cnn",
     "src.models.detect_any_sound.at_adapter": "transformer4sed_b200.src_models.detect_any_sound.at_adapter",
     "src.models.detect_any_sound.detect_any_sound": "transformer4sed_b200.src_models.detect_any_sound.detect_any_sound",
+    "src.postprocess.filter": "transformer4sed_b200.src_postprocess.filter",
 }
 
 
