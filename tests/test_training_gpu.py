@@ -41,3 +41,32 @@ def test_ema_update():
     ref = 0.99 * t + 0.01 * s
     _lib.check(_lib.load().t4s_ema_update(_lib.ptr(t), _lib.ptr(s), ctypes.c_void_p(0), 1000, 0.99, _lib.stream_ptr()), "ema")
     assert (t - ref).abs().max().item() < 1e-6
+
+
+def test_mean_teacher_matches_reference_ema():
+    """MeanTeacher.update == the reference's update_ema loop (src/utils/scheduler.py:125-130) on every parameter, arena-managed or not,
+    and the teacher's bf16 GEMM shadow follows."""
+    import copy
+    from transformer4sed_b200.training import MeanTeacher, ParamArena
+    torch.manual_seed(1)
+    student = torch.nn.Sequential(torch.nn.Linear(24, 16), torch.nn.LayerNorm(16), torch.nn.Linear(16, 8)).cuda()
+    student[2].bias.requires_grad_(False)                       # a frozen tensor: outside the arena, still averaged
+    ref_teacher = copy.deepcopy(student)
+    arena = ParamArena(student, [dict(name="all", params=list(student.parameters()), lr=1e-2, weight_decay=0.0)], shadow_bf16=True)
+    mt = MeanTeacher(student, arena)
+    assert all(not p.requires_grad for p in mt.teacher.parameters())
+    assert student[0].weight.data_ptr() != mt.teacher[0].weight.data_ptr()
+    for step in range(1, 5):
+        student(torch.randn(4, 24, device="cuda")).square().mean().backward()
+        arena.step()
+        with torch.no_grad():
+            student[2].bias.add_(0.1)
+        alpha = mt.update(step, ema_factor=0.999)
+        assert abs(alpha - min(1 - 1 / step, 0.999)) < 1e-12
+        with torch.no_grad():
+            for tp, sp in zip(ref_teacher.parameters(), student.parameters()):
+                tp.data.mul_(alpha).add_(sp.data, alpha=1 - alpha)
+        for (n, a), (_, b) in zip(mt.teacher.named_parameters(), ref_teacher.named_parameters()):
+            assert (a - b).abs().max().item() < 1e-6, (step, n)
+        w = mt.teacher[0].weight
+        assert (w._t4s_shadow.float() - w).abs().max().item() <= w.abs().max().item() * 2 ** -8

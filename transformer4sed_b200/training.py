@@ -116,6 +116,67 @@ class ParamArena:
             p.grad = None
 
 
+class MeanTeacher:
+    """EMA teacher of the mean-teacher recipes (reference src/utils/scheduler.py:125-130, recipes/desed/finetune/train.py:129-213):
+    teacher = alpha * teacher + (1 - alpha) * student with alpha = min(1 - 1/step, ema_factor), over EVERY parameter.
+
+    The teacher is a deep copy of the student whose arena-managed parameters are re-homed into one flat fp32 buffer with the
+    student arena's layout (plus a bf16 shadow for its GEMMs), so the whole update is ONE kernel launch over that buffer; the few
+    parameters outside the arena (frozen tensors, unused heads) are updated tensor by tensor.  Buffers (e.g. BatchNorm running
+    statistics) are not averaged, as upstream."""
+
+    def __init__(self, student: torch.nn.Module, arena: ParamArena):
+        import copy
+        # deep-copy with the arena views detached from the flat buffer (a view would drag the whole arena into every copy)
+        saved = [(p, p.data, getattr(p, "_t4s_shadow", None)) for p, _ in arena.layout]
+        for p, off in arena.layout:
+            p.data = p.data.clone()
+            if hasattr(p, "_t4s_shadow"):
+                del p._t4s_shadow
+        try:
+            self.teacher = copy.deepcopy(student)
+        finally:
+            for p, data, shadow in saved:
+                p.data = data
+                if shadow is not None:
+                    p._t4s_shadow = shadow
+        for p in self.teacher.parameters():
+            p.requires_grad_(False)
+        self.arena = arena
+        dev = arena.device
+        names = {id(p): n for n, p in student.named_parameters()}
+        tparams = dict(self.teacher.named_parameters())
+        self.flat = torch.zeros(arena.n, dtype=torch.float32, device=dev)
+        self.shadow = torch.empty(arena.n, dtype=torch.bfloat16, device=dev) if arena.shadow is not None else None
+        managed = set()
+        with torch.no_grad():
+            for p, off in arena.layout:
+                tp = tparams[names[id(p)]]
+                view = self.flat[off:off + p.numel()].view(p.shape)
+                view.copy_(tp.data)
+                tp.data = view
+                if self.shadow is not None:
+                    tp._t4s_shadow = self.shadow[off:off + p.numel()].view(p.shape)
+                managed.add(names[id(p)])
+        if self.shadow is not None:
+            F.convert(self.flat, self.shadow)
+        sparams = dict(student.named_parameters())
+        self.rest = [(tparams[n], sparams[n]) for n in tparams if n not in managed]
+
+    def update(self, step: int, ema_factor: float = 0.999):
+        alpha = min(1.0 - 1.0 / max(step, 1), ema_factor)
+        lib = _lib.load()
+        with torch.cuda.device(self.arena.device):
+            _lib.check(lib.t4s_ema_update(_lib.ptr(self.flat), _lib.ptr(self.arena.flat), _lib.ptr(self.shadow), self.arena.n, alpha,
+                                          _lib.stream_ptr()), "t4s_ema_update")
+            for tp, sp in self.rest:
+                if tp.dtype == torch.float32 and tp.is_contiguous() and sp.is_contiguous():
+                    _lib.check(lib.t4s_ema_update(_lib.ptr(tp.data), _lib.ptr(sp.data), ctypes.c_void_p(0), tp.numel(), alpha, _lib.stream_ptr()),
+                               "t4s_ema_update")
+                    F.invalidate_weight_cache(tp)
+        return alpha
+
+
 def mat_sed_param_groups(net, lr_encoder=5e-6, lr_decoder=1e-4, lr_head=1e-4, weight_decay=1e-4):
     """The three LR groups of config/mat-sed/base/finetune2.yaml:88-101 (encoder / decoder / head), by parameter-name prefix
     as reference recipes/desed/finetune/passt/setting.py:28-103 assigns them."""
