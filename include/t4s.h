@@ -357,6 +357,11 @@ int t4s_dropout(const void* x, void* out, size_t n, float dropout_p, uint64_t se
 int t4s_roll_rows(const float* x, float* out, const int* shifts_dev, int batch, int rows, int len, void* stream);
 /* mixup (data_aug.py:34-91): out[b] = w_self x[b] + w_other x[perm[b]] (perm: DEVICE int64 [batch]), optionally clamped to [0, 1] */
 int t4s_mixup(const float* x, const int64_t* perm_dev, float* out, int batch, int64_t inner, float w_self, float w_other, int clamp01, void* stream);
+/* freq_nonlinear (data_aug.py:239-254): out[b,k,t] = lerp(x[b, src_bin[k], t], x[b, src_bin[k]+1, t], weight[k]); src_bin / weight are the
+ * np.interp knots of the warped frequency axis, computed once on the host (DEVICE arrays of n_freq entries) */
+int t4s_freq_warp(const float* x, float* out, const int* src_bin_dev, const float* weight_dev, int batch, int n_freq, int n_frames, void* stream);
+/* FilterAugment on log-mel features (data_aug.py:150-190): out[r, t] = x[r, t] + bias[r], r = (clip, mel bin); bias: DEVICE [rows] */
+int t4s_add_rowbias(const float* x, const float* bias_dev, float* out, int64_t rows, int cols, void* stream);
 /* class-wise median filter of the post-processing (src/postprocess/filter.py:4-36): in / out [batch, length, classes]; class c uses the
  * odd window window_sizes[c] (HOST array) with replicate padding */
 #define T4S_MEDIAN_MAX_CLASSES 32

@@ -31,3 +31,23 @@ def median_filter(x, filter_size, n_classes_filtered=10):
         xi = torch.nn.functional.pad(x[:, :, c].unsqueeze(1), (k // 2, k // 2), mode="replicate").squeeze(1)
         out[:, :, c] = xi.unfold(1, k, 1).median(dim=-1)[0]
     return out
+
+
+def freq_nonlinear(mel, phase, f=1, bias=0.02):
+    """data_aug.py:239-254 with the single `random.random()` draw injected: np.interp of every (clip, frame) column over the warped
+    frequency knots (numpy float64 arithmetic, result stored as float32)."""
+    import numpy as np
+    m = mel.numpy().copy()
+    B, F, T = m.shape
+    m = np.reshape(np.transpose(m, (0, 2, 1)), (B * T, F))
+    ind = np.arange(F)
+    x = ind / F
+    ind_t = F * (x + bias * np.sin(2 * np.pi * (f * x + phase)))
+    for i in range(B * T):
+        m[i, :] = np.interp(ind, ind_t, m[i, :])
+    return torch.from_numpy(np.reshape(m, (B, T, F)).transpose((0, 2, 1)).copy())
+
+
+def filt_aug_apply(features, freq_filt, norm_std):
+    """data_aug.py:188-190 (log features): features + log(filter + 1e-5) / norm_std with filter [B, F, 1]."""
+    return features + torch.log(freq_filt + 0.00001) / norm_std

@@ -325,7 +325,18 @@ def golden_glue():
     sizes = [int(i / 156 * 1000) for i in [3, 28, 7, 4, 7, 22, 48, 19, 10, 50]][:10]    # train.py:225 with a DESED-style median_window
     sizes = [max(1, min(k, 101)) for k in sizes]
     med = median_filter_torch(probs, sizes)
-    out = dict(shifts=np.array(shifts, np.int32), fs_mel=f32(fs_mel[:, ::8, ::5]), fs_label=f32(fs_label), shifts4=np.array(shifts4, np.int32),
+    from src.preprocess.data_aug import filt_aug, freq_nonlinear
+    small = mel[:3, :, :200].contiguous()
+    random.seed(11)
+    fn = torch.from_numpy(freq_nonlinear(small.numpy(), bias=0.03 * 0.7))
+    random.seed(11)
+    fn_phase = random.random()
+    torch.manual_seed(21)
+    fa_step = filt_aug(small, db_range=[-6, 6], n_band=[3, 6], min_bw=6, filter_type="step", log=True, norm_std=5.0)
+    torch.manual_seed(22)
+    fa_lin = filt_aug(small, db_range=[-6, 6], n_band=[3, 6], min_bw=6, filter_type="linear", log=True, norm_std=5.0)
+    extra = dict(fn=f32(fn), fn_phase=np.array(fn_phase), fa_step=f32(fa_step), fa_lin=f32(fa_lin))
+    out = dict(**extra, shifts=np.array(shifts, np.int32), fs_mel=f32(fs_mel[:, ::8, ::5]), fs_label=f32(fs_label), shifts4=np.array(shifts4, np.int32),
                fs4_mel=f32(fs4_mel[:, ::8, ::5]), fs4_label=f32(fs4_label), c=np.array(c), perm=perm.numpy(), mx_mel=f32(mx_mel[:, ::8, ::5]),
                mx_label=f32(mx_label), c_h=np.array(c_h), perm_h=perm_h.numpy(), mh_mel=f32(mh_mel[:, ::8, ::5]), mh_label=f32(mh_label),
                med_sizes=np.array(sizes, np.int32), med=f32(med), mel_ck=checksum(mel), probs_ck=checksum(probs))

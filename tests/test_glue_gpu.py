@@ -49,3 +49,22 @@ def test_glue_kernels_match_reference(golden):
     assert np.array_equal(median_filter_torch(p12, s12, strict_upstream=False).cpu().numpy(), G.median_filter(p12.cpu(), s12, 12).numpy())
     with pytest.raises(IndexError):
         median_filter_torch(p12[:, :, :4].contiguous(), s12[:4])
+
+
+def test_feature_transforms_match_reference(golden):
+    """freq_nonlinear (upstream: np.interp per (clip, frame) on the host) and filt_aug on log-mel features against golden vectors of
+    the unmodified reference, the host RNG replayed draw for draw."""
+    from transformer4sed_b200.src_preprocess.data_aug import filt_aug, freq_nonlinear
+    g = golden("glue.npz")
+    small = synth.synth_tensor(31, "glue_mel", (6, 128, 1000))[:3, :, :200].contiguous().cuda()
+    random.seed(11)
+    fn = freq_nonlinear(small, bias=0.03 * 0.7)
+    np.testing.assert_allclose(fn.cpu().numpy(), g["fn"], rtol=1e-5, atol=2e-6)      # fp32 lerp vs numpy's float64 interp
+    torch.manual_seed(21)
+    fa = filt_aug(small, db_range=[-6, 6], n_band=[3, 6], min_bw=6, filter_type="step", log=True, norm_std=5.0)
+    np.testing.assert_allclose(fa.cpu().numpy(), g["fa_step"], rtol=1e-6, atol=1e-6)
+    torch.manual_seed(22)
+    fa = filt_aug(small, db_range=[-6, 6], n_band=[3, 6], min_bw=6, filter_type="linear", log=True, norm_std=5.0)
+    np.testing.assert_allclose(fa.cpu().numpy(), g["fa_lin"], rtol=1e-6, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        filt_aug(small, log=False)

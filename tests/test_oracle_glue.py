@@ -35,3 +35,25 @@ def test_glue_oracle_matches_reference(golden):
     np.testing.assert_allclose(mf[:, ::8, ::5].numpy(), g["mh_mel"], rtol=1e-6, atol=1e-7)
     np.testing.assert_array_equal(ml.numpy(), g["mh_label"])
     np.testing.assert_array_equal(G.median_filter(probs, [int(k) for k in g["med_sizes"]]).numpy(), g["med"])
+
+
+def test_freq_nonlinear_and_filt_aug_oracle_and_table(golden):
+    """Oracle vs the reference, and the host-side (source bin, weight) table the CUDA kernel consumes vs np.interp itself."""
+    import random
+    from transformer4sed_b200.src_preprocess.data_aug import freq_warp_table
+    g = golden("glue.npz")
+    mel, _, _, _ = _inputs(g)
+    small = mel[:3, :, :200].contiguous()
+    phase = float(g["fn_phase"])
+    np.testing.assert_array_equal(G.freq_nonlinear(small, phase, bias=0.03 * 0.7).numpy(), g["fn"])
+    for F_, f_, bias_, ph in ((128, 1, 0.021, phase), (128, 1, 0.03, 0.93), (64, 1, 0.0, 0.5), (128, 1, 0.03, 0.25)):
+        j, w = freq_warp_table(F_, f_, bias_, ph)
+        rows = np.random.default_rng(0).standard_normal((5, F_))
+        ind = np.arange(F_)
+        x = ind / F_
+        ind_t = F_ * (x + bias_ * np.sin(2 * np.pi * (f_ * x + ph)))
+        for r in rows:
+            ours = r[j] + w * (r[np.minimum(j + 1, F_ - 1)] - r[j])
+            np.testing.assert_allclose(ours, np.interp(ind, ind_t, r), rtol=1e-12, atol=1e-12)
+    random.seed(11)
+    assert random.random() == phase

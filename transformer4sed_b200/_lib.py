@@ -146,6 +146,8 @@ def _declare(lib):
         "t4s_roll_rows": (I, [P, P, P, I, I, I, P]),
         "t4s_mixup": (I, [P, P, P, I, L, F, F, I, P]),
         "t4s_median_filter": (I, [P, P, ctypes.POINTER(c_int), I, I, I, P]),
+        "t4s_freq_warp": (I, [P, P, P, P, I, I, I, P]),
+        "t4s_add_rowbias": (I, [P, P, P, L, I, P]),
         "t4s_patch_posbias": (I, [P, P, P, I, I, I, I, I, P]),
         "t4s_cls_dist_tokens": (I, [P, I, P, P, P, I, L, I, P]),
         "t4s_patch_small_grads": (I, [P, I, P, P, P, P, P, P, P, I, L, I, I, I, I, I, P]),

@@ -39,6 +39,31 @@ __global__ void mixup_kernel(const float* __restrict__ x, const long long* __res
   }
 }
 
+// freq_nonlinear (data_aug.py:239-254): every (b, t) column of the mel image is re-sampled along frequency with np.interp over the
+// SAME warped knots, so the source bin j0[k] and weight w[k] of every output bin are precomputed once on the host (float64, like
+// numpy) and the kernel is a two-row gather + lerp.  out[b, k, t] = x[b, j0[k], t] + w[k] (x[b, j0[k]+1, t] - x[b, j0[k], t])
+__global__ void freq_warp_kernel(const float* __restrict__ x, float* __restrict__ out, const int* __restrict__ j0, const float* __restrict__ w,
+                                 int B, int F, int T) {
+  const long long total = (long long)B * F * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % T);
+    const long long bf = i / T;
+    const int k = (int)(bf % F);
+    const long long b = bf / F;
+    const int j = j0[k];
+    const float a = x[(b * F + j) * T + t];
+    const float wk = w[k];
+    out[i] = wk == 0.f ? a : fmaf(wk, x[(b * F + min(j + 1, F - 1)) * T + t] - a, a);
+  }
+}
+
+// out[b, f, t] = x[b, f, t] + bias[b, f]   (FilterAugment on log-mel features: + log(filter + 1e-5) / norm_std, data_aug.py:188-190)
+__global__ void add_rowbias_kernel(const float* __restrict__ x, const float* __restrict__ bias, float* __restrict__ out, long long rows, int T) {
+  const long long total = rows * T;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+    out[i] = x[i] + bias[i / T];
+}
+
 struct Sizes { int v[T4S_MEDIAN_MAX_CLASSES]; };
 
 // in / out [B, L, C]; class c uses the odd window sizes.v[c] (<= T4S_MEDIAN_MAX_WINDOW) with replicate padding.  Block = 256
@@ -83,6 +108,21 @@ int t4s_mixup(const float* x, const int64_t* perm_dev, float* out, int batch, in
   const long long total = (long long)batch * inner;
   t4s::aug::mixup_kernel<<<t4s::aug::grid_for(total), 256, 0, t4s::as_stream(stream)>>>(x, (const long long*)perm_dev, out, batch, inner, w_self, w_other,
                                                                                    clamp01);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_freq_warp(const float* x, float* out, const int* src_bin_dev, const float* weight_dev, int batch, int n_freq, int n_frames, void* stream) {
+  T4S_REQUIRE(x && out && src_bin_dev && weight_dev && batch > 0 && n_freq > 0 && n_frames > 0 && x != out, "t4s_freq_warp: bad arguments");
+  const long long total = (long long)batch * n_freq * n_frames;
+  t4s::aug::freq_warp_kernel<<<t4s::aug::grid_for(total), 256, 0, t4s::as_stream(stream)>>>(x, out, src_bin_dev, weight_dev, batch, n_freq, n_frames);
+  T4S_LAUNCH_CHECK();
+  return T4S_OK;
+}
+
+int t4s_add_rowbias(const float* x, const float* bias_dev, float* out, int64_t rows, int cols, void* stream) {
+  T4S_REQUIRE(x && bias_dev && out && rows > 0 && cols > 0, "t4s_add_rowbias: bad arguments");
+  t4s::aug::add_rowbias_kernel<<<t4s::aug::grid_for(rows * cols), 256, 0, t4s::as_stream(stream)>>>(x, bias_dev, out, rows, cols);
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }

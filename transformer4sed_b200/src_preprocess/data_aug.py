@@ -2,6 +2,10 @@
 mel batch: `frame_shift` (:12-31) and `mixup` (:34-91).  The random draws are made on the host with the same generators, in the
 same order, as the reference (python `random`, `torch.randperm`, `np.random.beta`), so seeded runs pick the same shifts,
 permutation and mixing rate; the data movement is one libt4s kernel per tensor instead of a Python loop of `torch.roll` + stack.
+
+`freq_nonlinear` (:239-254) and `filt_aug` (:150-195) are the label-independent feature transforms: upstream the first one moves the
+batch to the host and calls `np.interp` once per (clip, frame) -- 64 000 calls per step at B = 64; here the warp is a table of 128
+(source bin, weight) pairs built once on the host in float64 and one gather-lerp kernel over the batch on the GPU.
 """
 import random
 
@@ -72,3 +76,71 @@ def mixup(features, label=None, permutation=None, c=None, alpha=0.2, beta=0.2, m
         else:
             raise NotImplementedError(f"mixup_label_type: {mixup_label_type} not implemented. choice in {'soft', 'hard'}")
         return mixed_features, mixed_label
+
+
+def freq_warp_table(n_freq, f, bias, phase):
+    """(source bin j[k], weight w[k]) such that np.interp(arange(F), ind_t, row)[k] == row[j] + w (row[j+1] - row[j]) for the warped
+    knots ind_t = F * trans(arange(F) / F), trans(x) = x + bias sin(2 pi (f x + phase))  (data_aug.py:247-251).  float64, like numpy."""
+    ind = np.arange(n_freq)
+    xin = ind / n_freq
+    ind_t = n_freq * (xin + bias * np.sin(2 * np.pi * (f * xin + phase)))      # monotone for the shipped bias <= 0.03
+    j = np.clip(np.searchsorted(ind_t, ind, side="right") - 1, 0, n_freq - 2)   # ind_t[j] <= k < ind_t[j+1]
+    w = (ind - ind_t[j]) / (ind_t[j + 1] - ind_t[j])
+    lo, hi = ind <= ind_t[0], ind >= ind_t[-1]                                  # np.interp clamps outside the knot range
+    j = np.where(lo, 0, np.where(hi, n_freq - 1, j))
+    w = np.where(lo | hi, 0.0, w)
+    return j.astype(np.int64), w
+
+
+def freq_nonlinear(mel, f=1, bias=0.02):
+    """mel [B, F, T] (cuda fp32; the reference takes / returns a numpy array) -> frequency-warped copy.  One `random.random()` draw
+    (the phase), as upstream where the lambda is evaluated once on the whole index vector."""
+    _lib.ensure_device(mel)
+    x = mel.contiguous().float()
+    B, Fq, T = x.shape
+    j, w = freq_warp_table(Fq, f, bias, random.random())
+    j_dev = torch.from_numpy(j.astype(np.int32)).to(x.device)
+    w_dev = torch.from_numpy(w.astype(np.float32)).to(x.device)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().t4s_freq_warp(_lib.ptr(x), _lib.ptr(out), _lib.ptr(j_dev), _lib.ptr(w_dev), B, Fq, T, _lib.stream_ptr()), "t4s_freq_warp")
+    return out
+
+
+def filt_aug(features, db_range=[-0.5, 0.5], n_band=[3, 6], min_bw=6, filter_type="step", log=False, norm_std=1):
+    """FilterAugment (ICASSP 2022 variant, data_aug.py:150-195) on log-mel features [B, F, T]: the per-(clip, bin) filter is drawn and
+    assembled on the host exactly as upstream (same torch CPU RNG calls), the additive log-filter is applied by one kernel."""
+    batch_size, n_freq_bin, n_frames = features.shape
+    n_freq_band = torch.randint(low=n_band[0], high=n_band[1], size=(1, )).item()
+    if n_freq_band <= 1:
+        return features
+    while n_freq_bin - n_freq_band * min_bw + 1 < 0:
+        min_bw -= 1
+    band_bndry_freqs = torch.sort(torch.randint(0, n_freq_bin - n_freq_band * min_bw + 1, (n_freq_band - 1, )))[0] + \
+        torch.arange(1, n_freq_band) * min_bw
+    band_bndry_freqs = torch.cat((torch.tensor([0]), band_bndry_freqs, torch.tensor([n_freq_bin])))
+    if filter_type == "step":
+        band_factors = torch.rand((batch_size, n_freq_band)) * (db_range[1] - db_range[0]) + db_range[0]
+        band_factors = 10 ** (band_factors / 20)
+        freq_filt = torch.ones((batch_size, n_freq_bin, 1))
+        for i in range(n_freq_band):
+            freq_filt[:, band_bndry_freqs[i]:band_bndry_freqs[i + 1], :] = band_factors[:, i].unsqueeze(-1).unsqueeze(-1)
+    elif filter_type == "linear":
+        band_factors = torch.rand((batch_size, n_freq_band + 1)) * (db_range[1] - db_range[0]) + db_range[0]
+        freq_filt = torch.ones((batch_size, n_freq_bin, 1))
+        for i in range(n_freq_band):
+            for j in range(batch_size):
+                freq_filt[j, band_bndry_freqs[i]:band_bndry_freqs[i + 1], :] = torch.linspace(
+                    band_factors[j, i], band_factors[j, i + 1], band_bndry_freqs[i + 1] - band_bndry_freqs[i]).unsqueeze(-1)
+    else:
+        raise Exception("Unkonwn filter augment type")
+    if not log:
+        raise NotImplementedError("[DEBUG] Don't support filter augumentation after log operation")
+    _lib.ensure_device(features)
+    x = features.contiguous().float()
+    bias = (torch.log(freq_filt + 0.00001) / norm_std).reshape(-1).to(x.device)
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().t4s_add_rowbias(_lib.ptr(x), _lib.ptr(bias), _lib.ptr(out), batch_size * n_freq_bin, n_frames, _lib.stream_ptr()),
+                   "t4s_add_rowbias")
+    return out
