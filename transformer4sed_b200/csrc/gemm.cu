@@ -1,16 +1,21 @@
 // K3: persistent warp-specialised tcgen05 GEMM with TMA-fed shared-memory pipeline and a fused epilogue.
 //
-//   C[z] = act(alpha * A[z] . B[z]^T + bias) + residual[z]      A:[M,K]  B:[N,K]  (both K-major), fp32 accumulate in TMEM
+//   C[z] = act(alpha * A[z] . B[z]^T + bias) + residual[z]      A:[M,K]  B:[N,K]  (K- or MN-major), fp32 accumulate in TMEM
 //
-// CTA = 8 warps, one CTA per SM, walking 128 x BN output tiles (m fastest so neighbouring CTAs share the B tile in L2):
-//   warp 0    TMA producer: 4-D tensor maps (k, row, batch1, batch2), SWIZZLE_128B boxes -> NS-stage smem ring
+// CTA = 12 warps, one CTA per SM, walking 128 x BN output tiles in a grouped n-fastest order (a wave streams each A row-block
+// once and keeps its B blocks in L2):
+//   warp 0    TMA producer: 4-D tensor maps (k, row, batch1, batch2), SWIZZLE_128B boxes -> 4..6-stage smem ring
 //   warp 1    MMA issuer:   one lane issues tcgen05.mma (M=128, N=BN, K=32 B per instruction), commits to mbarriers
 //   warp 2    TMEM allocator (2 x BN fp32 columns: accumulator double buffer, epilogue overlaps the next mainloop)
 //   warps 4-11 epilogue: two warps per TMEM lane quarter, each draining half of the tile's columns in 32-column chunks:
-//             tcgen05.ld 32x32b (next chunk in flight while this one is processed) -> bias / GELU / residual in registers ->
-//             each thread stores 64 (bf16) or 128 (fp32) contiguous bytes of its own row with 16-byte accesses; the
-//             accumulator buffer is handed back to the MMA warp as soon as its last chunk is in registers.
-//             Row / column predicates make ragged M/N tiles and TMA zero-fill compose.
+//             tcgen05.ld 32x32b (next chunk in flight while this one is processed) -> bias / GELU / GELU' / residual in registers
+//             (packed f32x2 math) -> staged variant (bf16 outputs): the chunk goes to a per-warp SWIZZLE_64B shared-memory box
+//             and leaves through ONE TMA tile store, the residual / pre-activation chunk arrives the same way by TMA load;
+//             direct variant (fp32 outputs, odd layouts): 16-byte row stores.  The accumulator buffer is handed back to the
+//             MMA warp as soon as its last chunk is in registers.  Row / column predicates and TMA clipping / zero-fill make
+//             ragged M/N tiles compose.
+// Pair mode (bf16, BN = 256): the two CTAs of a cluster (one TPC) share one 256 x 256 tile through tcgen05.mma.cta_group::2 --
+// each stages its 128 rows of A and half of the B tile, the leader issues the MMAs, commits are multicast to both CTAs.
 // bf16 inputs use kind::f16, fp32 inputs use kind::tf32 (tensor map type TFLOAT32 rounds on load).
 #include <algorithm>
 #include <cstdlib>
