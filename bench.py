@@ -28,6 +28,9 @@ BASE_KW = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_a
                decoder_layer_num=3, decoder_pos_emd_len=1000, mlm=False)  # config/mat-sed/base/finetune2.yaml:53-62
 N_SAMPLES = 320000       # 10 s @ 32 kHz (the model asserts 1000 frames: reference passt_sed.py:260)
 FWD_GFLOP_PER_CLIP = 297.3
+# config/mat-sed/base/finetune2.yaml:86-101 (opt.param_groups): stepped encoder LR (last 4 blocks and the norms at 2x), decoder, head
+FINETUNE2_OPT = dict(encoder=dict(lr=5.0e-6, weight_decay=1.0e-4, freeze_layer=0, step_lr=4), decoder=dict(lr=1.0e-4, weight_decay=1.0e-4),
+                     head=dict(lr=1.0e-4, weight_decay=1.0e-4))
 MIX = (16, 6, 21, 21)    # strong, synthetic, weak, unlabeled of a 64-clip DESED batch (finetune1.yaml:12 ratio 3:1:4:4)
 
 
@@ -96,7 +99,7 @@ def run_ours(args):
     import torch.distributed as dist
     from transformer4sed_b200 import _lib, functional as F, ops
     from transformer4sed_b200.src_models.passt.passt_sed import PaSST_SED
-    from transformer4sed_b200.training import ParamArena, mat_sed_param_groups
+    from transformer4sed_b200.training import ParamArena, passt_param_groups
     from transformer4sed_b200.utils import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -129,7 +132,7 @@ def run_ours(args):
     net.load_state_dict(synth.synth_state_dict_like(net, 4), strict=True)   # identical on every rank
     net = net.to(dev).train()
     ext = net.get_feature_extractor().eval()
-    arena = ParamArena(net, mat_sed_param_groups(net), shadow_bf16=(args.precision == "bf16"))
+    arena = ParamArena(net, passt_param_groups(net, FINETUNE2_OPT), shadow_bf16=(args.precision == "bf16"))
 
     n_distinct = min(B, 8)
     wav_host = synth.synth_wav(n_distinct, N_SAMPLES, seed=1234 + rank).repeat((B + n_distinct - 1) // n_distinct, 1)[:B].contiguous()

@@ -344,6 +344,34 @@ def golden_glue():
     print("glue.npz shifts", shifts, "c", c, "perm", perm.tolist(), "median sizes", sizes)
 
 
+def golden_param_groups(base_kw):
+    """Optimizer groups and requires_grad side effects of the reference's `get_params` (recipes/desed/finetune/passt/setting.py:28-103)
+    for the shipped finetune2 settings and three variants (no step_lr, frozen encoder, freeze_layer)."""
+    import json
+    import logging
+    from recipes.desed.finetune.passt.setting import get_params
+    variants = {
+        "finetune2": dict(encoder=dict(lr=5.0e-6, weight_decay=1.0e-4, freeze_layer=0, step_lr=4), decoder=dict(lr=1.0e-4, weight_decay=1.0e-4),
+                          head=dict(lr=1.0e-4, weight_decay=1.0e-4)),
+        "no_step": dict(encoder=dict(lr=1.0e-5, weight_decay=1.0e-4, freeze_layer=0, step_lr=0), decoder=dict(lr=1.0e-4, weight_decay=1.0e-4),
+                        head=dict(lr=2.0e-4, weight_decay=0.0)),
+        "frozen_encoder": dict(encoder=dict(lr=0.0, weight_decay=1.0e-4, freeze_layer=0, step_lr=0), decoder=dict(lr=1.0e-4, weight_decay=1.0e-4),
+                               head=dict(lr=1.0e-4, weight_decay=1.0e-4)),
+        "freeze_6": dict(encoder=dict(lr=5.0e-6, weight_decay=1.0e-4, freeze_layer=6, step_lr=2), decoder=dict(lr=0.0, weight_decay=1.0e-4),
+                         head=dict(lr=1.0e-4, weight_decay=1.0e-4)),
+    }
+    out = {}
+    for tag, lr_dict in variants.items():
+        net = PaSST_SED(load_pretrained_model=False, **base_kw)
+        names = {id(p): n for n, p in net.named_parameters()}
+        groups = get_params(net, {"opt": {"param_groups": lr_dict}}, logging.getLogger("golden"))
+        out[tag] = dict(lr_dict=lr_dict, groups=[dict(lr=g["lr"], weight_decay=g["weight_decay"], names=sorted(names[id(p)] for p in g["params"]))
+                                                 for g in groups],
+                        trainable=sorted(n for n, p in net.named_parameters() if p.requires_grad))
+    json.dump(out, open(os.path.join(OUT, "param_groups.json"), "w"))
+    print("param_groups.json", {k: [len(g["names"]) for g in v["groups"]] for k, v in out.items()})
+
+
 def golden_mlm(tag, kw, seed, batch):
     """MAT-SED pre-train forward (mlm=True): needs the synthetic PaSST checkpoint on disk."""
     import tempfile
@@ -416,7 +444,7 @@ if __name__ == "__main__":
     base = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_adapter=True, decoder="transformerXL",
                 decoder_layer_num=3, decoder_pos_emd_len=1000, mlm=False)  # config/mat-sed/base/finetune2.yaml:53-62
     pre = dict(base, mlm=True, mlm_dict=dict(strategy="block", block_width=10, mask_rate=0.75, out_dim=768))  # pretrain.yaml:39-52
-    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm", "pmam", "dasm", "glue"]
+    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm", "pmam", "dasm", "glue", "groups"]
     if "frontend" in which:
         golden_frontend()
         golden_frontend_16k()
@@ -432,6 +460,8 @@ if __name__ == "__main__":
         golden_pmam(seed=10, batch=2)
     if "dasm" in which:
         golden_dasm(seed=12, batch=2)
+    if "groups" in which:
+        golden_param_groups(base)
     if "glue" in which:
         golden_glue()
     if "mlm" in which:

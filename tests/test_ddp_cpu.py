@@ -122,3 +122,26 @@ def test_pmam_dasm_schemas_and_lora_merge_roundtrip_cpu():
     lin.train()
     assert not lin.merged and torch.allclose(lin.weight, w0, atol=1e-6)
     assert not lin.weight.requires_grad and lin.lora_A.requires_grad
+
+
+def test_passt_param_groups_match_reference_get_params():
+    """`training.passt_param_groups` builds the same optimizer groups (membership, lr, weight decay) and leaves the same requires_grad
+    flags as the reference's `get_params` for the shipped finetune2 settings and three variants (golden: oracle/make_golden.py groups).
+    The PaSST classification heads (never on the SED path: no gradient, skipped by torch's AdamW) are the only keys left out."""
+    import json
+    import os
+    from transformer4sed_b200.src_models.passt.passt_sed import PaSST_SED
+    from transformer4sed_b200.training import passt_param_groups
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "param_groups.json")))
+    base = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_adapter=True, decoder="transformerXL", decoder_layer_num=3,
+                decoder_pos_emd_len=1000, mlm=False)
+    unused = lambda n: n.startswith("backbone.head.") or n.startswith("backbone.head_dist.")   # noqa: E731
+    for tag, g in gold.items():
+        net = PaSST_SED(load_pretrained_model=False, **base)
+        names = {id(p): n for n, p in net.named_parameters()}
+        groups = passt_param_groups(net, g["lr_dict"])
+        assert len(groups) == len(g["groups"]), tag
+        for ours, ref in zip(groups, g["groups"]):
+            assert sorted(names[id(p)] for p in ours["params"]) == [n for n in ref["names"] if not unused(n)], (tag, ours["name"])
+            assert abs(ours["lr"] - ref["lr"]) < 1e-15 and abs(ours["weight_decay"] - ref["weight_decay"]) < 1e-15, (tag, ours["name"])
+        assert sorted(n for n, p in net.named_parameters() if p.requires_grad) == g["trainable"], tag

@@ -70,3 +70,26 @@ def test_mean_teacher_matches_reference_ema():
             assert (a - b).abs().max().item() < 1e-6, (step, n)
         w = mt.teacher[0].weight
         assert (w._t4s_shadow.float() - w).abs().max().item() <= w.abs().max().item() * 2 ** -8
+
+
+def test_param_without_gradient_is_left_untouched_like_torch_adamw():
+    """A trainable parameter that received no gradient this step (e.g. the mask token under the upstream no-op masking) is skipped by
+    torch.optim.AdamW: no weight decay, no moment update.  The arena's flat-range kernel must leave it (and its bf16 shadow) alone."""
+    from transformer4sed_b200.training import ParamArena
+    torch.manual_seed(2)
+    m1 = torch.nn.ModuleDict(dict(a=torch.nn.Linear(16, 16), unused=torch.nn.Linear(16, 4))).cuda()
+    import copy
+    m2 = copy.deepcopy(m1)
+    arena = ParamArena(m1, [dict(name="all", params=list(m1.parameters()), lr=1e-2, weight_decay=0.1)], shadow_bf16=True)
+    opt = torch.optim.AdamW(m2.parameters(), lr=1e-2, weight_decay=0.1)
+    w0 = m1["unused"].weight.detach().clone()
+    for _ in range(3):
+        x = torch.randn(8, 16, device="cuda")
+        for m in (m1, m2):
+            m["a"](x).square().mean().backward()
+        arena.step()
+        opt.step()
+        opt.zero_grad()
+    assert torch.equal(m1["unused"].weight, w0) and torch.equal(m2["unused"].weight, w0)
+    assert (m1["unused"].weight._t4s_shadow.float() - w0).abs().max().item() <= w0.abs().max().item() * 2 ** -8
+    assert (m1["a"].weight - m2["a"].weight).abs().max().item() < 2e-6

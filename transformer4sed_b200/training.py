@@ -96,6 +96,12 @@ class ParamArena:
         return all_reduce_flat(self.grad)
 
     def step(self, lr_scale=1.0):
+        # torch.optim.AdamW leaves a parameter whose grad is None completely untouched (no decay, no moment update); the fused
+        # kernel runs over whole flat ranges, so such (rare, e.g. the mask token under the upstream no-op masking) tensors are
+        # put back after the update
+        skipped = [(off, p.numel()) for p, off in self.layout if p.grad is None]
+        keep = [(off, n, self.flat[off:off + n].clone(), self.exp_avg[off:off + n].clone(), self.exp_avg_sq[off:off + n].clone())
+                for off, n in skipped]
         self.pack_grads()
         world = self.all_reduce()
         self.step_count += 1
@@ -112,6 +118,12 @@ class ParamArena:
                     ctypes.c_void_p(self.shadow.data_ptr() + o2) if self.shadow is not None else ctypes.c_void_p(0), n,
                     g["lr"] * lr_scale, self.betas[0], self.betas[1], self.eps, g["weight_decay"], self.step_count, 1.0 / world,
                     _lib.stream_ptr()), "t4s_adamw_step")
+        for off, n, w, m1, m2 in keep:
+            self.flat[off:off + n].copy_(w)
+            self.exp_avg[off:off + n].copy_(m1)
+            self.exp_avg_sq[off:off + n].copy_(m2)
+            if self.shadow is not None:
+                F.convert(w, self.shadow[off:off + n])
         for p, _ in self.layout:
             p.grad = None
 
@@ -175,6 +187,64 @@ class MeanTeacher:
                                "t4s_ema_update")
                     F.invalidate_weight_cache(tp)
         return alpha
+
+
+def check_tensor_name_decoder(tensor_name) -> bool:
+    """reference recipes/desed/finetune/passt/setting.py:18-25."""
+    return any(kw in tensor_name for kw in ("decoder", "f_pool_module", "transformer_projector"))
+
+
+def passt_param_groups(net, lr_dict):
+    """The optimizer groups of the DESED fine-tuning recipes, as reference recipes/desed/finetune/passt/setting.py:28-103 (`get_params`)
+    builds them from ``configs["opt"]["param_groups"]`` -- including its side effects on ``requires_grad``:
+
+      * encoder: every backbone parameter; with ``step_lr`` > 0 the blocks ``12 - idx <= step_lr`` and every key containing "norm."
+        (that is also the LayerNorms of the LOWER blocks: upstream's `elif "norm." in k`) train at 2 x lr, the rest at lr;
+        ``lr <= 0`` freezes everything but "norm." keys; ``freeze_layer`` > 0 freezes the blocks below it;
+      * decoder: names containing "decoder" / "f_pool_module" / "transformer_projector" (frozen when lr <= 0);
+      * head: everything else.
+
+    Returns ParamArena groups (dicts with name / params / lr / weight_decay).  Parameters that can never receive a gradient on
+    the SED path (the PaSST classification heads) are left out, which is what torch.optim.AdamW does with `grad is None`."""
+    import re
+    enc, dec = lr_dict["encoder"], lr_dict["decoder"]
+    head = lr_dict.get("head", dec)
+    backbone = [(k, p) for k, p in net.backbone.named_parameters()]
+    passt_ids = {id(p) for _, p in backbone}
+    unused = lambda k: k.startswith("head.") or k.startswith("head_dist.")   # noqa: E731
+    if not enc.get("step_lr"):
+        groups = [dict(name="encoder", params=[p for k, p in backbone if not unused(k)], lr=enc["lr"], weight_decay=enc["weight_decay"])]
+    else:
+        low, high = [], []
+        for k, p in backbone:
+            if unused(k):
+                continue
+            m = re.search(r"blocks.(\d+)", k)
+            if m and (12 - int(m.group(1)) <= enc["step_lr"]):
+                high.append(p)
+            elif "norm." in k:
+                high.append(p)
+            else:
+                low.append(p)
+        groups = [dict(name="encoder_low", params=low, lr=enc["lr"], weight_decay=enc["weight_decay"]),
+                  dict(name="encoder_high", params=high, lr=enc["lr"] * 2, weight_decay=enc["weight_decay"])]
+    if enc["lr"] <= 0:
+        for k, p in backbone:
+            if "norm." not in k:
+                p.requires_grad = False
+    if enc.get("freeze_layer", 0) > 0:
+        for k, p in backbone:
+            m = re.search(r"blocks.(\d+)", k)
+            p.requires_grad = bool((m and int(m.group(1)) + 1 > enc["freeze_layer"]) or "norm." in k)
+    decoder_params = [p for k, p in net.named_parameters() if check_tensor_name_decoder(k)]
+    decoder_ids = {id(p) for p in decoder_params}
+    if dec["lr"] <= 0:
+        for p in decoder_params:
+            p.requires_grad = False
+    head_params = [p for p in net.parameters() if id(p) not in passt_ids and id(p) not in decoder_ids]
+    groups.append(dict(name="decoder", params=decoder_params, lr=dec["lr"], weight_decay=dec["weight_decay"]))
+    groups.append(dict(name="head", params=head_params, lr=head["lr"], weight_decay=head["weight_decay"]))
+    return groups
 
 
 def mat_sed_param_groups(net, lr_encoder=5e-6, lr_decoder=1e-4, lr_head=1e-4, weight_decay=1e-4):
