@@ -145,3 +145,24 @@ def test_passt_param_groups_match_reference_get_params():
             assert sorted(names[id(p)] for p in ours["params"]) == [n for n in ref["names"] if not unused(n)], (tag, ours["name"])
             assert abs(ours["lr"] - ref["lr"]) < 1e-15 and abs(ours["weight_decay"] - ref["weight_decay"]) < 1e-15, (tag, ours["name"])
         assert sorted(n for n, p in net.named_parameters() if p.requires_grad) == g["trainable"], tag
+
+
+def test_dropin_install_registers_reference_import_paths():
+    """`dropin.install()` makes the reference's import statements (recipes/**/setting.py, main.py) resolve to the CUDA mirrors; run in
+    a subprocess so the registration does not leak into the other tests."""
+    import subprocess
+    import sys
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import transformer4sed_b200.dropin as d; d.install()\n"
+        "from src.models.passt.passt_sed import PaSST_SED\n"
+        "from src.models.cnn_transformer.passt_cnn import PaSST_CNN\n"
+        "from src.models.detect_any_sound.detect_any_sound import DASM\n"
+        "from src.models.passt.passt_win import PasstWithSlide\n"
+        "from src.postprocess.filter import median_filter_torch\n"
+        "import src.models.lora as lora\n"
+        "mods = {PaSST_SED.__module__, PaSST_CNN.__module__, DASM.__module__, PasstWithSlide.__module__, lora.Linear.__module__, median_filter_torch.__module__}\n"
+        "assert all(m.startswith('transformer4sed_b200.') for m in mods), mods\n"
+        "print('ok')\n") % __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
