@@ -6,7 +6,6 @@ load unchanged.  The arithmetic runs channels-last through libt4s: 3x3 convoluti
 `context_gate`, `avg_pool`).  Only the configuration the shipped PMAM / DASM YAMLs select is provided: kernel 3, stride 1,
 padding 1, BatchNorm, ContextGating activation.
 """
-import torch
 import torch.nn as nn
 
 from ... import functional as F

@@ -8,7 +8,6 @@ goes through the two [tokens, r] factors only.
 """
 import math
 
-import torch
 import torch.nn as nn
 
 from ... import functional as F
