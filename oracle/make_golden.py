@@ -231,6 +231,44 @@ def golden_pmam(seed, batch):
     print(f"pmam_base.npz loss={loss.item():.6f} masked={m.float().mean().item():.3f} trainable={len(out['trainable'])} grads={len(gn)}")
 
 
+def golden_pmam_finetune(seed, batch):
+    """PMAM fine-tuning model (config/pmam/finetune1.yaml:61-82: PaSST_CNN without LoRA / MLM, 10 classes): eval-mode forward with the
+    student kwargs (temp 1) and with a pad mask at the validation temperature."""
+    import tempfile
+    import yaml
+    from src.models.cnn_transformer.passt_cnn import PaSST_CNN
+    from src.models.passt.passt import PaSST
+    cfg = yaml.safe_load(open("/root/reference/config/pmam/finetune1.yaml"))["PaSST_CNN"]["init_kwargs"]
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "pretrained_model"))
+        os.chdir(d)
+        try:
+            bb = PaSST(u_patchout=0, s_patchout_t=0, s_patchout_f=0, img_size=(128, 998), patch_size=16, stride=10, in_chans=1,
+                       num_classes=527, embed_dim=768, depth=12, num_heads=12, mlp_ratio=4, qkv_bias=True, distilled=True)
+            torch.save(bb.state_dict(), "pretrained_model/passt-s-f128-p16-s10-ap.476-swa.pt")
+            net = PaSST_CNN(**cfg)
+        finally:
+            os.chdir(cwd)
+    sd = synth.synth_state_dict_like(net, seed)
+    net.load_state_dict(sd, strict=True)
+    net.eval()
+    ext = net.get_feature_extractor().eval()
+    wav = synth.synth_wav(batch, 320000, seed=seed + 1)
+    mel = ext.normalize(ext(wav))
+    pad_mask = torch.zeros(batch, 1000, dtype=torch.bool)
+    pad_mask[-1, 850:] = True
+    with torch.no_grad():
+        s1, w1, o1 = net(mel, temp_w=1)
+        s2, w2, _ = net(mel, temp_w=0.5, pad_mask=pad_mask)
+    out = dict(wav_ck=checksum(wav), mel_ck=checksum(mel), sd_keys=np.array(sorted(sd.keys())),
+               sd_ck=checksum(torch.cat([v.flatten().float() for k, v in sorted(sd.items()) if torch.is_floating_point(v)])),
+               strong=f32(s1), weak=f32(w1), at_out=f32(o1["at_out"]), argmax=s1.argmax(dim=1).numpy().astype(np.int8),
+               strong_pad=f32(s2), weak_pad=f32(w2))
+    np.savez_compressed(os.path.join(OUT, "pmam_finetune.npz"), **out)
+    print("pmam_finetune.npz strong range", s1.min().item(), s1.max().item())
+
+
 DASM_KW = dict(
     cnn_param=dict(n_in_channel=1, activation="cg", conv_dropout=0.0, kernel_size=[3] * 10, padding=[1] * 10, stride=[1] * 10,
                    nb_filters=[16, 16, 32, 32, 64, 64, 128, 128, 256, 384],
@@ -444,7 +482,7 @@ if __name__ == "__main__":
     base = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_adapter=True, decoder="transformerXL",
                 decoder_layer_num=3, decoder_pos_emd_len=1000, mlm=False)  # config/mat-sed/base/finetune2.yaml:53-62
     pre = dict(base, mlm=True, mlm_dict=dict(strategy="block", block_width=10, mask_rate=0.75, out_dim=768))  # pretrain.yaml:39-52
-    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm", "pmam", "dasm", "glue", "groups"]
+    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm", "pmam", "pmam_ft", "dasm", "glue", "groups"]
     if "frontend" in which:
         golden_frontend()
         golden_frontend_16k()
@@ -458,6 +496,8 @@ if __name__ == "__main__":
         golden_window("base", base, seed=8, batch=1)   # out_dim is hard-wired to 768 upstream (encoder_slide_window.py:10)
     if "pmam" in which:
         golden_pmam(seed=10, batch=2)
+    if "pmam_ft" in which:
+        golden_pmam_finetune(seed=14, batch=2)
     if "dasm" in which:
         golden_dasm(seed=12, batch=2)
     if "groups" in which:

@@ -301,8 +301,9 @@ def cnn_forward(x, sd, nb_filters, pooling, training=False, p="cnn.cnn.", new_st
 
 
 def passt_cnn_forward(mel, sd, nb_filters, pooling, decoder_layers=3, feature_layer=10, f_pool_mode="attention", decode_ratio=10,
-                      training=False, decoder_input_override=None, stages=None, new_stats=None):
-    """PaSST_CNN.forward (cnn_transformer/passt_cnn.py:32-70), mlm=True, encoder_win=False -> (pred [B,T,out_dim], other)."""
+                      training=False, decoder_input_override=None, stages=None, new_stats=None, mlm=True, temp_w=1.0, pad_mask=None):
+    """PaSST_CNN.forward (cnn_transformer/passt_cnn.py:32-88), encoder_win=False -> (pred [B,T,out_dim], other) with mlm, else
+    (strong [B,C,T], weak [B,C], other) through the classifier + linear-softmax pooling (:73-86)."""
     feat, frame, Fd, Td = passt_backbone(mel, sd, feature_layer=feature_layer)
     x = pad_interpolate(f_pool(feat, sd, Fd, Td, f_pool_mode), decode_ratio)
     cnn_feat = cnn_forward(mel.transpose(1, 2).unsqueeze(1), sd, nb_filters, pooling, training, new_stats=new_stats)
@@ -314,7 +315,10 @@ def passt_cnn_forward(mel, sd, nb_filters, pooling, decoder_layers=3, feature_la
     other["at_out"] = at_branch(frame, sd)
     if stages is not None:
         stages.update(cnn_feat=cnn_feat, frame_before_mask=x, decoder_in=dec_in, decoder_out=y)
-    return mlm_head(y, sd), other
+    if mlm:
+        return mlm_head(y, sd), other
+    strong, weak = sed_head(y, sd, temp_w, pad_mask)
+    return strong, weak, other
 
 
 def prototype_predict(logit, prototypes, temperature=0.1):

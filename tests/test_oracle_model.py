@@ -234,3 +234,27 @@ def test_dasm(golden):
         if str(name).startswith("cnn.cnn.conv") and str(name).endswith(".bias"):
             continue    # zero gradient in front of a training-mode BatchNorm (rounding noise only)
         np.testing.assert_allclose(gr.double().norm().item(), norm, rtol=5e-3, atol=1e-9, err_msg=str(name))
+
+
+def test_pmam_finetune_passt_cnn(golden):
+    """Oracle PaSST_CNN in its fine-tuning form (config/pmam/finetune1.yaml: no LoRA, no MLM, 10 classes): strong / weak / AT outputs,
+    frame-label argmax and the pad-mask + temperature path vs the unmodified reference."""
+    g = golden("pmam_finetune.npz")
+    seed, batch = 14, 2
+    shapes = schema.passt_cnn_shapes(class_num=10, mlm=False, lora_r=0)
+    assert sorted(shapes) == [k for k in g["sd_keys"] if not str(k).endswith("num_batches_tracked")]
+    sd = _sd(shapes, seed)
+    np.testing.assert_allclose(checksum(torch.cat([v.flatten() for _, v in sorted(sd.items())])), g["sd_ck"], rtol=1e-12)
+    mel = F.passt_logmel(synth.synth_wav(batch, 320000, seed=seed + 1))
+    np.testing.assert_allclose(checksum(mel), g["mel_ck"], rtol=1e-9)
+    pad = torch.zeros(batch, 1000, dtype=torch.bool)
+    pad[-1, 850:] = True
+    with torch.no_grad():
+        s, w, o = M.passt_cnn_forward(mel, sd, schema.PMAM_FILTERS, schema.PMAM_POOLING, mlm=False)
+        np.testing.assert_allclose(s.numpy(), g["strong"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(w.numpy(), g["weak"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(o["at_out"].numpy(), g["at_out"], rtol=1e-4, atol=1e-6)
+        assert (s.argmax(dim=1).numpy() == g["argmax"]).all()
+        s, w, _ = M.passt_cnn_forward(mel, sd, schema.PMAM_FILTERS, schema.PMAM_POOLING, mlm=False, temp_w=0.5, pad_mask=pad)
+        np.testing.assert_allclose(s.numpy(), g["strong_pad"], rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(w.numpy(), g["weak_pad"], rtol=1e-4, atol=1e-6)

@@ -115,6 +115,7 @@ PMAM_POOLING = ((2, 2), (1, 1), (2, 2), (1, 1), (1, 2), (1, 2), (1, 2), (1, 2), 
 
 def passt_cnn_shapes(embed_dim=768, decoder_dim=384, decoder_layer_num=3, class_num=30, f_pool="attention", mlm=True, lora_r=8,
                      nb_filters=PMAM_FILTERS):
+    # config/pmam/finetune{1,2}.yaml: class_num=10, mlm=False, lora_r=0
     """reference src/models/cnn_transformer/passt_cnn.py:9-19 on top of PaSST_SED (config/pmam/post_pretrain.yaml:48-79)."""
     d = mat_sed_shapes(embed_dim, decoder_dim, decoder_layer_num, class_num, True, f_pool, mlm, 768)
     if lora_r:
