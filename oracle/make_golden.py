@@ -373,7 +373,13 @@ def golden_glue():
     fa_step = filt_aug(small, db_range=[-6, 6], n_band=[3, 6], min_bw=6, filter_type="step", log=True, norm_std=5.0)
     torch.manual_seed(22)
     fa_lin = filt_aug(small, db_range=[-6, 6], n_band=[3, 6], min_bw=6, filter_type="linear", log=True, norm_std=5.0)
-    extra = dict(fn=f32(fn), fn_phase=np.array(fn_phase), fa_step=f32(fa_step), fa_lin=f32(fa_lin))
+    # the stack the recipes call (data_aug.py:111-147) with the shipped DESED settings (config/mat-sed/base/finetune2.yaml:44-51)
+    from src.preprocess.data_aug import feature_transformation
+    random.seed(31)
+    torch.manual_seed(31)
+    ft_a, ft_b = feature_transformation(small, n_transform=2, choice=[1, 0, 0, 1], filter_db_range=[-26, 26], filter_bands=[2, 5],
+                                        filter_minimum_bandwidth=4, filter_type="step", log=True, norm_std=5.0)
+    extra = dict(fn=f32(fn), fn_phase=np.array(fn_phase), fa_step=f32(fa_step), fa_lin=f32(fa_lin), ft_a=f32(ft_a), ft_b=f32(ft_b))
     out = dict(**extra, shifts=np.array(shifts, np.int32), fs_mel=f32(fs_mel[:, ::8, ::5]), fs_label=f32(fs_label), shifts4=np.array(shifts4, np.int32),
                fs4_mel=f32(fs4_mel[:, ::8, ::5]), fs4_label=f32(fs4_label), c=np.array(c), perm=perm.numpy(), mx_mel=f32(mx_mel[:, ::8, ::5]),
                mx_label=f32(mx_label), c_h=np.array(c_h), perm_h=perm_h.numpy(), mh_mel=f32(mh_mel[:, ::8, ::5]), mh_label=f32(mh_label),

@@ -161,6 +161,8 @@ def test_dropin_install_registers_reference_import_paths():
         "from src.models.passt.passt_win import PasstWithSlide\n"
         "from src.postprocess.filter import median_filter_torch\n"
         "import src.models.lora as lora\n"
+        "from src.preprocess.data_aug import mixup, frame_shift, feature_transformation\n"
+        "assert feature_transformation.__module__.startswith('transformer4sed_b200.')\n"
         "mods = {PaSST_SED.__module__, PaSST_CNN.__module__, DASM.__module__, PasstWithSlide.__module__, lora.Linear.__module__, median_filter_torch.__module__}\n"
         "assert all(m.startswith('transformer4sed_b200.') for m in mods), mods\n"
         "print('ok')\n") % __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))

@@ -68,3 +68,11 @@ def test_feature_transforms_match_reference(golden):
     np.testing.assert_allclose(fa.cpu().numpy(), g["fa_lin"], rtol=1e-6, atol=1e-6)
     with pytest.raises(NotImplementedError):
         filt_aug(small, log=False)
+    # the stack the recipes call (two independently augmented copies, shipped DESED settings): draw order as upstream
+    from transformer4sed_b200.src_preprocess.data_aug import feature_transformation
+    random.seed(31)
+    torch.manual_seed(31)
+    a, b = feature_transformation(small, n_transform=2, choice=[1, 0, 0, 1], filter_db_range=[-26, 26], filter_bands=[2, 5],
+                                  filter_minimum_bandwidth=4, filter_type="step", log=True, norm_std=5.0)
+    np.testing.assert_allclose(a.cpu().numpy(), g["ft_a"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(b.cpu().numpy(), g["ft_b"], rtol=1e-5, atol=2e-5)

@@ -57,3 +57,47 @@ def test_freq_nonlinear_and_filt_aug_oracle_and_table(golden):
             np.testing.assert_allclose(ours, np.interp(ind, ind_t, r), rtol=1e-12, atol=1e-12)
     random.seed(11)
     assert random.random() == phase
+
+
+def test_feature_transformation_host_logic(golden, monkeypatch):
+    """The mirror's `feature_transformation` / `filt_aug` / `freq_nonlinear` host side (RNG draw order, filter assembly, warp table)
+    against the reference's stack on the shipped settings.  The two kernel launches are replaced by CPU doubles that compute what
+    the kernels are specified to compute (csrc/aug.cu: gather-lerp, row bias) -- the kernels themselves are checked in
+    tests/test_glue_gpu.py."""
+    import random
+    from transformer4sed_b200.src_preprocess import data_aug as A
+
+    def warp_double(mel, j, w):
+        jt = torch.from_numpy(j)
+        wt = torch.from_numpy(w.astype(np.float32)).view(1, -1, 1)
+        a = mel[:, jt]
+        return torch.where(wt == 0, a, a + wt * (mel[:, torch.clamp(jt + 1, max=mel.shape[1] - 1)] - a))
+
+    def bias_double(features, bias_host):
+        return features + bias_host.view(features.shape[0], features.shape[1], 1)
+
+    monkeypatch.setattr(A, "_launch_freq_warp", warp_double)
+    monkeypatch.setattr(A, "_launch_add_rowbias", bias_double)
+    g = golden("glue.npz")
+    mel, _, _, _ = _inputs(g)
+    small = mel[:3, :, :200].contiguous()
+    keep = small.clone()
+    random.seed(31)
+    torch.manual_seed(31)
+    a, b = A.feature_transformation(small, n_transform=2, choice=[1, 0, 0, 1], filter_db_range=[-26, 26], filter_bands=[2, 5],
+                                    filter_minimum_bandwidth=4, filter_type="step", log=True, norm_std=5.0)
+    np.testing.assert_allclose(a.numpy(), g["ft_a"], rtol=0, atol=2e-5)
+    np.testing.assert_allclose(b.numpy(), g["ft_b"], rtol=0, atol=2e-5)
+    assert torch.equal(small, keep)                                   # the input batch is not modified
+    one = A.feature_transformation(small, n_transform=1, choice=[0, 0, 0, 0], filter_db_range=[-26, 26], filter_bands=[2, 5],
+                                   filter_minimum_bandwidth=4, filter_type="step", log=True)
+    assert torch.equal(one, small) and one.data_ptr() != small.data_ptr()
+    import pytest
+    with pytest.raises(NotImplementedError):
+        A.feature_transformation(small, 1, [0, 1, 0, 0], [-26, 26], [2, 5], 4, "step")
+    # single transforms against their own golden entries (same doubles)
+    random.seed(11)
+    np.testing.assert_allclose(A.freq_nonlinear(small, bias=0.03 * 0.7).numpy(), g["fn"], rtol=0, atol=2e-5)
+    torch.manual_seed(21)
+    np.testing.assert_allclose(A.filt_aug(small, db_range=[-6, 6], n_band=[3, 6], min_bw=6, filter_type="step", log=True, norm_std=5.0).numpy(),
+                               g["fa_step"], rtol=0, atol=1e-6)

@@ -95,10 +95,15 @@ def freq_warp_table(n_freq, f, bias, phase):
 def freq_nonlinear(mel, f=1, bias=0.02):
     """mel [B, F, T] (cuda fp32; the reference takes / returns a numpy array) -> frequency-warped copy.  One `random.random()` draw
     (the phase), as upstream where the lambda is evaluated once on the whole index vector."""
+    j, w = freq_warp_table(mel.shape[1], f, bias, random.random())
+    return _launch_freq_warp(mel, j, w)
+
+
+def _launch_freq_warp(mel, j, w):
+    """out[b, i, t] = (1 - w[i]) * mel[b, j[i], t] + w[i] * mel[b, j[i] + 1, t] -- one gather-lerp kernel over the batch."""
     _lib.ensure_device(mel)
     x = mel.contiguous().float()
     B, Fq, T = x.shape
-    j, w = freq_warp_table(Fq, f, bias, random.random())
     j_dev = torch.from_numpy(j.astype(np.int32)).to(x.device)
     w_dev = torch.from_numpy(w.astype(np.float32)).to(x.device)
     out = torch.empty_like(x)
@@ -136,11 +141,43 @@ def filt_aug(features, db_range=[-0.5, 0.5], n_band=[3, 6], min_bw=6, filter_typ
         raise Exception("Unkonwn filter augment type")
     if not log:
         raise NotImplementedError("[DEBUG] Don't support filter augumentation after log operation")
+    return _launch_add_rowbias(features, (torch.log(freq_filt + 0.00001) / norm_std).reshape(-1))
+
+
+def _launch_add_rowbias(features, bias_host):
+    """out[b, f, :] = features[b, f, :] + bias[b * F + f] -- one kernel over the batch."""
     _lib.ensure_device(features)
     x = features.contiguous().float()
-    bias = (torch.log(freq_filt + 0.00001) / norm_std).reshape(-1).to(x.device)
+    batch_size, n_freq_bin, n_frames = x.shape
+    bias = bias_host.to(x.device)
     out = torch.empty_like(x)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().t4s_add_rowbias(_lib.ptr(x), _lib.ptr(bias), _lib.ptr(out), batch_size * n_freq_bin, n_frames, _lib.stream_ptr()),
                    "t4s_add_rowbias")
     return out
+
+
+def feature_transformation(features, n_transform, choice, filter_db_range, filter_bands, filter_minimum_bandwidth, filter_type,
+                           freq_mask_ratio=None, noise_snrs=None, norm_std=5, log=False):
+    """The label-independent transform stack the recipes call every step (data_aug.py:111-147; e.g. recipes/desed/finetune/train.py,
+    mlm_passt/train.py:32): `n_transform` independently augmented copies of the mel batch (student / teacher inputs).
+    ``choice`` = [FilterAugment, freq_mask, add_noise, frequency distortion]; every shipped config uses [1, 0, 0, 1].  Host RNG draws
+    are made in upstream's order (per copy: `random.random()` for the warp bias, one for its phase, then FilterAugment's torch
+    draws).  The features stay on the GPU -- upstream's frequency distortion round-trips the batch through host numpy."""
+    if choice[1] or choice[2]:
+        raise NotImplementedError("freq_mask / add_noise are not selected by any shipped config and are not on the B200 path")
+    feature_list = []
+    for _ in range(n_transform):
+        features_temp = features
+        if choice[3]:
+            bias = 0.03 * random.random()
+            features_temp = freq_nonlinear(features_temp, bias=bias)
+        if choice[0]:
+            features_temp = filt_aug(features_temp, db_range=filter_db_range, n_band=filter_bands, min_bw=filter_minimum_bandwidth,
+                                     filter_type=filter_type, norm_std=norm_std, log=log)
+        if features_temp is features:            # upstream works on a deep copy: every returned tensor is distinct from the input
+            features_temp = features.clone()
+        feature_list.append(features_temp)
+    if n_transform == 1:
+        return feature_list[0]
+    return feature_list
