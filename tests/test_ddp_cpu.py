@@ -168,3 +168,45 @@ def test_dropin_install_registers_reference_import_paths():
         "print('ok')\n") % __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp", timeout=300)
     assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+
+
+def test_arena_shadow_follows_torch_side_parameter_updates(monkeypatch):
+    """Host logic of `functional._arena_shadow`: the bf16 shadow of an arena parameter is re-converted when the parameter was
+    modified through torch (load_state_dict / copy_ bump the version counter) and left alone otherwise.  `convert` is replaced by
+    a CPU double; the kernel itself is covered by tests/test_training_gpu.py."""
+    import torch
+    from transformer4sed_b200 import functional as F
+    calls = []
+
+    def convert_double(src, dst):
+        calls.append(src.data_ptr())
+        dst.copy_(src.reshape(dst.shape))
+        return dst
+
+    monkeypatch.setattr(F, "convert", convert_double)
+    monkeypatch.setattr(F, "_MODE", "bf16")
+    flat, shadow = torch.zeros(16), torch.zeros(16, dtype=torch.bfloat16)
+    lin = torch.nn.Linear(4, 3, bias=False)
+    p = lin.weight
+    with torch.no_grad():                                     # what ParamArena.__init__ does with every managed parameter
+        v = flat[2:14].view(3, 4)
+        v.copy_(p.data)
+        p.data = v
+    p._t4s_shadow = shadow[2:14].view(3, 4)
+    shadow.copy_(flat)
+    p._t4s_shadow_version = p._version
+    assert F.cast_weight(p) is p._t4s_shadow and calls == []
+    flat.mul_(2.0)                                            # kernel-style update of master (+ shadow): no version bump, no refresh
+    shadow.copy_(flat)
+    assert F.cast_weight(p) is p._t4s_shadow and calls == []
+    lin.load_state_dict({"weight": torch.full((3, 4), 0.5)})  # checkpoint resume after the arena was built
+    assert torch.equal(flat[2:14], torch.full((12,), 0.5))    # written through the view into the flat master ...
+    out = F.cast_weight(p)
+    assert len(calls) == 1 and torch.equal(out.float(), torch.full((3, 4), 0.5))   # ... and the shadow caught up exactly once
+    assert F.cast_weight(p) is out and len(calls) == 1
+    with torch.no_grad():
+        p.copy_(torch.full((3, 4), 0.25))
+    assert torch.equal(F.to_plain(p, torch.bfloat16).float(), torch.full((3, 4), 0.25)) and len(calls) == 2
+    q = torch.nn.Parameter(torch.ones(2, 2))                  # a shadow without version bookkeeping keeps the old behaviour
+    q._t4s_shadow = torch.zeros(2, 2, dtype=torch.bfloat16)
+    assert F.cast_weight(q) is q._t4s_shadow and len(calls) == 2

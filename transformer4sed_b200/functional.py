@@ -61,11 +61,23 @@ def _pad8(n):
 _wcache = {}
 
 
+def _arena_shadow(w):
+    """bf16 shadow of a parameter that lives in a `training.ParamArena` (None otherwise).  The fused AdamW / EMA kernels write the
+    fp32 master and the shadow together; anything that changes the parameter through torch instead (`load_state_dict`, `copy_`:
+    resuming from a checkpoint after the arena was built, reference recipes/desed/finetune/passt/main.py:63-69) bumps its version
+    counter, and the shadow is re-converted here before it is used."""
+    shadow = getattr(w, "_t4s_shadow", None)
+    if shadow is not None and getattr(w, "_t4s_shadow_version", w._version) != w._version:
+        convert(w.detach(), shadow)
+        w._t4s_shadow_version = w._version
+    return shadow
+
+
 def cast_weight(w: torch.Tensor) -> torch.Tensor:
     """fp32 master weight -> GEMM operand dtype (bf16 copy cached until the parameter is modified)."""
     if _MODE != "bf16":
         return w.detach()
-    shadow = getattr(w, "_t4s_shadow", None)  # kept fresh by the fused AdamW kernel (training.ParamArena)
+    shadow = _arena_shadow(w)
     if shadow is not None:
         return shadow
     if w._base is not None and w._base.dtype == torch.float32:  # a slice of a parameter: cast the parameter once, re-slice the copy
@@ -1368,6 +1380,7 @@ def invalidate_weight_cache(w):
     shadow = getattr(w, "_t4s_shadow", None)
     if shadow is not None:      # parameter-arena bf16 shadow: refresh it in place
         convert(w.detach(), shadow)
+        w._t4s_shadow_version = w._version
 
 
 class _LoraLinear(torch.autograd.Function):
@@ -1445,7 +1458,7 @@ class _LoraLinear(torch.autograd.Function):
 
 def to_plain(p, dtype):
     """Small parameter -> contiguous tensor of the activation dtype (no caching: LoRA factors change every step)."""
-    shadow = getattr(p, "_t4s_shadow", None)   # bf16 copy kept fresh by the fused AdamW kernel (training.ParamArena)
+    shadow = _arena_shadow(p)
     if shadow is not None and shadow.dtype == dtype:
         return shadow
     p = p.detach().contiguous()

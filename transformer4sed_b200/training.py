@@ -71,6 +71,8 @@ class ParamArena:
                     p._t4s_shadow = self.shadow[off:off + p.numel()].view(p.shape)
         if self.shadow is not None:
             F.convert(self.flat, self.shadow)
+            for p, _ in layout:
+                p._t4s_shadow_version = p._version      # functional._arena_shadow re-converts after load_state_dict / copy_
         self.betas, self.eps, self.step_count = betas, eps, 0
         self._table_host = torch.empty(len(layout), 3, dtype=torch.int64).pin_memory()
         self._table_dev = torch.empty(len(layout), 3, dtype=torch.int64, device=dev)
@@ -151,7 +153,7 @@ class MeanTeacher:
             for p, data, shadow in saved:
                 p.data = data
                 if shadow is not None:
-                    p._t4s_shadow = shadow
+                    p._t4s_shadow = shadow          # (`_t4s_shadow_version` stays on the parameter; `.data =` does not bump the version)
         for p in self.teacher.parameters():
             p.requires_grad_(False)
         self.arena = arena
@@ -172,6 +174,9 @@ class MeanTeacher:
                 managed.add(names[id(p)])
         if self.shadow is not None:
             F.convert(self.flat, self.shadow)
+            for p, _ in arena.layout:
+                tp = tparams[names[id(p)]]
+                tp._t4s_shadow_version = tp._version
         sparams = dict(student.named_parameters())
         self.rest = [(tparams[n], sparams[n]) for n in tparams if n not in managed]
 
