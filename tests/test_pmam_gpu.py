@@ -108,6 +108,45 @@ def test_passt_cnn_matches_reference(golden, mode, tol, gtol):
         F.set_precision("bf16")
 
 
+@pytest.mark.parametrize("mode,tol", [("tf32x3", 1e-3), ("bf16", 0.1)])
+def test_passt_cnn_finetune_form_matches_reference(golden, mode, tol):
+    """`PaSST_CNN` as the PMAM fine-tuning stages build it (config/pmam/finetune1.yaml:61-82: no LoRA, no MLM, 10 classes, frozen
+    merge weight): strong / weak / AT outputs, frame-label argmax, and the pad-mask + temperature path vs the unmodified reference."""
+    from transformer4sed_b200 import functional as F
+    from transformer4sed_b200.src_models.cnn_transformer.passt_cnn import PaSST_CNN
+    g = golden("pmam_finetune.npz")
+    seed, batch = 14, 2
+    F.set_precision(mode)
+    try:
+        sed_param = dict(passt_feature_layer=10, f_pool="attention", decode_ratio=10, at_adapter=True, decoder="transformerXL",
+                         decoder_layer_num=3, decoder_pos_emd_len=1000, decoder_dim=384, mlm=False, load_pretrained_model=False)
+        net = PaSST_CNN(sed_param, dict(CNN_PARAM, conv_dropout=0.5))
+        sd = synth.synth_state_dict_like(net, seed)
+        net.load_state_dict(sd, strict=True)
+        assert sorted(sd.keys()) == [str(k) for k in g["sd_keys"]]
+        np.testing.assert_allclose(checksum(torch.cat([v.flatten().float() for k, v in sorted(sd.items()) if torch.is_floating_point(v)])),
+                                   g["sd_ck"], rtol=1e-12)
+        assert not net.merge_weight.requires_grad
+        net = net.cuda().eval()
+        ext = net.get_feature_extractor().eval()
+        mel = ext.normalize(ext(synth.synth_wav(batch, 320000, seed=seed + 1).cuda()))
+        pad = torch.zeros(batch, 1000, dtype=torch.bool, device="cuda")
+        pad[-1, 850:] = True
+        with torch.no_grad():
+            s1, w1, o1 = net(mel, temp_w=1)
+            s2, w2, _ = net(mel, temp_w=0.5, pad_mask=pad)
+        assert tuple(s1.shape) == (batch, 10, 1000) and tuple(w1.shape) == (batch, 10)
+        r = dict(strong=relmax(s1, g["strong"]), weak=relmax(w1, g["weak"]), at=relmax(o1["at_out"], g["at_out"]),
+                 strong_pad=relmax(s2, g["strong_pad"]), weak_pad=relmax(w2, g["weak_pad"]))
+        print(mode, r)
+        assert max(r.values()) < tol, r
+        assert float(s2[-1, :, 850:].abs().max()) == 0.0
+        if mode == "tf32x3":      # smallest top-2 margin of the recorded output is 3.6 %: the frame decisions must be identical
+            assert (s1.argmax(dim=1).cpu().numpy() == g["argmax"]).all()
+    finally:
+        F.set_precision("bf16")
+
+
 def test_lora_merge_on_eval_roundtrip():
     from transformer4sed_b200 import functional as F
     from transformer4sed_b200.src_models import lora
