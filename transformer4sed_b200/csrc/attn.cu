@@ -20,214 +20,10 @@
 #include <cstdlib>
 
 #include "attn_common.cuh"
+#include "attn_fwd.cuh"
 
 namespace t4s {
 namespace attn {
-
-// ======================================================================================================
-// forward
-// ======================================================================================================
-namespace fwd {
-constexpr int kThreads = 192;
-constexpr int oQ = 0, oK = oQ + kTileBytes, oV = oK + 2 * kTileBytes, oP = oV + 2 * kTileBytes, oBar = oP + kPBytes;
-constexpr int kSmem = oBar + 128;
-constexpr int kTmemCols = 256;  // S: [0,128)  O: [128,192), [192,256)
-enum { bQFull = 0, bKvFull = 1, bKvEmpty = 3, bSFull = 5, bSFree = 6, bPFull = 7, bOFull = 8, bOFree = 10, bCount = 12 };
-}  // namespace fwd
-
-__global__ void __launch_bounds__(fwd::kThreads, 2)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const Args a) {
-  using namespace fwd;
-  extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = a.n_tiles;
-
-  if (threadIdx.x == 0) {
-    if (ptx::smem_u32(smem) & 1023u) {
-      printf("t4s attn_fwd: dynamic shared memory is not 1024-byte aligned\n");
-      __trap();
-    }
-    ptx::mbar_init(&bars[bQFull], 1);
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&bars[bKvFull + i], 1);
-      ptx::mbar_init(&bars[bKvEmpty + i], 1);
-      ptx::mbar_init(&bars[bOFull + i], 1);
-      ptx::mbar_init(&bars[bOFree + i], 4);
-    }
-    ptx::mbar_init(&bars[bSFull], 1);
-    ptx::mbar_init(&bars[bSFree], 4);
-    ptx::mbar_init(&bars[bPFull], 4);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 4 && lane == 0) {
-    ptx::prefetch_tmap(&tmQ);
-    ptx::prefetch_tmap(&tmK);
-    ptx::prefetch_tmap(&tmV);
-  }
-  if (warp == 5) {
-    ptx::tmem_alloc(tmem_slot, kTmemCols);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 4) {
-    // ---------------- TMA producer ----------------
-    if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(&bars[bQFull], kTileBytes);
-      ptx::tma_load_4d(smem + oQ, &tmQ, &bars[bQFull], 0, q0, h, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        ptx::mbar_wait(&bars[bKvEmpty + s], ((j >> 1) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&bars[bKvFull + s], 2 * kTileBytes);
-        ptx::tma_load_4d(smem + oK + s * kTileBytes, &tmK, &bars[bKvFull + s], 0, j * kTile, h, b);
-        ptx::tma_load_4d(smem + oV + s * kTileBytes, &tmV, &bars[bKvFull + s], 0, j * kTile, h, b);
-      }
-    }
-  } else if (warp == 5) {
-    // ---------------- MMA issuer ----------------
-    const uint32_t sQ = ptx::smem_u32(smem + oQ), sK = ptx::smem_u32(smem + oK), sV = ptx::smem_u32(smem + oV),
-                   sP = ptx::smem_u32(smem + oP);
-    ptx::mbar_wait(&bars[bQFull], 0);
-    ptx::mbar_wait(&bars[bKvFull + 0], 0);
-    ptx::tc_fence_after();
-    if (lane == 0) {
-      mma_k64(tmem, sQ, sK, kIdescS, false);
-      ptx::tc_commit(&bars[bSFull]);
-    }
-    __syncwarp();
-    for (int j = 0; j < n_tiles; ++j) {
-      const int s = j & 1;
-      if (j + 1 < n_tiles) {
-        ptx::mbar_wait(&bars[bKvFull + (s ^ 1)], ((j + 1) >> 1) & 1);
-        ptx::mbar_wait(&bars[bSFree], j & 1);  // softmax warps have read S_j out of TMEM
-        ptx::tc_fence_after();
-        if (lane == 0) {
-          mma_k64(tmem, sQ, sK + (s ^ 1) * kTileBytes, kIdescS, false);
-          ptx::tc_commit(&bars[bSFull]);
-        }
-        __syncwarp();
-      }
-      ptx::mbar_wait(&bars[bPFull], j & 1);                       // P_j is in shared memory
-      ptx::mbar_wait(&bars[bOFree + s], ((j >> 1) & 1) ^ 1);      // O buffer s was folded (tile j-2)
-      ptx::tc_fence_after();
-      if (lane == 0) {
-        mma_k128_mn(tmem + 128 + 64 * s, sP, sV + s * kTileBytes, kIdescPV, false);
-        ptx::tc_commit(&bars[bKvEmpty + s]);
-        ptx::tc_commit(&bars[bOFull + s]);
-      }
-      __syncwarp();
-    }
-  } else {
-    // ---------------- softmax / accumulate warps: thread = query row ----------------
-    const int r = warp * 32 + lane;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-    const float sl2 = a.sl2;
-
-    auto fold = [&](int jj) {  // acc = acc * alpha_prev + O_jj
-      const int s = jj & 1;
-      ptx::mbar_wait(&bars[bOFull + s], (jj >> 1) & 1);
-      ptx::tc_fence_after();
-      uint32_t v0[32], v1[32];
-      ptx::tmem_ld_32x32(t_lane + 128 + 64 * s, v0);
-      ptx::tmem_ld_32x32(t_lane + 128 + 64 * s + 32, v1);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars[bOFree + s]);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(v0[i]));
-        acc[32 + i] = fmaf(acc[32 + i], alpha_prev, __uint_as_float(v1[i]));
-      }
-    };
-
-    for (int j = 0; j < n_tiles; ++j) {
-      const int nvalid = a.N - j * kTile;  // key columns of this tile that exist (>= 1)
-      const bool full = nvalid >= kTile;
-      ptx::mbar_wait(&bars[bSFull], j & 1);
-      ptx::tc_fence_after();
-      // pass 1: running max
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
-        ptx::tmem_ld_wait();
-        if (nvalid >= 32 * c + 32) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (32 * c + i < nvalid) mx = fmaxf(mx, __uint_as_float(v[i]));
-        }
-      }
-      const float m_new = fmaxf(m, mx);
-      const float alpha = ex2((m - m_new) * sl2);  // 0 on the first tile (m = -inf)
-      const float mneg = -m_new * sl2;
-      // the previous tile's P V product must have retired before P is overwritten; fold it in while we are here
-      if (j > 0) fold(j - 1);
-      // pass 2: exponentials, row sum, P tile
-      float rs = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
-        ptx::tmem_ld_wait();
-        if (c == 3) {  // S_j fully read: the MMA warp may overwrite it with S_{j+1}
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bars[bSFree]);
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, mneg));
-          float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, mneg));
-          if (!full) {
-            if (32 * c + 2 * i >= nvalid) p0 = 0.f;
-            if (32 * c + 2 * i + 1 >= nvalid) p1 = 0.f;
-          }
-          rs += p0 + p1;
-          pk[i] = pack_bf16(p0, p1);
-        }
-        store_row_chunk(smem + oP, r, 32 * c, pk);
-      }
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars[bPFull]);
-      l = fmaf(l, alpha, rs);
-      m = m_new;
-      alpha_prev = alpha;
-    }
-    fold(n_tiles - 1);
-    const int row = q0 + r;
-    const float inv = 1.f / l;
-    a.lse[((long long)b * a.H + h) * a.Nl + row] = fmaf(m, sl2, log2f(l));
-    if (row < a.N) {
-      store_row64(a.o + (long long)b * a.o_bs + (long long)row * a.o_ld + h * kHd, acc, inv);
-      if (a.o32) store_row64_f32(a.o32 + ((long long)b * a.N + row) * ((long long)a.H * kHd) + h * kHd, acc, inv);
-    }
-  }
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 5) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, kTmemCols);
-  }
-}
 
 // ======================================================================================================
 // backward: delta = rowsum(dO * O)
@@ -352,7 +148,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::mbar_init(&bars[bDqFree], 8);
     ptx::fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) {
+  if (warp == 8 && ptx::elect_one()) {
     if (kFused) ptx::prefetch_tmap(&tmDQ);
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
@@ -376,7 +172,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 8) {
     // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_arrive_expect_tx(&bars[bResFull], 2 * kTileBytes);
       if (kDq) {
         ptx::tma_load_4d(sRes0, &tmQ, &bars[bResFull], 0, t0, h, b);
@@ -409,7 +205,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     ptx::mbar_wait(&bars[bResFull], 0);
     ptx::mbar_wait(&bars[bStrFull + 0], 0);
     ptx::tc_fence_after();
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       mma_k64(tmem, r0, str, kIdescS, false);                      // S / S^T
       mma_k64(tmem + 128, r1, str + kTileBytes, kIdescS, false);   // dP / dP^T
       ptx::tc_commit(&bars[bSFull]);
@@ -422,7 +218,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         ptx::mbar_wait(&bars[bStrFull + (s ^ 1)], ((i + 1) >> 1) & 1);
         ptx::mbar_wait(&bars[bSFree], i & 1);
         ptx::tc_fence_after();
-        if (lane == 0) {
+        if (ptx::elect_one()) {
           mma_k64(tmem, r0, nx, kIdescS, false);
           mma_k64(tmem + 128, r1, nx + kTileBytes, kIdescS, false);
           ptx::tc_commit(&bars[bSFull]);
@@ -431,7 +227,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
       ptx::mbar_wait(&bars[bPFull], i & 1);
       ptx::tc_fence_after();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         const uint32_t cur = str + s * 2 * kTileBytes;
         const uint32_t pb = sP + s * kPBuf, db = sDs + s * kPBuf;
         if (kDq) {
@@ -475,7 +271,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         ptx::mbar_arrive(&bars[bDqFree]);
         ptx::bulk_wait_read_all();           // the previous reduce has finished reading the box
       }
@@ -485,7 +281,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int q = 0; q < 8; ++q) dst[q ^ (lane & 7)] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         tma_reduce_add_4d(&tmDQ, dq_box, 32 * g, it * kTile + 32 * wq, h, b);
         ptx::bulk_commit();
       }
@@ -565,7 +361,313 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       ptx::tmem_ld_wait();
       if (row < a.N) store_row32(a.dk + (long long)b * a.dk_bs + (long long)row * a.dk_ld + h * kHd + 32 * g, v, a.scale);
     }
-    if (kFused && lane == 0) ptx::bulk_wait_all();   // the staging boxes must outlive the last reduce
+    if (kFused && ptx::elect_one()) ptx::bulk_wait_all();   // the staging boxes must outlive the last reduce
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem, kTmemCols);
+  }
+}
+
+// ======================================================================================================
+// backward, one kernel (the default): persistent CTAs walk (clip, head, key tile) work items
+// ======================================================================================================
+// Per work item the CTA keeps K_j / V_j resident and streams the query tiles: S^T = K Q_i^T and dP^T = V dO_i^T land in TMEM,
+// the 8 softmax warps (thread = key row, warp g = w >> 2 takes query columns 64 g ..) form P^T = exp2(S^T c - lse_i) and
+// dS^T = P^T (dP^T - delta_i) with packed f32x2 math and write them (bf16) into SWIZZLE_128B operand tiles, the tensor core
+// accumulates dV += P^T dO_i and dK += dS^T Q_i in TMEM and forms the dQ_i tile = dS K_j, which the softmax warps add into the
+// fp32 dQ buffer with TMA reduce-add.  Everything is software-pipelined around the softmax warps, which never wait for the
+// tensor core in steady state:
+//   * S / dP of tile T+1 are issued as soon as tile T's S / dP are in registers (they run under tile T's exponentials);
+//   * dS is double buffered and P is released by its own commit right after dV, so tile T+1's softmax overlaps tile T's MMAs;
+//   * the dQ tile of T-1 is drained AFTER tile T's P / dS have been handed over (its MMA finished long before);
+//   * the CTA is persistent: barriers, TMEM and tensor maps are set up once per SM and the accumulator write-back of one work
+//     item overlaps the operand loads and first MMAs of the next (r1: 24 % of the warp samples sat in per-CTA prologue /
+//     epilogue code with one CTA per SM).
+#ifdef T4S_TRACE
+#define T4S_TRACE_B(w, j, e)                                                                    \
+  do {                                                                                          \
+    if (blockIdx.x == 70 && (threadIdx.x & 31) == 0 && (j) >= 20 && (j) < 36)                   \
+      g_trace[((w) * 16 + ((j) - 20)) * 8 + (e)] = clock64();                                   \
+  } while (0)
+#else
+#define T4S_TRACE_B(w, j, e) do {} while (0)
+#endif
+namespace fbw {
+constexpr int kThreads = 320;  // warps 0-7 softmax, 8 TMA, 9 MMA
+constexpr int kDqBox = 32 * 128;
+constexpr int kStr = 3;        // stages of the streamed (Q_i, dO_i) ring
+constexpr int oRes = 0, oStr = oRes + 2 * kTileBytes, oP = oStr + kStr * 2 * kTileBytes, oDs = oP + kPBytes, oDq = oDs + kPBytes,
+              oStat = oDq + 8 * kDqBox, oBar = oStat + 2 * 2 * kTile * 4;
+constexpr int kSmem = oBar + 192;
+static_assert(kSmem <= 232448, "fused attention backward: shared memory");
+constexpr int kTmemCols = 512;  // S^T [0,128)  dP^T [128,256)  dV [256,320)  dK [320,384)  dQ tile [384,448)
+enum { bResFull = 0, bStrFull = 1, bStrEmpty = 4, bStatFull = 7, bStatEmpty = 9, bSFull = 11, bSFree = 12, bPFull = 13, bPvFree = 14, bDsFree = 15,
+       bDqFull = 16, bDqFree = 17, bAccFull = 18, bAccFree = 19, bCount = 20 };
+}  // namespace fbw
+
+__global__ void __launch_bounds__(fbw::kThreads, 1)
+attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                      const __grid_constant__ CUtensorMap tmDQ, const Args a, const int n_items) {
+  using namespace fbw;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = a.n_tiles;
+
+  if (threadIdx.x == 0) {
+    if (ptx::smem_u32(smem) & 1023u) {
+      printf("t4s attn_bwd: dynamic shared memory is not 1024-byte aligned\n");
+      __trap();
+    }
+    ptx::mbar_init(&bars[bResFull], 1);
+    for (int i = 0; i < kStr; ++i) {
+      ptx::mbar_init(&bars[bStrFull + i], 1);
+      ptx::mbar_init(&bars[bStrEmpty + i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&bars[bStatFull + i], 1);
+      ptx::mbar_init(&bars[bStatEmpty + i], 8);
+    }
+    ptx::mbar_init(&bars[bSFull], 1);
+    ptx::mbar_init(&bars[bSFree], 8);
+    ptx::mbar_init(&bars[bPFull], 8);
+    ptx::mbar_init(&bars[bPvFree], 1);
+    ptx::mbar_init(&bars[bDsFree], 1);
+    ptx::mbar_init(&bars[bDqFull], 1);
+    ptx::mbar_init(&bars[bDqFree], 8);
+    ptx::mbar_init(&bars[bAccFull], 1);
+    ptx::mbar_init(&bars[bAccFree], 8);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 8 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmDQ);
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmK);
+    ptx::prefetch_tmap(&tmV);
+    ptx::prefetch_tmap(&tmDO);
+  }
+  if (warp == 9) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  unsigned char* sRes0 = smem + oRes;               // K_j
+  unsigned char* sRes1 = smem + oRes + kTileBytes;  // V_j
+  float* sStat = reinterpret_cast<float*>(smem + oStat);  // [stage][lse(128) | delta(128)]
+
+  // work item -> (key tile, head, clip): key tiles of one (clip, head) run on neighbouring SMs and share Q / dO in L2
+  auto decode = [&](int item, int& t0, int& h, int& b) {
+    const int kt = item % n_tiles, bh = item / n_tiles;
+    t0 = kt * kTile;
+    h = bh % a.H;
+    b = bh / a.H;
+  };
+
+  if (warp == 8) {
+    // ---------------- TMA producer ----------------
+    if (ptx::elect_one()) {
+      int T = 0, W = 0, st = 0, sph = 0;   // st = T % kStr, sph = (T / kStr) & 1
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++W) {
+        int t0, h, b;
+        decode(item, t0, h, b);
+        if (W > 0) ptx::mbar_wait(&bars[bAccFull], (W - 1) & 1);   // every MMA of the previous item has read K / V
+        ptx::mbar_arrive_expect_tx(&bars[bResFull], 2 * kTileBytes);
+        ptx::tma_load_4d(sRes0, &tmK, &bars[bResFull], 0, t0, h, b);
+        ptx::tma_load_4d(sRes1, &tmV, &bars[bResFull], 0, t0, h, b);
+        const long long stat_base = ((long long)b * a.H + h) * a.Nl;
+        for (int i = 0; i < n_tiles; ++i, ++T) {
+          unsigned char* st0 = smem + oStr + st * 2 * kTileBytes;
+          ptx::mbar_wait(&bars[bStrEmpty + st], sph ^ 1);
+          ptx::mbar_arrive_expect_tx(&bars[bStrFull + st], 2 * kTileBytes);
+          ptx::tma_load_4d(st0, &tmQ, &bars[bStrFull + st], 0, i * kTile, h, b);
+          ptx::tma_load_4d(st0 + kTileBytes, &tmDO, &bars[bStrFull + st], 0, i * kTile, h, b);
+          const int s2 = T & 1;
+          ptx::mbar_wait(&bars[bStatEmpty + s2], ((T >> 1) & 1) ^ 1);
+          ptx::mbar_arrive_expect_tx(&bars[bStatFull + s2], 2 * kTile * 4);
+          bulk_load(sStat + s2 * 2 * kTile, a.lse + stat_base + i * kTile, kTile * 4, &bars[bStatFull + s2]);
+          bulk_load(sStat + s2 * 2 * kTile + kTile, a.delta + stat_base + i * kTile, kTile * 4, &bars[bStatFull + s2]);
+          if (++st == kStr) { st = 0; sph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t r0 = ptx::smem_u32(sRes0), r1 = ptx::smem_u32(sRes1), str = ptx::smem_u32(smem + oStr), sP = ptx::smem_u32(smem + oP),
+                   sDs = ptx::smem_u32(smem + oDs);
+    int T = 0, W = 0;
+    int st = 0, sph = 0;      // stage / phase of global tile T
+    int stn = 0, sphn = 0;    // stage / phase of the next tile whose S / dP have not been issued yet
+    int Tn = 0;               // that tile's global index
+    auto issue_s = [&]() {   // S^T / dP^T of global tile Tn
+      const uint32_t nx = str + stn * 2 * kTileBytes;
+      ptx::mbar_wait(&bars[bStrFull + stn], sphn);
+      if (Tn > 0) ptx::mbar_wait(&bars[bSFree], (Tn - 1) & 1);   // tile Tn-1's S / dP are in registers
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        mma_k64(tmem, r0, nx, kIdescS, false);
+        mma_k64(tmem + 128, r1, nx + kTileBytes, kIdescS, false);
+        ptx::tc_commit(&bars[bSFull]);
+      }
+      __syncwarp();
+      ++Tn;
+      if (++stn == kStr) { stn = 0; sphn ^= 1; }
+    };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++W) {
+      ptx::mbar_wait(&bars[bResFull], W & 1);
+      issue_s();
+      for (int i = 0; i < n_tiles; ++i, ++T) {
+        T4S_TRACE_B(9, T, 0);
+        if (i + 1 < n_tiles) issue_s();
+        T4S_TRACE_B(9, T, 1);
+        ptx::mbar_wait(&bars[bPFull], T & 1);
+        T4S_TRACE_B(9, T, 2);
+        if (i == 0 && W > 0) ptx::mbar_wait(&bars[bAccFree], (W - 1) & 1);   // the previous item's dV / dK have been read out
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t cur = str + st * 2 * kTileBytes;
+          mma_k128_mn(tmem + 320, sDs, cur, kIdescPV, i > 0);                            // dK += dS^T Q_i
+          ptx::mbar_wait(&bars[bDqFree], (T & 1) ^ 1);                                   // tile T-1's dQ product has been read out
+          ptx::tc_fence_after();
+          bwd::mma_k128_amn(tmem + 384, sDs, r0, false);                                 // dQ_i tile = dS K_j
+          ptx::tc_commit(&bars[bDsFree]);
+          ptx::tc_commit(&bars[bDqFull]);
+          mma_k128_mn(tmem + 256, sP, cur + kTileBytes, kIdescPV, i > 0);                // dV += P^T dO_i
+          ptx::tc_commit(&bars[bPvFree]);
+          ptx::tc_commit(&bars[bStrEmpty + st]);
+          if (i == n_tiles - 1) ptx::tc_commit(&bars[bAccFull]);
+        }
+        __syncwarp();
+        T4S_TRACE_B(9, T, 3);
+        if (++st == kStr) { st = 0; sph ^= 1; }
+      }
+    }
+    (void)sph;
+  } else {
+    // ---------------- softmax warps: thread = key row of the resident tile, query-column half g ----------------
+    const int wq = warp & 3, g = warp >> 2;
+    const int r = wq * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(wq * 32) << 16);
+    const uint64_t nsl2 = ptx::pack2(-a.sl2, -a.sl2);
+    unsigned char* dq_box = smem + oDq + warp * kDqBox;
+    int T = 0, W = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++W) {
+      int t0, h, b;
+      decode(item, t0, h, b);
+      for (int i = 0; i <= n_tiles; ++i) {
+        const bool tail = i == n_tiles;       // extra round at the end of the item: only the drain of the last tile
+        uint32_t pp[2][16];
+        if (!tail) {
+          const int s2 = T & 1;
+          const float* stt = sStat + s2 * 2 * kTile + 64 * g;
+          T4S_TRACE_B(warp, T, 0);
+          ptx::mbar_wait(&bars[bStatFull + s2], (T >> 1) & 1);   // lse / delta of this query tile have landed
+          ptx::mbar_wait(&bars[bSFull], T & 1);
+          ptx::tc_fence_after();
+          T4S_TRACE_B(warp, T, 1);
+          uint32_t vs0[32], vp0[32], vs1[32], vp1[32];
+          ptx::tmem_ld_32x32(t_lane + 64 * g, vs0);
+          ptx::tmem_ld_32x32(t_lane + 128 + 64 * g, vp0);
+          ptx::tmem_ld_32x32(t_lane + 64 * g + 32, vs1);
+          ptx::tmem_ld_32x32(t_lane + 128 + 64 * g + 32, vp1);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars[bSFree]);
+          T4S_TRACE_B(warp, T, 2);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const uint32_t (&vs)[32] = c ? vs1 : vs0;
+            const uint32_t (&vp)[32] = c ? vp1 : vp0;
+            uint32_t pd[16];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 Lq = *reinterpret_cast<const float4*>(stt + 32 * c + 4 * q);
+              const float4 Dq = *reinterpret_cast<const float4*>(stt + kTile + 32 * c + 4 * q);
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const uint64_t s2v = ptx::pack2(__uint_as_float(vs[4 * q + 2 * e]), __uint_as_float(vs[4 * q + 2 * e + 1]));
+                const uint64_t dp2 = ptx::pack2(__uint_as_float(vp[4 * q + 2 * e]), __uint_as_float(vp[4 * q + 2 * e + 1]));
+                const uint64_t l2 = e ? ptx::pack2(Lq.z, Lq.w) : ptx::pack2(Lq.x, Lq.y);
+                const uint64_t d2 = e ? ptx::pack2(Dq.z, Dq.w) : ptx::pack2(Dq.x, Dq.y);
+                float u0, u1;
+                ptx::unpack2(ptx::fma2(s2v, nsl2, l2), u0, u1);          // lse - s c
+                const float p0 = ex2(-u0), p1 = ex2(-u1);
+                float d0, d1;
+                ptx::unpack2(ptx::mul2(ptx::pack2(p0, p1), ptx::sub2(dp2, d2)), d0, d1);
+                pp[c][2 * q + e] = pack_bf16(p0, p1);
+                pd[2 * q + e] = pack_bf16(d0, d1);
+              }
+            }
+            if (c == 0) ptx::mbar_wait(&bars[bDsFree], (T & 1) ^ 1);   // tile T-1's dK / dQ MMAs have finished with the dS tile
+            store_row_chunk(smem + oDs, r, 64 * g + 32 * c, pd);
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bars[bStatEmpty + s2]);
+          T4S_TRACE_B(warp, T, 3);
+        }
+        // dQ product of the previous tile (this warp: query rows 32 wq .., columns 32 g ..) -> staging box
+        const bool drain = i > 0;   // tile i-1 of this item (the last one in the extra round)
+        if (drain) {
+          ptx::mbar_wait(&bars[bDqFull], (T - 1) & 1);
+          ptx::tc_fence_after();
+          uint32_t v[32];
+          ptx::tmem_ld_32x32(t_lane + 384 + 32 * g, v);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive(&bars[bDqFree]);
+            ptx::bulk_wait_read_all();           // the previous reduce has finished reading the box
+          }
+          __syncwarp();
+          uint4* dst = reinterpret_cast<uint4*>(dq_box + lane * 128);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) dst[q ^ (lane & 7)] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        if (!tail) T4S_TRACE_B(warp, T, 4);
+        if (!tail) {
+          ptx::mbar_wait(&bars[bPvFree], (T & 1) ^ 1);   // tile T-1's dV MMA has finished reading P
+          store_row_chunk(smem + oP, r, 64 * g, pp[0]);
+          store_row_chunk(smem + oP, r, 64 * g + 32, pp[1]);
+        }
+        ptx::fence_proxy_async();                        // one fence for P, dS and the dQ box
+        __syncwarp();
+        if (ptx::elect_one()) {
+          if (!tail) ptx::mbar_arrive(&bars[bPFull]);
+          if (drain) {
+            bwd::tma_reduce_add_4d(&tmDQ, dq_box, 32 * g, (i - 1) * kTile + 32 * wq, h, b);
+            ptx::bulk_commit();
+          }
+        }
+        if (!tail) T4S_TRACE_B(warp, T, 5);
+        if (!tail) ++T;
+      }
+      // ---- dV / dK of this work item: each column half writes 32 of the 64 head-dim columns ----
+      ptx::mbar_wait(&bars[bAccFull], W & 1);
+      ptx::tc_fence_after();
+      uint32_t v[32], w[32];
+      ptx::tmem_ld_32x32(t_lane + 256 + 32 * g, v);
+      ptx::tmem_ld_32x32(t_lane + 320 + 32 * g, w);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&bars[bAccFree]);
+      const int row = t0 + r;
+      if (row < a.N) {
+        store_row32(a.dv + (long long)b * a.dv_bs + (long long)row * a.dv_ld + h * kHd + 32 * g, v, 1.f);
+        store_row32(a.dk + (long long)b * a.dk_bs + (long long)row * a.dk_ld + h * kHd + 32 * g, w, a.scale);
+      }
+    }
+    if (ptx::elect_one()) ptx::bulk_wait_all();   // the staging boxes must outlive the last reduce
   }
 
   ptx::tc_fence_before();
@@ -673,6 +775,14 @@ static void fill_args(Args& a, const T4sAttn* p) {
 }  // namespace attn
 }  // namespace t4s
 
+#ifdef T4S_TRACE
+extern "C" int t4s_debug_trace(long long* out, int n) {
+  if (n > 4096) n = 4096;
+  T4S_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * n));
+  return T4S_OK;
+}
+#endif
+
 extern "C" int64_t t4s_attn_padded_len(int tokens) {
   return (int64_t)((tokens + t4s::attn::kTile - 1) / t4s::attn::kTile) * t4s::attn::kTile;
 }
@@ -681,15 +791,17 @@ extern "C" int t4s_attn_fwd(const T4sAttn* p, void* stream) {
   using namespace t4s::attn;
   int rc = check_common(p);
   if (rc) return rc;
-  CUtensorMap tq, tk, tv;
-  if ((rc = make_map(&tq, p->q, p->q_ld, p->q_bs, p->batch, p->heads, p->tokens, "q"))) return rc;
-  if ((rc = make_map(&tk, p->k, p->k_ld, p->k_bs, p->batch, p->heads, p->tokens, "k"))) return rc;
-  if ((rc = make_map(&tv, p->v, p->v_ld, p->v_bs, p->batch, p->heads, p->tokens, "v"))) return rc;
+  fwd2::Maps tm;
+  if ((rc = make_map(&tm.q, p->q, p->q_ld, p->q_bs, p->batch, p->heads, p->tokens, "q"))) return rc;
+  if ((rc = make_map(&tm.k, p->k, p->k_ld, p->k_bs, p->batch, p->heads, p->tokens, "k"))) return rc;
+  if ((rc = make_map(&tm.v, p->v, p->v_ld, p->v_bs, p->batch, p->heads, p->tokens, "v"))) return rc;
+  tm.qv = tm.q;
+  tm.pos = tm.q;
   Args a;
   fill_args(a, p);
-  T4S_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmem));
-  dim3 grid(a.n_tiles, p->heads, p->batch);
-  attn_fwd_kernel<<<grid, fwd::kThreads, fwd::kSmem, t4s::as_stream(stream)>>>(tq, tk, tv, a);
+  T4S_CUDA(cudaFuncSetAttribute(fwd2::attn_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2::Layout<false>::kSmem));
+  dim3 grid((a.n_tiles + 1) / 2, p->heads, p->batch);
+  fwd2::attn_fwd2_kernel<false><<<grid, fwd2::Layout<false>::kThreads, fwd2::Layout<false>::kSmem, t4s::as_stream(stream)>>>(tm, a);
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }
@@ -737,8 +849,10 @@ extern "C" int t4s_attn_bwd(const T4sAttnBwd* p, void* stream) {
       T4S_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled(dq32) failed with CUresult %d", (int)cr);
     }
     T4S_CUDA(cudaMemsetAsync(p->dq32, 0, (size_t)f->batch * f->tokens * D * sizeof(float), st));
-    T4S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
-    attn_bwd_kernel<2><<<grid, bwd::kThreads, bwd::kSmem, st>>>(tq, tk, tv, tdo, tdq, a);
+    T4S_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fbw::kSmem));
+    const int n_items = a.n_tiles * f->heads * f->batch;
+    const int pgrid = std::min(n_items, t4s::sm_count());
+    attn_bwd_fused_kernel<<<pgrid, fbw::kThreads, fbw::kSmem, st>>>(tq, tk, tv, tdo, tdq, a, n_items);
     T4S_LAUNCH_CHECK();
     const long long total8 = (long long)f->batch * f->tokens * D / 8;
     const int fgrid = (int)std::min<long long>((total8 + 255) / 256, (long long)t4s::sm_count() * 16);

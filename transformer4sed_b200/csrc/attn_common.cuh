@@ -3,6 +3,19 @@
 #include "common.cuh"
 #include "ptx.cuh"
 
+// Optional pipeline trace (build with -DT4S_TRACE: scripts/trace_attn.sh): one CTA records clock64() at the hand-over points of
+// its warps; read back with t4s_debug_trace().  Compiled out of the product library.
+#ifdef T4S_TRACE
+static __device__ long long g_trace[4096];
+#define T4S_TRACE_AT(w, j, e)                                                                                  \
+  do {                                                                                                         \
+    if (blockIdx.x == 2 && blockIdx.y == 0 && blockIdx.z == 5 && (threadIdx.x & 31) == 0 && (j) < 16)           \
+      g_trace[((w) * 16 + (j)) * 8 + (e)] = clock64();                                                         \
+  } while (0)
+#else
+#define T4S_TRACE_AT(w, j, e) do {} while (0)
+#endif
+
 namespace t4s {
 namespace attn {
 

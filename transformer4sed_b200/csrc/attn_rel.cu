@@ -18,6 +18,7 @@
 //              dK/dV (CTA = key tile, loops over query tiles) consumes the P / dS tiles transposed in place as MN-major A
 //              operands.  P is recomputed from lse (no max pass); dP reuses the S columns of TMEM once P is in registers.
 #include "attn_common.cuh"
+#include "attn_fwd.cuh"
 
 namespace t4s {
 namespace attn {
@@ -60,226 +61,6 @@ __device__ __forceinline__ void mma_k128_amn(uint32_t d_tmem, uint32_t a_addr, u
   const uint64_t adesc = ptx::umma_desc_sw128(a_addr, kTileBytes, 1024), bdesc = ptx::umma_desc_sw128(b_addr, 8192, 1024);
 #pragma unroll
   for (int k = 0; k < 8; ++k) ptx::mma_f16(d_tmem, adesc + 128 * k, bdesc + 128 * k, kIdescAmn, (accumulate || k > 0) ? 1u : 0u);
-}
-
-// ======================================================================================================
-// forward
-// ======================================================================================================
-namespace fwd {
-constexpr int oQU = 0, oQV = oQU + kTileBytes, oK = oQV + kTileBytes, oV = oK + 2 * kTileBytes, oPw = oV + 2 * kTileBytes,
-              oP = oPw + kPwBytes, oScr = oP + kPBytes, oBar = oScr + 4 * kWarpScratch;
-constexpr int kSmem = oBar + 128;
-constexpr int kTmemCols = 512;  // S: [0,128)  BD: [128,384)  O: [384,448), [448,512)
-enum { bQFull = 0, bKvFull = 1, bKvEmpty = 3, bPwFull = 5, bPwEmpty = 6, bSFull = 7, bSFree = 8, bPFull = 9, bOFull = 10, bOFree = 12,
-       bCount = 14 };
-}  // namespace fwd
-
-__global__ void __launch_bounds__(kThreads, 1)
-relattn_fwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_constant__ CUtensorMap tmQV,
-                   const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
-                   const __grid_constant__ CUtensorMap tmPos, const Args a) {
-  using namespace fwd;
-  extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
-  const int n_tiles = a.n_tiles;
-
-  if (threadIdx.x == 0) {
-    if (ptx::smem_u32(smem) & 1023u) {
-      printf("t4s relattn_fwd: dynamic shared memory is not 1024-byte aligned\n");
-      __trap();
-    }
-    ptx::mbar_init(&bars[bQFull], 1);
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&bars[bKvFull + i], 1);
-      ptx::mbar_init(&bars[bKvEmpty + i], 1);
-      ptx::mbar_init(&bars[bOFull + i], 1);
-      ptx::mbar_init(&bars[bOFree + i], 4);
-    }
-    ptx::mbar_init(&bars[bPwFull], 1);
-    ptx::mbar_init(&bars[bPwEmpty], 1);
-    ptx::mbar_init(&bars[bSFull], 1);
-    ptx::mbar_init(&bars[bSFree], 4);
-    ptx::mbar_init(&bars[bPFull], 4);
-    ptx::fence_barrier_init();
-  }
-  if (warp == 4 && lane == 0) {
-    ptx::prefetch_tmap(&tmQU);
-    ptx::prefetch_tmap(&tmQV);
-    ptx::prefetch_tmap(&tmK);
-    ptx::prefetch_tmap(&tmV);
-    ptx::prefetch_tmap(&tmPos);
-  }
-  if (warp == 5) {
-    ptx::tmem_alloc(tmem_slot, kTmemCols);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  if (warp == 4) {
-    if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(&bars[bQFull], 2 * kTileBytes);
-      ptx::tma_load_4d(smem + oQU, &tmQU, &bars[bQFull], 0, q0, h, b);
-      ptx::tma_load_4d(smem + oQV, &tmQV, &bars[bQFull], 0, q0, h, b);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j & 1;
-        ptx::mbar_wait(&bars[bKvEmpty + s], ((j >> 1) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&bars[bKvFull + s], 2 * kTileBytes);
-        ptx::tma_load_4d(smem + oK + s * kTileBytes, &tmK, &bars[bKvFull + s], 0, j * kTile, h, b);
-        ptx::tma_load_4d(smem + oV + s * kTileBytes, &tmV, &bars[bKvFull + s], 0, j * kTile, h, b);
-        ptx::mbar_wait(&bars[bPwEmpty], (j & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&bars[bPwFull], kPwBytes);
-        ptx::tma_load_4d(smem + oPw, &tmPos, &bars[bPwFull], 0, a.N - kTile - q0 + j * kTile, h, 0);
-      }
-    }
-  } else if (warp == 5) {
-    const uint32_t sQU = ptx::smem_u32(smem + oQU), sQV = ptx::smem_u32(smem + oQV), sK = ptx::smem_u32(smem + oK),
-                   sV = ptx::smem_u32(smem + oV), sPw = ptx::smem_u32(smem + oPw), sP = ptx::smem_u32(smem + oP);
-    ptx::mbar_wait(&bars[bQFull], 0);
-    ptx::mbar_wait(&bars[bKvFull + 0], 0);
-    ptx::mbar_wait(&bars[bPwFull], 0);
-    ptx::tc_fence_after();
-    if (lane == 0) {
-      mma_k64(tmem, sQU, sK, kIdescS, false);
-      mma_k64(tmem + 128, sQV, sPw, kIdescBD, false);
-      ptx::tc_commit(&bars[bPwEmpty]);
-      ptx::tc_commit(&bars[bSFull]);
-    }
-    __syncwarp();
-    for (int j = 0; j < n_tiles; ++j) {
-      const int s = j & 1;
-      if (j + 1 < n_tiles) {
-        ptx::mbar_wait(&bars[bKvFull + (s ^ 1)], ((j + 1) >> 1) & 1);
-        ptx::mbar_wait(&bars[bPwFull], (j + 1) & 1);
-        ptx::mbar_wait(&bars[bSFree], j & 1);
-        ptx::tc_fence_after();
-        if (lane == 0) {
-          mma_k64(tmem, sQU, sK + (s ^ 1) * kTileBytes, kIdescS, false);
-          mma_k64(tmem + 128, sQV, sPw, kIdescBD, false);
-          ptx::tc_commit(&bars[bPwEmpty]);
-          ptx::tc_commit(&bars[bSFull]);
-        }
-        __syncwarp();
-      }
-      ptx::mbar_wait(&bars[bPFull], j & 1);
-      ptx::mbar_wait(&bars[bOFree + s], ((j >> 1) & 1) ^ 1);
-      ptx::tc_fence_after();
-      if (lane == 0) {
-        mma_k128_mn(tmem + 384 + 64 * s, sP, sV + s * kTileBytes, kIdescPV, false);
-        ptx::tc_commit(&bars[bKvEmpty + s]);
-        ptx::tc_commit(&bars[bOFull + s]);
-      }
-      __syncwarp();
-    }
-  } else {
-    const int r = warp * 32 + lane;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    float* scr = reinterpret_cast<float*>(smem + oScr + warp * kWarpScratch) + lane * kScrRow;
-    float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
-    float acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-    const float sl2 = a.sl2;
-
-    auto fold = [&](int jj) {
-      const int s = jj & 1;
-      ptx::mbar_wait(&bars[bOFull + s], (jj >> 1) & 1);
-      ptx::tc_fence_after();
-      uint32_t v0[32], v1[32];
-      ptx::tmem_ld_32x32(t_lane + 384 + 64 * s, v0);
-      ptx::tmem_ld_32x32(t_lane + 384 + 64 * s + 32, v1);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars[bOFree + s]);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        acc[i] = fmaf(acc[i], alpha_prev, __uint_as_float(v0[i]));
-        acc[32 + i] = fmaf(acc[32 + i], alpha_prev, __uint_as_float(v1[i]));
-      }
-    };
-
-    for (int j = 0; j < n_tiles; ++j) {
-      const int nvalid = a.N - j * kTile;
-      const bool full = nvalid >= kTile;
-      ptx::mbar_wait(&bars[bSFull], j & 1);
-      ptx::tc_fence_after();
-      // pass 1: shifted scores = AC + skew(BD), written back over AC; running max
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        float bd[32];
-        skew_chunk(t_lane + 128, scr, warp, lane, 32 * c, bd);
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float sc = __uint_as_float(v[i]) + bd[i];
-          v[i] = __float_as_uint(sc);
-          if (full || 32 * c + i < nvalid) mx = fmaxf(mx, sc);
-        }
-        ptx::tmem_st_32x32(t_lane + 32 * c, v);
-      }
-      ptx::tmem_st_wait();
-      const float m_new = fmaxf(m, mx);
-      const float alpha = ex2((m - m_new) * sl2);
-      const float mneg = -m_new * sl2;
-      if (j > 0) fold(j - 1);
-      // pass 2: exponentials, row sum, P tile
-      float rs = 0.f;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
-        ptx::tmem_ld_wait();
-        if (c == 3) {
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bars[bSFree]);
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2(fmaf(__uint_as_float(v[2 * i]), sl2, mneg));
-          float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]), sl2, mneg));
-          if (!full) {
-            if (32 * c + 2 * i >= nvalid) p0 = 0.f;
-            if (32 * c + 2 * i + 1 >= nvalid) p1 = 0.f;
-          }
-          rs += p0 + p1;
-          pk[i] = pack_bf16(p0, p1);
-        }
-        store_row_chunk(smem + oP, r, 32 * c, pk);
-      }
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars[bPFull]);
-      l = fmaf(l, alpha, rs);
-      m = m_new;
-      alpha_prev = alpha;
-    }
-    fold(n_tiles - 1);
-    const int row = q0 + r;
-    const float inv = 1.f / l;
-    a.lse[((long long)b * a.H + h) * a.Nl + row] = fmaf(m, sl2, log2f(l));
-    if (row < a.N) {
-      store_row64(a.o + (long long)b * a.o_bs + (long long)row * a.o_ld + h * kHd, acc, inv);
-      if (a.o32) store_row64_f32(a.o32 + ((long long)b * a.N + row) * ((long long)a.H * kHd) + h * kHd, acc, inv);
-    }
-  }
-
-  ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 5) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem, kTmemCols);
-  }
 }
 
 // ======================================================================================================
@@ -332,7 +113,7 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
     ptx::mbar_init(&bars[bAccFull], 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 4 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmQU);
     ptx::prefetch_tmap(&tmQV);
     ptx::prefetch_tmap(&tmK);
@@ -351,7 +132,7 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
 
   if (warp == 4) {
     // ---------------- TMA producer ----------------
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       if (kDq) {
         ptx::mbar_arrive_expect_tx(&bars[bResFull], 3 * kTileBytes);
         ptx::tma_load_4d(sQU, &tmQU, &bars[bResFull], 0, t0, h, b);
@@ -386,7 +167,7 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
     for (int t = 0; t < n_tiles; ++t) {
       ptx::mbar_wait(&bars[bStrFull], t & 1);
       ptx::tc_fence_after();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         mma_k64(tmem, uQU, uK, kIdescS, false);          // AC = (q+u) k^T
         mma_k64(tmem + 128, uQV, uPw, kIdescBD, false);  // BD = (q+v) Pw^T
         ptx::tc_commit(&bars[bSFull]);
@@ -394,14 +175,14 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
       __syncwarp();
       ptx::mbar_wait(&bars[bPReady], t & 1);             // P is in registers: the S columns are free
       ptx::tc_fence_after();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         mma_k64(tmem, uDO, uV, kIdescS, false);          // dP = dO v^T
         ptx::tc_commit(&bars[bDpFull]);
       }
       __syncwarp();
       ptx::mbar_wait(&bars[bDsFull], t & 1);             // P / dS tiles are in shared memory
       ptx::tc_fence_after();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
         if (kDq) {
           mma_k128_mn(tmem + 384, uDs, uK, kIdescPV, t > 0);   // d(q+u) += dS K
         } else {
@@ -587,17 +368,17 @@ extern "C" int t4s_relattn_fwd(const T4sRelAttn* p, void* stream) {
   int rc = check_rel(p);
   if (rc) return rc;
   const int B = p->batch, H = p->heads, T = p->tokens;
-  CUtensorMap tqu, tqv, tk, tv, tpos;
-  if ((rc = make_map(&tqu, p->qu, p->qu_ld, p->qu_bs, B, H, T, "qu"))) return rc;
-  if ((rc = make_map(&tqv, p->qv, p->qv_ld, p->qv_bs, B, H, T, "qv"))) return rc;
-  if ((rc = make_map(&tk, p->k, p->k_ld, p->k_bs, B, H, T, "k"))) return rc;
-  if ((rc = make_map(&tv, p->v, p->v_ld, p->v_bs, B, H, T, "v"))) return rc;
-  if ((rc = make_map(&tpos, p->pos, p->pos_ld, p->pos_ld * (2LL * T - 1), 1, H, 2 * T - 1, "pos", 256))) return rc;
+  fwd2::Maps tm;
+  if ((rc = make_map(&tm.q, p->qu, p->qu_ld, p->qu_bs, B, H, T, "qu"))) return rc;
+  if ((rc = make_map(&tm.qv, p->qv, p->qv_ld, p->qv_bs, B, H, T, "qv"))) return rc;
+  if ((rc = make_map(&tm.k, p->k, p->k_ld, p->k_bs, B, H, T, "k"))) return rc;
+  if ((rc = make_map(&tm.v, p->v, p->v_ld, p->v_bs, B, H, T, "v"))) return rc;
+  if ((rc = make_map(&tm.pos, p->pos, p->pos_ld, p->pos_ld * (2LL * T - 1), 1, H, 2 * T - 1, "pos", 256))) return rc;
   Args a;
   fill_rel_args(a, p);
-  T4S_CUDA(cudaFuncSetAttribute(relattn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd::kSmem));
+  T4S_CUDA(cudaFuncSetAttribute(fwd2::attn_fwd2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2::Layout<true>::kSmem));
   dim3 grid(a.n_tiles, H, B);
-  relattn_fwd_kernel<<<grid, kThreads, fwd::kSmem, t4s::as_stream(stream)>>>(tqu, tqv, tk, tv, tpos, a);
+  fwd2::attn_fwd2_kernel<true><<<grid, fwd2::Layout<true>::kThreads, fwd2::Layout<true>::kSmem, t4s::as_stream(stream)>>>(tm, a);
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }

@@ -283,7 +283,7 @@ __device__ __forceinline__ void stage_store(const CUtensorMap* map, unsigned cha
                                             int gcol, int row0, int z1, int z2, bool single_box) {
   unsigned char* box = boxes + (seq & 1) * 2048;
   ++seq;
-  if (lane == 0) {   // the store that last used this box has drained it
+  if (ptx::elect_one()) {   // the store that last used this box has drained it (same elected lane commits and waits)
     if (single_box) ptx::bulk_wait_read_all();
     else ptx::bulk_wait_read_1();
   }
@@ -302,7 +302,7 @@ __device__ __forceinline__ void stage_store(const CUtensorMap* map, unsigned cha
   }
   ptx::fence_proxy_async();
   __syncwarp();
-  if (lane == 0) {
+  if (ptx::elect_one()) {
     ptx::tma_store_4d(map, box, gcol, row0, z1, z2);
     ptx::bulk_commit();
   }
@@ -475,7 +475,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       uint32_t it = 0;
       for (long long tile = tile_first; tile < a.total_tiles; tile += tile_step) {
         const int zs = (int)(tile / tiles_per_batch);
@@ -551,7 +551,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t ph = (it / kNStages) & 1;
         ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
-        if (lane == 0) {
+        if (ptx::elect_one()) {
           // tf32 MN-major: 32-byte-atom swizzle, 4-row K groups (512 B); everything else: SWIZZLE_128B, 8-row groups
           const uint64_t adesc = ptx::umma_desc_sw128(ptx::smem_u32(sA + s * C::kStageA), kAMn ? kBoxBytes : 16,
                                                       (kAMn && kTf32) ? 512 : 1024, (kAMn && kTf32) ? 1 : 2);
@@ -609,7 +609,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int col_base = n0 + half * kHalfCols;
       const bool tile_live = m0 + q * 32 < a.M;      // warp-uniform: this warp's 32 rows exist
       if (rtma) {
-        if (tile_live && col_base < a.N && lane == 0) {
+        if (tile_live && col_base < a.N && ptx::elect_one()) {
           ptx::fence_proxy_async();
           ptx::mbar_arrive_expect_tx(rbar, 2048);
           ptx::tma_load_4d(boxes, &tmR, rbar, col_base, m0 + q * 32, z1, z2);
@@ -648,7 +648,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             rph ^= 1;
             read_box_row(boxes, lane, rt);
             __syncwarp();
-            if (c + 1 < kChunks && col_base + 32 * (c + 1) < a.N && lane == 0) {   // next chunk's residual lands while this one is processed
+            if (c + 1 < kChunks && col_base + 32 * (c + 1) < a.N && ptx::elect_one()) {   // next chunk's residual lands while this one is processed
               ptx::fence_proxy_async();
               ptx::mbar_arrive_expect_tx(rbar, 2048);
               ptx::tma_load_4d(boxes, &tmR, rbar, col_base + 32 * (c + 1), m0 + q * 32, z1, z2);
@@ -664,7 +664,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
     }
-    if (kStaged && lane == 0) ptx::bulk_wait_all();   // the staging boxes must outlive the last stores
+    if (kStaged && ptx::elect_one()) ptx::bulk_wait_all();   // the staging boxes must outlive the last stores
   }
 
   ptx::tc_fence_before();
