@@ -5,6 +5,13 @@ Metric (BASELINE.json): 10 s-clips/s of a MAT-SED base training step (fused STFT
 TransformerXL context net + frame classifier, forward + losses + backward + gradient all-reduce + AdamW) on N B200s.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B] [--precision bf16|tf32|tf32x3]
+                    [--workload matsed|matsed_finetune2|pmam|dasm]
+
+`--workload` selects the other BASELINE.json configurations (default: the headline MAT-SED base step):
+  matsed_finetune2  the real mean-teacher step of config/mat-sed/base/finetune2.yaml: student fwd+bwd, EMA teacher forward without
+                    gradient through the sliding-window fusion (encoder_win=True, win_param=[512, 49]), fused six-loss kernel, AdamW, EMA
+  pmam              PMAM post-pre-training (config/pmam/post_pretrain.yaml: PaSST_CNN, LoRA, CNN branch, d=384 decoder), 32 clips/GPU
+  dasm              DASM open-vocabulary path (K = 407 queries), 8 clips/GPU
 
 N > 1 is launched by torchrun (one rank per GPU, NCCL).  Rank 0 prints ONE JSON line.
 `--impl reference` times the reference's own CPU path (the oracle port of it: the reference is Python and does not travel to
@@ -31,6 +38,12 @@ FWD_GFLOP_PER_CLIP = 297.3
 # config/mat-sed/base/finetune2.yaml:86-101 (opt.param_groups): stepped encoder LR (last 4 blocks and the norms at 2x), decoder, head
 FINETUNE2_OPT = dict(encoder=dict(lr=5.0e-6, weight_decay=1.0e-4, freeze_layer=0, step_lr=4), decoder=dict(lr=1.0e-4, weight_decay=1.0e-4),
                      head=dict(lr=1.0e-4, weight_decay=1.0e-4))
+# config/pmam/post_pretrain.yaml:48-79 and config/detect_any_sound (init kwargs as the golden generator uses them)
+PMAM_PASST = dict(passt_feature_layer=10, class_num=30, f_pool="attention", decode_ratio=10, at_adapter=True, decoder="transformerXL",
+                  decoder_layer_num=3, decoder_pos_emd_len=1000, decoder_dim=384, mlm=True,
+                  lora_config=dict(r=8, lora_alpha=1, requires_grad_pretrain=False),
+                  mlm_dict=dict(strategy="block", block_width=10, mask_rate=0.8, out_dim=768, mask_style=[0.9, 0.05, 0.05]))
+WORKLOAD_BATCH = dict(matsed=64, matsed_finetune2=64, pmam=32, dasm=8)
 MIX = (16, 6, 21, 21)    # strong, synthetic, weak, unlabeled of a 64-clip DESED batch (finetune1.yaml:12 ratio 3:1:4:4)
 
 
@@ -95,12 +108,126 @@ def sub_batches(batch):
 # ------------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------------
+# ------------------------------------------------------------------------------------------------------------------
+# workloads: (model, front end, parameter arena, train_step(wav) -> loss, description, host clips)
+# ------------------------------------------------------------------------------------------------------------------
+def build_workload(name, precision, B, dev, rank):
+    import copy
+    from transformer4sed_b200 import functional as F, schema
+    from transformer4sed_b200.training import MeanTeacher, ParamArena, mean_teacher_step, passt_param_groups
+    from transformer4sed_b200.utils import synth
+    n_distinct = min(B, 8)
+    wav_host = synth.synth_wav(n_distinct, N_SAMPLES, seed=1234 + rank).repeat((B + n_distinct - 1) // n_distinct, 1)[:B].contiguous()
+    shadow = precision == "bf16"
+    if name in ("matsed", "matsed_finetune2"):
+        from transformer4sed_b200.src_models.passt.passt_sed import PaSST_SED
+        net = PaSST_SED(load_pretrained_model=False, **BASE_KW)
+        net.load_state_dict(synth.synth_state_dict_like(net, 4), strict=True)   # identical on every rank
+        net = net.to(dev).train()
+        ext = net.get_feature_extractor().eval()
+        arena = ParamArena(net, passt_param_groups(net, FINETUNE2_OPT), shadow_bf16=shadow)
+        y, yw = make_labels(B, 99 + rank)
+        y, yw = y.to(dev), yw.to(dev)
+        n_s, n_w = sub_batches(B)
+        if name == "matsed":
+            def train_step(wav):
+                mel = ext.logmel(wav)
+                strong, weak, other = net(mel)
+                loss = F.bce_loss(strong[:n_s], y[:n_s])
+                if n_w:
+                    loss = loss + 0.5 * F.bce_loss(weak[n_s:n_s + n_w], yw[n_s:n_s + n_w])
+                loss = loss + 2.0 * F.bce_loss(other["at_out"][:n_s + n_w], yw[:n_s + n_w])
+                loss.backward()
+                arena.step()
+                return loss
+            desc = ("MAT-SED base (config/mat-sed/base/finetune2.yaml init_kwargs, all 100.95 M params trainable), "
+                    f"DESED-shape synthetic batch={B}/GPU of 10 s @ 32 kHz clips (320000 samples -> 1000 frames), step = fused "
+                    "STFT+mel front end + student fwd + BCE strong/weak/AT losses + bwd + grad all-reduce + fused AdamW")
+            return net, ext, arena, train_step, desc, wav_host
+        teacher = MeanTeacher(net, arena)
+        teacher.teacher.train()
+        stu_kw = dict(encoder_win=False, win_param=[512, 49], mix_rate=0.5, temp_w=1)     # finetune2.yaml:64-78
+        tch_kw = dict(encoder_win=True, win_param=[512, 49], mix_rate=0.5, temp_w=1)
+        weights = dict(w_weak=0.5, w_at=1.0, w_cons=40.0, w_weak_cons=1.0)
+        state = {"step": 1}
+        if B < 3:
+            raise SystemExit("matsed_finetune2 needs at least 3 clips per GPU (strong / weak / unlabelled rows)")
+        n_w = max(1, min(n_w, B - n_s - 1))
+
+        def train_step(wav):
+            mel = ext.logmel(wav)
+            state["step"] += 1
+            total, _ = mean_teacher_step(net, teacher, arena, mel, mel, y, yw, (0, n_s), (n_s, n_s + n_w), stu_kwargs=stu_kw, tch_kwargs=tch_kw,
+                                         loss_weights=weights, step_num=state["step"], ema_factor=0.999)
+            return total
+        desc = ("MAT-SED base mean-teacher step (config/mat-sed/base/finetune2.yaml; recipes/desed/finetune/train.py:129-199): front end, student "
+                f"fwd+bwd, EMA teacher forward without gradient with encoder_win=True win_param=[512, 49] (1 global + 11 window passes folded into one "
+                f"batched pass), fused six-loss kernel, grad all-reduce + fused AdamW, one-kernel EMA; batch={B}/GPU of 10 s @ 32 kHz clips")
+        return net, ext, arena, train_step, desc, wav_host
+    generic = lambda net: [dict(name="all", params=[p for p in net.parameters() if p.requires_grad], lr=1e-4, weight_decay=1e-4)]  # noqa: E731
+    if name == "pmam":
+        from transformer4sed_b200.src_models.cnn_transformer.passt_cnn import PaSST_CNN
+        cnn = dict(n_in_channel=1, activation="cg", conv_dropout=0.5, kernel_size=[3] * 10, padding=[1] * 10, stride=[1] * 10,
+                   nb_filters=list(schema.PMAM_FILTERS), pooling=[list(p) for p in schema.PMAM_POOLING])
+        net = PaSST_CNN(dict(PMAM_PASST, load_pretrained_model=False), cnn)
+        net.load_state_dict(synth.synth_state_dict_like(net, 1))
+        net = net.to(dev).train()
+        ext = net.get_feature_extractor().eval()
+        arena = ParamArena(net, generic(net), shadow_bf16=shadow)
+        g = torch.Generator().manual_seed(7 + rank)
+        protos = torch.nn.functional.normalize(torch.randn(30, 768, generator=g), dim=-1).to(dev)
+        labels = (torch.rand(B, 1000, 30, generator=g) < 0.1).float().to(dev)
+        lw = labels.amax(1)
+
+        def train_step(wav):
+            mel = ext.logmel(wav)
+            pred, other = net(mel)
+            strong = F.prototype_predict(pred, protos)
+            rows = other["mask_id_seq"].reshape(-1)
+            loss = F.bce_loss(strong.reshape(-1, 30)[rows], labels.reshape(-1, 30)[rows]) + 0.5 * F.bce_loss(other["at_out"], lw)
+            loss.backward()
+            arena.step()
+            return loss
+        desc = (f"PMAM post-pre-training (config/pmam/post_pretrain.yaml: PaSST_CNN, LoRA r=8 backbone, CNN branch, TransformerXL d=384, block "
+                f"masking + prototype BCE on the masked frames + AT loss), batch={B}/GPU of 10 s @ 32 kHz clips, fwd + bwd + all-reduce + fused AdamW "
+                "on the trainable (LoRA / CNN / decoder / head) parameters")
+        return net, ext, arena, train_step, desc, wav_host
+    if name == "dasm":
+        from transformer4sed_b200.src_models.detect_any_sound.detect_any_sound import DASM
+        K = 407
+        kw = dict(cnn_param=dict(n_in_channel=1, activation="cg", conv_dropout=0.0, kernel_size=[3] * 10, padding=[1] * 10, stride=[1] * 10,
+                                 nb_filters=list(schema.PMAM_FILTERS), pooling=[list(p) for p in schema.PMAM_POOLING]),
+                  backbone_param=dict(embed_dim=768, passt_feature_layer=10, pretrain_model_path=None,
+                                      lora_config=dict(r=8, lora_alpha=1, requires_grad_pretrain=False)),
+                  at_param=dict(at_decoder_layer=2, query_projector=True, query_dim=768, out_type="sigmoid", query=None), mlm_dict=None,
+                  backbone_upsample_ratio=10, decoder_dim=384, num_heads=12, decoder="transformerXL", decoder_layer_num=3, decoder_pos_emd_len=1000,
+                  decoder_expand_rate=1, class_num=K)
+        net = DASM(**copy.deepcopy(kw))
+        net.load_state_dict(synth.synth_state_dict_like(net, 1))
+        net = net.to(dev).train()
+        ext = net.get_feature_extractor().eval()
+        arena = ParamArena(net, generic(net), shadow_bf16=shadow)
+        g = torch.Generator().manual_seed(7 + rank)
+        query = (torch.nn.functional.normalize(torch.randn(K, 768, generator=g), dim=-1) * 3).to(dev)
+        labels = (torch.rand(B, K, 1000, generator=g) < 0.05).float().to(dev)
+        lw = labels.amax(-1)
+
+        def train_step(wav):
+            mel = ext.logmel(wav)
+            s_, w_, o_ = net(mel, temp_w=4.0, query=query)
+            loss = F.bce_loss(s_, labels) + 0.5 * F.bce_loss(w_, lw) + 0.5 * F.bce_loss(o_["at_out"], lw)
+            loss.backward()
+            arena.step()
+            return loss
+        desc = (f"DASM open-vocabulary path (K={K} text/audio queries, LoRA backbone, CNN branch, 2-layer tagging decoder, TransformerXL d=384, "
+                f"query x frame scores), batch={B}/GPU of 10 s @ 32 kHz clips, fwd + BCE strong/weak/AT + bwd + all-reduce + fused AdamW")
+        return net, ext, arena, train_step, desc, wav_host
+    raise SystemExit(f"unknown workload {name}")
+
+
 def run_ours(args):
     import torch.distributed as dist
     from transformer4sed_b200 import _lib, functional as F, ops
-    from transformer4sed_b200.src_models.passt.passt_sed import PaSST_SED
-    from transformer4sed_b200.training import ParamArena, passt_param_groups
-    from transformer4sed_b200.utils import synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -125,33 +252,12 @@ def run_ours(args):
             os.dup2(saved, 1)
             os.close(saved)
     F.set_precision(args.precision)
-    B = args.batch
+    B = args.batch if args.batch else WORKLOAD_BATCH[args.workload]
 
     torch.manual_seed(1234)
-    net = PaSST_SED(load_pretrained_model=False, **BASE_KW)
-    net.load_state_dict(synth.synth_state_dict_like(net, 4), strict=True)   # identical on every rank
-    net = net.to(dev).train()
-    ext = net.get_feature_extractor().eval()
-    arena = ParamArena(net, passt_param_groups(net, FINETUNE2_OPT), shadow_bf16=(args.precision == "bf16"))
-
-    n_distinct = min(B, 8)
-    wav_host = synth.synth_wav(n_distinct, N_SAMPLES, seed=1234 + rank).repeat((B + n_distinct - 1) // n_distinct, 1)[:B].contiguous()
+    net, ext, arena, train_step, wl_desc, wav_host = build_workload(args.workload, args.precision, B, dev, rank)
     wav_pinned = [wav_host.clone().pin_memory() for _ in range(2)]
     wav_dev = wav_host.to(dev)
-    y, yw = make_labels(B, 99 + rank)
-    y, yw = y.to(dev), yw.to(dev)
-    n_s, n_w = sub_batches(B)
-
-    def train_step(wav):
-        mel = ext.logmel(wav)
-        strong, weak, other = net(mel)
-        loss = F.bce_loss(strong[:n_s], y[:n_s])
-        if n_w:
-            loss = loss + 0.5 * F.bce_loss(weak[n_s:n_s + n_w], yw[n_s:n_s + n_w])
-        loss = loss + 2.0 * F.bce_loss(other["at_out"][:n_s + n_w], yw[:n_s + n_w])
-        loss.backward()
-        arena.step()
-        return loss
 
     def barrier():
         if world > 1:
@@ -213,35 +319,136 @@ def run_ours(args):
     elif world > 1:
         train_step(wav_dev)   # the instrumented step contains the gradient all-reduce: every rank has to take part in it
         torch.cuda.synchronize()
-    cpu_base = None
+    # ---- replicas in sync? every rank started from the same weights and applied the same all-reduced gradients -------------------
+    in_sync = None
+    if world > 1:
+        cs = arena.flat.double().abs().sum().reshape(1)
+        ref = cs.clone()
+        dist.broadcast(ref, 0)
+        diff = (cs - ref).abs() / ref.abs().clamp_min(1e-30)
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        in_sync = {"max_rel_checksum_diff_vs_rank0": float(diff.item()), "ok": bool(diff.item() == 0.0)}
+    cpu_base = strict = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference_sample(target_seconds=15.0)
+    if rank == 0 and world == 1 and args.workload == "matsed" and not args.no_extra_legs:
+        del train_step, net, arena
+        torch.cuda.empty_cache()
+        strict = strict_mode_throughput(B, dev, rank)
+        eager = gpu_eager_baseline(dev)
     if rank == 0:
         clips = B * world * args.steps
         pk, pk_src = peaks()
         value = clips / (ms / 1e3)
+        names = dict(matsed="10s-clips/sec fwd+bwd MAT-SED", matsed_finetune2="10s-clips/sec MAT-SED mean-teacher step (finetune2)",
+                     pmam="10s-clips/sec fwd+bwd PMAM post-pre-training", dasm="10s-clips/sec fwd+bwd DASM (K=407)")
+        cfg = {"workload": wl_desc, "workload_name": args.workload, "global_batch": B * world, "per_gpu_batch": B,
+               "sample_rate_note": "BASELINE.json says 16 kHz; every reference recipe is 32 kHz and the model asserts 1000 frames (SURVEY §0.1, §8d)",
+               "parallelism": f"dp{world}", "l2_policy": "inputs larger than L2 (82 MB of clips + GBs of activations per step)",
+               "loss": float(loss_val), "peaks": pk_src}
+        if args.workload == "matsed":
+            cfg["tc_frac_of_sustained_bf16"] = value / world * 3 * FWD_GFLOP_PER_CLIP / 1e3 / pk["bf16_tflops_sustained"]
+        elif roof is not None:
+            cfg["tc_frac_of_sustained_bf16_gemm_flops_only"] = roof["gemm_tflop_per_step"] / (ms / args.steps / 1e3) / pk["bf16_tflops_sustained"]
+        if in_sync is not None:
+            cfg["params_in_sync"] = in_sync
+        if strict is not None:
+            cfg["strict_mode_clips_per_s"] = strict
         out = {
-            "metric": "10s-clips/sec fwd+bwd MAT-SED", "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "metric": names[args.workload], "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"bf16": "bf16", "tf32": "tf32", "tf32x3": "tf32x3"}[args.precision], "data": "synthetic",
-            "config": {"workload": "MAT-SED base (config/mat-sed/base/finetune2.yaml init_kwargs, all 100.95 M params trainable), "
-                                   f"DESED-shape synthetic batch={B}/GPU of 10 s @ 32 kHz clips (320000 samples -> 1000 frames), step = fused "
-                                   "STFT+mel front end + student fwd + BCE strong/weak/AT losses + bwd + grad all-reduce + fused AdamW",
-                       "global_batch": B * world, "per_gpu_batch": B, "sample_rate_note": "BASELINE.json says 16 kHz; every reference recipe is "
-                       "32 kHz and the model asserts 1000 frames (SURVEY §0.1, §8d)", "parallelism": f"dp{world}",
-                       "l2_policy": "inputs larger than L2 (82 MB of clips + GBs of activations per step)", "loss": float(loss_val),
-                       "tc_frac_of_sustained_bf16": value / world * 3 * FWD_GFLOP_PER_CLIP / 1e3 / pk["bf16_tflops_sustained"],
-                       "peaks": pk_src},
+            "config": cfg,
             "clocks": clocks,
             "e2e": {"value": clips / (ms_e2e / 1e3), "unit": "clips/s", "h2d_bytes_per_step": B * N_SAMPLES * 4, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": roof, "roofline_mel": mel_roof, "kernel_time_breakdown_ms": breakdown,
-            "cpu_baseline": cpu_base,
+            "cpu_baseline": cpu_base, "gpu_eager_baseline": eager,
         }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def strict_mode_throughput(B, dev, rank):
+    """What the <=1e-3 / argmax-exact contract costs: the same MAT-SED step in the tf32 and tf32x3 precision modes (3 timed steps each)."""
+    from transformer4sed_b200 import functional as F
+    res = {}
+    for mode in ("tf32", "tf32x3"):
+        try:
+            F.set_precision(mode)
+            net, ext, arena, step, _, wav_host = build_workload("matsed", mode, B, dev, rank)
+            wav = wav_host.to(dev)
+            for _ in range(2):
+                step(wav)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                step(wav)
+            e1.record()
+            torch.cuda.synchronize()
+            res[mode] = B * 3 / (e0.elapsed_time(e1) / 1e3)
+        except Exception as e:  # noqa: BLE001
+            res[mode] = f"failed: {type(e).__name__}: {e}"[:200]
+        finally:
+            F.set_precision("bf16")
+            net = ext = arena = step = None
+            torch.cuda.empty_cache()
+    res["note"] = "same model / batch / step as the bf16 line; the parity contract (<=1e-3 rel, exact argmax) is asserted in tf32x3 (tests/test_model_gpu.py)"
+    return res
+
+
+def gpu_eager_baseline(dev):
+    """BASELINE.md §4.5 / SURVEY §8(d): the reference's own PyTorch modules on this GPU.  The reference does not travel to the GPU box, so
+    the oracle port of it (plain torch ops: oracle/model.py + oracle/frontend.py, the code the parity tests pin to the reference) runs the
+    same model / loss / fwd+bwd in eager fp32 and under autocast(bfloat16), at the largest batch of {32, 16, 8, 4} that fits.  A reported
+    baseline leg outside every timed region; nothing of the product path goes through it."""
+    try:
+        from oracle import frontend as OF
+        from oracle import model as OM
+        from transformer4sed_b200 import schema
+        from transformer4sed_b200.utils import synth
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    out = {}
+    sd = {k: v.to(dev).requires_grad_(True) for k, v in synth.synth_state_dict(schema.mat_sed_shapes(), 4).items()}
+    for tag, ctx in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        for batch in (32, 16, 8, 4):
+            try:
+                wav = synth.synth_wav(4, N_SAMPLES, seed=1234).repeat(batch // 4, 1).to(dev)
+                y, yw = make_labels(batch, 99)
+                y, yw = y.to(dev), yw.to(dev)
+
+                def step():
+                    for v in sd.values():
+                        v.grad = None
+                    with torch.autocast("cuda", dtype=ctx, enabled=ctx is not None):
+                        mel = OF.passt_logmel(wav)
+                        strong, weak, other = OM.mat_sed_forward(mel, sd, decoder_layers=3)
+                    loss = OM.bce(strong.float(), y) + 0.5 * OM.bce(weak.float(), yw) + 2.0 * OM.bce(other["at_out"].float(), yw)
+                    loss.backward()
+                for _ in range(2):
+                    step()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+                out[tag] = {"clips_per_s": batch * 3 / (e0.elapsed_time(e1) / 1e3), "batch": batch}
+                break
+            except torch.cuda.OutOfMemoryError:
+                torch.cuda.empty_cache()
+                continue
+            except Exception as e:  # noqa: BLE001
+                out[tag] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+                break
+        torch.cuda.empty_cache()
+    out["what"] = "oracle port of the reference modules (plain PyTorch eager) on this B200: fwd + same losses + bwd, no optimizer step"
+    return out
 
 
 def instrumented_step(train_step, wav_dev, ext, ops, B):
@@ -269,7 +476,7 @@ def instrumented_step(train_step, wav_dev, ext, ops, B):
             gemm_ms += s.elapsed_time(e)
             gemm_flops += 2.0 * M * N * K * nb
             n_gemm += 1
-        elif name in ("t4s_attn_fwd", "t4s_attn_bwd"):
+        elif name in ("t4s_attn_fwd", "t4s_attn_bwd", "t4s_relattn_fwd", "t4s_relattn_bwd"):
             attn_ms += s.elapsed_time(e)
     summary = prof.summary()
     shapes = {}
@@ -306,7 +513,7 @@ def instrumented_step(train_step, wav_dev, ext, ops, B):
             # dram__bytes_read.sum + dram__bytes_write.sum of ONE captured launch (fc1 shape M=76160 N=3072 K=768, bias epilogue) from the
             # committed `ncu --set full` capture; algorithmic bytes of that launch: 589.6 MB (profiles/r1j_ncu_full_summary.md)
             "traffic": 537.2e6, "traffic_note": "bytes per launch of the fc1-shape GEMM (359.4 GFLOP); profiles/r1j_ncu_full_summary.md",
-            "launches": n_gemm, "gemm_ms_per_step": gemm_ms, "share_of_step": gemm_ms / step_ms, "peak_source": pk_src + " (sustained bf16)",
+            "launches": n_gemm, "gemm_ms_per_step": gemm_ms, "gemm_tflop_per_step": gemm_flops / 1e12, "share_of_step": gemm_ms / step_ms, "peak_source": pk_src + " (sustained bf16)",
             "how": "CUDA events around every t4s_gemm launch of one extra instrumented step; flops = 2MNK per launch"}
     mel_roof = {"bound": "hbm", "kernel": "t4s::mel::mel_kernel (+peak kernel)", "achieved": mel_bytes / mel_ms / 1e6, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": mel_bytes / mel_ms / 1e6 / pk["hbm_gbs"],
@@ -398,7 +605,9 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="clips per GPU per step (default: 64 MAT-SED, 32 PMAM, 8 DASM)")
+    ap.add_argument("--workload", default="matsed", choices=["matsed", "matsed_finetune2", "pmam", "dasm"])
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the strict-mode and GPU-eager baseline legs (rank 0, N=1, after the timed regions)")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "tf32", "tf32x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

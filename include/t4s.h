@@ -368,6 +368,40 @@ int t4s_add_rowbias(const float* x, const float* bias_dev, float* out, int64_t r
 #define T4S_MEDIAN_MAX_WINDOW 255
 int t4s_median_filter(const float* in, float* out, const int* window_sizes, int batch, int length, int classes, void* stream);
 
+/* ---- callers either side of the hot path (csrc/post.cu; SURVEY §8 a1', f3, f4), fp32 ------------------------------------------------
+ * TorchScaler.forward (src/preprocess/scaler.py:91-121) with statistics over every dimension but the first:
+ * instance mode 0 'mean' (x - mean), 1 'standard' ((x - mean) / (std + eps), unbiased std like torch.std), 2 'minmax'
+ * ((x - min) / (max - min + eps)); dataset mode with the fitted scalars `mean`, `mean_squared` (DEVICE, one float each) */
+int t4s_scaler_instance(const float* x, float* out, int batch, int64_t inner, int mode, float eps, void* stream);
+int t4s_scaler_dataset(const float* x, float* out, int64_t total, const float* mean_dev, const float* mean_sq_dev, int standard, float eps, void* stream);
+/* scipy.ndimage.median_filter / maximum_filter per class as batched_decode_preds applies them (src/codec/decoder.py:86-92):
+ * in / out [batch, length, classes]; window of class c = window_sizes[c] (HOST array, any size in [1, 255]) samples starting at
+ * l - size / 2, borders mirrored with the edge sample repeated (scipy 'reflect'); op 0 = element of rank size / 2, 1 = maximum */
+int t4s_rank_filter(const float* in, float* out, const int* window_sizes, int batch, int length, int classes, int op, void* stream);
+/* Threshold sweep + run-length event decoding (src/codec/decoder.py:15-35 decode_pred_batch_fast, src/codec/encoder.py:51-84
+ * decode_strong / find_contiguous_regions).  scores [batch, length, classes] are the filtered frame probabilities, weak [batch, classes]
+ * (may be NULL) the clip probabilities, thresholds_dev DEVICE [n_thresholds].  Column q = (threshold, clip, class) is silent when
+ * weak < threshold; its events are the maximal runs of score > threshold as (onset frame, offset frame = last + 1).
+ * Pass 1 (events == NULL): counts[q] = number of events.  Pass 2: offsets[q] (DEVICE int64, exclusive prefix sum of counts) and
+ * events [total, 5] int32 rows (threshold index, clip, class, onset, offset), ordered by q then by onset. */
+int t4s_event_sweep(const float* scores, const float* weak, const float* thresholds_dev, int n_thresholds, int batch, int length, int classes, int* counts,
+                    const int64_t* offsets, int* events, void* stream);
+/* The six losses of the mean-teacher step and their weighted total in one pass (recipes/desed/finetune/train.py:166-188):
+ *   out[0] BCE(strong[s0:s1], y[s0:s1])   out[1] BCE(weak[w0:w1], yw[w0:w1])   out[2] BCE(at[w0:w1], yw[w0:w1])
+ *   out[3] MSE(strong, t_strong)          out[4] MSE(weak, t_at)               out[5] MSE(at, t_at)
+ *   out[6] = out[0] + w_weak out[1] + w_at out[2] + w_cons (out[3] + w_weak_cons out[4] + w_at out[5])
+ * strong / t_strong / y: [batch, strong_inner] (classes x frames in any common layout); weak / at / t_at / yw: [batch, classes].
+ * Deterministic two-stage reductions (ws: 768 floats).  The backward writes d out[6] / d strong, d weak, d at times grad_total[0]. */
+typedef struct {
+  const float *strong, *weak, *at, *t_strong, *t_at, *y, *yw;
+  int batch, classes;
+  int64_t strong_inner;
+  int s0, s1, w0, w1;
+  float w_weak, w_at, w_cons, w_weak_cons;
+} T4sSedLosses;
+int t4s_sed_losses_fwd(const T4sSedLosses* p, float* ws, float* out, void* stream);
+int t4s_sed_losses_bwd(const T4sSedLosses* p, const float* grad_total, float* d_strong, float* d_weak, float* d_at, void* stream);
+
 /* ---- K9: parameter-side kernels of a training step (csrc/optim.cu) ------------------------------------------------
  * torch.optim.AdamW semantics (recipes/desed/setting.py:254-258) over a flat fp32 arena; `bf16_shadow` (optional) receives the
  * updated weights as bf16 GEMM operands in the same pass; `grad_scale` folds the 1/world_size of the gradient all-reduce. */

@@ -51,3 +51,75 @@ def freq_nonlinear(mel, phase, f=1, bias=0.02):
 def filt_aug_apply(features, freq_filt, norm_std):
     """data_aug.py:188-190 (log features): features + log(filter + 1e-5) / norm_std with filter [B, F, 1]."""
     return features + torch.log(freq_filt + 0.00001) / norm_std
+
+
+# ---- callers either side of the hot path: scaler, decoding, mean-teacher losses (SURVEY §8 a1', f3, f4) -----------------------------
+def torch_scaler(x, statistic, normtype, dims=(1, 2), eps=1e-8, mean=None, mean_squared=None):
+    """src/preprocess/scaler.py:91-121."""
+    if statistic is None or normtype is None:
+        return x
+    if statistic == "dataset":
+        if normtype == "mean":
+            return x - mean
+        std = torch.sqrt(mean_squared - mean ** 2)
+        return (x - mean) / (std + eps)
+    if normtype == "mean":
+        return x - torch.mean(x, dims, keepdim=True)
+    if normtype == "standard":
+        return (x - torch.mean(x, dims, keepdim=True)) / (torch.std(x, dims, keepdim=True) + eps)
+    lo, hi = torch.amin(x, dim=dims, keepdim=True), torch.amax(x, dim=dims, keepdim=True)
+    return (x - lo) / (hi - lo + eps)
+
+
+def find_contiguous_regions(array):
+    """src/codec/encoder.py:71-84."""
+    import numpy as np
+    change = np.logical_xor(array[1:], array[:-1]).nonzero()[0] + 1
+    if array[0]:
+        change = np.r_[0, change]
+    if array[-1]:
+        change = np.r_[change, array.size]
+    return change.reshape((-1, 2))
+
+
+def decode_pred_batch_fast(outputs, weak_preds, thresholds, filter_size):
+    """src/codec/decoder.py:15-35 down to frame indices: rows (threshold index, clip, class, onset frame, offset frame) in the
+    order the reference appends them (threshold, clip, class, onset)."""
+    import numpy as np
+    rows = []
+    for ti, th in enumerate(thresholds):
+        out = outputs.transpose(1, 2).clone()
+        b_idx, c_idx = torch.where(weak_preds < th)
+        out[b_idx, :, c_idx] = 0
+        out = (median_filter(out, filter_size) > th).float().numpy()
+        for b in range(out.shape[0]):
+            for c, col in enumerate(out[b].T):
+                for on, off in find_contiguous_regions(col):
+                    rows.append((ti, b, c, int(on), int(off)))
+    return np.array(rows, dtype=np.int32).reshape(-1, 5)
+
+
+def rank_filter_scores(scores, sizes, filter_type="median"):
+    """src/codec/decoder.py:86-92: scipy.ndimage filters per class on a [T, C] score array (first len(sizes) classes)."""
+    from scipy import ndimage
+    out = scores.copy()
+    for idx in range(len(sizes)):
+        if filter_type == "median":
+            out[:, idx] = ndimage.median_filter(scores[:, idx], (sizes[idx]))
+        else:
+            out[:, idx] = ndimage.maximum_filter(scores[:, idx], (sizes[idx]))
+    return out
+
+
+def sed_losses(stu_strong, stu_weak, stu_at, tch_strong, tch_at, labels, labels_weak, mask_strong, mask_weak, w_weak, w_at, w_cons, w_weak_cons):
+    """recipes/desed/finetune/train.py:166-188 (BCELoss / MSELoss, mean reduction).  Returns (total, [six parts])."""
+    bce, mse = torch.nn.BCELoss(), torch.nn.MSELoss()
+    l_at = bce(stu_at[mask_weak], labels_weak[mask_weak])
+    c_at = mse(stu_at, tch_at.detach())
+    l_strong = bce(stu_strong[mask_strong], labels[mask_strong])
+    l_weak = bce(stu_weak[mask_weak], labels_weak[mask_weak])
+    c_strong = mse(stu_strong, tch_strong.detach())
+    c_weak = mse(stu_weak, tch_at.detach())
+    self_loss = (c_strong + w_weak_cons * c_weak + w_at * c_at) * w_cons
+    total = l_strong + w_weak * l_weak + self_loss + l_at * w_at
+    return total, [l_strong, l_weak, l_at, c_strong, c_weak, c_at]

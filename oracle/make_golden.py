@@ -388,6 +388,100 @@ def golden_glue():
     print("glue.npz shifts", shifts, "c", c, "perm", perm.tolist(), "median sizes", sizes)
 
 
+def golden_post():
+    """TorchScaler (src/preprocess/scaler.py), the decoding pieces of src/codec/{encoder,decoder}.py and the loss block of
+    recipes/desed/finetune/train.py:166-188, from the unmodified reference where it imports here.  `src/codec/decoder.py` itself needs
+    `sed_scores_eval` (absent) and `DataFrame.append` (removed in pandas 2), so its loop (:22-33) is replayed around the reference's own
+    `median_filter_torch` and `Encoder.decode_strong`; its scipy filters (:86-92) and the trainer's loss lines are called as written."""
+    from scipy import ndimage
+    from src.codec.encoder import Encoder
+    from src.postprocess.filter import median_filter_torch
+    from src.preprocess.scaler import TorchScaler
+    out = {}
+    x = synth.synth_tensor(41, "post_feat", (5, 128, 250)) * 3.0 + 1.5
+    out["feat_ck"] = checksum(x)
+    for nt in ("mean", "standard", "minmax"):
+        r = TorchScaler("instance", nt, dims=(1, 2))(x)
+        out[f"scaler_instance_{nt}"], out[f"scaler_instance_{nt}_ck"] = f32(r[:, ::4, ::5]), checksum(r)
+    ds = TorchScaler("dataset", "standard", dims=(1, 2))
+    ds.fit([(x[:2],), (x[2:4],), (x[4:],)])
+    out["scaler_dataset_standard"], out["scaler_dataset_standard_ck"] = f32(ds(x)[:, ::4, ::5]), checksum(ds(x))
+    out["scaler_mean"], out["scaler_mean_squared"] = f32(ds.mean), f32(ds.mean_squared)
+    dm = TorchScaler("dataset", "mean", dims=(1, 2))
+    dm.fit([(x[:2],), (x[2:4],), (x[4:],)])
+    out["scaler_dataset_mean"], out["scaler_dataset_mean_ck"] = f32(dm(x)[:, ::4, ::5]), checksum(dm(x))
+    # ---- decoding: 156-frame DESED grid (10 s, hop 256 @ 16 kHz, net_pooling 4) and the 1000-frame PaSST grid
+    labels = [f"class{i}" for i in range(10)]
+    for tag, T, enc in (("156", 156, Encoder(labels, 10, 2048, 256, net_pooling=4, sr=16000)),
+                        ("1000", 1000, Encoder(labels, 10, 800, 320, net_pooling=1, sr=32000))):
+        B = 4
+        smooth = torch.nn.functional.avg_pool1d(synth.synth_tensor(43, f"post_strong{tag}", (B, 10, T + 8)), 9, 1)
+        strong = torch.sigmoid(6.0 * smooth)                                       # [B, C, T] frame probabilities with runs
+        weak = torch.sigmoid(2.0 * synth.synth_tensor(43, f"post_weak{tag}", (B, 10)))
+        out[f"strong{tag}_ck"], out[f"weak{tag}_ck"] = checksum(strong), checksum(weak)
+        sizes = [3, 28, 7, 4, 7, 22, 48, 19, 10, 50] if T == 156 else [int(i / 156 * 1000) for i in [3, 28, 7, 4, 7, 22, 48, 19, 10, 50]]
+        sizes = [min(k, 101) for k in sizes]
+        thresholds = [0.25, 0.5, 0.75]
+        rows, times = [], []
+        for ti, c_th in enumerate(thresholds):                                      # decoder.py:22-33
+            output = strong.transpose(1, 2).detach().clone()
+            neg = torch.where(weak < c_th)
+            output[neg[0], :, neg[1]] = 0
+            output = median_filter_torch(output, sizes)
+            output = (output > c_th).float().cpu().numpy()
+            for b in range(B):
+                for lab, on, off in enc.decode_strong(output[b]):
+                    c = labels.index(lab)
+                    rows.append((ti, b, c))
+                    times.append((on, off))
+        out[f"events{tag}_idx"] = np.array(rows, np.int32).reshape(-1, 3)
+        out[f"events{tag}_time"] = np.array(times, np.float64).reshape(-1, 2)
+        out[f"sizes{tag}"] = np.array(sizes, np.int32)
+        # batched_decode_preds' filters (decoder.py:86-92) on the soft-masked scores of clip 0 and 1
+        for ft in ("median", "max"):
+            res = []
+            for j in range(2):
+                c_scores = (strong[j].transpose(0, 1) * weak[j, :]).numpy().copy()
+                for idx in range(len(sizes)):
+                    if ft == "median":
+                        c_scores[:, idx] = ndimage.median_filter(c_scores[:, idx], (sizes[idx]))
+                    else:
+                        c_scores[:, idx] = ndimage.maximum_filter(c_scores[:, idx], (sizes[idx]))
+                res.append(c_scores)
+            out[f"scores{tag}_{ft}"] = np.stack(res).astype(np.float32)
+    # ---- the six losses (train.py:48-49, 166-188) with the shipped weights of config/mat-sed/base/finetune2.yaml
+    B, C, T = 12, 10, 1000
+    mk = lambda name, shape: torch.sigmoid(synth.synth_tensor(47, name, shape))  # noqa: E731
+    stu_strong, stu_weak, stu_at = mk("l_ss", (B, C, T)).requires_grad_(), mk("l_sw", (B, C)).requires_grad_(), mk("l_sa", (B, C)).requires_grad_()
+    tch_strong, tch_at = mk("l_ts", (B, C, T)), mk("l_ta", (B, C))
+    y = (synth.synth_tensor(47, "l_y", (B, C, T)) > 0.5).float()
+    yw = (synth.synth_tensor(47, "l_yw", (B, C)) > 0.3).float()
+    mask_strong = torch.zeros(B).bool()
+    mask_strong[:4] = 1
+    mask_weak = torch.zeros(B).bool()
+    mask_weak[4:8] = 1
+    supervised_loss, selfsup_loss = torch.nn.BCELoss(), torch.nn.MSELoss()
+    w_weak, w_AT, w_cons, w_weak_cons = 0.5, 1.0, 40.0 * 0.37, 1.0
+    loss_class_at_specific = supervised_loss(stu_at[mask_weak], yw[mask_weak])
+    loss_cons_at_specific = selfsup_loss(stu_at, tch_at.detach())
+    loss_class_strong = supervised_loss(stu_strong[mask_strong], y[mask_strong])
+    loss_class_weak = supervised_loss(stu_weak[mask_weak], yw[mask_weak])
+    loss_cons_strong = selfsup_loss(stu_strong, tch_strong.detach())
+    loss_cons_weak = selfsup_loss(stu_weak, tch_at.detach())
+    self_loss = (loss_cons_strong + w_weak_cons * loss_cons_weak + w_AT * loss_cons_at_specific) * w_cons
+    at_branch_loss = loss_class_at_specific * w_AT
+    loss_total = loss_class_strong + w_weak * loss_class_weak + self_loss + at_branch_loss
+    loss_total.backward()
+    out["loss_parts"] = np.array([v.item() for v in (loss_class_strong, loss_class_weak, loss_class_at_specific, loss_cons_strong, loss_cons_weak,
+                                                     loss_cons_at_specific)], np.float64)
+    out["loss_total"] = np.array(loss_total.item())
+    out["loss_weights"] = np.array([w_weak, w_AT, w_cons, w_weak_cons])
+    out["d_strong"], out["d_weak"], out["d_at"] = f32(stu_strong.grad[:, ::3, ::25]), f32(stu_weak.grad), f32(stu_at.grad)
+    out["d_strong_ck"] = checksum(stu_strong.grad)
+    np.savez_compressed(os.path.join(OUT, "post.npz"), **out)
+    print("post.npz events", {k: v.shape for k, v in out.items() if k.startswith("events")}, "loss", out["loss_total"])
+
+
 def golden_param_groups(base_kw):
     """Optimizer groups and requires_grad side effects of the reference's `get_params` (recipes/desed/finetune/passt/setting.py:28-103)
     for the shipped finetune2 settings and three variants (no step_lr, frozen encoder, freeze_layer)."""
@@ -488,7 +582,7 @@ if __name__ == "__main__":
     base = dict(passt_feature_layer=10, f_pool="mean_pool", decode_ratio=10, at_adapter=True, decoder="transformerXL",
                 decoder_layer_num=3, decoder_pos_emd_len=1000, mlm=False)  # config/mat-sed/base/finetune2.yaml:53-62
     pre = dict(base, mlm=True, mlm_dict=dict(strategy="block", block_width=10, mask_rate=0.75, out_dim=768))  # pretrain.yaml:39-52
-    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm", "pmam", "pmam_ft", "dasm", "glue", "groups"]
+    which = sys.argv[1:] or ["frontend", "ops", "small", "base", "window", "mlm", "pmam", "pmam_ft", "dasm", "glue", "post", "groups"]
     if "frontend" in which:
         golden_frontend()
         golden_frontend_16k()
@@ -510,6 +604,8 @@ if __name__ == "__main__":
         golden_param_groups(base)
     if "glue" in which:
         golden_glue()
+    if "post" in which:
+        golden_post()
     if "mlm" in which:
         golden_mlm("base", pre, seed=6, batch=2)  # B>1: upstream masking is a silent no-op
         golden_mlm("base", pre, seed=6, batch=1)  # B=1: reshape is a view, masking applies

@@ -60,8 +60,17 @@ def test_dasm_matches_reference(golden, mode, tol, gtol):
             mism = float((s.argmax(dim=1).cpu().numpy() != g["eval_argmax"]).mean())
             print(mode, "eval", r, "argmax mismatch", mism)
             assert max(r.values()) < tol, r
-            # argmax over 407 near-tied query scores (synthetic weights): exact in the strict mode, a tie-rate in bf16
-            assert mism < (1e-3 if mode == "tf32x3" else 0.15)
+            # argmax over 407 near-tied query scores (synthetic weights): exact in the strict mode.  In bf16 the raw flip rate is a
+            # tie rate (6 % .. 40 % for the same 6e-2 value error, depending on rounding details), so the check is tie-aware: wherever
+            # our argmax differs, the reference's choice must score within the value tolerance of our maximum.
+            if mode == "tf32x3":
+                assert mism < 1e-3
+            else:
+                ref_idx = torch.from_numpy(g["eval_argmax"]).long().cuda().unsqueeze(1)
+                gap = (s.max(dim=1, keepdim=True).values - s.gather(1, ref_idx)).float()
+                real = float((gap > 2 * tol * s.max().item()).float().mean())
+                print(mode, "argmax flips beyond the value tolerance", real)
+                assert real == 0.0, real
             s, w, o = net(mel, temp_w=4.0, pad_mask=pad, query=query.unsqueeze(0), tgt_mask=tgt_mask.unsqueeze(0))   # DataParallel-style 3-D inputs
             r = dict(strong=relmax(s[:, ::3, ::4], g["evalm_strong"]), weak=relmax(w, g["evalm_weak"]), at=relmax(o["at_out"], g["evalm_at"]))
             print(mode, "eval masked", r)

@@ -106,13 +106,51 @@ def test_tf32_mode(golden, tag, kw, seed, batch):
 
 @pytest.mark.parametrize("tag,kw,seed,batch", [("small", SMALL, 3, 2), ("base", BASE, 4, 1)])
 def test_bf16_mode(golden, tag, kw, seed, batch):
+    """The benchmarked mode.  Thresholds = 3 x the values measured on B200 (probabilities 8e-3, gradients 1e-2, no argmax
+    flips on the base fixture), so a regression of the bf16 path fails here and not only in the strict mode."""
     r = run_golden(tag, kw, seed, batch, golden, "bf16")
     print(tag, "bf16", r)
     for k in ("strong", "weak", "at_out"):
-        assert r[k] < 6e-2, (k, r)
-    assert r["loss"] < 2e-2, r
-    assert r["argmax_mismatch"] < 0.05, r
-    assert r["grad_worst"] < 0.25, r
+        assert r[k] < 2.5e-2, (k, r)
+    assert r["loss"] < 1e-2, r
+    # the 192-wide synthetic model has near-tied class probabilities on ~2 % of its frames (flips there are ties: its value errors
+    # are the same 7e-3 as the base model's); the base fixture must not flip at all
+    assert r["argmax_mismatch"] <= (0.05 if tag == "small" else 0.0), r
+    assert r["grad_worst"] < 4e-2, r
+
+
+def test_batch_invariance_at_bench_shape():
+    """Nothing above checks the B=64 shape the benchmark runs (GEMM tiles, split-K, CTA-pair selection and the attention grids all depend
+    on M = B x 1190).  64 clips = 8 distinct clips repeated 8 times: every row must equal the B=1 result of the same clip, and the
+    gradient of the mean loss must equal the gradient of the 8-clip batch (bf16 mode, the benchmarked configuration)."""
+    from transformer4sed_b200 import functional as F
+    F.set_precision("bf16")
+    net, _ = build(BASE, 4)
+    net.train()
+    ext = net.get_feature_extractor().eval()
+    wav8 = synth.synth_wav(8, 320000, seed=21).cuda()
+    y8 = synth.synth_strong_labels(8, 10, 1000, 22).cuda()
+    yw8 = (y8.sum(-1) > 0).float()
+
+    def run(wav, y, yw):
+        for p in net.parameters():
+            p.grad = None
+        strong, weak, other = net(ext.logmel(wav))
+        loss = F.bce_loss(strong, y) + 0.5 * F.bce_loss(weak, yw) + 2.0 * F.bce_loss(other["at_out"], yw)
+        loss.backward()
+        return strong.detach().float(), weak.detach().float(), loss.item(), {n: p.grad.double().norm().item() for n, p in net.named_parameters()
+                                                                                if p.grad is not None}
+
+    s64, w64, l64, g64 = run(wav8.repeat(8, 1), y8.repeat(8, 1, 1), yw8.repeat(8, 1))
+    s8, w8, l8, g8 = run(wav8, y8, yw8)
+    s1, w1, _, _ = run(wav8[3:4], y8[3:4], yw8[3:4])
+    assert relmax(s64[:8], s8) < 1e-2 and relmax(s64[56:], s8) < 1e-2, (relmax(s64[:8], s8), relmax(s64[56:], s8))
+    assert relmax(s64[3:4], s1) < 1e-2 and relmax(w64[3:4], w1) < 1e-2
+    assert float((s64[:8].argmax(1) != s8.argmax(1)).float().mean()) <= 2e-3
+    assert abs(l64 - l8) / abs(l8) < 2e-3, (l64, l8)
+    assert set(g64) == set(g8)
+    worst = max(abs(g64[n] - g8[n]) / max(g8[n], 1e-9) for n in g8 if g8[n] > 1e-7)
+    assert worst < 3e-2, worst
 
 
 def test_mlm_pretrain_forward_matches_reference(golden):

@@ -77,6 +77,12 @@ class RelAttnBwd(ctypes.Structure):
                 ("dbd", c_void_p), ("dbd_ld", ctypes.c_int64)]
 
 
+class SedLosses(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("strong", "weak", "at", "t_strong", "t_at", "y", "yw")] + [
+        ("batch", c_int), ("classes", c_int), ("strong_inner", ctypes.c_int64), ("s0", c_int), ("s1", c_int), ("w0", c_int), ("w1", c_int),
+        ("w_weak", c_float), ("w_at", c_float), ("w_cons", c_float), ("w_weak_cons", c_float)]
+
+
 class WindowSegment(ctypes.Structure):
     _fields_ = [("ptr", c_void_p), ("batch_stride", ctypes.c_int64), ("out_start", c_int), ("frames", c_int)]
 
@@ -147,6 +153,12 @@ def _declare(lib):
         "t4s_mixup": (I, [P, P, P, I, L, F, F, I, P]),
         "t4s_median_filter": (I, [P, P, ctypes.POINTER(c_int), I, I, I, P]),
         "t4s_freq_warp": (I, [P, P, P, P, I, I, I, P]),
+        "t4s_scaler_instance": (I, [P, P, I, L, I, F, P]),
+        "t4s_scaler_dataset": (I, [P, P, L, P, P, I, F, P]),
+        "t4s_rank_filter": (I, [P, P, ctypes.POINTER(c_int), I, I, I, I, P]),
+        "t4s_event_sweep": (I, [P, P, P, I, I, I, I, P, P, P, P]),
+        "t4s_sed_losses_fwd": (I, [ctypes.POINTER(SedLosses), P, P, P]),
+        "t4s_sed_losses_bwd": (I, [ctypes.POINTER(SedLosses), P, P, P, P, P]),
         "t4s_add_rowbias": (I, [P, P, P, L, I, P]),
         "t4s_patch_posbias": (I, [P, P, P, I, I, I, I, I, P]),
         "t4s_cls_dist_tokens": (I, [P, I, P, P, P, I, L, I, P]),

@@ -24,6 +24,7 @@ _MIRRORS = {
     "src.models.detect_any_sound.at_adapter": "transformer4sed_b200.src_models.detect_any_sound.at_adapter",
     "src.models.detect_any_sound.detect_any_sound": "transformer4sed_b200.src_models.detect_any_sound.detect_any_sound",
     "src.postprocess.filter": "transformer4sed_b200.src_postprocess.filter",
+    "src.preprocess.scaler": "transformer4sed_b200.src_preprocess.scaler",
     # the three names every recipe imports (`mixup, frame_shift, feature_transformation`: recipes/desed/finetune/train.py:18)
     "src.preprocess.data_aug": "transformer4sed_b200.src_preprocess.data_aug",
 }

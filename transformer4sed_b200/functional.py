@@ -81,7 +81,8 @@ def cast_weight(w: torch.Tensor) -> torch.Tensor:
     if shadow is not None:
         return shadow
     if w._base is not None and w._base.dtype == torch.float32:  # a slice of a parameter: cast the parameter once, re-slice the copy
-        return cast_weight(w._base).as_strided(w.shape, w.stride(), w.storage_offset())
+        c = cast_weight(w._base)    # (the copy may start elsewhere in its own storage than the base does: offsets are relative)
+        return c.as_strided(w.shape, w.stride(), c.storage_offset() + w.storage_offset() - w._base.storage_offset())
     key = id(w)
     ent = _wcache.get(key)
     ver = (w._version, w.data_ptr(), w.device)

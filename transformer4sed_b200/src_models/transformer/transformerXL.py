@@ -4,7 +4,9 @@
 Upstream semantics kept bit-for-bit in structure: the block's residual is taken from the *normalised* input
 (``x = norm1(x); x = x + attn(x)``, :31-35), scores are ``((q+u)k^T + shift((q+v)p^T)) / sqrt(hd)`` with
 ``p = linear_pos(pos_emb)`` (no bias), and row k of the position table holds relative position T-1-k.
-We keep activations batch-major [B, T, C]; the reference's (T, B, C) permutes are layout only.
+Activations are stored batch-major [B, T, C]; a block takes and returns the reference's (T, B, C) layout as a strided VIEW of
+that storage (no copy), so forward hooks on ``decoder.encoder_blocks[i]`` see what they see upstream
+(recipes/desed/pmam/extractor_feature.py:83-89 does ``fea_out.transpose(0, 1).reshape(-1, C)``).
 """
 import math
 
@@ -81,9 +83,11 @@ class TransformerXL(nn.Module):
         self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), act_layer=act_layer, drop=drop)
 
     def forward(self, x, pos_emb, att_mask=None, in_scale=1.0):
+        """x (T, B, C) -> (T, B, C), both views of batch-major storage (a genuinely time-major tensor is copied once)."""
         if att_mask is not None:
             raise NotImplementedError("decoder_win_len attention masks are unused by the shipped configs")
+        x = x.transpose(0, 1)
         x = F.layer_norm(x, self.norm1.weight, self.norm1.bias, self.norm1.eps, in_scale=in_scale)
         x = self.attn(x, pos_emb, residual=x)           # residual from the NORMALISED input (upstream semantics)
         y, res = F.layer_norm_res(x, self.norm2.weight, self.norm2.bias, self.norm2.eps)
-        return self.mlp(y, residual=res)
+        return self.mlp(y, residual=res).transpose(0, 1)

@@ -22,6 +22,7 @@ class TransformerXLDecoder(nn.Module):
         """x [B, T, C] -> [B, T, C]"""
         x, pos_emb = self.pos_embedding(x)
         scale = self.pos_embedding.xscale
+        x = x.transpose(0, 1)          # (T, B, C) view, as upstream permutes (reference :112); the blocks undo it without a copy
         for i, block in enumerate(self.encoder_blocks):
             x = block(x, pos_emb, in_scale=scale if i == 0 else 1.0)  # x*sqrt(d) folded into the first LayerNorm
-        return x
+        return x.transpose(0, 1)

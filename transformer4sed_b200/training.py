@@ -39,6 +39,11 @@ def shard_for_rank(n_items, rank, world):
     return lo, min(n_items, lo + per)
 
 
+def _world_size():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
 def all_reduce_flat(buf):
     """The path's single collective: in-place sum of the packed gradient buffer over ranks; returns the world size."""
     import torch.distributed as dist
@@ -74,12 +79,21 @@ class ParamArena:
             for p, _ in layout:
                 p._t4s_shadow_version = p._version      # functional._arena_shadow re-converts after load_state_dict / copy_
         self.betas, self.eps, self.step_count = betas, eps, 0
-        self._table_host = torch.empty(len(layout), 3, dtype=torch.int64).pin_memory()
-        self._table_dev = torch.empty(len(layout), 3, dtype=torch.int64, device=dev)
+        # pointer tables of the pack kernel: the host never rewrites a pinned table whose upload may still be queued (the step has
+        # no host sync, so the host can run more than a step ahead of the GPU): two tables, each guarded by the event of its copy
+        self._tables = [(torch.empty(len(layout), 3, dtype=torch.int64).pin_memory(),
+                         torch.empty(len(layout), 3, dtype=torch.int64, device=dev), torch.cuda.Event()) for _ in range(2)]
+        self._table_used = [False, False]
+        self._table_turn = 0
+        self._agreed = self._agreed_local = None
 
     def pack_grads(self):
         """Gather every parameter's .grad into the flat buffer (missing grads -> zeros) with one kernel."""
-        t = self._table_host
+        turn = self._table_turn
+        self._table_turn ^= 1
+        t, t_dev, copied = self._tables[turn]
+        if self._table_used[turn]:
+            copied.synchronize()            # the upload that last read this pinned table has finished
         for i, (p, off) in enumerate(self.layout):
             g = p.grad
             if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
@@ -88,9 +102,11 @@ class ParamArena:
             t[i, 0] = g.data_ptr() if g is not None else 0
             t[i, 1] = off
             t[i, 2] = p.numel()
-        self._table_dev.copy_(t, non_blocking=True)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.load().t4s_grad_pack(_lib.ptr(self._table_dev), len(self.layout), _lib.ptr(self.grad), _lib.stream_ptr()),
+            t_dev.copy_(t, non_blocking=True)
+            copied.record()
+            self._table_used[turn] = True
+            _lib.check(_lib.load().t4s_grad_pack(_lib.ptr(t_dev), len(self.layout), _lib.ptr(self.grad), _lib.stream_ptr()),
                        "t4s_grad_pack")
 
     def all_reduce(self):
@@ -98,10 +114,29 @@ class ParamArena:
         return all_reduce_flat(self.grad)
 
     def step(self, lr_scale=1.0):
+        """pack -> all-reduce -> fused AdamW.  Differences from torch.optim.AdamW (documented): bias correction uses one
+        global step count (torch keeps one per tensor: identical unless a tensor first receives a gradient late), and under data
+        parallelism a tensor counts as "without gradient" only when it has none on every rank.  Per-rank mean losses are averaged
+        with weight 1/world: shard batches so that every rank holds the same number of strong / weak / unlabelled clips
+        (`shard_for_rank` on each subset) if the reference's global-batch means are to be reproduced exactly."""
         # torch.optim.AdamW leaves a parameter whose grad is None completely untouched (no decay, no moment update); the fused
         # kernel runs over whole flat ranges, so such (rare, e.g. the mask token under the upstream no-op masking) tensors are
         # put back after the update
-        skipped = [(off, p.numel()) for p, off in self.layout if p.grad is None]
+        has_grad = [p.grad is not None for p, _ in self.layout]
+        if _world_size() > 1:
+            # every rank must skip the same tensors or the replicas drift apart: a tensor is skipped only if NO rank has a gradient.
+            # The set is agreed on the first step and re-checked every 100 steps (the agreement needs a device -> host read, which
+            # would otherwise stall the launch queue every step); in between a rank whose own set changed fails loudly.
+            import torch.distributed as dist
+            if self._agreed is None or self.step_count % 100 == 0:
+                flags = torch.tensor(has_grad, dtype=torch.int32, device=self.device)
+                dist.all_reduce(flags, op=dist.ReduceOp.MAX)
+                self._agreed, self._agreed_local = flags.bool().tolist(), has_grad
+            elif has_grad != self._agreed_local:
+                raise _lib.T4sError("the set of parameters without a gradient changed on this rank between two agreement points; "
+                                    "under data parallelism every rank must run the same graph (ParamArena.step)")
+            has_grad = self._agreed
+        skipped = [(off, p.numel()) for (p, off), h in zip(self.layout, has_grad) if not h]
         keep = [(off, n, self.flat[off:off + n].clone(), self.exp_avg[off:off + n].clone(), self.exp_avg_sq[off:off + n].clone())
                 for off, n in skipped]
         self.pack_grads()
@@ -252,19 +287,69 @@ def passt_param_groups(net, lr_dict):
     return groups
 
 
-def mat_sed_param_groups(net, lr_encoder=5e-6, lr_decoder=1e-4, lr_head=1e-4, weight_decay=1e-4):
-    """The three LR groups of config/mat-sed/base/finetune2.yaml:88-101 (encoder / decoder / head), by parameter-name prefix
-    as reference recipes/desed/finetune/passt/setting.py:28-103 assigns them."""
-    enc, dec, head = [], [], []
-    for name, p in net.named_parameters():
-        if name.startswith("backbone.head"):
-            continue  # PaSST classification heads are not on the SED path (no gradient): keep them out of the arena
-        if name.startswith("backbone.") or name.startswith("out_norm."):
-            enc.append(p)
-        elif name.startswith("decoder.") or name.startswith("mask_token") or name.startswith("f_pool_module."):
-            dec.append(p)
-        else:
-            head.append(p)
-    return [dict(name="encoder", params=enc, lr=lr_encoder, weight_decay=weight_decay),
-            dict(name="decoder", params=dec, lr=lr_decoder, weight_decay=weight_decay),
-            dict(name="head", params=head, lr=lr_head, weight_decay=weight_decay)]
+class _SedLosses(torch.autograd.Function):
+    """The six losses of the mean-teacher step and their weighted total in one pass (csrc/post.cu `t4s_sed_losses_*`)."""
+
+    @staticmethod
+    def forward(ctx, strong, weak, at, t_strong, t_at, y, yw, rows, weights):
+        _lib.ensure_device(strong)
+        dev = strong.device
+        f = lambda t: t.detach().contiguous().float()  # noqa: E731
+        strong_c, weak_c, at_c, ts_c, ta_c, y_c, yw_c = map(f, (strong, weak, at, t_strong, t_at, y, yw))
+        d = _lib.SedLosses()
+        d.strong, d.weak, d.at, d.t_strong, d.t_at, d.y, d.yw = (t.data_ptr() for t in (strong_c, weak_c, at_c, ts_c, ta_c, y_c, yw_c))
+        d.batch, d.classes = weak_c.shape[0], weak_c.shape[1]
+        d.strong_inner = strong_c[0].numel()
+        d.s0, d.s1, d.w0, d.w1 = rows
+        d.w_weak, d.w_at, d.w_cons, d.w_weak_cons = weights
+        with torch.cuda.device(dev):
+            ws = torch.empty(768, dtype=torch.float32, device=dev)
+            out = torch.empty(7, dtype=torch.float32, device=dev)
+            _lib.check(_lib.load().t4s_sed_losses_fwd(ctypes.byref(d), _lib.ptr(ws), _lib.ptr(out), _lib.stream_ptr()), "t4s_sed_losses_fwd")
+        ctx.desc, ctx.keep = d, (strong_c, weak_c, at_c, ts_c, ta_c, y_c, yw_c)
+        ctx.shapes = (strong.shape, weak.shape, at.shape)
+        parts = out[:6].clone()
+        ctx.mark_non_differentiable(parts)
+        return out[6], parts
+
+    @staticmethod
+    def backward(ctx, g_total, _g_parts):
+        strong_c, weak_c, at_c = ctx.keep[:3]
+        dev = strong_c.device
+        with torch.cuda.device(dev):
+            g = g_total.detach().reshape(1).float().contiguous()
+            ds, dw, da = torch.empty_like(strong_c), torch.empty_like(weak_c), torch.empty_like(at_c)
+            _lib.check(_lib.load().t4s_sed_losses_bwd(ctypes.byref(ctx.desc), _lib.ptr(g), _lib.ptr(ds), _lib.ptr(dw), _lib.ptr(da), _lib.stream_ptr()),
+                       "t4s_sed_losses_bwd")
+        return ds.view(ctx.shapes[0]), dw.view(ctx.shapes[1]), da.view(ctx.shapes[2]), None, None, None, None, None, None
+
+
+def sed_losses(stu_strong, stu_weak, stu_at, tch_strong, tch_at, labels, labels_weak, strong_rows, weak_rows, w_weak=1.0, w_at=1.0, w_cons=1.0,
+               w_weak_cons=1.0):
+    """Reference recipes/desed/finetune/train.py:166-188 as ONE forward and ONE backward kernel pair:
+
+        total = BCE(strong[S], y[S]) + w_weak BCE(weak[W], yw[W]) + w_at BCE(at[W], yw[W])
+                + w_cons (MSE(strong, tch_strong) + w_weak_cons MSE(weak, tch_at) + w_at MSE(at, tch_at))
+
+    S = rows [strong_rows[0], strong_rows[1]), W = rows [weak_rows[0], weak_rows[1]) (the contiguous masks of `get_mask`).  Returns
+    (total, parts) with parts = the six un-weighted losses in the order (class_strong, class_weak, class_at, cons_strong, cons_weak,
+    cons_at).  Gradients flow to the three student tensors only (the teacher side is detached upstream)."""
+    return _SedLosses.apply(stu_strong, stu_weak, stu_at, tch_strong, tch_at, labels, labels_weak, (*strong_rows, *weak_rows),
+                            (float(w_weak), float(w_at), float(w_cons), float(w_weak_cons)))
+
+
+def mean_teacher_step(student, teacher: MeanTeacher, arena: ParamArena, stu_feat, tch_feat, labels, labels_weak, strong_rows, weak_rows,
+                      stu_kwargs=None, tch_kwargs=None, loss_weights=None, step_num=2, ema_factor=0.999, lr_scale=1.0):
+    """One mean-teacher fine-tuning step (reference recipes/desed/finetune/train.py:129-199): student forward, teacher forward without
+    gradient (its `train_tch_kwargs`, e.g. the sliding-window fusion of finetune2.yaml:72-78), the fused six-loss kernel, backward,
+    packed all-reduce + fused AdamW, and the one-kernel EMA update.  `step_num` is the reference's `scheduler.step_num` AFTER
+    `scheduler.step()` (2 on the first update).  Returns (total, parts)."""
+    stu = student(stu_feat, **(stu_kwargs or {}))
+    with torch.no_grad():
+        tch = teacher.teacher(tch_feat, **(tch_kwargs or {}))
+    total, parts = sed_losses(stu[0], stu[1], stu[2]["at_out"], tch[0], tch[2]["at_out"], labels, labels_weak, strong_rows, weak_rows,
+                              **(loss_weights or {}))
+    total.backward()
+    arena.step(lr_scale)
+    teacher.update(step_num, ema_factor)
+    return total.detach(), parts
