@@ -119,6 +119,9 @@ typedef struct {
   const float* bias;  /* optional [N] fp32 */
   float alpha;
   int act;
+  float* colsum;      /* optional [N] fp32 (zeroed by the caller): colsum[n] += sum_m C[m, n], the un-rounded epilogue values added with
+                         atomics by the epilogue warps -- the bias gradient of the layer whose output gradient this GEMM produces
+                         (fc1: the fc2-dgrad GEMM with T4S_ACT_GELU_GRAD) without re-reading C.  bf16 un-split outputs only. */
 } T4sGemm;
 
 int t4s_gemm(const T4sGemm* g, void* stream);
@@ -141,9 +144,11 @@ int t4s_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
                       int cols, float eps, float in_scale, int dtype, int64_t n_inner, int64_t x_bstride, void* stream);
 size_t t4s_layernorm_bwd_workspace(int64_t rows, int cols);
 /* dx (same addressing as x) = dLN/dx (+ dx_add, same addressing); dgamma/dbeta may be NULL (frozen). */
+/* dx_colsum (optional [cols] fp32, bf16 fast path only): column sums of the OUTPUT dx (after dx_add).  dx is the gradient of the residual
+ * stream, i.e. the output gradient of the linear layer that wrote it (proj / fc2), so this is that layer's bias gradient for free. */
 int t4s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dx_add,
-                      void* dx, float* dgamma, float* dbeta, float* ws, size_t ws_bytes, int64_t rows, int cols, float in_scale,
-                      int dtype, int64_t n_inner, int64_t x_bstride, void* stream);
+                      void* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws, size_t ws_bytes, int64_t rows, int cols,
+                      float in_scale, int dtype, int64_t n_inner, int64_t x_bstride, void* stream);
 size_t t4s_colsum_workspace(int64_t rows, int cols);
 /* out[c] (+)= sum_r x[r*ld + c] */
 int t4s_colsum(const void* x, int dtype, int64_t rows, int cols, int64_t ld, float* ws, size_t ws_bytes, float* out, int accumulate,
@@ -189,6 +194,9 @@ typedef struct {
   float* dq32;          /* optional workspace [B, N, heads*64] fp32.  When given, ONE fused kernel computes dK / dV and adds the dQ tiles
                            into dq32 with TMA reduce-add (S, P, dS are formed once instead of twice), then dq = scale * dq32 is written;
                            the fp32 summation order over key tiles is not fixed.  NULL: the deterministic two-kernel backward. */
+  float* dqkv_colsum;   /* optional [3 * heads * 64] fp32, zeroed by the caller (one-kernel backward only): column sums of dq | dk | dv as
+                           written, i.e. the bias gradient of the qkv projection (passt.py:330-334), accumulated with atomics by the
+                           kernels that produce dq / dk / dv instead of a separate pass over dqkv */
 } T4sAttnBwd;
 int64_t t4s_attn_padded_len(int tokens);
 int t4s_attn_fwd(const T4sAttn* a, void* stream);

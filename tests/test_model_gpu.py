@@ -153,6 +153,35 @@ def test_batch_invariance_at_bench_shape():
     assert worst < 3e-2, worst
 
 
+def test_fused_bias_gradients_match_column_sum_pass():
+    """Bias gradients accumulated by the producers of the output gradients (LayerNorm backward -> proj / fc2, fused attention backward ->
+    qkv, the fc2-dgrad GEMM epilogue -> fc1) against the separate column-sum pass they replace (bf16 mode, base width)."""
+    from transformer4sed_b200 import functional as F
+    F.set_precision("bf16")
+    net, _ = build(BASE, 4)
+    net.train()
+    ext = net.get_feature_extractor().eval()
+    mel = ext.logmel(synth.synth_wav(2, 320000, seed=31).cuda())
+    y = synth.synth_strong_labels(2, 10, 1000, 32).cuda()
+
+    def grads(fused):
+        F.set_fused_bias_grad(fused)
+        try:
+            for p in net.parameters():
+                p.grad = None
+            strong, weak, other = net(mel)
+            (F.bce_loss(strong, y) + F.bce_loss(weak, (y.sum(-1) > 0).float())).backward()
+            return {n: p.grad.double().clone() for n, p in net.named_parameters() if p.grad is not None and n.endswith("bias")}
+        finally:
+            F.set_fused_bias_grad(True)
+
+    a, b = grads(True), grads(False)
+    assert set(a) == set(b) and len(a) > 60
+    for n in a:
+        scale = b[n].abs().max().clamp_min(1e-12)
+        assert ((a[n] - b[n]).abs().max() / scale).item() < 2e-3, n      # same bf16 values summed in fp32, different order only
+
+
 def test_mlm_pretrain_forward_matches_reference(golden):
     """MAT-SED pre-training (mlm=True): same mask as the reference for the same torch seed; B>1 keeps the upstream no-op."""
     from transformer4sed_b200 import functional as F

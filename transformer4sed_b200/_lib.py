@@ -39,7 +39,7 @@ class Matrix(ctypes.Structure):
 class Gemm(ctypes.Structure):
     _fields_ = [("M", c_int), ("N", c_int), ("K", c_int), ("in_dtype", c_int), ("nb1", c_int), ("nb2", c_int),
                 ("split_k", c_int), ("c_split_stride", ctypes.c_int64), ("A", Operand), ("B", Operand), ("C", Matrix),
-                ("aux", Matrix), ("residual", Matrix), ("bias", c_void_p), ("alpha", c_float), ("act", c_int)]
+                ("aux", Matrix), ("residual", Matrix), ("bias", c_void_p), ("alpha", c_float), ("act", c_int), ("colsum", c_void_p)]
 
 
 class Attn(ctypes.Structure):
@@ -55,7 +55,7 @@ class AttnBwd(ctypes.Structure):
     _fields_ = [("fwd", Attn), ("d_o", c_void_p), ("do_ld", ctypes.c_int64), ("do_bs", ctypes.c_int64), ("delta", c_void_p),
                 ("dq", c_void_p), ("dq_ld", ctypes.c_int64), ("dq_bs", ctypes.c_int64),
                 ("dk", c_void_p), ("dk_ld", ctypes.c_int64), ("dk_bs", ctypes.c_int64),
-                ("dv", c_void_p), ("dv_ld", ctypes.c_int64), ("dv_bs", ctypes.c_int64), ("dq32", c_void_p)]
+                ("dv", c_void_p), ("dv_ld", ctypes.c_int64), ("dv_bs", ctypes.c_int64), ("dq32", c_void_p), ("dqkv_colsum", c_void_p)]
 
 
 class RelAttn(ctypes.Structure):
@@ -114,7 +114,7 @@ def _declare(lib):
         "t4s_split_tf32": (I, [ctypes.POINTER(Operand), I, P, L, I, P]),
         "t4s_layernorm_fwd": (I, [P, P, P, P, P, P, L, I, F, F, I, L, L, P]),
         "t4s_layernorm_bwd_workspace": (Z, [L, I]),
-        "t4s_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, P, Z, L, I, F, I, L, L, P]),
+        "t4s_layernorm_bwd": (I, [P, P, P, P, P, P, P, P, P, P, P, Z, L, I, F, I, L, L, P]),
         "t4s_colsum_workspace": (Z, [L, I]),
         "t4s_colsum": (I, [P, I, L, I, L, P, Z, P, I, P]),
         "t4s_gelu_bwd": (I, [P, P, P, Z, I, P]),

@@ -666,6 +666,12 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         store_row32(a.dv + (long long)b * a.dv_bs + (long long)row * a.dv_ld + h * kHd + 32 * g, v, 1.f);
         store_row32(a.dk + (long long)b * a.dk_bs + (long long)row * a.dk_ld + h * kHd + 32 * g, w, a.scale);
       }
+      if (a.colsum) {   // qkv bias gradient: column sums of this warp's 32 key rows
+        const int D = a.H * kHd;
+        const float sv = warp_colsum32(v, row < a.N, lane), sk = warp_colsum32(w, row < a.N, lane);
+        atomicAdd(a.colsum + 2 * D + h * kHd + 32 * g + lane, sv);
+        atomicAdd(a.colsum + D + h * kHd + 32 * g + lane, sk * a.scale);
+      }
     }
     if (ptx::elect_one()) ptx::bulk_wait_all();   // the staging boxes must outlive the last reduce
   }
@@ -695,6 +701,35 @@ __global__ void dq_finish_kernel(const float* __restrict__ dq32, __nv_bfloat16* 
     u.w = pack_bf16(y.z * scale, y.w * scale);
     *reinterpret_cast<uint4*>(dq + b * dq_bs + (long long)n * dq_ld + d) = u;
   }
+}
+
+// Same, plus the column sums of dq (the q third of the qkv bias gradient): a block walks a strip of token rows, thread = one 8-column
+// chunk of one of the `rpp` rows of a pass, per-thread partial sums, 8 atomics per thread at the end.
+__global__ void __launch_bounds__(256) dq_finish_colsum_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dq, long long dq_ld,
+                                                               long long dq_bs, int N, int D, float scale, long long rows, int rows_per_block,
+                                                               float* __restrict__ colsum) {
+  const int c8n = D >> 3, rpp = 256 / c8n;
+  if ((int)threadIdx.x >= rpp * c8n) return;
+  const int c = threadIdx.x % c8n, rr = threadIdx.x / c8n;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long row = r0 + rr; row < r1; row += rpp) {
+    const float* src = dq32 + row * D + 8 * c;
+    const float4 x = *reinterpret_cast<const float4*>(src), y = *reinterpret_cast<const float4*>(src + 4);
+    const float f[8] = {x.x * scale, x.y * scale, x.z * scale, x.w * scale, y.x * scale, y.y * scale, y.z * scale, y.w * scale};
+    uint4 u;
+    u.x = pack_bf16(f[0], f[1]);
+    u.y = pack_bf16(f[2], f[3]);
+    u.z = pack_bf16(f[4], f[5]);
+    u.w = pack_bf16(f[6], f[7]);
+    const long long b = row / N;
+    const int n = (int)(row - b * N);
+    *reinterpret_cast<uint4*>(dq + b * dq_bs + (long long)n * dq_ld + 8 * c) = u;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) atomicAdd(colsum + 8 * c + e, acc[e]);
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -770,6 +805,7 @@ static void fill_args(Args& a, const T4sAttn* p) {
   a.delta = nullptr;
   a.dq = a.dk = a.dv = nullptr;
   a.dq_ld = a.dq_bs = a.dk_ld = a.dk_bs = a.dv_ld = a.dv_bs = 0;
+  a.colsum = nullptr;
 }
 
 }  // namespace attn
@@ -836,6 +872,8 @@ extern "C" int t4s_attn_bwd(const T4sAttnBwd* p, void* stream) {
     // one kernel: dK / dV as before, dQ tiles reduce-added (fp32, TMA) into dq32, then scaled and rounded into the dq slot
     const int D = f->heads * kHd;
     T4S_REQUIRE(!(reinterpret_cast<uintptr_t>(p->dq32) & 15), "t4s_attn_bwd: dq32 must be 16-byte aligned");
+    T4S_REQUIRE(!p->dqkv_colsum || f->heads * kHd / 8 <= 256, "t4s_attn_bwd: dqkv_colsum supports up to 32 heads");
+    a.colsum = p->dqkv_colsum;
     CUtensorMap tdq;
     {
       t4s::ensure_context();
@@ -854,12 +892,22 @@ extern "C" int t4s_attn_bwd(const T4sAttnBwd* p, void* stream) {
     const int pgrid = std::min(n_items, t4s::sm_count());
     attn_bwd_fused_kernel<<<pgrid, fbw::kThreads, fbw::kSmem, st>>>(tq, tk, tv, tdo, tdq, a, n_items);
     T4S_LAUNCH_CHECK();
+    if (p->dqkv_colsum) {
+      const long long rows = (long long)f->batch * f->tokens;
+      const int blocks = (int)std::min<long long>((rows + 31) / 32, (long long)t4s::sm_count() * 8);
+      const int rpb = (int)((rows + blocks - 1) / blocks);
+      dq_finish_colsum_kernel<<<(int)((rows + rpb - 1) / rpb), 256, 0, st>>>(p->dq32, a.dq, a.dq_ld, a.dq_bs, f->tokens, D, a.scale, rows, rpb,
+                                                                               p->dqkv_colsum);
+      T4S_LAUNCH_CHECK();
+      return T4S_OK;
+    }
     const long long total8 = (long long)f->batch * f->tokens * D / 8;
     const int fgrid = (int)std::min<long long>((total8 + 255) / 256, (long long)t4s::sm_count() * 16);
     dq_finish_kernel<<<fgrid, 256, 0, st>>>(p->dq32, a.dq, a.dq_ld, a.dq_bs, f->tokens, D, a.scale, total8);
     T4S_LAUNCH_CHECK();
     return T4S_OK;
   }
+  T4S_REQUIRE(!p->dqkv_colsum, "t4s_attn_bwd: dqkv_colsum needs the one-kernel backward (dq32 workspace)");
   T4S_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
   attn_bwd_kernel<0><<<grid, bwd::kThreads, bwd::kSmem, st>>>(tq, tk, tv, tdo, tq, a);
   T4S_LAUNCH_CHECK();

@@ -78,7 +78,26 @@ struct Args {
   __nv_bfloat16* dq; long long dq_ld, dq_bs;
   __nv_bfloat16* dk; long long dk_ld, dk_bs;
   __nv_bfloat16* dv; long long dv_ld, dv_bs;
+  float* colsum;     // optional [3 * H * 64]: column sums of dq | dk | dv (qkv bias gradient)
 };
+
+// Column sums of a warp's 32 x 32 fp32 chunk (thread = row, v = its 32 columns) by a butterfly reduce-scatter over the lanes
+// (31 shuffles); lane c returns the sum of column c.  `ok` = this lane's row exists.
+__device__ __forceinline__ float warp_colsum32(const uint32_t (&v)[32], bool ok, int lane) {
+  float y[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) y[i] = ok ? __uint_as_float(v[i]) : 0.f;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? y[i] : y[i + o], keep = up ? y[i + o] : y[i];
+      y[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return y[0];
+}
 
 __device__ __forceinline__ void store_row64(__nv_bfloat16* dst, const float (&v)[64], float mul) {
 #pragma unroll

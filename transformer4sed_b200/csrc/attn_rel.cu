@@ -67,16 +67,23 @@ __device__ __forceinline__ void mma_k128_amn(uint32_t d_tmem, uint32_t a_addr, u
 // backward
 // ======================================================================================================
 namespace bwd {
+// 10 warps: 0-7 softmax (thread = query row 32 (w & 3) + lane, column half g = w >> 2 of the 128-key tile), 8 TMA producer, 9 MMA issuer.
 // operand region (112 KB): dQ  kernel: resident [QU][QV][dO], streamed [K][V][Pw]
 //                          dKV kernel: resident [K][V],       streamed [QU][QV][dO][Pw]
-constexpr int oOps = 0, oP = oOps + 7 * kTileBytes, oDs = oP + kPBytes, oScr = oDs + kPBytes, oBar = oScr + 4 * kWarpScratch;
+// Skew scratch: every thread parks a 48-column BD window of its row (pitch 50 floats: 8-byte stores and 4-byte skewed reads are bank
+// conflict free) and reads 16 shifted values back, four times per tile.  dQ kernel: the P tile's place holds the dBD staging rows.
+constexpr int kBThreads = 320;
+constexpr int kPitch = 50;
+constexpr int kScr = 32 * kPitch * 4;   // 6400 B per warp
+constexpr int oOps = 0, oP = oOps + 7 * kTileBytes, oDs = oP + kPBytes, oScr = oDs + kPBytes, oBar = oScr + 8 * kScr;
 constexpr int kSmem = oBar + 128;
+static_assert(kSmem <= 232448, "rel-pos attention backward: shared memory");
 constexpr int kTmemCols = 512;  // S / dP: [0,128)  BD: [128,384)  acc0: [384,448)  acc1: [448,512)
 enum { bResFull = 0, bStrFull = 1, bStrEmpty = 2, bSFull = 3, bPReady = 4, bDpFull = 5, bDsFull = 6, bFin = 7, bAccFull = 8, bCount = 9 };
 }  // namespace bwd
 
 template <bool kDq>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(bwd::kBThreads, 1)
 relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_constant__ CUtensorMap tmQV,
                    const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                    const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmPos, const RelArgs ra) {
@@ -106,14 +113,14 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
     ptx::mbar_init(&bars[bStrFull], 1);
     ptx::mbar_init(&bars[bStrEmpty], 1);
     ptx::mbar_init(&bars[bSFull], 1);
-    ptx::mbar_init(&bars[bPReady], 4);
+    ptx::mbar_init(&bars[bPReady], 8);
     ptx::mbar_init(&bars[bDpFull], 1);
-    ptx::mbar_init(&bars[bDsFull], 4);
+    ptx::mbar_init(&bars[bDsFull], 8);
     ptx::mbar_init(&bars[bFin], 1);
     ptx::mbar_init(&bars[bAccFull], 1);
     ptx::fence_barrier_init();
   }
-  if (warp == 4 && ptx::elect_one()) {
+  if (warp == 8 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmQU);
     ptx::prefetch_tmap(&tmQV);
     ptx::prefetch_tmap(&tmK);
@@ -121,7 +128,7 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
     ptx::prefetch_tmap(&tmDO);
     ptx::prefetch_tmap(&tmPos);
   }
-  if (warp == 5) {
+  if (warp == 9) {
     ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
   }
@@ -130,7 +137,7 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ---------------- TMA producer ----------------
     if (ptx::elect_one()) {
       if (kDq) {
@@ -159,7 +166,7 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
         ptx::tma_load_4d(sPw, &tmPos, &bars[bStrFull], 0, a.N - kTile - i0 + j0, h, 0);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ---------------- MMA issuer ----------------
     const uint32_t uQU = ptx::smem_u32(sQU), uQV = ptx::smem_u32(sQV), uDO = ptx::smem_u32(sDO), uK = ptx::smem_u32(sK),
                    uV = ptx::smem_u32(sV), uPw = ptx::smem_u32(sPw), uP = ptx::smem_u32(smem + oP), uDs = ptx::smem_u32(smem + oDs);
@@ -196,13 +203,14 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
       __syncwarp();
     }
   } else {
-    // ---------------- softmax warps: thread = query row ----------------
-    const int r = warp * 32 + lane;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    unsigned char* wscr = smem + oScr + warp * kWarpScratch;
-    float* scr = reinterpret_cast<float*>(wscr) + lane * kScrRow;
-    unsigned char* stage_row = wscr + lane * kStageRow;
+    // ---------------- softmax warps: thread = (query row, column half) ----------------
+    const int wq = warp & 3, g = warp >> 2;
+    const int r = wq * 32 + lane;
+    const uint32_t t_lane = tmem + ((uint32_t)(wq * 32) << 16);
+    float* scr = reinterpret_cast<float*>(smem + oScr + warp * kScr) + lane * kPitch;
+    unsigned char* stage = smem + oP + warp * 4096;          // dQ kernel: 32 staged dS rows x 128 B (this warp's 64 columns)
     const float sl2 = a.sl2;
+    const uint64_t sl2_2 = ptx::pack2(sl2, sl2);
     float my_lse = 0.f, my_delta = 0.f;
     if (kDq) {
       my_lse = a.lse[stat_base + t0 + r];
@@ -214,118 +222,139 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
         my_lse = a.lse[stat_base + i0 + r];
         my_delta = a.delta[stat_base + i0 + r];
       }
-      const int nvalid = a.N - j0;  // key columns that exist
-      const bool full = nvalid >= kTile;
+      const int nvalid = a.N - j0 - 64 * g;  // key columns of this half that exist (may be <= 0 or >= 64)
       ptx::mbar_wait(&bars[bSFull], t & 1);
       ptx::tc_fence_after();
-      ptx::mbar_wait(&bars[bFin], (t & 1) ^ 1);  // previous step's MMAs have finished with the P / dS tiles
-      // phase A: P = exp2((AC + shift(BD)) * c - lse), kept packed in registers (and in shared memory for P^T dO)
-      uint32_t pk[4][16];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        float bd[32];
-        skew_chunk(t_lane + 128, scr, warp, lane, 32 * c, bd);
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
+      // phase A: P = exp2((AC + shift(BD)) * c - lse), kept packed in registers
+      float s[64];
+      {
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32(t_lane + 64 * g, v0);
+        ptx::tmem_ld_32x32(t_lane + 64 * g + 32, v1);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float p0 = ex2(fmaf(__uint_as_float(v[2 * i]) + bd[2 * i], sl2, -my_lse));
-          float p1 = ex2(fmaf(__uint_as_float(v[2 * i + 1]) + bd[2 * i + 1], sl2, -my_lse));
-          if (!full) {
-            if (32 * c + 2 * i >= nvalid) p0 = 0.f;
-            if (32 * c + 2 * i + 1 >= nvalid) p1 = 0.f;
-          }
-          pk[c][i] = pack_bf16(p0, p1);
+        for (int i = 0; i < 32; ++i) {
+          s[i] = __uint_as_float(v0[i]);
+          s[32 + i] = __uint_as_float(v1[i]);
         }
-        if (!kDq) store_row_chunk(smem + oP, r, 32 * c, pk[c]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        // s[16 q + cc] += BD[r][127 - r + 64 g + 16 q + cc]: a 48-column window of this warp's rows, read back at the lane's offset
+        const int wb = 96 - 32 * wq + 64 * g + 16 * q;
+        uint32_t x0[32], x1[16];
+        ptx::tmem_ld_32x32(t_lane + 128 + wb, x0);
+        ptx::tmem_ld_32x16(t_lane + 128 + wb + 32, x1);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) *reinterpret_cast<uint2*>(scr + 2 * k) = make_uint2(x0[2 * k], x0[2 * k + 1]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) *reinterpret_cast<uint2*>(scr + 32 + 2 * k) = make_uint2(x1[2 * k], x1[2 * k + 1]);
+        const volatile float* rd = scr + (31 - lane);
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) s[16 * q + cc] += rd[cc];
+      }
+      const uint64_t nlse2 = ptx::pack2(-my_lse, -my_lse);
+      uint32_t pk[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float t0_, t1_;
+        ptx::unpack2(ptx::fma2(ptx::pack2(s[2 * i], s[2 * i + 1]), sl2_2, nlse2), t0_, t1_);
+        float p0 = ex2(t0_), p1 = ex2(t1_);
+        if (nvalid < 64) {
+          if (2 * i >= nvalid) p0 = 0.f;
+          if (2 * i + 1 >= nvalid) p1 = 0.f;
+        }
+        pk[i] = pack_bf16(p0, p1);
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars[bPReady]);
+      // the previous step's MMAs have finished with the P / dS tiles
+      ptx::mbar_wait(&bars[bFin], (t & 1) ^ 1);
+      if (!kDq) {
+        uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[0]);
+        uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[16]);
+        store_row_chunk(smem + oP, r, 64 * g, lo);
+        store_row_chunk(smem + oP, r, 64 * g + 32, hi);
+      }
       // phase B: dS = P (dP - delta)
       ptx::mbar_wait(&bars[bDpFull], t & 1);
       ptx::tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32(t_lane + 32 * c, v);
+      uint32_t pd[32];
+      {
+        uint32_t v0[32], v1[32];
+        ptx::tmem_ld_32x32(t_lane + 64 * g, v0);
+        ptx::tmem_ld_32x32(t_lane + 64 * g + 32, v1);
         ptx::tmem_ld_wait();
-        uint32_t pd[16];
+        const uint64_t nd2 = ptx::pack2(-my_delta, -my_delta);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[c][i]));
-          pd[i] = pack_bf16(p.x * (__uint_as_float(v[2 * i]) - my_delta), p.y * (__uint_as_float(v[2 * i + 1]) - my_delta));
+        for (int i = 0; i < 32; ++i) {
+          const uint32_t (&v)[32] = (i < 16) ? v0 : v1;
+          const int k = (i & 15) * 2;
+          const float2 p = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&pk[i]));
+          float d0, d1;
+          ptx::unpack2(ptx::mul2(ptx::pack2(p.x, p.y), ptx::add2(ptx::pack2(__uint_as_float(v[k]), __uint_as_float(v[k + 1])), nd2)), d0, d1);
+          pd[i] = pack_bf16(d0, d1);
         }
-        store_row_chunk(smem + oDs, r, 32 * c, pd);
-        if (kDq) {
+      }
+      {
+        uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pd[0]);
+        uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pd[16]);
+        store_row_chunk(smem + oDs, r, 64 * g, lo);
+        store_row_chunk(smem + oDs, r, 64 * g + 32, hi);
+      }
+      if (kDq) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<uint4*>(stage_row + c * 64 + q * 16) = make_uint4(pd[4 * q], pd[4 * q + 1], pd[4 * q + 2], pd[4 * q + 3]);
-        }
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(stage + lane * 128 + q * 16) = make_uint4(pd[4 * q], pd[4 * q + 1], pd[4 * q + 2], pd[4 * q + 3]);
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars[bDsFull]);
       if (kDq) {
-        // dBD[b, h, i, T-1-i+j0 + e] <- dS[i, j0 + e]: this warp's 32 staged rows, 64 destination words per row
-        const uint32_t* st32 = reinterpret_cast<const uint32_t*>(wscr);
+        // dBD[b, h, i, T-1-i+j0 + 64 g + e] <- dS[i, j0 + 64 g + e]: this warp's 32 staged rows, 32 destination words per row
+        const uint32_t* st32 = reinterpret_cast<const uint32_t*>(stage);
+        const int nv = min(nvalid, 64);
 #pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
-          const int i = i0 + warp * 32 + rr;
+          const int i = i0 + wq * 32 + rr;
           if (i >= a.N) break;
-          const int x0 = a.N - 1 - i + j0;
+          const int x0 = a.N - 1 - i + j0 + 64 * g;
           __nv_bfloat16* drow = ra.dbd + (((long long)b * a.H + h) * a.N + i) * ra.dbd_ld + x0;
           const int par = x0 & 1;  // rows start 16-byte aligned, so the word alignment of the destination is the parity of x0
-          const uint32_t* srow = st32 + rr * (kStageRow / 4);
-#pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            const int w = lane + 32 * hh;
-            const int e = par + 2 * w;  // first source element of destination word w
-            const uint32_t val = __funnelshift_r(srow[w], srow[w + 1], 16 * par);
-            if (e + 1 < nvalid) *reinterpret_cast<uint32_t*>(drow + e) = val;
-            else if (e < nvalid) *reinterpret_cast<unsigned short*>(drow + e) = (unsigned short)(val & 0xffffu);
-          }
-          if (par && lane == 0) *reinterpret_cast<unsigned short*>(drow) = (unsigned short)(srow[0] & 0xffffu);
+          const uint32_t* srow = st32 + rr * 32;
+          const int e = par + 2 * lane;  // first source element of destination word `lane`
+          const uint32_t nxt = (lane < 31) ? srow[lane + 1] : 0u;
+          const uint32_t val = __funnelshift_r(srow[lane], nxt, 16 * par);
+          if (e + 1 < nv) *reinterpret_cast<uint32_t*>(drow + e) = val;
+          else if (e < nv) *reinterpret_cast<unsigned short*>(drow + e) = (unsigned short)(val & 0xffffu);
+          if (par && lane == 0 && nv > 0) *reinterpret_cast<unsigned short*>(drow) = (unsigned short)(srow[0] & 0xffffu);
         }
         __syncwarp();
       }
     }
-    // ---- accumulators ----
+    // ---- accumulators: each column half writes 32 of the 64 head-dim columns ----
     ptx::mbar_wait(&bars[bAccFull], 0);
     ptx::tc_fence_after();
     const int row = t0 + r;
-    uint32_t v0[32], v1[32];
-    ptx::tmem_ld_32x32(t_lane + 384, v0);
-    ptx::tmem_ld_32x32(t_lane + 416, v1);
+    uint32_t v0[32];
+    ptx::tmem_ld_32x32(t_lane + 384 + 32 * g, v0);
     ptx::tmem_ld_wait();
     if (kDq) {
-      if (row < a.N) {
-        __nv_bfloat16* dst = ra.dqu + (long long)b * ra.dqu_bs + (long long)row * ra.dqu_ld + h * kHd;
-        store_row32(dst, v0, a.scale);
-        store_row32(dst + 32, v1, a.scale);
-      }
+      if (row < a.N) store_row32(ra.dqu + (long long)b * ra.dqu_bs + (long long)row * ra.dqu_ld + h * kHd + 32 * g, v0, a.scale);
     } else {
-      if (row < a.N) {
-        __nv_bfloat16* dst = a.dv + (long long)b * a.dv_bs + (long long)row * a.dv_ld + h * kHd;
-        store_row32(dst, v0, 1.f);
-        store_row32(dst + 32, v1, 1.f);
-      }
-      ptx::tmem_ld_32x32(t_lane + 448, v0);
-      ptx::tmem_ld_32x32(t_lane + 480, v1);
+      if (row < a.N) store_row32(a.dv + (long long)b * a.dv_bs + (long long)row * a.dv_ld + h * kHd + 32 * g, v0, 1.f);
+      ptx::tmem_ld_32x32(t_lane + 448 + 32 * g, v0);
       ptx::tmem_ld_wait();
-      if (row < a.N) {
-        __nv_bfloat16* dst = a.dk + (long long)b * a.dk_bs + (long long)row * a.dk_ld + h * kHd;
-        store_row32(dst, v0, a.scale);
-        store_row32(dst + 32, v1, a.scale);
-      }
+      if (row < a.N) store_row32(a.dk + (long long)b * a.dk_bs + (long long)row * a.dk_ld + h * kHd + 32 * g, v0, a.scale);
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem, kTmemCols);
   }
@@ -417,10 +446,10 @@ extern "C" int t4s_relattn_bwd(const T4sRelAttnBwd* p, void* stream) {
   if (rc) return rc;
   dim3 grid(ra.a.n_tiles, H, B);
   T4S_CUDA(cudaFuncSetAttribute(relattn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
-  relattn_bwd_kernel<true><<<grid, kThreads, bwd::kSmem, st>>>(tqu, tqv, tk, tv, tdo, tpos, ra);
+  relattn_bwd_kernel<true><<<grid, bwd::kBThreads, bwd::kSmem, st>>>(tqu, tqv, tk, tv, tdo, tpos, ra);
   T4S_LAUNCH_CHECK();
   T4S_CUDA(cudaFuncSetAttribute(relattn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd::kSmem));
-  relattn_bwd_kernel<false><<<grid, kThreads, bwd::kSmem, st>>>(tqu, tqv, tk, tv, tdo, tpos, ra);
+  relattn_bwd_kernel<false><<<grid, bwd::kBThreads, bwd::kSmem, st>>>(tqu, tqv, tk, tv, tdo, tpos, ra);
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }

@@ -51,6 +51,7 @@ struct Args {
   float alpha;
   int act;
   int res_tma;   // staged epilogue: the residual / pre-activation tile arrives by TMA (tensor map tmR) instead of per-row loads
+  float* colsum; // staged epilogue: column sums of the output, accumulated with atomics
 };
 
 template <int BN>
@@ -382,6 +383,22 @@ __device__ __forceinline__ void epilogue_chunk_staged(const Args& a, const CUten
     } else if (row_ok) {
       add32(a.res, r_row + gcol, nvalid, x);
     }
+  }
+  if (a.colsum) {
+    // column sums of this warp's 32 x 32 chunk: butterfly reduce-scatter over the lanes (31 shuffles), lane c ends with column c
+    float y[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) y[i] = row_ok ? x[i] : 0.f;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const bool up = (lane & o) != 0;
+#pragma unroll
+      for (int i = 0; i < o; ++i) {
+        const float send = up ? y[i] : y[i + o], keep = up ? y[i + o] : y[i];
+        y[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+    if (lane < nvalid) atomicAdd(a.colsum + gcol + lane, y[0]);
   }
   stage_store(mapC, boxes, seq, lane, x, gcol, row0, z1, z2, a.res_tma != 0);
 }
@@ -850,6 +867,7 @@ extern "C" int t4s_gemm(const T4sGemm* g, void* stream) {
                   (!a.b_b2 || g->B.nb2 == g->nb2), "t4s_gemm: operand batch extents must be 1 or match nb1/nb2");
   a.C = mat_arg(g->C); a.aux = mat_arg(g->aux); a.res = mat_arg(g->residual);
   a.bias = g->bias; a.alpha = g->alpha; a.act = g->act;
+  a.colsum = g->colsum;
   a.bias_vec = g->bias && !(reinterpret_cast<uintptr_t>(g->bias) & 15);
   a.split_k = g->split_k > 1 ? g->split_k : 1;
   a.c_split = g->c_split_stride;
@@ -874,6 +892,7 @@ extern "C" int t4s_gemm(const T4sGemm* g, void* stream) {
       a.res_tma = 1;
     }
   }
+  T4S_REQUIRE(!g->colsum || (pC && g->nb1 * g->nb2 == 1), "t4s_gemm: colsum needs an un-batched, un-split bf16 output with a TMA-storable layout");
   const int variant = (tf32 ? 4 : 0) | (g->A.mn_major ? 2 : 0) | (g->B.mn_major ? 1 : 0);
 #define T4S_GEMM_CASE(V, TF, AM, BM_)                                                \
   case V:                                                                            \

@@ -195,22 +195,28 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
-template <int kC8>
+// kDxSum: additionally accumulates the column sums of the OUTPUT dx (third partial row): dx is the gradient of the residual stream,
+// i.e. the output gradient of the linear layer (proj / fc2) that wrote that stream, so this is that layer's bias gradient.
+template <int kC8, bool kDxSum>
 __global__ void __launch_bounds__(kThreads, 2)
 ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
                    const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dx_add,
                    __nv_bfloat16* __restrict__ dx, float* __restrict__ part /*[grid][2][cols]*/, long long rows, int cols,
                    float in_scale, long long n_inner, long long bstride) {
-  extern __shared__ float s_part[];  // [kWarpsPerBlock][2][cols]
+  extern __shared__ float s_part[];  // [kWarpsPerBlock][kRows][cols]
+  constexpr int kRows = kDxSum ? 3 : 2;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + warp;
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
   const int nc = cols >> 3;
-  float ag[kC8][8], ab[kC8][8];
+  float ag[kC8][8], ab[kC8][8], ad[kDxSum ? kC8 : 1][8];
 #pragma unroll
   for (int i = 0; i < kC8; ++i)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) ag[i][e] = ab[i][e] = 0.f;
+    for (int e = 0; e < 8; ++e) {
+      ag[i][e] = ab[i][e] = 0.f;
+      if (kDxSum) ad[i][e] = 0.f;
+    }
   const float inv_cols = 1.0f / (float)cols;
   for (long long r = warp_global; r < rows; r += nwarps) {
     const long long xoff = (r / n_inner) * bstride + (r % n_inner) * cols;
@@ -269,12 +275,16 @@ ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] += av[e];
         }
+        if (kDxSum) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) ad[i][e] += o[e];
+        }
         dxr[c] = pack8(o);
       }
     }
   }
   if (part) {
-    float* sp = s_part + warp * 2 * cols;
+    float* sp = s_part + warp * kRows * cols;
 #pragma unroll
     for (int i = 0; i < kC8; ++i) {
       const int c = lane + 32 * i;
@@ -283,15 +293,16 @@ ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
         for (int e = 0; e < 8; ++e) {
           sp[8 * c + e] = ag[i][e];
           sp[cols + 8 * c + e] = ab[i][e];
+          if (kDxSum) sp[2 * cols + 8 * c + e] = ad[i][e];
         }
       }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < 2 * cols; j += kThreads) {
+    for (int j = threadIdx.x; j < kRows * cols; j += kThreads) {
       float acc = 0.f;
 #pragma unroll
-      for (int w = 0; w < kWarpsPerBlock; ++w) acc += s_part[w * 2 * cols + j];
-      part[(size_t)blockIdx.x * 2 * cols + j] = acc;
+      for (int w = 0; w < kWarpsPerBlock; ++w) acc += s_part[w * kRows * cols + j];
+      part[(size_t)blockIdx.x * kRows * cols + j] = acc;
     }
   }
 }
@@ -698,19 +709,20 @@ int t4s_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
 
 size_t t4s_layernorm_bwd_workspace(int64_t rows, int cols) {
   const int grid = (int)std::min<long long>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock, 2L * t4s::sm_count());
-  return (size_t)std::max(grid, 1) * 2 * cols * sizeof(float);
+  return (size_t)std::max(grid, 1) * 3 * cols * sizeof(float);
 }
 
 int t4s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd, const void* dx_add,
-                      void* dx, float* dgamma, float* dbeta, float* ws, size_t ws_bytes, int64_t rows, int cols, float in_scale,
-                      int dtype, int64_t n_inner, int64_t x_bstride, void* stream) {
+                      void* dx, float* dgamma, float* dbeta, float* dx_colsum, float* ws, size_t ws_bytes, int64_t rows, int cols,
+                      float in_scale, int dtype, int64_t n_inner, int64_t x_bstride, void* stream) {
   T4S_REQUIRE(dy && x && gamma && mean && rstd && dx && rows > 0, "t4s_layernorm_bwd: bad arguments");
   T4S_REQUIRE(cols % 4 == 0 && cols > 0 && cols <= 128 * kLnMaxV, "t4s_layernorm_bwd: cols must be a multiple of 4 and <= %d", 128 * kLnMaxV);
   if (n_inner <= 0) { n_inner = rows; x_bstride = 0; }
-  const bool want_params = dgamma != nullptr || dbeta != nullptr;
+  const bool want_params = dgamma != nullptr || dbeta != nullptr || dx_colsum != nullptr;
+  const int prows = dx_colsum ? 3 : 2;
   int grid = (int)std::max<long long>(1, std::min<long long>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock, 2L * t4s::sm_count()));
-  if (want_params) T4S_REQUIRE(ws && ws_bytes >= (size_t)grid * 2 * cols * sizeof(float), "t4s_layernorm_bwd: workspace too small");
-  const size_t smem = want_params ? (size_t)kWarpsPerBlock * 2 * cols * sizeof(float) : 0;
+  if (want_params) T4S_REQUIRE(ws && ws_bytes >= (size_t)grid * prows * cols * sizeof(float), "t4s_layernorm_bwd: workspace too small");
+  const size_t smem = want_params ? (size_t)kWarpsPerBlock * prows * cols * sizeof(float) : 0;
   cudaStream_t st = t4s::as_stream(stream);
   const bool fast = dtype == T4S_BF16 && cols % 8 == 0 && cols <= 256 * kLnMaxC8 && x_bstride % 8 == 0 &&
                     !((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
@@ -725,12 +737,20 @@ int t4s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
       return T4S_OK;
     };
     int rc;
-    if (cols <= 256) rc = launch(ln_bwd_bf16_kernel<1>);
-    else if (cols <= 512) rc = launch(ln_bwd_bf16_kernel<2>);
-    else if (cols <= 768) rc = launch(ln_bwd_bf16_kernel<3>);
-    else rc = launch(ln_bwd_bf16_kernel<4>);
+    if (dx_colsum) {
+      if (cols <= 256) rc = launch(ln_bwd_bf16_kernel<1, true>);
+      else if (cols <= 512) rc = launch(ln_bwd_bf16_kernel<2, true>);
+      else if (cols <= 768) rc = launch(ln_bwd_bf16_kernel<3, true>);
+      else rc = launch(ln_bwd_bf16_kernel<4, true>);
+    } else {
+      if (cols <= 256) rc = launch(ln_bwd_bf16_kernel<1, false>);
+      else if (cols <= 512) rc = launch(ln_bwd_bf16_kernel<2, false>);
+      else if (cols <= 768) rc = launch(ln_bwd_bf16_kernel<3, false>);
+      else rc = launch(ln_bwd_bf16_kernel<4, false>);
+    }
     if (rc) return rc;
   } else {
+    T4S_REQUIRE(!dx_colsum, "t4s_layernorm_bwd: dx_colsum needs the bf16 fast path (16-byte aligned bf16 tensors, cols %% 8 == 0)");
     T4S_DISPATCH_DTYPE(dtype, {
       if (smem > 48 * 1024) T4S_CUDA(cudaFuncSetAttribute(ln_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       ln_bwd_kernel<T><<<grid, kThreads, smem, st>>>(static_cast<const T*>(dy), static_cast<const T*>(x), gamma, mean, rstd,
@@ -740,14 +760,19 @@ int t4s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   }
   T4S_LAUNCH_CHECK();
   if (want_params) {
+    const long long pstride = (long long)prows * cols;
     if (dgamma && dbeta) {
-      reduce_parts_kernel<<<(2 * cols + 31) / 32, 256, 0, st>>>(ws, grid, 2LL * cols, cols, cols, dgamma, dbeta, 0);
+      reduce_parts_kernel<<<(2 * cols + 31) / 32, 256, 0, st>>>(ws, grid, pstride, cols, cols, dgamma, dbeta, 0);
       T4S_LAUNCH_CHECK();
     } else if (dgamma) {
-      reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(ws, grid, 2LL * cols, cols, 0, dgamma, nullptr, 0);
+      reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(ws, grid, pstride, cols, 0, dgamma, nullptr, 0);
       T4S_LAUNCH_CHECK();
-    } else {
-      reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(ws + cols, grid, 2LL * cols, cols, 0, dbeta, nullptr, 0);
+    } else if (dbeta) {
+      reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(ws + cols, grid, pstride, cols, 0, dbeta, nullptr, 0);
+      T4S_LAUNCH_CHECK();
+    }
+    if (dx_colsum) {
+      reduce_parts_kernel<<<(cols + 31) / 32, 256, 0, st>>>(ws + 2 * cols, grid, pstride, cols, 0, dx_colsum, nullptr, 0);
       T4S_LAUNCH_CHECK();
     }
   }

@@ -184,6 +184,25 @@ def weight_grad(dy2d, x2d, n_out, k_in):
     return dw
 
 
+_FUSE_BIAS_GRAD = True
+
+
+def set_fused_bias_grad(flag: bool):
+    """A/B switch: False recomputes every bias gradient with a separate column-sum pass over the output gradient."""
+    global _FUSE_BIAS_GRAD
+    _FUSE_BIAS_GRAD = bool(flag)
+
+
+def _attached_colsum(dy, n):
+    """Column sums that the kernel which produced `dy` accumulated on the way out (LayerNorm backward: residual-stream gradients,
+    fused attention backward: dqkv).  Found on the tensor object autograd hands over; anything else (a sum of several gradients,
+    a dtype conversion, a different producer) has no attribute and the caller falls back to a column-sum pass."""
+    cs = getattr(dy, "_t4s_colsum", None)
+    if cs is not None and _FUSE_BIAS_GRAD and cs.numel() == n and cs.device == dy.device:
+        return cs
+    return None
+
+
 def colsum(x2d, cols=None, ld=None, rows=None):
     rows = x2d.shape[0] if rows is None else rows
     cols = x2d.shape[1] if cols is None else cols
@@ -261,7 +280,9 @@ class _Linear(torch.autograd.Function):
             if ctx.needs_input_grad[1]:
                 dw = weight_grad(dh, x2, N, K)
             if ctx.has_bias and ctx.needs_input_grad[2]:
-                db = colsum(dh)
+                db = _attached_colsum(dy, N) if ctx.act != ops.ACT_GELU else None
+                if db is None:
+                    db = colsum(dh)
         return dx, dw, db, d_res, None, None
 
 
@@ -313,17 +334,25 @@ class _Mlp(torch.autograd.Function):
                 dy2 = convert(dy2, torch.empty(M, N, dtype=x2.dtype, device=dev))
             w1q, w2q = cast_weight(w1), cast_weight(w2)
             dpre = torch.empty(M, Hd, dtype=x2.dtype, device=dev)
+            # bf16: the fc1 bias gradient (column sums of dpre) is accumulated by the epilogue of the GEMM that produces dpre
+            fused_db1 = ng[2] and x2.dtype == torch.bfloat16 and M >= 32 and Hd % 8 == 0
+            db1 = torch.zeros(Hd, dtype=torch.float32, device=dev) if fused_db1 else None
             mm(Op(dy2, M, dy2.stride(0)), Op(w2q, Hd, w2q.stride(0), mn_major=True), Out(dpre, Hd), M, Hd, N, residual=Out(pre, Hd),
-               act=ops.ACT_GELU_GRAD)
+               act=ops.ACT_GELU_GRAD, colsum=db1)
             dw2 = weight_grad(dy2, h, N, Hd) if ng[3] else None
-            db2 = colsum(dy2) if ng[4] else None
+            db2 = None
+            if ng[4]:
+                db2 = _attached_colsum(dy, N)
+                if db2 is None:
+                    db2 = colsum(dy2)
             dx = None
             if ng[0]:
                 dx = torch.empty(M, K, dtype=x2.dtype, device=dev)
                 mm(Op(dpre, M, Hd), Op(w1q, K, w1q.stride(0), mn_major=True), Out(dx, K), M, K, Hd)
                 dx = dx.reshape(ctx.in_shape)
             dw1 = weight_grad(dpre, x2, Hd, K) if ng[1] else None
-            db1 = colsum(dpre) if ng[2] else None
+            if ng[2] and not fused_db1:
+                db1 = colsum(dpre)
         d_res = dy if ctx.has_res else None
         return dx, dw1, db1, dw2, db2, d_res
 
@@ -378,8 +407,8 @@ class _LayerNorm(torch.autograd.Function):
             ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
             es = x.element_size()
             _lib_call("t4s_layernorm_bwd", _p(dy), ctypes.c_void_p(x.data_ptr() + off * es), _p(gamma.detach()), _p(mean), _p(rstd),
-                      ctypes.c_void_p(0), ctypes.c_void_p(dx.data_ptr() + off * es), _p(dg), _p(db), _p(ws), nbytes, rows, C, in_scale,
-                      ops.dtype_code(x.dtype), n_inner, bstride, _st())
+                      ctypes.c_void_p(0), ctypes.c_void_p(dx.data_ptr() + off * es), _p(dg), _p(db), ctypes.c_void_p(0), _p(ws), nbytes, rows, C,
+                      in_scale, ops.dtype_code(x.dtype), n_inner, bstride, _st())
         return dx, dg, db, None, None, None
 
 
@@ -428,10 +457,16 @@ class _LayerNormRes(torch.autograd.Function):
             want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
             dg = torch.empty(C, dtype=torch.float32, device=dev) if want else None
             db = torch.empty(C, dtype=torch.float32, device=dev) if want else None
-            nbytes = lib.t4s_layernorm_bwd_workspace(rows, C) if want else 0
+            # dx is the output gradient of the layer that wrote the residual stream (proj / fc2): its column sums are that layer's
+            # bias gradient; the kernel accumulates them on the way out and the consumer finds them on the tensor (`_t4s_colsum`)
+            fuse = _FUSE_BIAS_GRAD and x.dtype == torch.bfloat16 and C % 8 == 0
+            dxs = torch.empty(C, dtype=torch.float32, device=dev) if fuse else None
+            nbytes = lib.t4s_layernorm_bwd_workspace(rows, C) if (want or fuse) else 0
             ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
-            _lib_call("t4s_layernorm_bwd", _p(dy), _p(x), _p(gamma.detach()), _p(mean), _p(rstd), _p(dres), _p(dx), _p(dg), _p(db), _p(ws),
-                      nbytes, rows, C, 1.0, ops.dtype_code(x.dtype), 0, 0, _st())
+            _lib_call("t4s_layernorm_bwd", _p(dy), _p(x), _p(gamma.detach()), _p(mean), _p(rstd), _p(dres), _p(dx), _p(dg), _p(db), _p(dxs),
+                      _p(ws), nbytes, rows, C, 1.0, ops.dtype_code(x.dtype), 0, 0, _st())
+            if fuse:
+                dx._t4s_colsum = dxs
         return dx, dg, db, None
 
 
@@ -569,7 +604,12 @@ class _FlashAttention(torch.autograd.Function):
             g.dq_bs = g.dk_bs = g.dv_bs = N * 3 * D
             dq32 = torch.empty(B, N, D, dtype=torch.float32, device=dev) if _FUSED_ATTN_BWD else None   # zeroed by the call
             g.dq32 = dq32.data_ptr() if dq32 is not None else None
+            # the qkv projection's bias gradient = column sums of dqkv: accumulated by the kernels that write dq / dk / dv
+            cs = torch.zeros(3 * D, dtype=torch.float32, device=dev) if (_FUSED_ATTN_BWD and _FUSE_BIAS_GRAD and D // 8 <= 256) else None
+            g.dqkv_colsum = cs.data_ptr() if cs is not None else None
             _lib_call("t4s_attn_bwd", ctypes.byref(g), _st())
+            if cs is not None:
+                dqkv._t4s_colsum = cs
         return dqkv, None
 
 

@@ -53,8 +53,9 @@ _NULL_MAT = Matrix(ctypes.c_void_p(0), 0, 0, 0, 0)
 
 
 def gemm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, bias=None, aux: Out = None, residual: Out = None, alpha=1.0,
-         act=ACT_NONE, split_k=1, c_split_stride=0):
-    """C[z] = act(alpha * A[z] @ B[z]^T + bias) + residual[z] on tensor cores (tcgen05)."""
+         act=ACT_NONE, split_k=1, c_split_stride=0, colsum=None):
+    """C[z] = act(alpha * A[z] @ B[z]^T + bias) + residual[z] on tensor cores (tcgen05).  `colsum` (fp32 [N], zeroed by the caller)
+    receives the column sums of C from the epilogue (bf16 un-split, un-batched outputs only)."""
     _lib.ensure_device(A.t)
     if A.t.dtype != B.t.dtype:
         raise _lib.T4sError("gemm operands must share a dtype")
@@ -68,6 +69,7 @@ def gemm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, bias=None, aux: Out = None
         raise _lib.T4sError("gemm bias must be float32")
     g.bias = ctypes.c_void_p(bias.data_ptr()) if bias is not None else ctypes.c_void_p(0)
     g.alpha, g.act = float(alpha), act
+    g.colsum = ctypes.c_void_p(colsum.data_ptr()) if colsum is not None else ctypes.c_void_p(0)
     with torch.cuda.device(A.t.device):
         if _lib.profiler is not None:
             key = (M, N, K, nb1 * nb2, "T" if A.mn_major else "N", "T" if B.mn_major else "N", split_k)
