@@ -40,4 +40,4 @@ for w in (0, 4, 8, 12):
     print(f"   epilogue start {at(w, 15, 0) - t0}, stores done {at(w, 15, 1) - t0}, past final barrier {at(w, 15, 2) - t0}")
 print("MMA warp: per tile: [group 0: wait-start, P ready, issued] [group 1: ...]")
 for j in range(10):
-    print(f"   j={j}: " + " ".join(f"{at(17, j, e) - t0:7d}" for e in (0, 1, 2, 4, 5, 6)))
+    print(f"   j={j}: " + " ".join(f"{at(17, j, e) - t0:7d}" for e in (0, 1, 2)) + " | " + " ".join(f"{at(18, j, e) - t0:7d}" for e in (0, 1, 2)))

@@ -9,7 +9,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libt4s.so")
+LIB_PATH = os.environ.get("T4S_LIBRARY") or os.path.join(_HERE, "libt4s.so")   # (override: A/B builds of the diagnostics scripts)
 _lock = threading.Lock()
 _lib = None
 _device_ok = set()

@@ -2,25 +2,20 @@
 //
 // No [N, N] matrix ever reaches HBM.  Per (clip, head) the kernels walk 128 x 128 score tiles:
 //
-//   forward   CTA = one 128-query tile.  S = Q K_j^T (tcgen05, fp32 in TMEM) -> 4 softmax warps (thread = query row) read S
-//             with tcgen05.ld, keep the running max / sum, write P_j (bf16) into a SWIZZLE_128B shared-memory tile ->
-//             O_j = P_j V_j (tcgen05, V consumed MN-major straight from its [keys, hd] TMA tile) -> the same warps fold O_j
-//             into fp32 registers with the online-softmax rescale.  2 CTAs per SM (256 TMEM columns, 112 KB smem each) so
-//             one CTA's MMAs overlap the other's exponentials.  Also emits lse (log2 units) for the backward.
-//   bwd dK/dV CTA = one 128-key tile, loops over query tiles: S^T = K Q_i^T, dP^T = V dO_i^T (thread = key row),
-//             P^T = exp2(S^T*c - lse_i), dS^T = P^T (dP^T - delta_i) -> shared memory (bf16) ->
-//             dV += P^T dO_i, dK += dS^T Q_i accumulate in TMEM across the whole loop.
-//   bwd dQ    CTA = one 128-query tile, loops over key tiles: S, dP, dS as above (thread = query row), dQ += dS K_j in TMEM.
-//             (S / dP are recomputed once more instead of pushing dQ through global atomics: deterministic results.)
-//   Both backward kernels run 8 softmax warps (two per TMEM lane quarter, each taking half of the 128 columns), one TMA
-//   producer warp and one MMA-issuing warp; S/dP for tile t+1 are issued before the dV/dK (dQ) MMAs of tile t so the
-//   tensor pipe stays busy while the exponentials run.
+//   forward   attn_fwd_plain.cuh: CTA = two 128-query tiles, 16 softmax warps (thread = query row x column half), S read once
+//             from TMEM into registers, P handed to the tensor core through TMEM, O accumulated in TMEM with lazy rescaling,
+//             S_{j+1} issued under tile j's exponentials, a share of the exponentials on the FMA pipe.  Emits lse (log2 units).
+//   backward  attn_bwd_fused_kernel (default): persistent CTAs over (clip, head, key tile) work items, thread = key row:
+//             S^T = K Q_i^T, dP^T = V dO_i^T, P^T = exp2(S^T c - lse_i), dS^T = P^T (dP^T - delta_i) -> shared memory (bf16) ->
+//             dV += P^T dO_i, dK += dS^T Q_i in TMEM, dQ_i tile = dS K_j reduce-added (TMA) into an fp32 buffer.
+//             attn_bwd_kernel<0> / <1>: the deterministic two-kernel backward (dK/dV kernel + dQ kernel), selected when no fp32
+//             dQ workspace is given.
 //
 // Out-of-range rows are handled by TMA zero fill (loads) and row predicates (stores); out-of-range key columns are masked.
 #include <cstdlib>
 
 #include "attn_common.cuh"
-#include "attn_fwd.cuh"
+#include "attn_fwd_plain.cuh"
 
 namespace t4s {
 namespace attn {
@@ -827,17 +822,15 @@ extern "C" int t4s_attn_fwd(const T4sAttn* p, void* stream) {
   using namespace t4s::attn;
   int rc = check_common(p);
   if (rc) return rc;
-  fwd2::Maps tm;
+  fwd3::Maps tm;
   if ((rc = make_map(&tm.q, p->q, p->q_ld, p->q_bs, p->batch, p->heads, p->tokens, "q"))) return rc;
   if ((rc = make_map(&tm.k, p->k, p->k_ld, p->k_bs, p->batch, p->heads, p->tokens, "k"))) return rc;
   if ((rc = make_map(&tm.v, p->v, p->v_ld, p->v_bs, p->batch, p->heads, p->tokens, "v"))) return rc;
-  tm.qv = tm.q;
-  tm.pos = tm.q;
   Args a;
   fill_args(a, p);
-  T4S_CUDA(cudaFuncSetAttribute(fwd2::attn_fwd2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd2::Layout<false>::kSmem));
+  T4S_CUDA(cudaFuncSetAttribute(fwd3::attn_fwd3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd3::kSmem));
   dim3 grid((a.n_tiles + 1) / 2, p->heads, p->batch);
-  fwd2::attn_fwd2_kernel<false><<<grid, fwd2::Layout<false>::kThreads, fwd2::Layout<false>::kSmem, t4s::as_stream(stream)>>>(tm, a);
+  fwd3::attn_fwd3_kernel<<<grid, fwd3::kThreads, fwd3::kSmem, t4s::as_stream(stream)>>>(tm, a);
   T4S_LAUNCH_CHECK();
   return T4S_OK;
 }

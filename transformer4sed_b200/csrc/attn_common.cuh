@@ -29,6 +29,24 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 2^x for a packed pair on the FMA / ALU pipes instead of MUFU (head size 64 attention is bound by the 16 exp2 / clk / SM of the
+// special-function unit: 1024 clk per 128 x 128 tile against 512 clk of MMA, so a fixed share of the exponentials is moved
+// here).  Cody-Waite split by the 1.5 * 2^23 rounding trick, degree-3 minimax polynomial of 2^f on [-0.5, 0.5] (relative error
+// 7.5e-5, far below the bf16 rounding of P), exponent inserted with an integer shift-add.  Arguments below -126 are clamped.
+__device__ __forceinline__ void exp2_poly2(float x0, float x1, float& p0, float& p1) {
+  const uint64_t magic = ptx::pack2(12582912.f, 12582912.f);
+  const uint64_t x = ptx::pack2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t t = ptx::add2(x, magic);
+  const uint64_t f = ptx::sub2(x, ptx::sub2(t, magic));
+  uint64_t p = ptx::fma2(f, ptx::pack2(0.055171654f, 0.055171654f), ptx::pack2(0.24261113f, 0.24261113f));
+  p = ptx::fma2(p, f, ptx::pack2(0.69326097f, 0.69326097f));
+  p = ptx::fma2(p, f, ptx::pack2(0.99992806f, 0.99992806f));
+  float ta, tb, pa, pb;
+  ptx::unpack2(t, ta, tb);
+  ptx::unpack2(p, pa, pb);
+  p0 = __uint_as_float(__float_as_uint(pa) + (__float_as_uint(ta) << 23));
+  p1 = __uint_as_float(__float_as_uint(pb) + (__float_as_uint(tb) << 23));
+}
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&t);

@@ -1,4 +1,5 @@
-// Forward kernel of the fused attention family (plain MHSA: attn.cu, Transformer-XL rel-pos MHSA: attn_rel.cu), head_dim 64, bf16.
+// Forward kernel of the Transformer-XL rel-pos attention (attn_rel.cu instantiates kRel = true; the plain MHSA forward has its own
+// kernel in attn_fwd_plain.cuh and the kRel = false instantiation of this template is kept as its shared-memory-P variant), head_dim 64, bf16.
 //
 // CTA = one (plain: two) 128-query tile(s) of one (clip, head); it walks the 128-key tiles.  Per query tile:
 //   warps 0-7  softmax.  Warp w owns TMEM lane quarter wq = w & 3 (query rows 32 wq ..) and the column half g = w >> 2 of every

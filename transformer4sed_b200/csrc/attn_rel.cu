@@ -8,15 +8,18 @@
 // per-row skew, BD_shifted[r, c] = BD[r, 127 - r + c], applied by the softmax warps on the way out of TMEM: each thread (= query
 // row) parks 64 accumulator columns in a private, bank-conflict-free shared-memory row and reads them back at its own offset.
 //
-//   forward    as attn.cu's forward (online softmax, P in shared memory, O folded in registers); the shifted scores are written
-//              back to TMEM (tcgen05.st) by the max pass so the exponential pass is unchanged.  One CTA per SM (512 TMEM columns).
-//   backward   two kernels, both with thread = query row: dQ (CTA = query tile, loops over key tiles) accumulates
-//              d(q+u) = scale dS K in TMEM and streams dS, un-shifted back to position coordinates, into dBD: every warp stages
-//              its 32 dS rows in shared memory and writes them out with coalesced 4-byte stores, a funnel shift absorbing the odd
-//              element offsets (TMA tile stores cannot: they need 16-byte aligned inner coordinates).  The [T, 2T-1] gradient is
-//              consumed by two plain GEMMs: d(q+v) = dBD p, dp = sum_b dBD^T (q+v);
+//   forward    attn_fwd.cuh (kRel): 8 softmax warps, thread = (query row, column half); the two halves of a row are independent
+//              online-softmax streams with their own O accumulators in TMEM, merged in the epilogue; lazy rescaling; the skewed
+//              position scores are added to the AC scores in registers.  One CTA per SM (512 TMEM columns).
+//   backward   two kernels, both with 8 softmax warps and thread = (query row, column half): dQ (CTA = query tile, loops over
+//              key tiles) accumulates d(q+u) = scale dS K in TMEM and streams dS, un-shifted back to position coordinates, into
+//              dBD: every warp stages its 32 x 64 dS block in shared memory and writes it out with coalesced 4-byte stores, a
+//              funnel shift absorbing the odd element offsets (TMA tile stores cannot: they need 16-byte aligned inner
+//              coordinates).  The [T, 2T-1] gradient is consumed by two plain GEMMs: d(q+v) = dBD p, dp = sum_b dBD^T (q+v);
 //              dK/dV (CTA = key tile, loops over query tiles) consumes the P / dS tiles transposed in place as MN-major A
 //              operands.  P is recomputed from lse (no max pass); dP reuses the S columns of TMEM once P is in registers.
+//              (Keeping dBD out of HBM needs a 64 KB un-skewed dS operand tile next to 112 KB of operands, 32 KB of dS and the
+//              skew scratch: it does not fit the 227 KB of one SM with 128-wide tiles; DESIGN.md §3 has the budget.)
 #include "attn_common.cuh"
 #include "attn_fwd.cuh"
 
@@ -24,11 +27,7 @@ namespace t4s {
 namespace attn {
 namespace rel {
 
-constexpr int kThreads = 192;          // warps 0-3 softmax (thread = query row), 4 TMA producer, 5 MMA issuer
 constexpr int kPwBytes = 256 * 128;    // position window: 256 rows x 64 bf16
-constexpr int kWarpScratch = 8704;     // per softmax warp: 32 skew rows x 66 floats (8448 B) / 32 dBD staging rows x 256 B
-constexpr int kScrRow = 66;            // floats; lanes l read at 65 l + const -> conflict free, 8-byte stores conflict free
-constexpr int kStageRow = 256;         // bytes (dense rows of 128 bf16)
 constexpr uint32_t kIdescBD = ptx::umma_idesc(1, 128, 256, 0, 0);
 constexpr uint32_t kIdescAmn = ptx::umma_idesc(1, 128, 64, 1, 1);  // A and B MN-major
 
@@ -37,23 +36,6 @@ struct RelArgs {
   __nv_bfloat16* dqu; long long dqu_ld, dqu_bs;
   __nv_bfloat16* dbd; long long dbd_ld;
 };
-
-// bd[cc] = BD[r][127 - r + c0 + cc] for this thread's row r = 32 w + l; t_bd = TMEM address of BD column 0 (lane quarter applied)
-__device__ __forceinline__ void skew_chunk(uint32_t t_bd, float* scr, int w, int l, int c0, float (&bd)[32]) {
-  const int wb = 96 - 32 * w + c0;  // first of the 64 columns this warp's rows can reference for this chunk
-  uint32_t x0[32], x1[32];
-  ptx::tmem_ld_32x32(t_bd + wb, x0);
-  ptx::tmem_ld_32x32(t_bd + wb + 32, x1);
-  ptx::tmem_ld_wait();
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    *reinterpret_cast<uint2*>(scr + 2 * k) = make_uint2(x0[2 * k], x0[2 * k + 1]);
-    *reinterpret_cast<uint2*>(scr + 32 + 2 * k) = make_uint2(x1[2 * k], x1[2 * k + 1]);
-  }
-  const volatile float* rd = scr + (31 - l);
-#pragma unroll
-  for (int cc = 0; cc < 32; ++cc) bd[cc] = rd[cc];
-}
 
 // D[128 x 64] (+)= A^T . B with A = a [128 (K) x 128 (M)] K-major-written tile consumed MN-major (two 64-wide M blocks 16 KB
 // apart) and B = [128 rows (K) x 64] tile consumed MN-major.
