@@ -210,3 +210,58 @@ def test_arena_shadow_follows_torch_side_parameter_updates(monkeypatch):
     q = torch.nn.Parameter(torch.ones(2, 2))                  # a shadow without version bookkeeping keeps the old behaviour
     q._t4s_shadow = torch.zeros(2, 2, dtype=torch.bfloat16)
     assert F.cast_weight(q) is q._t4s_shadow and len(calls) == 2
+
+
+def _bucket_worker(rank, world, port, out):
+    """GradBuckets with a torch copy standing in for the pack kernel: hooks fire during backward, buckets are reduced asynchronously."""
+    from transformer4sed_b200.training import GradBuckets, flat_layout, shard_for_rank
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = _model()
+        extra = torch.nn.Parameter(torch.zeros(5))           # a parameter that never receives a gradient (e.g. an unused mask token)
+        groups = _groups(m)
+        groups[1]["params"].append(extra)
+        layout, ranges, total = flat_layout(groups)
+        flat = torch.zeros(total)
+        launched = []
+
+        def pack(i0, i1):
+            launched.append((i0, i1))
+            for p, off in layout[i0:i1]:
+                flat[off:off + p.numel()] = p.grad.flatten() if p.grad is not None else 0.0
+
+        gb = GradBuckets(layout, total, flat, pack, bucket_elems=64)
+        x, y = _data()
+        lo, hi = shard_for_rank(x.shape[0], rank, world)
+        for step in range(2):                                # two steps: the counters must re-arm
+            for p, _ in layout:
+                p.grad = None
+            launched.clear()
+            torch.nn.functional.mse_loss(m(x[lo:hi]), y[lo:hi]).backward()
+            in_backward = list(launched)
+            gb.finish()
+        if rank == 0:
+            torch.save(dict(flat=flat / world, buckets=gb.buckets, in_backward=in_backward, all=list(launched)), out)
+        gb.remove()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_bucketed_overlapped_all_reduce_matches_single_process(tmp_path):
+    from transformer4sed_b200.training import bucket_ranges, flat_layout
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_bucket_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out, weights_only=False)
+    m = _model()
+    layout, ranges, total = flat_layout(_groups(m))
+    x, y = _data()
+    torch.nn.functional.mse_loss(m(x), y).backward()
+    for p, off in layout:
+        assert torch.allclose(r["flat"][off:off + p.numel()], p.grad.flatten(), atol=1e-6)
+    b = r["buckets"]
+    assert len(b) >= 3 and b[0][0] == 0 and all(x[1] == y[0] and x[3] == y[2] for x, y in zip(b, b[1:]))
+    assert len(r["in_backward"]) >= len(b) - 1          # every bucket but the one holding the gradient-less parameter fired from a hook
+    assert sorted(r["all"]) == sorted((x[0], x[1]) for x in b)
+    # bucket boundaries only depend on the layout
+    assert bucket_ranges(layout, total, 64)[:2] == [tuple(x) for x in b[:2]]

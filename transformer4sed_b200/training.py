@@ -53,9 +53,78 @@ def all_reduce_flat(buf):
     return 1
 
 
+def bucket_ranges(layout, total, bucket_elems):
+    """Cut the arena layout into contiguous buckets of about `bucket_elems` elements: [(first entry, last entry + 1, start, end)]
+    (entry indices into `layout`, element offsets into the flat buffers).  Same on every rank: it only depends on the layout."""
+    out, i0 = [], 0
+    for i, (p, off) in enumerate(layout):
+        nxt = layout[i + 1][1] if i + 1 < len(layout) else total
+        if nxt - layout[i0][1] >= bucket_elems or i + 1 == len(layout):
+            out.append((i0, i + 1, layout[i0][1], nxt))
+            i0 = i + 1
+    return out
+
+
+class GradBuckets:
+    """Overlap of the gradient exchange with the backward pass: the arena is cut into a few contiguous buckets; a
+    post-accumulate-grad hook on every parameter counts the bucket's gradients in, and the moment the last one lands the bucket is
+    packed into the flat buffer (`pack(first, last)`: the t4s_grad_pack kernel on the product path) and its slice is all-reduced
+    asynchronously (NCCL runs on its own stream while autograd keeps producing the gradients of the earlier layers).  `finish()`
+    packs and reduces whatever did not fire (parameters without a gradient this step) and waits for every handle."""
+
+    def __init__(self, layout, total, flat_grad, pack, bucket_elems=1 << 24):
+        import torch.distributed as dist
+        self.dist = dist
+        self.layout, self.flat, self.pack = layout, flat_grad, pack
+        self.buckets = bucket_ranges(layout, total, bucket_elems)
+        self.bucket_of = {}
+        for b, (i0, i1, _, _) in enumerate(self.buckets):
+            for i in range(i0, i1):
+                self.bucket_of[id(layout[i][0])] = b
+        self.pending = [i1 - i0 for i0, i1, _, _ in self.buckets]
+        self.handles = [None] * len(self.buckets)
+        self.dirty = [False] * len(self.buckets)
+        self.hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p, _ in layout]
+
+    def _launch(self, b):
+        i0, i1, start, end = self.buckets[b]
+        self.pack(i0, i1)
+        self.handles[b] = self.dist.all_reduce(self.flat[start:end], async_op=True)
+
+    def _on_grad(self, p):
+        b = self.bucket_of[id(p)]
+        if self.handles[b] is not None:
+            self.dirty[b] = True           # a second backward before the step (gradient accumulation): reduce again in finish()
+            return
+        self.pending[b] -= 1
+        if self.pending[b] == 0:
+            self._launch(b)
+
+    def finish(self):
+        for b in range(len(self.buckets)):
+            if self.handles[b] is None:
+                self._launch(b)
+            elif self.dirty[b]:
+                self.handles[b].wait()
+                self._launch(b)
+        for h in self.handles:
+            h.wait()
+        self.pending = [i1 - i0 for i0, i1, _, _ in self.buckets]
+        self.handles = [None] * len(self.buckets)
+        self.dirty = [False] * len(self.buckets)
+
+    def remove(self):
+        for h in self.hooks:
+            h.remove()
+        self.hooks = []
+
+
 class ParamArena:
-    def __init__(self, module: torch.nn.Module, groups, shadow_bf16=True, betas=(0.9, 0.999), eps=1e-8):
-        """groups: list of dicts {name, params (list of nn.Parameter), lr, weight_decay}.  Parameters not listed are frozen."""
+    def __init__(self, module: torch.nn.Module, groups, shadow_bf16=True, betas=(0.9, 0.999), eps=1e-8, overlap=None,
+                 bucket_elems=1 << 24):
+        """groups: list of dicts {name, params (list of nn.Parameter), lr, weight_decay}.  Parameters not listed are frozen.
+        overlap=True (or T4S_OVERLAP_ALLREDUCE=1): bucketed all-reduce launched from autograd hooks while the backward pass is still
+        running (`GradBuckets`); default: one all-reduce over the whole buffer after backward, which measured faster on NVSwitch."""
         dev = next(module.parameters()).device
         _lib.ensure_device(next(module.parameters()))
         layout, self.groups, total = flat_layout(groups)
@@ -86,6 +155,42 @@ class ParamArena:
         self._table_used = [False, False]
         self._table_turn = 0
         self._agreed = self._agreed_local = None
+        self.buckets = None
+        if overlap is None:
+            import os
+            # measured on 2 and 8 B200 (64 and 32 clips per GPU): the bucketed exchange is 0.3-1.2 ms per step SLOWER than one
+            # all-reduce after backward (NCCL's kernels take SMs from the persistent GEMM / attention CTAs and every bucket costs a
+            # pointer-table upload and a launch), so it is opt-in (profiles/r2_multi_gpu.md)
+            overlap = _world_size() > 1 and os.environ.get("T4S_OVERLAP_ALLREDUCE", "0") == "1"
+        if overlap and _world_size() > 1:
+            self.buckets = GradBuckets(layout, total, self.grad, self._pack_range, bucket_elems)
+            # one pinned + device pointer table per bucket and parity (see pack_grads for the hazard)
+            self._btables = [[(torch.empty(i1 - i0, 3, dtype=torch.int64).pin_memory(), torch.empty(i1 - i0, 3, dtype=torch.int64, device=dev),
+                               torch.cuda.Event(), [False]) for _ in range(2)] for i0, i1, _, _ in self.buckets.buckets]
+            self._bturn = [0] * len(self.buckets.buckets)
+
+    def _pack_range(self, i0, i1):
+        """Pack the gradients of layout entries [i0, i1) (one bucket) into the flat buffer; called from autograd hooks."""
+        b = next(k for k, r in enumerate(self.buckets.buckets) if r[0] == i0)
+        turn = self._bturn[b]
+        self._bturn[b] ^= 1
+        t, t_dev, copied, used = self._btables[b][turn]
+        if used[0]:
+            copied.synchronize()
+        for k in range(i0, i1):
+            p, off = self.layout[k]
+            g = p.grad
+            if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
+                g = g.float().contiguous()
+                p.grad = g
+            t[k - i0, 0] = g.data_ptr() if g is not None else 0
+            t[k - i0, 1] = off
+            t[k - i0, 2] = p.numel()
+        with torch.cuda.device(self.device):
+            t_dev.copy_(t, non_blocking=True)
+            copied.record()
+            used[0] = True
+            _lib.check(_lib.load().t4s_grad_pack(_lib.ptr(t_dev), i1 - i0, _lib.ptr(self.grad), _lib.stream_ptr()), "t4s_grad_pack")
 
     def pack_grads(self):
         """Gather every parameter's .grad into the flat buffer (missing grads -> zeros) with one kernel."""
@@ -139,8 +244,12 @@ class ParamArena:
         skipped = [(off, p.numel()) for (p, off), h in zip(self.layout, has_grad) if not h]
         keep = [(off, n, self.flat[off:off + n].clone(), self.exp_avg[off:off + n].clone(), self.exp_avg_sq[off:off + n].clone())
                 for off, n in skipped]
-        self.pack_grads()
-        world = self.all_reduce()
+        if self.buckets is not None:
+            self.buckets.finish()          # every bucket was packed and all-reduced from the autograd hooks (stragglers: here)
+            world = _world_size()
+        else:
+            self.pack_grads()
+            world = self.all_reduce()
         self.step_count += 1
         lib = _lib.load()
         with torch.cuda.device(self.device):
