@@ -469,15 +469,28 @@ def instrumented_step(train_step, wav_dev, ext, ops, B):
     step_ms = t0.elapsed_time(t1)
     gemm_ms = gemm_flops = 0.0
     n_gemm = 0
-    attn_ms = 0.0
+    attn_ms = attn_flops = 0.0
+    attn_parts = {}
+    # algorithmic flops of the fused attention calls (head size 64): forward 4 N^2 hd per (clip, head) (S = Q K^T and O = P V), backward
+    # 2.5 x (five products); Transformer-XL: + the position scores 2 N (2N-1) hd forward, backward 2.7 x forward
+    fl = {"t4s_attn_fwd": lambda B_, H, N: 4.0 * N * N * 64 * H * B_, "t4s_attn_bwd": lambda B_, H, N: 10.0 * N * N * 64 * H * B_,
+          "t4s_relattn_fwd": lambda B_, H, N: (4.0 * N * N + 2.0 * N * (2 * N - 1)) * 64 * H * B_,
+          "t4s_relattn_bwd": lambda B_, H, N: 2.7 * (4.0 * N * N + 2.0 * N * (2 * N - 1)) * 64 * H * B_}
     for name, key, s, e in prof.records:
         if name == "t4s_gemm":
             M, N, K, nb = key[:4]
             gemm_ms += s.elapsed_time(e)
             gemm_flops += 2.0 * M * N * K * nb
             n_gemm += 1
-        elif name in ("t4s_attn_fwd", "t4s_attn_bwd", "t4s_relattn_fwd", "t4s_relattn_bwd"):
-            attn_ms += s.elapsed_time(e)
+        elif name in fl:
+            dt = s.elapsed_time(e)
+            attn_ms += dt
+            f = fl[name](*key) if key is not None else 0.0
+            attn_flops += f
+            a = attn_parts.setdefault(name, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += dt
+            a[2] += f
     summary = prof.summary()
     shapes = {}
     for name, key, s, e in prof.records:
@@ -520,6 +533,15 @@ def instrumented_step(train_step, wav_dev, ext, ops, B):
                 "traffic": 93.75e6 * B / 64, "traffic_note": "ncu --set full, 64 clips per launch: 82.0 MB read + 11.8 MB written (profiles/r1j_ncu_full_summary.md)",
                 "ms": mel_ms, "clips_per_s": B / mel_ms * 1e3,
                 "algorithmic_bytes_per_clip": 4 * N_SAMPLES + 4 * 128 * 1000, "peak_source": pk_src}
+    if attn_ms > 0:
+        roof["attention"] = {
+            "bound": "tensor", "kernel": "t4s::attn fused attention kernels (tcgen05; head size 64), all launches of one step (incl. delta / dq-finish passes)",
+            "achieved": attn_flops / attn_ms / 1e9, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+            "frac": attn_flops / attn_ms / 1e9 / pk["bf16_tflops_sustained"], "ms_per_step": attn_ms,
+            "per_call": {k: {"launches": v[0], "ms": round(v[1], 3), "tflops": round(v[2] / v[1] / 1e9, 1)} for k, v in attn_parts.items()},
+            "note": "head size 64 is bound by the special-function unit and the shared-memory operand pipe before the tensor pipe: 16 exp2 / clk / SM = "
+                    "1024 clk per 128 x 128 tile against 512 clk of MMA, so 0.5 of the tensor roofline is the ceiling of the forward without "
+                    "polynomial exponentials (profiles/r2_attention_analysis.md)"}
     return roof, mel_roof, {"step_instrumented": step_ms, "gemm": gemm_ms, "fused_attention": attn_ms, "front_end": mel_ms,
                             "other": step_ms - gemm_ms - attn_ms - mel_ms}
 

@@ -49,14 +49,14 @@ def passt_power_mel(wav, n_mels=128, sr=32000, win_length=800, hop=320, n_fft=10
     pad = n_fft // 2
     x = torch.nn.functional.pad(x.unsqueeze(1), (pad, pad), mode="reflect").squeeze(1)  # center=True
     frames = x.unfold(1, n_fft, hop)  # [B, T, n_fft]
-    win = torch.hann_window(win_length, periodic=False, dtype=dtype)  # :41
+    win = torch.hann_window(win_length, periodic=False, dtype=dtype, device=x.device)  # :41
     left = (n_fft - win_length) // 2  # torch.stft centres a short window inside n_fft
     win = torch.nn.functional.pad(win, (left, n_fft - win_length - left))
     spec = torch.fft.rfft(frames * win, dim=-1)
     power = spec.real ** 2 + spec.imag ** 2  # :65   [B, T, n_fft//2+1]
     if mel_basis is None:
         mel_basis = passt_mel_basis(n_mels, n_fft, sr, fmin, fmax, dtype)
-    return torch.matmul(mel_basis.to(dtype), power.transpose(1, 2))  # :84
+    return torch.matmul(mel_basis.to(device=power.device, dtype=dtype), power.transpose(1, 2))  # :84
 
 
 def passt_normalize(melspec):

@@ -138,7 +138,7 @@ def rel_shift(bd):
     """transformerXL.py:254-297: out[..., i, j] = bd[..., i, T-1-i+j]."""
     T = bd.shape[-2]
     idx = (T - 1 - torch.arange(T).unsqueeze(1)) + torch.arange(T).unsqueeze(0)
-    return bd.gather(-1, idx.expand(bd.shape[:-2] + (T, T)))
+    return bd.gather(-1, idx.to(bd.device).expand(bd.shape[:-2] + (T, T)))
 
 
 def relpos_attention(x, pos, sd, p, num_heads):
@@ -171,7 +171,7 @@ def txl_block(x, pos, sd, p, num_heads):
 def txl_decoder(x, sd, n_layers, num_heads=12, p="decoder."):
     """transformer_decoder.py:110-122 + RelPositionalEncoding.forward (transformerXL.py:104-127)."""
     B, T, C = x.shape
-    pos = rel_pos_table(T, C, x.dtype)
+    pos = rel_pos_table(T, C, x.dtype).to(x.device)
     x = x * math.sqrt(C)
     for i in range(n_layers):
         x = txl_block(x, pos, sd, f"{p}encoder_blocks.{i}.", num_heads)
@@ -205,7 +205,7 @@ def block_mask_from_noise(noise, mask_rate, block_width, seq_len):
     """mask.py:93-100 with the `torch.rand` draw injected: threshold at sorted-noise index int(n*rate)."""
     n_seg = noise.shape[1]
     thr = noise.sort()[0][:, min(int(n_seg * mask_rate), n_seg - 1)]
-    m = torch.zeros(noise.shape[0], seq_len, dtype=torch.bool)
+    m = torch.zeros(noise.shape[0], seq_len, dtype=torch.bool, device=noise.device)
     m[:, :n_seg * block_width] = (noise <= thr.unsqueeze(-1)).repeat_interleave(block_width, dim=1)
     return m
 
@@ -246,7 +246,7 @@ def slide_window_embed(mel, sd, win_param, emb_len, feature_layer=10, f_pool_mod
         if ratio != 1:
             out = F.interpolate(out.transpose(1, 2), scale_factor=ratio, mode="linear").transpose(1, 2)
         if emb is None:
-            emb = torch.zeros(B, emb_len, out.shape[-1], dtype=out.dtype)
+            emb = torch.zeros(B, emb_len, out.shape[-1], dtype=out.dtype, device=out.device)
             acc = torch.zeros_like(emb)
         out_left = round(w_left * scale)
         out_right = int(min(emb_len, out_left + out.shape[1]))

@@ -35,10 +35,10 @@ def act_dtype():
     return torch.bfloat16 if _MODE == "bf16" else torch.float32
 
 
-def _lib_call(name, *args):
+def _lib_call(name, *args, _key=None):
     fn = getattr(_lib.load(), name)
     if _lib.profiler is not None:
-        _lib.check(_lib.profiler.timed(name, None, lambda: fn(*args)), name)
+        _lib.check(_lib.profiler.timed(name, _key, lambda: fn(*args)), name)
     else:
         _lib.check(fn(*args), name)
 
@@ -576,7 +576,7 @@ class _FlashAttention(torch.autograd.Function):
             # un-rounded copy of o for the backward's delta (kept only when a backward can follow)
             o32 = torch.empty(B, N, D, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
             a = _attn_desc(qkv, o, lse, B, N, D, H, (D // H) ** -0.5, o32)
-            _lib_call("t4s_attn_fwd", ctypes.byref(a), _st())
+            _lib_call("t4s_attn_fwd", ctypes.byref(a), _st(), _key=(B, H, N))
         ctx.save_for_backward(qkv, o, lse, o32)
         ctx.H = H
         return o
@@ -607,7 +607,7 @@ class _FlashAttention(torch.autograd.Function):
             # the qkv projection's bias gradient = column sums of dqkv: accumulated by the kernels that write dq / dk / dv
             cs = torch.zeros(3 * D, dtype=torch.float32, device=dev) if (_FUSED_ATTN_BWD and _FUSE_BIAS_GRAD and D // 8 <= 256) else None
             g.dqkv_colsum = cs.data_ptr() if cs is not None else None
-            _lib_call("t4s_attn_bwd", ctypes.byref(g), _st())
+            _lib_call("t4s_attn_bwd", ctypes.byref(g), _st(), _key=(B, H, N))
             if cs is not None:
                 dqkv._t4s_colsum = cs
         return dqkv, None
@@ -775,7 +775,7 @@ class _FlashRelPosAttention(torch.autograd.Function):
             lse = torch.empty(B, H, Nl, dtype=torch.float32, device=dev)
             o32 = torch.empty(B, T, D, dtype=torch.float32, device=dev) if any(ctx.needs_input_grad[:4]) else None
             a = _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, (D // H) ** -0.5, o32)
-            _lib_call("t4s_relattn_fwd", ctypes.byref(a), _st())
+            _lib_call("t4s_relattn_fwd", ctypes.byref(a), _st(), _key=(B, H, T))
         ctx.save_for_backward(qkv, p_lin, u, v, qu, qv, o, lse, o32)
         ctx.H = H
         return o
@@ -810,7 +810,7 @@ class _FlashRelPosAttention(torch.autograd.Function):
             g.dk_ld = g.dv_ld = 3 * D
             g.dk_bs = g.dv_bs = T * 3 * D
             g.dbd, g.dbd_ld = dBD.data_ptr(), Lp
-            _lib_call("t4s_relattn_bwd", ctypes.byref(g), _st())
+            _lib_call("t4s_relattn_bwd", ctypes.byref(g), _st(), _key=(B, H, T))
             bm = dict(nb1=H, stride1=T * Lp, nb2=B, stride2=H * T * Lp)
             # d(q+v) = scale dBD p ; dp = scale sum_b dBD^T (q+v)
             dqv = torch.empty(B, T, D, dtype=dt, device=dev)
