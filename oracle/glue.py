@@ -100,7 +100,9 @@ def decode_pred_batch_fast(outputs, weak_preds, thresholds, filter_size):
 
 
 def rank_filter_scores(scores, sizes, filter_type="median"):
-    """src/codec/decoder.py:86-92: scipy.ndimage filters per class on a [T, C] score array (first len(sizes) classes)."""
+    """src/codec/decoder.py:86-92: scipy.ndimage filters per class on a [T, C] score array (first len(sizes) classes).
+    For windows of more than 2 T + 1 taps scipy's 1-D fast path (taken here, as upstream) and its N-D filter disagree about the
+    border; the CUDA kernel follows the N-D (periodic reflection) rule there -- tests/test_post_gpu.py pins both regimes."""
     from scipy import ndimage
     out = scores.copy()
     for idx in range(len(sizes)):
