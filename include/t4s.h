@@ -122,6 +122,9 @@ typedef struct {
   float* colsum;      /* optional [N] fp32 (zeroed by the caller): colsum[n] += sum_m C[m, n], the un-rounded epilogue values added with
                          atomics by the epilogue warps -- the bias gradient of the layer whose output gradient this GEMM produces
                          (fc1: the fc2-dgrad GEMM with T4S_ACT_GELU_GRAD) without re-reading C.  bf16 un-split outputs only. */
+  int band_lo, band_hi; /* optional (band_hi > 0): the caller guarantees A[z][m, k] == 0 unless band_lo <= m + k < band_hi (an anti-diagonal
+                         band, e.g. the un-shifted position-score gradient of csrc/attn_rel.cu); k-blocks wholly outside the band of
+                         an M tile are neither loaded nor multiplied */
 } T4sGemm;
 
 int t4s_gemm(const T4sGemm* g, void* stream);

@@ -1,11 +1,12 @@
-"""Top stall sites of one kernel in an `ncu --set full --import-source on` report (SASS view): `python scripts/ncu_source_top.py rep regex [n]`."""
+"""Top stall sites of one kernel in an `ncu --set full --import-source on` report (SASS view): `python scripts/ncu_source_top.py rep regex [n [skip]]` (skip = matching launches to pass over)."""
 import csv
 import subprocess
 import sys
 
 
-def main(path, regex, n=40):
-    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--kernel-name", f"regex:{regex}"], capture_output=True, text=True).stdout
+def main(path, regex, n=40, skip=0):
+    out = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv", "--kernel-name", f"regex:{regex}", "--launch-skip", str(skip), "--launch-count", "1"],
+                         capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[1]
     ia, isrc, isamp, iex = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
@@ -31,7 +32,7 @@ def main(path, regex, n=40):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40)
+    main(sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40, int(sys.argv[4]) if len(sys.argv) > 4 else 0)
 
 
 def buckets(path, regex, step=40):

@@ -107,6 +107,49 @@ def test_gemm_split_k_weight_gradient():
         assert (dw.double() - ref).abs().max().item() < (5e-3 if dtype == torch.bfloat16 else 0.3)
 
 
+def test_gemm_anti_diagonal_band():
+    """`band` = (lo, hi): A[m, k] == 0 unless lo <= m + k < hi (the un-shifted position-score gradient of the rel-pos attention
+    backward, functional._FlashRelPosAttention.backward): the clipped GEMM equals the full one, K-major and MN-major A, batched,
+    bf16 (single-CTA and pair tiles) and with a split contraction."""
+    ops = _ops()
+    T, hd, H, B = 333, 64, 2, 3
+    L, Lp = 2 * T - 1, 672
+    g = torch.Generator(device="cuda").manual_seed(5)
+    dbd = torch.zeros(B, H, T, Lp, device="cuda", dtype=torch.bfloat16)
+    i, k = torch.arange(T, device="cuda")[:, None], torch.arange(Lp, device="cuda")[None, :]
+    inband = ((i + k >= T - 1) & (i + k < 2 * T - 1)).expand(B, H, T, Lp)
+    dbd[inband] = torch.randn(int(inband.sum()), generator=g, device="cuda").to(torch.bfloat16)
+    p = _rand((L, H * hd), torch.bfloat16, 6)
+    qv = _rand((B, T, H * hd), torch.bfloat16, 7)
+    bm = dict(nb1=H, stride1=T * Lp, nb2=B, stride2=H * T * Lp)
+    outs = []
+    for band in (None, (T - 1, 2 * T - 1)):
+        dqv = torch.zeros(B, T, H * hd, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(ops.Op(dbd, T, Lp, 0, **bm), ops.Op(p, hd, H * hd, 0, nb1=H, stride1=hd, mn_major=True), ops.Out(dqv, H * hd, 0, hd, T * H * hd),
+                 T, hd, L, nb1=H, nb2=B, band=band)
+        ws = torch.zeros(B, L, H * hd, device="cuda", dtype=torch.float32)
+        ops.gemm(ops.Op(dbd, L, Lp, 0, mn_major=True, **bm), ops.Op(qv, hd, H * hd, 0, nb1=H, stride1=hd, nb2=B, stride2=T * H * hd, mn_major=True),
+                 ops.Out(ws, H * hd, 0, hd, L * H * hd), L, hd, T, nb1=H, nb2=B, band=band)
+        outs.append((dqv, ws))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    ref = torch.einsum("bhik,khd->bihd", dbd[..., :L].double(), p.double().view(L, H, hd)).reshape(B, T, H * hd)
+    assert (outs[1][0].double() - ref).abs().max().item() < 0.02 * ref.abs().max().item()
+    # wide output (pair tiles) and a split contraction over a band that leaves some splits empty
+    M, N, K = 512, 256, 1024
+    A = torch.zeros(M, K, device="cuda", dtype=torch.bfloat16)
+    mi, ki = torch.arange(M, device="cuda")[:, None], torch.arange(K, device="cuda")[None, :]
+    msk = (mi + ki >= 700) & (mi + ki < 900)
+    A[msk] = torch.randn(int(msk.sum()), generator=g, device="cuda").to(torch.bfloat16)
+    Bm = _rand((N, K), torch.bfloat16, 8)
+    ref = A.double() @ Bm.double().t()
+    C = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(ops.Op(A, M, K), ops.Op(Bm, N, K), ops.Out(C, N), M, N, K, band=(700, 900))
+    assert (C.double() - ref).abs().max().item() < 2e-3
+    ws = torch.empty(4, M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(ops.Op(A, M, K), ops.Op(Bm, N, K), ops.Out(ws, N), M, N, K, split_k=4, c_split_stride=M * N, band=(700, 900))
+    assert (ws.sum(0).double() - ref).abs().max().item() < 2e-3
+
+
 def test_gemm_rejects_bad_arguments():
     from transformer4sed_b200 import _lib
     ops = _ops()

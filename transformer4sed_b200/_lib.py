@@ -39,7 +39,8 @@ class Matrix(ctypes.Structure):
 class Gemm(ctypes.Structure):
     _fields_ = [("M", c_int), ("N", c_int), ("K", c_int), ("in_dtype", c_int), ("nb1", c_int), ("nb2", c_int),
                 ("split_k", c_int), ("c_split_stride", ctypes.c_int64), ("A", Operand), ("B", Operand), ("C", Matrix),
-                ("aux", Matrix), ("residual", Matrix), ("bias", c_void_p), ("alpha", c_float), ("act", c_int), ("colsum", c_void_p)]
+                ("aux", Matrix), ("residual", Matrix), ("bias", c_void_p), ("alpha", c_float), ("act", c_int), ("colsum", c_void_p),
+                ("band_lo", c_int), ("band_hi", c_int)]
 
 
 class Attn(ctypes.Structure):

@@ -27,8 +27,6 @@ namespace t4s {
 namespace attn {
 namespace rel {
 
-constexpr int kPwBytes = 256 * 128;    // position window: 256 rows x 64 bf16
-constexpr uint32_t kIdescBD = ptx::umma_idesc(1, 128, 256, 0, 0);
 constexpr uint32_t kIdescAmn = ptx::umma_idesc(1, 128, 64, 1, 1);  // A and B MN-major
 
 struct RelArgs {
@@ -50,18 +48,35 @@ __device__ __forceinline__ void mma_k128_amn(uint32_t d_tmem, uint32_t a_addr, u
 // ======================================================================================================
 namespace bwd {
 // 10 warps: 0-7 softmax (thread = query row 32 (w & 3) + lane, column half g = w >> 2 of the 128-key tile), 8 TMA producer, 9 MMA issuer.
-// operand region (112 KB): dQ  kernel: resident [QU][QV][dO], streamed [K][V][Pw]
-//                          dKV kernel: resident [K][V],       streamed [QU][QV][dO][Pw]
-// Skew scratch: every thread parks a 48-column BD window of its row (pitch 50 floats: 8-byte stores and 4-byte skewed reads are bank
-// conflict free) and reads 16 shifted values back, four times per tile.  dQ kernel: the P tile's place holds the dBD staging rows.
+// Operand region, nine 16 KB tiles:
+//   dQ  kernel: resident [QU][QV][dO] | ring [K][K'] | [V]  |        position chunks [Pw0][Pw1][Pw2]
+//   dKV kernel: resident [K][V]       | ring [QU][QU'] | [dO] | [QV] | position chunks [Pw0][Pw1][Pw2]
+// The ring operand is needed from the first to the last MMA of a step, so it is double-buffered; the others are re-filled inside the
+// step, as soon as the one MMA that reads them has retired.  The 256-row position window of step t is two 128-row chunks; consecutive
+// windows share one, so one chunk is loaded per step into a ring of three (BD = two N = 128 MMAs).
+// Pipeline of step t:   [S(t), BD(t) were issued during step t-1]  phase A: P = exp2(AC + shift(BD) - lse)  ->  dP(t), S(t+1)  ->
+// phase B: dS = P (dP - delta)  [BD(t+1) once dP is in registers]  ->  dQ += dS K  |  dV += P^T dO, dK += dS^T QU.
+// TMEM: S [0,128)   BD [128,384), its first half re-used for dP once the skew has consumed it   accumulators [384,512).
+// Skew scratch: a thread parks a 48-column BD window of its row (pitch 50 floats: 8-byte stores and 4-byte skewed reads are bank
+// conflict free) and reads 16 shifted values back, four times per tile.  Rows 0-19 of a warp live in the warp's own 4 KB block of the
+// P tile, which is dead between the dV MMA of step t-1 and the P store of step t (in the dQ kernel the P tile is not an operand: its
+// place is the dBD staging area, below); rows 20-31 live in a 2432-byte slot of their own whose first 32 bytes (the bank phase of row
+// 20 is 32) hold four of the mbarriers.
+// dBD (dQ kernel): dS un-shifted back to position coordinates, dBD[i, T-1-i+j] = dS[i, j].  The two warps of a lane quarter stage their 32
+// rows x 128 columns row-contiguously (256 B per row, 16-byte chunks XOR-swizzled by the row) and each writes 16 whole rows.  A row whose
+// first destination column is odd is written one element to the left, the missing element being the last one of the same row from the
+// previous key tile (kept in a register), so that every store is a full 4-byte word: two-lane half-word stores at the ends of the
+// rows cost more than all the word stores together (measured: 4.4 k clk per step with them, 1.7 k without).
 constexpr int kBThreads = 320;
 constexpr int kPitch = 50;
-constexpr int kScr = 32 * kPitch * 4;   // 6400 B per warp
-constexpr int oOps = 0, oP = oOps + 7 * kTileBytes, oDs = oP + kPBytes, oScr = oDs + kPBytes, oBar = oScr + 8 * kScr;
-constexpr int kSmem = oBar + 128;
+constexpr int kScrSlot = 2432;
+constexpr int oOps = 0, oP = oOps + 9 * kTileBytes, oDs = oP + kPBytes, oScr = oDs + kPBytes;
+constexpr int kSmem = oScr + 8 * kScrSlot;
 static_assert(kSmem <= 232448, "rel-pos attention backward: shared memory");
-constexpr int kTmemCols = 512;  // S / dP: [0,128)  BD: [128,384)  acc0: [384,448)  acc1: [448,512)
-enum { bResFull = 0, bStrFull = 1, bStrEmpty = 2, bSFull = 3, bPReady = 4, bDpFull = 5, bDsFull = 6, bFin = 7, bAccFull = 8, bCount = 9 };
+constexpr int kTmemCols = 512;
+enum { bResFull = 0, bRingFull = 1, bRingEmpty = 3, bXFull = 5, bXEmpty = 6, bYFull = 7, bYEmpty = 8, bPwFull = 9, bPwEmpty = 12, bSFull = 15,
+       bPReady = 16, bDpFull = 17, bDpRead = 18, bDsFull = 19, bFin = 20, bAccFull = 21, bPFree = 22, bCount = 23 };
+
 }  // namespace bwd
 
 template <bool kDq>
@@ -72,34 +87,25 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
   using namespace bwd;
   const Args& a = ra.a;
   extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + bCount);
+  auto bar = [&](int i) { return reinterpret_cast<uint64_t*>(smem + oScr + (i >> 2) * kScrSlot + (i & 3) * 8); };   // the slots' leading holes
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar(bCount));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = blockIdx.x * kTile, h = blockIdx.y, b = blockIdx.z;
   const int n_tiles = a.n_tiles;
   const long long stat_base = ((long long)b * a.H + h) * a.Nl;
   // operand tiles
-  unsigned char* sQU = smem + oOps + (kDq ? 0 : 2) * kTileBytes;
-  unsigned char* sQV = smem + oOps + (kDq ? 1 : 3) * kTileBytes;
-  unsigned char* sDO = smem + oOps + (kDq ? 2 : 4) * kTileBytes;
-  unsigned char* sK = smem + oOps + (kDq ? 3 : 0) * kTileBytes;
-  unsigned char* sV = smem + oOps + (kDq ? 4 : 1) * kTileBytes;
-  unsigned char* sPw = smem + oOps + 5 * kTileBytes;
+  unsigned char* sRes = smem + oOps;                                   // dQ: QU, QV, dO     dKV: K, V
+  unsigned char* sRing = smem + oOps + (kDq ? 3 : 2) * kTileBytes;     // dQ: K              dKV: QU
+  unsigned char* sX = smem + oOps + (kDq ? 5 : 4) * kTileBytes;        // dQ: V              dKV: dO
+  unsigned char* sY = smem + oOps + 5 * kTileBytes;                    //                    dKV: QV
+  unsigned char* sPw = smem + oOps + 6 * kTileBytes;
 
   if (threadIdx.x == 0) {
     if (ptx::smem_u32(smem) & 1023u) {
       printf("t4s relattn_bwd: dynamic shared memory is not 1024-byte aligned\n");
       __trap();
     }
-    ptx::mbar_init(&bars[bResFull], 1);
-    ptx::mbar_init(&bars[bStrFull], 1);
-    ptx::mbar_init(&bars[bStrEmpty], 1);
-    ptx::mbar_init(&bars[bSFull], 1);
-    ptx::mbar_init(&bars[bPReady], 8);
-    ptx::mbar_init(&bars[bDpFull], 1);
-    ptx::mbar_init(&bars[bDsFull], 8);
-    ptx::mbar_init(&bars[bFin], 1);
-    ptx::mbar_init(&bars[bAccFull], 1);
+    for (int i = 0; i < bCount; ++i) ptx::mbar_init(bar(i), (i == bPReady || i == bDpRead || i == bDsFull) ? 8 : 1);
     ptx::fence_barrier_init();
   }
   if (warp == 8 && ptx::elect_one()) {
@@ -121,66 +127,121 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
 
   if (warp == 8) {
     // ---------------- TMA producer ----------------
+    // Position chunk n (n = 0 .. n_tiles) goes to slot n % 3; step t reads chunks t and t + 1.
+    //   dQ  kernel (query tile fixed, keys advance): chunk n = rows T - 128 - i0 + 128 n, (lower, upper) half of the window = (t, t + 1)
+    //   dKV kernel (key tile fixed, queries advance): chunk n = rows T - 128 n + j0,      (lower, upper) = (t + 1, t)
     if (ptx::elect_one()) {
+      auto load_pw = [&](int n) {
+        const int slot = n % 3;
+        if (n >= 3) ptx::mbar_wait(bar(bPwEmpty + slot), ((n / 3) - 1) & 1);
+        ptx::mbar_arrive_expect_tx(bar(bPwFull + slot), kTileBytes);
+        ptx::tma_load_4d(sPw + slot * kTileBytes, &tmPos, bar(bPwFull + slot), 0, kDq ? a.N - kTile - t0 + kTile * n : a.N - kTile * n + t0, h, 0);
+      };
+      auto load_ring = [&](int t) {
+        const int slot = t & 1;
+        if (t >= 2) ptx::mbar_wait(bar(bRingEmpty + slot), ((t >> 1) - 1) & 1);
+        ptx::mbar_arrive_expect_tx(bar(bRingFull + slot), kTileBytes);
+        ptx::tma_load_4d(sRing + slot * kTileBytes, kDq ? &tmK : &tmQU, bar(bRingFull + slot), 0, t * kTile, h, b);
+      };
+      auto load_y = [&](int t) {   // dKV only
+        if (t >= 1) ptx::mbar_wait(bar(bYEmpty), (t - 1) & 1);
+        ptx::mbar_arrive_expect_tx(bar(bYFull), kTileBytes);
+        ptx::tma_load_4d(sY, &tmQV, bar(bYFull), 0, t * kTile, h, b);
+      };
+      auto load_x = [&](int t) {
+        if (t >= 1) ptx::mbar_wait(bar(bXEmpty), (t - 1) & 1);
+        ptx::mbar_arrive_expect_tx(bar(bXFull), kTileBytes);
+        ptx::tma_load_4d(sX, kDq ? &tmV : &tmDO, bar(bXFull), 0, t * kTile, h, b);
+      };
       if (kDq) {
-        ptx::mbar_arrive_expect_tx(&bars[bResFull], 3 * kTileBytes);
-        ptx::tma_load_4d(sQU, &tmQU, &bars[bResFull], 0, t0, h, b);
-        ptx::tma_load_4d(sQV, &tmQV, &bars[bResFull], 0, t0, h, b);
-        ptx::tma_load_4d(sDO, &tmDO, &bars[bResFull], 0, t0, h, b);
+        ptx::mbar_arrive_expect_tx(bar(bResFull), 3 * kTileBytes);
+        ptx::tma_load_4d(sRes, &tmQU, bar(bResFull), 0, t0, h, b);
+        ptx::tma_load_4d(sRes + kTileBytes, &tmQV, bar(bResFull), 0, t0, h, b);
+        ptx::tma_load_4d(sRes + 2 * kTileBytes, &tmDO, bar(bResFull), 0, t0, h, b);
       } else {
-        ptx::mbar_arrive_expect_tx(&bars[bResFull], 2 * kTileBytes);
-        ptx::tma_load_4d(sK, &tmK, &bars[bResFull], 0, t0, h, b);
-        ptx::tma_load_4d(sV, &tmV, &bars[bResFull], 0, t0, h, b);
+        ptx::mbar_arrive_expect_tx(bar(bResFull), 2 * kTileBytes);
+        ptx::tma_load_4d(sRes, &tmK, bar(bResFull), 0, t0, h, b);
+        ptx::tma_load_4d(sRes + kTileBytes, &tmV, bar(bResFull), 0, t0, h, b);
       }
+      load_pw(0);
+      // the operands of step t, in the order in which their buffers fall free
       for (int t = 0; t < n_tiles; ++t) {
-        ptx::mbar_wait(&bars[bStrEmpty], (t & 1) ^ 1);
-        const int i0 = kDq ? t0 : t * kTile, j0 = kDq ? t * kTile : t0;
-        if (kDq) {
-          ptx::mbar_arrive_expect_tx(&bars[bStrFull], 2 * kTileBytes + kPwBytes);
-          ptx::tma_load_4d(sK, &tmK, &bars[bStrFull], 0, j0, h, b);
-          ptx::tma_load_4d(sV, &tmV, &bars[bStrFull], 0, j0, h, b);
-        } else {
-          ptx::mbar_arrive_expect_tx(&bars[bStrFull], 3 * kTileBytes + kPwBytes);
-          ptx::tma_load_4d(sQU, &tmQU, &bars[bStrFull], 0, i0, h, b);
-          ptx::tma_load_4d(sQV, &tmQV, &bars[bStrFull], 0, i0, h, b);
-          ptx::tma_load_4d(sDO, &tmDO, &bars[bStrFull], 0, i0, h, b);
-        }
-        ptx::tma_load_4d(sPw, &tmPos, &bars[bStrFull], 0, a.N - kTile - i0 + j0, h, 0);
+        load_pw(t + 1);
+        if (!kDq) load_y(t);
+        load_ring(t);
+        load_x(t);
       }
     }
   } else if (warp == 9) {
     // ---------------- MMA issuer ----------------
-    const uint32_t uQU = ptx::smem_u32(sQU), uQV = ptx::smem_u32(sQV), uDO = ptx::smem_u32(sDO), uK = ptx::smem_u32(sK),
-                   uV = ptx::smem_u32(sV), uPw = ptx::smem_u32(sPw), uP = ptx::smem_u32(smem + oP), uDs = ptx::smem_u32(smem + oDs);
-    ptx::mbar_wait(&bars[bResFull], 0);
+    const uint32_t uRes = ptx::smem_u32(sRes), uRing = ptx::smem_u32(sRing), uX = ptx::smem_u32(sX), uY = ptx::smem_u32(sY), uPw = ptx::smem_u32(sPw),
+                   uP = ptx::smem_u32(smem + oP), uDs = ptx::smem_u32(smem + oDs);
+    const uint32_t uQV = kDq ? uRes + kTileBytes : uY;
+    ptx::mbar_wait(bar(bResFull), 0);
+    auto issue_s = [&](int t) {      // AC(t) = (q+u) k^T
+      ptx::mbar_wait(bar(bRingFull + (t & 1)), (t >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t ring = uRing + (t & 1) * kTileBytes;
+      if (ptx::elect_one()) mma_k64(tmem, kDq ? uRes : ring, kDq ? ring : uRes, kIdescS, false);
+      __syncwarp();
+    };
+    // BD(t) = (q+v) Pw^T over chunks t and t + 1, as two N = 128 halves: the upper half of the window can be formed as soon as the skew of
+    // step t-1 is over, the lower half shares its columns with dP(t-1) and waits until that is in registers.
+    auto issue_bd_hi = [&](int t) {
+      if (t == 0) ptx::mbar_wait(bar(bPwFull), 0);
+      if (kDq) ptx::mbar_wait(bar(bPwFull + (t + 1) % 3), ((t + 1) / 3) & 1);
+      else ptx::mbar_wait(bar(bYFull), t & 1);
+      ptx::tc_fence_after();
+      const uint32_t c0 = uPw + (t % 3) * kTileBytes, c1 = uPw + ((t + 1) % 3) * kTileBytes;
+      if (ptx::elect_one()) mma_k64(tmem + 256, uQV, kDq ? c1 : c0, kIdescS, false);
+      __syncwarp();
+    };
+    auto issue_bd_lo = [&](int t) {
+      if (!kDq) ptx::mbar_wait(bar(bPwFull + (t + 1) % 3), ((t + 1) / 3) & 1);
+      ptx::tc_fence_after();
+      const uint32_t c0 = uPw + (t % 3) * kTileBytes, c1 = uPw + ((t + 1) % 3) * kTileBytes;
+      if (ptx::elect_one()) {
+        mma_k64(tmem + 128, uQV, kDq ? c0 : c1, kIdescS, false);
+        ptx::tc_commit(bar(bSFull));
+        ptx::tc_commit(bar(bPwEmpty + t % 3));     // chunk t leaves the window
+        if (!kDq) ptx::tc_commit(bar(bYEmpty));
+      }
+      __syncwarp();
+    };
+    issue_s(0);
+    issue_bd_hi(0);
+    issue_bd_lo(0);
     for (int t = 0; t < n_tiles; ++t) {
-      ptx::mbar_wait(&bars[bStrFull], t & 1);
+      ptx::mbar_wait(bar(bPReady), t & 1);             // P is in registers: the S and BD columns are free
+      ptx::mbar_wait(bar(bXFull), t & 1);
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
-        mma_k64(tmem, uQU, uK, kIdescS, false);          // AC = (q+u) k^T
-        mma_k64(tmem + 128, uQV, uPw, kIdescBD, false);  // BD = (q+v) Pw^T
-        ptx::tc_commit(&bars[bSFull]);
+        mma_k64(tmem + 128, kDq ? uRes + 2 * kTileBytes : uX, kDq ? uX : uRes + kTileBytes, kIdescS, false);   // dP = dO v^T
+        ptx::tc_commit(bar(bDpFull));
+        if (kDq) ptx::tc_commit(bar(bXEmpty));
       }
       __syncwarp();
-      ptx::mbar_wait(&bars[bPReady], t & 1);             // P is in registers: the S columns are free
-      ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        mma_k64(tmem, uDO, uV, kIdescS, false);          // dP = dO v^T
-        ptx::tc_commit(&bars[bDpFull]);
+      if (t + 1 < n_tiles) {
+        issue_s(t + 1);
+        issue_bd_hi(t + 1);
       }
-      __syncwarp();
-      ptx::mbar_wait(&bars[bDsFull], t & 1);             // P / dS tiles are in shared memory
+      ptx::mbar_wait(bar(bDpRead), t & 1);             // dP is in registers
+      if (t + 1 < n_tiles) issue_bd_lo(t + 1);
+      ptx::mbar_wait(bar(bDsFull), t & 1);             // P / dS tiles are in shared memory
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
+        const uint32_t ring = uRing + (t & 1) * kTileBytes;
         if (kDq) {
-          mma_k128_mn(tmem + 384, uDs, uK, kIdescPV, t > 0);   // d(q+u) += dS K
+          mma_k128_mn(tmem + 384, uDs, ring, kIdescPV, t > 0);   // d(q+u) += dS K
         } else {
-          mma_k128_amn(tmem + 384, uP, uDO, t > 0);            // dV += P^T dO
-          mma_k128_amn(tmem + 448, uDs, uQU, t > 0);           // dK += dS^T (q+u)
+          mma_k128_amn(tmem + 384, uP, uX, t > 0);               // dV += P^T dO
+          ptx::tc_commit(bar(bPFree));                           // the P tile (= the next step's skew scratch) is free
+          ptx::tc_commit(bar(bXEmpty));
+          mma_k128_amn(tmem + 448, uDs, ring, t > 0);            // dK += dS^T (q+u)
         }
-        ptx::tc_commit(&bars[bStrEmpty]);
-        ptx::tc_commit(&bars[bFin]);
-        if (t == n_tiles - 1) ptx::tc_commit(&bars[bAccFull]);
+        ptx::tc_commit(bar(bRingEmpty + (t & 1)));
+        ptx::tc_commit(bar(bFin));
+        if (t == n_tiles - 1) ptx::tc_commit(bar(bAccFull));
       }
       __syncwarp();
     }
@@ -189,8 +250,11 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
     const int wq = warp & 3, g = warp >> 2;
     const int r = wq * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(wq * 32) << 16);
-    float* scr = reinterpret_cast<float*>(smem + oScr + warp * kScr) + lane * kPitch;
-    unsigned char* stage = smem + oP + warp * 4096;          // dQ kernel: 32 staged dS rows x 128 B (this warp's 64 columns)
+    // this warp's rows of the P tile; dQ kernel: its half of the lane quarter's 8 KB dBD staging area
+    unsigned char* blkP = smem + oP + (kDq ? wq * 8192 + g * 4096 : g * kTileBytes + wq * 4096);
+    uint32_t cw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // dQ kernel: last staged word of the odd rows this warp writes (previous key tile)
+    // rows 0-19: own P block; rows 20-31: own slot, placed so that row 20 keeps its bank phase (20 * 200 = 4000 = 32 mod 128)
+    float* scr = reinterpret_cast<float*>(lane < 20 ? blkP : smem + oScr + warp * kScrSlot + 32 - 4000) + lane * kPitch;
     const float sl2 = a.sl2;
     const uint64_t sl2_2 = ptx::pack2(sl2, sl2);
     float my_lse = 0.f, my_delta = 0.f;
@@ -205,14 +269,34 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
         my_delta = a.delta[stat_base + i0 + r];
       }
       const int nvalid = a.N - j0 - 64 * g;  // key columns of this half that exist (may be <= 0 or >= 64)
-      ptx::mbar_wait(&bars[bSFull], t & 1);
+      T4S_TRACE_AT(warp + (kDq ? 0 : 10), t, 0);
+      ptx::mbar_wait(bar(bSFull), t & 1);
       ptx::tc_fence_after();
-      // phase A: P = exp2((AC + shift(BD)) * c - lse), kept packed in registers
+      T4S_TRACE_AT(warp + (kDq ? 0 : 10), t, 1);
+      // phase A: P = exp2((AC + shift(BD)) * c - lse), kept packed in registers.
+      // s[16 q + cc] += BD[r][127 - r + 64 g + 16 q + cc]: a 48-column window of this warp's rows is parked in the scratch row and read back
+      // at the lane's offset, four times; the TMEM load of window q + 1 is in flight while window q goes through shared memory.
       float s[64];
+      uint32_t xa0[32], xa1[16], xb0[32], xb1[16];
+      auto ld_win = [&](int q, uint32_t (&y0)[32], uint32_t (&y1)[16]) {
+        const int wb = 96 - 32 * wq + 64 * g + 16 * q;
+        ptx::tmem_ld_32x32(t_lane + 128 + wb, y0);
+        ptx::tmem_ld_32x16(t_lane + 128 + wb + 32, y1);
+      };
+      auto skew = [&](int q, const uint32_t (&y0)[32], const uint32_t (&y1)[16]) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) *reinterpret_cast<uint2*>(scr + 2 * k) = make_uint2(y0[2 * k], y0[2 * k + 1]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) *reinterpret_cast<uint2*>(scr + 32 + 2 * k) = make_uint2(y1[2 * k], y1[2 * k + 1]);
+        const volatile float* rd = scr + (31 - lane);
+#pragma unroll
+        for (int cc = 0; cc < 16; ++cc) s[16 * q + cc] += rd[cc];
+      };
       {
         uint32_t v0[32], v1[32];
         ptx::tmem_ld_32x32(t_lane + 64 * g, v0);
         ptx::tmem_ld_32x32(t_lane + 64 * g + 32, v1);
+        ld_win(0, xa0, xa1);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -220,22 +304,20 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
           s[32 + i] = __uint_as_float(v1[i]);
         }
       }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        // s[16 q + cc] += BD[r][127 - r + 64 g + 16 q + cc]: a 48-column window of this warp's rows, read back at the lane's offset
-        const int wb = 96 - 32 * wq + 64 * g + 16 * q;
-        uint32_t x0[32], x1[16];
-        ptx::tmem_ld_32x32(t_lane + 128 + wb, x0);
-        ptx::tmem_ld_32x16(t_lane + 128 + wb + 32, x1);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) *reinterpret_cast<uint2*>(scr + 2 * k) = make_uint2(x0[2 * k], x0[2 * k + 1]);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) *reinterpret_cast<uint2*>(scr + 32 + 2 * k) = make_uint2(x1[2 * k], x1[2 * k + 1]);
-        const volatile float* rd = scr + (31 - lane);
-#pragma unroll
-        for (int cc = 0; cc < 16; ++cc) s[16 * q + cc] += rd[cc];
-      }
+      if (!kDq) ptx::mbar_wait(bar(bPFree), (t & 1) ^ 1);   // the previous step's dV MMA has finished with the P tile (= scratch rows 0-19)
+      else ptx::bar_sync(1 + wq, 64);                       // the partner warp has written out the rows it read from this warp's staging half
+      T4S_TRACE_AT(warp + (kDq ? 0 : 10), t, 2);
+      ld_win(1, xb0, xb1);
+      skew(0, xa0, xa1);
+      ptx::tmem_ld_wait();
+      ld_win(2, xa0, xa1);
+      skew(1, xb0, xb1);
+      ptx::tmem_ld_wait();
+      ld_win(3, xb0, xb1);
+      skew(2, xa0, xa1);
+      ptx::tmem_ld_wait();
+      skew(3, xb0, xb1);
+      T4S_TRACE_AT(warp + (kDq ? 0 : 10), t, 3);
       const uint64_t nlse2 = ptx::pack2(-my_lse, -my_lse);
       uint32_t pk[32];
 #pragma unroll
@@ -251,9 +333,7 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars[bPReady]);
-      // the previous step's MMAs have finished with the P / dS tiles
-      ptx::mbar_wait(&bars[bFin], (t & 1) ^ 1);
+      if (lane == 0) ptx::mbar_arrive(bar(bPReady));
       if (!kDq) {
         uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[0]);
         uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pk[16]);
@@ -261,14 +341,19 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
         store_row_chunk(smem + oP, r, 64 * g + 32, hi);
       }
       // phase B: dS = P (dP - delta)
-      ptx::mbar_wait(&bars[bDpFull], t & 1);
+      T4S_TRACE_AT(warp + (kDq ? 0 : 10), t, 4);
+      ptx::mbar_wait(bar(bDpFull), t & 1);
       ptx::tc_fence_after();
+      T4S_TRACE_AT(warp + (kDq ? 0 : 10), t, 5);
       uint32_t pd[32];
       {
         uint32_t v0[32], v1[32];
-        ptx::tmem_ld_32x32(t_lane + 64 * g, v0);
-        ptx::tmem_ld_32x32(t_lane + 64 * g + 32, v1);
+        ptx::tmem_ld_32x32(t_lane + 128 + 64 * g, v0);
+        ptx::tmem_ld_32x32(t_lane + 128 + 64 * g + 32, v1);
         ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar(bDpRead));
         const uint64_t nd2 = ptx::pack2(-my_delta, -my_delta);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
@@ -280,6 +365,7 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
           pd[i] = pack_bf16(d0, d1);
         }
       }
+      ptx::mbar_wait(bar(bFin), (t & 1) ^ 1);   // the previous step's MMAs have finished with the dS tile
       {
         uint32_t (&lo)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pd[0]);
         uint32_t (&hi)[16] = *reinterpret_cast<uint32_t (*)[16]>(&pd[16]);
@@ -287,38 +373,48 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
         store_row_chunk(smem + oDs, r, 64 * g + 32, hi);
       }
       if (kDq) {
+        uint4* dst = reinterpret_cast<uint4*>(smem + oP + wq * 8192 + lane * 256) + 8 * g;
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<uint4*>(stage + lane * 128 + q * 16) = make_uint4(pd[4 * q], pd[4 * q + 1], pd[4 * q + 2], pd[4 * q + 3]);
+        for (int q = 0; q < 8; ++q) dst[q ^ (lane & 7)] = make_uint4(pd[4 * q], pd[4 * q + 1], pd[4 * q + 2], pd[4 * q + 3]);
       }
-      ptx::tc_fence_before();
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&bars[bDsFull]);
+      if (lane == 0) ptx::mbar_arrive(bar(bDsFull));
+      T4S_TRACE_AT(warp + (kDq ? 0 : 10), t, 6);
       if (kDq) {
-        // dBD[b, h, i, T-1-i+j0 + 64 g + e] <- dS[i, j0 + 64 g + e]: this warp's 32 staged rows, 32 destination words per row
-        const uint32_t* st32 = reinterpret_cast<const uint32_t*>(stage);
-        const int nv = min(nvalid, 64);
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-          const int i = i0 + wq * 32 + rr;
-          if (i >= a.N) break;
-          const int x0 = a.N - 1 - i + j0 + 64 * g;
-          __nv_bfloat16* drow = ra.dbd + (((long long)b * a.H + h) * a.N + i) * ra.dbd_ld + x0;
-          const int par = x0 & 1;  // rows start 16-byte aligned, so the word alignment of the destination is the parity of x0
-          const uint32_t* srow = st32 + rr * 32;
-          const int e = par + 2 * lane;  // first source element of destination word `lane`
-          const uint32_t nxt = (lane < 31) ? srow[lane + 1] : 0u;
-          const uint32_t val = __funnelshift_r(srow[lane], nxt, 16 * par);
-          if (e + 1 < nv) *reinterpret_cast<uint32_t*>(drow + e) = val;
-          else if (e < nv) *reinterpret_cast<unsigned short*>(drow + e) = (unsigned short)(val & 0xffffu);
-          if (par && lane == 0 && nv > 0) *reinterpret_cast<unsigned short*>(drow) = (unsigned short)(srow[0] & 0xffffu);
+        // dBD[b, h, i, T-1-i+j0 + c] <- dS[i, j0 + c], c < 128: rows 4 m + 2 g + {0, 1} of the lane quarter, lane = destination words l, l + 32
+        ptx::bar_sync(1 + wq, 64);                         // both halves of the quarter's rows are staged
+        // Branch-free: row rl goes to dbase + rl (ld - 1) - par with par = parity of its first destination column = P0 ^ (rl & 1), the
+        // same for every key tile; the number of elements to store, N - j0 (+ the borrowed one), is the same for every row.
+        const uint32_t* stq = reinterpret_cast<const uint32_t*>(smem + oP + wq * 8192);
+        const int ib = i0 + wq * 32, X0 = a.N - 1 - ib + j0, P0 = X0 & 1;
+        const int rows = a.N - ib, nkeys = a.N - j0, pitch1 = (int)ra.dbd_ld - 1;
+        __nv_bfloat16* dbase = ra.dbd + (((long long)b * a.H + h) * a.N + ib) * ra.dbd_ld + X0 + 2 * g * pitch1;
+        const int lg = lane ^ (g << 3), lgm = ((lane + 63) & 63) ^ (g << 3), lg31 = (lane + 31) ^ (g << 3);
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int par = P0 ^ u, sw = (((m & 1) << 2) | u) << 2;
+            const uint32_t* srow = stq + (4 * m + u) * 64 + g * 128;
+            const uint32_t A = srow[lg ^ sw], Bw = srow[(lg ^ sw) + 32], Ams = srow[lgm ^ sw], Bm = srow[lg31 ^ sw];
+            const uint32_t Am = lane ? Ams : cw[m];
+            const int sh = par ? 16 : 32;
+            const uint32_t o0 = __funnelshift_rc(Am, A, sh), o1 = __funnelshift_rc(Bm, Bw, sh);
+            const uint32_t last = __shfl_sync(0xffffffffu, Bw, 31);
+            if (par) cw[m] = last;
+            uint32_t* d = reinterpret_cast<uint32_t*>(dbase + (4 * m + u) * pitch1 - par);
+            const int lim = (4 * m + 2 * g + u < rows) ? nkeys + par : 0;
+            if (2 * lane < lim) d[lane] = o0;
+            if (2 * lane + 64 < lim) d[lane + 32] = o1;
+            if (par && t == n_tiles - 1 && lane == 0 && 128 < lim) d[64] = last >> 16;   // N = 128 n: the band's very last element
+          }
         }
-        __syncwarp();
       }
+      T4S_TRACE_AT(warp + (kDq ? 0 : 10), t, 7);
     }
     // ---- accumulators: each column half writes 32 of the 64 head-dim columns ----
-    ptx::mbar_wait(&bars[bAccFull], 0);
+    ptx::mbar_wait(bar(bAccFull), 0);
     ptx::tc_fence_after();
     const int row = t0 + r;
     uint32_t v0[32];
@@ -373,6 +469,14 @@ static void fill_rel_args(Args& a, const T4sRelAttn* p) {
 }  // namespace attn
 }  // namespace t4s
 
+#ifdef T4S_TRACE
+extern "C" int t4s_debug_trace_rel(long long* out, int n) {
+  if (n > 4096) n = 4096;
+  T4S_CUDA(cudaMemcpyFromSymbol(out, g_trace, sizeof(long long) * n));
+  return T4S_OK;
+}
+#endif
+
 extern "C" int t4s_relattn_fwd(const T4sRelAttn* p, void* stream) {
   using namespace t4s::attn;
   using namespace t4s::attn::rel;
@@ -413,7 +517,7 @@ extern "C" int t4s_relattn_bwd(const T4sRelAttnBwd* p, void* stream) {
   if ((rc = make_map(&tk, f->k, f->k_ld, f->k_bs, B, H, T, "k"))) return rc;
   if ((rc = make_map(&tv, f->v, f->v_ld, f->v_bs, B, H, T, "v"))) return rc;
   if ((rc = make_map(&tdo, p->d_o, p->do_ld, p->do_bs, B, H, T, "d_o"))) return rc;
-  if ((rc = make_map(&tpos, f->pos, f->pos_ld, f->pos_ld * (2LL * T - 1), 1, H, 2 * T - 1, "pos", 256))) return rc;
+  if ((rc = make_map(&tpos, f->pos, f->pos_ld, f->pos_ld * (2LL * T - 1), 1, H, 2 * T - 1, "pos", kTile))) return rc;   // 128-row chunks
   T4S_REQUIRE(!(reinterpret_cast<uintptr_t>(p->dbd) & 15) && !(p->dbd_ld % 8) && p->dbd_ld >= 2LL * T - 1,
               "t4s_relattn_bwd: dbd needs a 16-byte aligned base and a row pitch >= 2T-1 that is a multiple of 8 elements");
   RelArgs ra;

@@ -52,6 +52,7 @@ struct Args {
   int act;
   int res_tma;   // staged epilogue: the residual / pre-activation tile arrives by TMA (tensor map tmR) instead of per-row loads
   float* colsum; // staged epilogue: column sums of the output, accumulated with atomics
+  int band_lo, band_hi;  // band_hi > 0: A[m, k] == 0 unless band_lo <= m + k < band_hi
 };
 
 template <int BN>
@@ -414,6 +415,24 @@ __device__ __forceinline__ void tile_coords(const Args& a, int r, int& tm, int& 
   tn = g * a.group_n + (rem - tm * width);
 }
 
+// k-blocks [kb0, kb1) of split `sp` for the M tile `tm`: the split's share of K, clipped to the blocks that meet the tile's part of the
+// anti-diagonal band when the caller declared one.  Never empty (an all-zero block stands in): the accumulator is always written.
+__device__ __forceinline__ void k_range(const Args& a, int sp, int tm, int tile_rows, int kblocks_all, int bk, int& kb0, int& kb1) {
+  kb0 = sp * a.kb_per_split;
+  kb1 = min(kblocks_all, kb0 + a.kb_per_split);
+  if (a.band_hi > 0) {
+    const int m0 = tm * tile_rows, m1 = min(a.M, m0 + tile_rows) - 1;
+    const int lo = max(0, a.band_lo - m1) / bk, hi = (min(a.K, a.band_hi - m0) + bk - 1) / bk;
+    const int c0 = max(kb0, lo), c1 = min(kb1, hi);
+    if (c1 > c0) {
+      kb0 = c0;
+      kb1 = c1;
+    } else {
+      kb1 = kb0 + 1;
+    }
+  }
+}
+
 // kPair: the CTAs of a 2-CTA cluster (one TPC) work on one 256 x BN tile with tcgen05.mma.cta_group::2: CTA rank r owns rows
 // [256 tm + 128 r, +128) of A / C and stages rows [n0 + 128 r, +128) of B; the leader (rank 0) issues the MMAs for both, its
 // `full` barriers collect the TMA bytes of both CTAs, commits are multicast to both CTAs' `empty` / `tfull` barriers, and the
@@ -503,7 +522,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const int nbz = a.nb1 * a.nb2;
         const int sp = zs / nbz, z = zs - sp * nbz;
         const int z1 = z % a.nb1, z2 = z / a.nb1;
-        const int kb0 = sp * a.kb_per_split, kb1 = min(kblocks_all, kb0 + a.kb_per_split);
+        int kb0, kb1;
+        k_range(a, sp, tm, kTileM, kblocks_all, kBK, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kNStages;
           const uint32_t ph = (it / kNStages) & 1;
@@ -559,7 +579,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int as = ai & 1;
       const uint32_t aph = (ai >> 1) & 1;
       const int sp = (int)(tile / (tiles_per_batch * a.nb1 * a.nb2));
-      const int kb0 = sp * a.kb_per_split, kb1 = min(kblocks_all, kb0 + a.kb_per_split);
+      int kb0, kb1, tm = 0, tn = 0;
+      if (a.band_hi > 0) tile_coords(a, (int)(tile % tiles_per_batch), tm, tn);
+      k_range(a, sp, tm, kTileM, kblocks_all, kBK, kb0, kb1);
       ptx::mbar_wait(&tempty[as], aph ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
@@ -868,6 +890,9 @@ extern "C" int t4s_gemm(const T4sGemm* g, void* stream) {
   a.C = mat_arg(g->C); a.aux = mat_arg(g->aux); a.res = mat_arg(g->residual);
   a.bias = g->bias; a.alpha = g->alpha; a.act = g->act;
   a.colsum = g->colsum;
+  a.band_lo = g->band_hi > 0 ? g->band_lo : 0;
+  a.band_hi = g->band_hi > 0 ? g->band_hi : 0;
+  T4S_REQUIRE(g->band_hi <= 0 || g->band_hi > g->band_lo, "t4s_gemm: band_hi must exceed band_lo");
   a.bias_vec = g->bias && !(reinterpret_cast<uintptr_t>(g->bias) & 15);
   a.split_k = g->split_k > 1 ? g->split_k : 1;
   a.c_split = g->c_split_stride;

@@ -704,13 +704,15 @@ class _RelPosAttention(torch.autograd.Function):
                nb2=B, alpha=scale)
             # d(q+v) = scale dBD p ; dp = scale sum_b dBD^T (q+v)
             dqv = torch.empty(B, T, D, dtype=dt, device=dev)
+            # dBD[i, k] is zero unless T-1 <= i + k <= 2T-2 (the kernel only ever writes that band): the GEMMs skip the k-blocks outside it
+            band = (T - 1, 2 * T - 1)
             mm(Op(dBD, T, Lp, 0, **bm), Op(p_lin, hd, D, 0, nb1=H, stride1=hd, mn_major=True), Out(dqv, D, 0, hd, T * D), T, hd, L, nb1=H, nb2=B,
-               alpha=scale)
+               alpha=scale, band=band)
             dp_lin = None
             if ctx.needs_input_grad[1]:
                 ws = torch.empty(B, L, D, dtype=torch.float32, device=dev)
                 mm(Op(dBD, L, Lp, 0, mn_major=True, **bm), _tok_heads(qv, B, T, D, H, mn=True), Out(ws, D, 0, hd, L * D), L, hd, T, nb1=H, nb2=B,
-                   alpha=scale)
+                   alpha=scale, band=band)
                 dp32 = torch.empty(L, D, dtype=torch.float32, device=dev)
                 ops.reduce_splits(ws, B, L * D, dp32)
                 dp_lin = dp32 if dt == torch.float32 else convert(dp32, torch.empty(L, D, dtype=dt, device=dev))
@@ -814,13 +816,15 @@ class _FlashRelPosAttention(torch.autograd.Function):
             bm = dict(nb1=H, stride1=T * Lp, nb2=B, stride2=H * T * Lp)
             # d(q+v) = scale dBD p ; dp = scale sum_b dBD^T (q+v)
             dqv = torch.empty(B, T, D, dtype=dt, device=dev)
+            # dBD[i, k] is zero unless T-1 <= i + k <= 2T-2 (the kernel only ever writes that band): the GEMMs skip the k-blocks outside it
+            band = (T - 1, 2 * T - 1)
             mm(Op(dBD, T, Lp, 0, **bm), Op(p_lin, hd, D, 0, nb1=H, stride1=hd, mn_major=True), Out(dqv, D, 0, hd, T * D), T, hd, L, nb1=H, nb2=B,
-               alpha=scale)
+               alpha=scale, band=band)
             dp_lin = None
             if ctx.needs_input_grad[1]:
                 ws = torch.empty(B, L, D, dtype=torch.float32, device=dev)
                 mm(Op(dBD, L, Lp, 0, mn_major=True, **bm), _tok_heads(qv, B, T, D, H, mn=True), Out(ws, D, 0, hd, L * D), L, hd, T, nb1=H, nb2=B,
-                   alpha=scale)
+                   alpha=scale, band=band)
                 dp32 = torch.empty(L, D, dtype=torch.float32, device=dev)
                 ops.reduce_splits(ws, B, L * D, dp32)
                 dp_lin = convert(dp32, torch.empty(L, D, dtype=dt, device=dev))

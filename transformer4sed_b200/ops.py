@@ -53,9 +53,10 @@ _NULL_MAT = Matrix(ctypes.c_void_p(0), 0, 0, 0, 0)
 
 
 def gemm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, bias=None, aux: Out = None, residual: Out = None, alpha=1.0,
-         act=ACT_NONE, split_k=1, c_split_stride=0, colsum=None):
+         act=ACT_NONE, split_k=1, c_split_stride=0, colsum=None, band=None):
     """C[z] = act(alpha * A[z] @ B[z]^T + bias) + residual[z] on tensor cores (tcgen05).  `colsum` (fp32 [N], zeroed by the caller)
-    receives the column sums of C from the epilogue (bf16 un-split, un-batched outputs only)."""
+    receives the column sums of C from the epilogue (bf16 un-split, un-batched outputs only).  `band` = (lo, hi): the caller
+    guarantees A[z][m, k] == 0 unless lo <= m + k < hi; k-blocks outside an M tile's band are skipped."""
     _lib.ensure_device(A.t)
     if A.t.dtype != B.t.dtype:
         raise _lib.T4sError("gemm operands must share a dtype")
@@ -70,6 +71,7 @@ def gemm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, bias=None, aux: Out = None
     g.bias = ctypes.c_void_p(bias.data_ptr()) if bias is not None else ctypes.c_void_p(0)
     g.alpha, g.act = float(alpha), act
     g.colsum = ctypes.c_void_p(colsum.data_ptr()) if colsum is not None else ctypes.c_void_p(0)
+    g.band_lo, g.band_hi = (int(band[0]), int(band[1])) if band is not None else (0, 0)
     with torch.cuda.device(A.t.device):
         if _lib.profiler is not None:
             key = (M, N, K, nb1 * nb2, "T" if A.mn_major else "N", "T" if B.mn_major else "N", split_k)
