@@ -682,49 +682,76 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // dq[b, n, h*64 + d] (bf16, strided) = scale * dq32[b, n, h*64 + d]   (fused backward: fp32 reduce buffer -> gradient slot)
 __global__ void dq_finish_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dq, long long dq_ld, long long dq_bs, int N, int D,
                                  float scale, long long total8) {
+  const int c8n = D >> 3;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
-    const long long e = i * 8;
-    const int d = (int)(e % D);
-    const long long bn = e / D;
-    const int n = (int)(bn % N);
-    const long long b = bn / N;
-    const float4 x = *reinterpret_cast<const float4*>(dq32 + e), y = *reinterpret_cast<const float4*>(dq32 + e + 4);
+    const int row = (int)((unsigned)i / (unsigned)c8n), c = (int)i - row * c8n;   // total8 < 2^31 (checked by the host)
+    const int b = row / N, n = row - b * N;
+    const float* src = dq32 + i * 8;
+    const float4 x = *reinterpret_cast<const float4*>(src), y = *reinterpret_cast<const float4*>(src + 4);
     uint4 u;
     u.x = pack_bf16(x.x * scale, x.y * scale);
     u.y = pack_bf16(x.z * scale, x.w * scale);
     u.z = pack_bf16(y.x * scale, y.y * scale);
     u.w = pack_bf16(y.z * scale, y.w * scale);
-    *reinterpret_cast<uint4*>(dq + b * dq_bs + (long long)n * dq_ld + d) = u;
+    *reinterpret_cast<uint4*>(dq + (long long)b * dq_bs + (long long)n * dq_ld + 8 * c) = u;
   }
 }
 
-// Same, plus the column sums of dq (the q third of the qkv bias gradient): a block walks a strip of token rows, thread = one 8-column
-// chunk of one of the `rpp` rows of a pass, per-thread partial sums, 8 atomics per thread at the end.
-__global__ void __launch_bounds__(256) dq_finish_colsum_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dq, long long dq_ld,
-                                                               long long dq_bs, int N, int D, float scale, long long rows, int rows_per_block,
-                                                               float* __restrict__ colsum) {
-  const int c8n = D >> 3, rpp = 256 / c8n;
-  if ((int)threadIdx.x >= rpp * c8n) return;
+// Same, plus the column sums of dq (the q third of the qkv bias gradient).  Block = rpp rows x (D / 8) chunks of 8 columns; a thread
+// keeps four rows in flight (8 x 16-byte loads), accumulates its 8 columns in registers, the rpp row lanes are combined through shared
+// memory and one lane per column issues the atomic.  `flat`: dq_bs == N * dq_ld (the q third of a packed qkv gradient), no row split.
+__global__ void __launch_bounds__(384) dq_finish_colsum_kernel(const float* __restrict__ dq32, __nv_bfloat16* __restrict__ dq, long long dq_ld,
+                                                               long long dq_bs, int N, int D, float scale, int rows, int rows_per_block,
+                                                               int flat, float* __restrict__ colsum) {
+  extern __shared__ float s_sum[];   // [rpp][D]
+  const int c8n = D >> 3, rpp = blockDim.x / c8n;
   const int c = threadIdx.x % c8n, rr = threadIdx.x / c8n;
-  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long long row = r0 + rr; row < r1; row += rpp) {
-    const float* src = dq32 + row * D + 8 * c;
-    const float4 x = *reinterpret_cast<const float4*>(src), y = *reinterpret_cast<const float4*>(src + 4);
-    const float f[8] = {x.x * scale, x.y * scale, x.z * scale, x.w * scale, y.x * scale, y.y * scale, y.z * scale, y.w * scale};
-    uint4 u;
-    u.x = pack_bf16(f[0], f[1]);
-    u.y = pack_bf16(f[2], f[3]);
-    u.z = pack_bf16(f[4], f[5]);
-    u.w = pack_bf16(f[6], f[7]);
-    const long long b = row / N;
-    const int n = (int)(row - b * N);
-    *reinterpret_cast<uint4*>(dq + b * dq_bs + (long long)n * dq_ld + 8 * c) = u;
+  if (rr < rpp) {
+    for (int row = r0 + rr; row < r1; row += 4 * rpp) {
+      float4 x[4], y[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] += f[e];
+      for (int u = 0; u < 4; ++u) {
+        const int rw = row + u * rpp;
+        if (rw < r1) {
+          const float* src = dq32 + (long long)rw * D + 8 * c;
+          x[u] = *reinterpret_cast<const float4*>(src);
+          y[u] = *reinterpret_cast<const float4*>(src + 4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int rw = row + u * rpp;
+        if (rw < r1) {
+          const float f[8] = {x[u].x * scale, x[u].y * scale, x[u].z * scale, x[u].w * scale, y[u].x * scale, y[u].y * scale, y[u].z * scale, y[u].w * scale};
+          uint4 o;
+          o.x = pack_bf16(f[0], f[1]);
+          o.y = pack_bf16(f[2], f[3]);
+          o.z = pack_bf16(f[4], f[5]);
+          o.w = pack_bf16(f[6], f[7]);
+          long long off;
+          if (flat) {
+            off = (long long)rw * dq_ld;
+          } else {
+            const int bb = rw / N;
+            off = (long long)bb * dq_bs + (long long)(rw - bb * N) * dq_ld;
+          }
+          *reinterpret_cast<uint4*>(dq + off + 8 * c) = o;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += f[e];
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) s_sum[rr * D + 8 * c + e] = acc[e];
   }
-#pragma unroll
-  for (int e = 0; e < 8; ++e) atomicAdd(colsum + 8 * c + e, acc[e]);
+  __syncthreads();
+  for (int j = threadIdx.x; j < D; j += blockDim.x) {
+    float t = 0.f;
+    for (int q = 0; q < rpp; ++q) t += s_sum[q * D + j];
+    atomicAdd(colsum + j, t);
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------
@@ -887,14 +914,16 @@ extern "C" int t4s_attn_bwd(const T4sAttnBwd* p, void* stream) {
     T4S_LAUNCH_CHECK();
     if (p->dqkv_colsum) {
       const long long rows = (long long)f->batch * f->tokens;
-      const int blocks = (int)std::min<long long>((rows + 31) / 32, (long long)t4s::sm_count() * 8);
-      const int rpb = (int)((rows + blocks - 1) / blocks);
-      dq_finish_colsum_kernel<<<(int)((rows + rpb - 1) / rpb), 256, 0, st>>>(p->dq32, a.dq, a.dq_ld, a.dq_bs, f->tokens, D, a.scale, rows, rpb,
-                                                                               p->dqkv_colsum);
+      T4S_REQUIRE(rows < (1LL << 31) && D <= 3072, "t4s_attn_bwd: batch * tokens / width exceed the dq-finish kernel's limits");
+      const int c8n = D / 8, rpp = std::max(1, std::min(4, 384 / c8n));
+      const int rpb = 16 * rpp;    // four passes of four rows per thread
+      dq_finish_colsum_kernel<<<(int)((rows + rpb - 1) / rpb), c8n * rpp, (size_t)rpp * D * sizeof(float), st>>>(
+          p->dq32, a.dq, a.dq_ld, a.dq_bs, f->tokens, D, a.scale, (int)rows, rpb, a.dq_bs == (long long)f->tokens * a.dq_ld ? 1 : 0, p->dqkv_colsum);
       T4S_LAUNCH_CHECK();
       return T4S_OK;
     }
     const long long total8 = (long long)f->batch * f->tokens * D / 8;
+    T4S_REQUIRE(total8 < (1LL << 31), "t4s_attn_bwd: batch * tokens * width exceeds the dq-finish kernel's limit");
     const int fgrid = (int)std::min<long long>((total8 + 255) / 256, (long long)t4s::sm_count() * 16);
     dq_finish_kernel<<<fgrid, 256, 0, st>>>(p->dq32, a.dq, a.dq_ld, a.dq_bs, f->tokens, D, a.scale, total8);
     T4S_LAUNCH_CHECK();

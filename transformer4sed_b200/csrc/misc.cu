@@ -182,6 +182,71 @@ __global__ void add_rowvec_kernel(const T* __restrict__ x, long long ld, const f
   }
 }
 
+// bf16 fast path of the two strided element-wise kernels (cols % 8 == 0, pitches % 8 == 0, 16-byte aligned bases): a thread moves 8
+// elements per 16-byte access and keeps two independent chunks in flight; 32-bit index arithmetic (rows * cols / 8 < 2^31).
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+  return u;
+}
+// out[r*ldo + c] = alpha * x[r*ldx + c] + beta * y[r*ldy + c] + vec[c]   (y and / or vec may be NULL)
+__global__ void __launch_bounds__(256) axpby_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ y,
+                                                           long long ldy, const float* __restrict__ vec, __nv_bfloat16* __restrict__ out,
+                                                           long long ldo, int total8, int c8n, float alpha, float beta) {
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += 2 * stride) {
+    uint4 xv[2], yv[2];
+    int row[2], c[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = i + u * stride;
+      if (j < total8) {
+        row[u] = (int)((unsigned)j / (unsigned)c8n);
+        c[u] = 8 * (j - row[u] * c8n);
+        xv[u] = *reinterpret_cast<const uint4*>(x + (long long)row[u] * ldx + c[u]);
+        if (y) yv[u] = *reinterpret_cast<const uint4*>(y + (long long)row[u] * ldy + c[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (i + u * stride < total8) {
+        float a[8], b[8];
+        bf16x8_to_f32(xv[u], a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] *= alpha;
+        if (y) {
+          bf16x8_to_f32(yv[u], b);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) a[e] = fmaf(beta, b[e], a[e]);
+        }
+        if (vec) {
+          const float4 v0 = *reinterpret_cast<const float4*>(vec + c[u]), v1 = *reinterpret_cast<const float4*>(vec + c[u] + 4);
+          a[0] += v0.x; a[1] += v0.y; a[2] += v0.z; a[3] += v0.w; a[4] += v1.x; a[5] += v1.y; a[6] += v1.z; a[7] += v1.w;
+        }
+        *reinterpret_cast<uint4*>(out + (long long)row[u] * ldo + c[u]) = f32_to_bf16x8(a);
+      }
+    }
+  }
+}
+static bool axpby_fast(const void* x, long long ldx, const void* y, long long ldy, const float* vec, void* out, long long ldo, long long rows, int cols,
+                       int dtype) {
+  if (dtype != T4S_BF16 || cols % 8 || ldx % 8 || ldo % 8 || (y && ldy % 8) || rows * (cols / 8) >= (1LL << 30)) return false;
+  return !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(vec) | reinterpret_cast<uintptr_t>(out)) & 15);
+}
+
 // ---- out[r*ldo + c] = alpha * x[r*ldx + c] + beta * y[r*ldy + c]
 template <typename T>
 __global__ void add2_kernel(const T* __restrict__ x, long long ldx, const T* __restrict__ y, long long ldy, T* __restrict__ out, long long ldo,
@@ -327,6 +392,13 @@ int t4s_pad_interp_bwd(const void* dout, void* dx, int dtype, int batch, int t_i
 
 int t4s_add_rowvec(const void* x, int64_t ld, const float* vec, void* out, int64_t rows, int cols, float scale, int dtype, void* stream) {
   T4S_REQUIRE(x && out && rows > 0 && cols > 0, "t4s_add_rowvec: bad arguments");
+  if (axpby_fast(x, ld, nullptr, 0, vec, out, cols, rows, cols, dtype)) {
+    const int total8 = (int)(rows * (cols / 8));
+    axpby_bf16x8_kernel<<<grid_for((total8 + 1) / 2), 256, 0, t4s::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x), ld, nullptr, 0, vec,
+                                                                                      static_cast<__nv_bfloat16*>(out), cols, total8, cols / 8, scale, 0.f);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (add_rowvec_kernel<T><<<grid_for(rows * cols), 256, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(x), ld, vec, static_cast<T*>(out), rows, cols, scale)));
   T4S_LAUNCH_CHECK();
@@ -336,6 +408,14 @@ int t4s_add_rowvec(const void* x, int64_t ld, const float* vec, void* out, int64
 int t4s_add2(const void* x, int64_t ldx, const void* y, int64_t ldy, void* out, int64_t ldo, int64_t rows, int cols, float alpha, float beta,
              int dtype, void* stream) {
   T4S_REQUIRE(x && y && out && rows > 0 && cols > 0, "t4s_add2: bad arguments");
+  if (axpby_fast(x, ldx, y, ldy, nullptr, out, ldo, rows, cols, dtype)) {
+    const int total8 = (int)(rows * (cols / 8));
+    axpby_bf16x8_kernel<<<grid_for((total8 + 1) / 2), 256, 0, t4s::as_stream(stream)>>>(static_cast<const __nv_bfloat16*>(x), ldx,
+                                                                                      static_cast<const __nv_bfloat16*>(y), ldy, nullptr,
+                                                                                      static_cast<__nv_bfloat16*>(out), ldo, total8, cols / 8, alpha, beta);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (add2_kernel<T><<<grid_for(rows * cols), 256, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(x), ldx, static_cast<const T*>(y), ldy, static_cast<T*>(out), ldo, rows, cols, alpha, beta)));
   T4S_LAUNCH_CHECK();

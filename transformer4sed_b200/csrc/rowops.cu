@@ -37,6 +37,10 @@ template <> struct Vec4<__nv_bfloat16> {
 // LayerNorm.  Row r lives at x + (r / n_inner) * bstride + (r % n_inner) * cols  (a [B, skip:, C] slice is a view).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kLnMaxV = 8;  // float4 per lane -> cols <= 1024
+// the common case (one contiguous [rows, cols] block) skips the 64-bit divisions of the sliced-view address
+__device__ __forceinline__ long long ln_row_offset(long long r, long long rows, int cols, long long n_inner, long long bstride) {
+  return n_inner >= rows ? r * cols : (r / n_inner) * bstride + (r % n_inner) * cols;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) ln_fwd_kernel(const T* __restrict__ x, const float* __restrict__ gamma,
@@ -49,7 +53,7 @@ __global__ void __launch_bounds__(kThreads) ln_fwd_kernel(const T* __restrict__ 
   const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
   const int nv = cols >> 2;
   for (long long r = warp_global; r < rows; r += nwarps) {
-    const T* xr = x + (r / n_inner) * bstride + (r % n_inner) * cols;
+    const T* xr = x + ln_row_offset(r, rows, cols, n_inner, bstride);
     float4 v[kLnMaxV];
     float s = 0.f;
 #pragma unroll
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ 
 #pragma unroll
   for (int i = 0; i < kLnMaxV; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long r = warp_global; r < rows; r += nwarps) {
-    const long long xoff = (r / n_inner) * bstride + (r % n_inner) * cols;
+    const long long xoff = ln_row_offset(r, rows, cols, n_inner, bstride);
     const T* xr = x + xoff;
     const T* dyr = dy + r * cols;
     const float mu = mean[r], rs = rstd[r];
@@ -219,7 +223,7 @@ ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
     }
   const float inv_cols = 1.0f / (float)cols;
   for (long long r = warp_global; r < rows; r += nwarps) {
-    const long long xoff = (r / n_inner) * bstride + (r % n_inner) * cols;
+    const long long xoff = ln_row_offset(r, rows, cols, n_inner, bstride);
     const uint4* xr = reinterpret_cast<const uint4*>(x + xoff);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + r * cols);
     uint4 xp[kC8], dp[kC8];

@@ -140,6 +140,7 @@ def mm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, **kw):
     if _MODE == "tf32x3" and A.t.dtype == torch.float32:
         with torch.cuda.device(A.t.device):
             A3, B3 = _split3(A, K, 0, nb1, nb2), _split3(B, K, 1, nb1, nb2)
+        kw.pop("band", None)   # the [hi | lo | hi] operand has three copies of every k: the band hint does not carry over
         ops.gemm(A3, B3, C, M, N, 3 * K, nb1=nb1, nb2=nb2, **kw)
     else:
         ops.gemm(A, B, C, M, N, K, nb1=nb1, nb2=nb2, **kw)
