@@ -6,6 +6,7 @@
 #include <initializer_list>
 
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace t4s {
 namespace rowops {
@@ -176,9 +177,7 @@ __global__ void __launch_bounds__(kThreads) ln_bwd_kernel(const T* __restrict__ 
 }
 
 
-// bf16 fast path of the LayerNorm backward (cols % 8 == 0, cols <= 1024): 16-byte loads, the row stays packed in registers
-// (converted twice instead of held as fp32) so that two blocks fit per SM, per-lane dgamma / dbeta accumulators.
-constexpr int kLnMaxC8 = 4;  // 16-byte chunks per lane -> cols <= 1024
+constexpr int kLnMaxC8 = 4;  // bf16 fast paths: 16-byte chunks per lane -> cols <= 1024
 
 __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
@@ -199,56 +198,169 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return u;
 }
 
-// kDxSum: additionally accumulates the column sums of the OUTPUT dx (third partial row): dx is the gradient of the residual stream,
-// i.e. the output gradient of the linear layer (proj / fc2) that wrote that stream, so this is that layer's bias gradient.
-template <int kC8, bool kDxSum>
+// kDxSum (staged kernel below): additionally accumulates the column sums of the OUTPUT dx (third partial row): dx is the gradient of
+// the residual stream, i.e. the output gradient of the linear layer (proj / fc2) that wrote that stream, so this is that layer's bias
+// gradient.
+// ------------------------------------------------------------------------------------------------------------
+// bf16 LayerNorm with rows staged through shared memory by the bulk-copy engine (cols % 8 == 0, cols <= 1024, 16-byte aligned rows).
+// A warp owns a ring of row slots; lane 0 issues `cp.async.bulk` copies a few rows ahead (completion on a per-slot mbarrier), so the
+// memory latency of a row is hidden behind the arithmetic of the rows before it and does not occupy registers.  gamma (/ beta) stay
+// in registers for the whole kernel.  Statistics and the arithmetic order per row are those of the register kernels above.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ptx::smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+constexpr int kFwdStages = 4, kBwdStages = 3;
+static size_t ln_fwd_staged_smem(int cols) { return (size_t)kWarpsPerBlock * kFwdStages * (cols * 2 + 8); }
+static size_t ln_bwd_staged_smem(int cols) { return (size_t)kWarpsPerBlock * kBwdStages * (3 * cols * 2 + 8); }
+
+template <int kC8>
 __global__ void __launch_bounds__(kThreads, 2)
-ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
-                   const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dx_add,
-                   __nv_bfloat16* __restrict__ dx, float* __restrict__ part /*[grid][2][cols]*/, long long rows, int cols,
-                   float in_scale, long long n_inner, long long bstride) {
-  extern __shared__ float s_part[];  // [kWarpsPerBlock][kRows][cols]
-  constexpr int kRows = kDxSum ? 3 : 2;
+ln_fwd_bf16_staged_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          __nv_bfloat16* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, long long rows, int cols, float eps,
+                          float in_scale, long long n_inner, long long bstride) {
+  extern __shared__ __align__(128) unsigned char ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + warp;
-  const long long nwarps = (long long)gridDim.x * kWarpsPerBlock;
-  const int nc = cols >> 3;
-  float ag[kC8][8], ab[kC8][8], ad[kDxSum ? kC8 : 1][8];
+  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + warp, nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const int nc = cols >> 3, row_bytes = cols * 2;
+  unsigned char* ring = ln_smem + warp * kFwdStages * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + kWarpsPerBlock * kFwdStages * row_bytes) + warp * kFwdStages;
+  if (lane == 0) {
+    for (int st = 0; st < kFwdStages; ++st) ptx::mbar_init(&bars[st], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncwarp();
+  auto issue = [&](long long r, int st) {
+    ptx::mbar_arrive_expect_tx(&bars[st], row_bytes);
+    bulk_g2s(ring + st * row_bytes, x + ln_row_offset(r, rows, cols, n_inner, bstride), row_bytes, &bars[st]);
+  };
+  if (lane == 0)
+    for (int st = 0; st < kFwdStages; ++st)
+      if (warp_global + st * nwarps < rows) issue(warp_global + st * nwarps, st);
+  float g[kC8][8], b[kC8][8];
 #pragma unroll
-  for (int i = 0; i < kC8; ++i)
+  for (int i = 0; i < kC8; ++i) {
+    const int c = lane + 32 * i;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      ag[i][e] = ab[i][e] = 0.f;
-      if (kDxSum) ad[i][e] = 0.f;
+      g[i][e] = c < nc ? gamma[8 * c + e] : 0.f;
+      b[i][e] = c < nc ? beta[8 * c + e] : 0.f;
     }
+  }
   const float inv_cols = 1.0f / (float)cols;
-  for (long long r = warp_global; r < rows; r += nwarps) {
-    const long long xoff = ln_row_offset(r, rows, cols, n_inner, bstride);
-    const uint4* xr = reinterpret_cast<const uint4*>(x + xoff);
-    const uint4* dyr = reinterpret_cast<const uint4*>(dy + r * cols);
-    uint4 xp[kC8], dp[kC8];
+  int it = 0;
+  for (long long r = warp_global; r < rows; r += nwarps, ++it) {
+    const int st = it % kFwdStages;
+    ptx::mbar_wait(&bars[st], (it / kFwdStages) & 1);
+    const uint4* xs = reinterpret_cast<const uint4*>(ring + st * row_bytes);
+    float v[kC8][8];
+    float s = 0.f;
 #pragma unroll
     for (int i = 0; i < kC8; ++i) {
       const int c = lane + 32 * i;
       if (c < nc) {
-        xp[i] = xr[c];
-        dp[i] = dyr[c];
+        unpack8(xs[c], v[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[i][e] *= in_scale;
+        s += ((v[i][0] + v[i][1]) + (v[i][2] + v[i][3])) + ((v[i][4] + v[i][5]) + (v[i][6] + v[i][7]));
       }
     }
+    __syncwarp();                                     // every lane has its values: the slot can be refilled
+    const long long rn = r + kFwdStages * nwarps;
+    if (lane == 0 && rn < rows) issue(rn, st);
+    const float mu = warp_sum(s) * inv_cols;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kC8; ++i) {
+      if (lane + 32 * i < nc) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float d = v[i][e] - mu;
+          q = fmaf(d, d, q);
+        }
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) * inv_cols + eps);
+    uint4* yr = reinterpret_cast<uint4*>(y + r * cols);
+#pragma unroll
+    for (int i = 0; i < kC8; ++i) {
+      const int c = lane + 32 * i;
+      if (c < nc) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = fmaf((v[i][e] - mu) * rs, g[i][e], b[i][e]);
+        yr[c] = pack8(o);
+      }
+    }
+    if (lane == 0) {
+      if (mean) mean[r] = mu;
+      if (rstd) rstd[r] = rs;
+    }
+  }
+}
+
+template <int kC8, bool kDxSum>
+__global__ void __launch_bounds__(kThreads, 2)
+ln_bwd_bf16_staged_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ gamma,
+                          const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ dx_add,
+                          __nv_bfloat16* __restrict__ dx, float* __restrict__ part /*[grid][2 or 3][cols]*/, long long rows, int cols,
+                          float in_scale, long long n_inner, long long bstride) {
+  extern __shared__ __align__(128) unsigned char ln_smem[];
+  constexpr int kRows = kDxSum ? 3 : 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long warp_global = (long long)blockIdx.x * kWarpsPerBlock + warp, nwarps = (long long)gridDim.x * kWarpsPerBlock;
+  const int nc = cols >> 3, row_bytes = cols * 2, slot_bytes = 3 * row_bytes;
+  unsigned char* ring = ln_smem + warp * kBwdStages * slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + kWarpsPerBlock * kBwdStages * slot_bytes) + warp * kBwdStages;
+  if (lane == 0) {
+    for (int st = 0; st < kBwdStages; ++st) ptx::mbar_init(&bars[st], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncwarp();
+  auto issue = [&](long long r, int st) {      // slot = [x | dy | dx_add]
+    const long long xoff = ln_row_offset(r, rows, cols, n_inner, bstride);
+    unsigned char* slot = ring + st * slot_bytes;
+    ptx::mbar_arrive_expect_tx(&bars[st], (dx_add ? 3 : 2) * row_bytes);
+    bulk_g2s(slot, x + xoff, row_bytes, &bars[st]);
+    bulk_g2s(slot + row_bytes, dy + r * cols, row_bytes, &bars[st]);
+    if (dx_add) bulk_g2s(slot + 2 * row_bytes, dx_add + xoff, row_bytes, &bars[st]);
+  };
+  if (lane == 0)
+    for (int st = 0; st < kBwdStages; ++st)
+      if (warp_global + st * nwarps < rows) issue(warp_global + st * nwarps, st);
+  float g[kC8][8], ag[kC8][8], ab[kC8][8], ad[kDxSum ? kC8 : 1][8];
+#pragma unroll
+  for (int i = 0; i < kC8; ++i) {
+    const int c = lane + 32 * i;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      g[i][e] = c < nc ? gamma[8 * c + e] : 0.f;
+      ag[i][e] = ab[i][e] = 0.f;
+      if (kDxSum) ad[i][e] = 0.f;
+    }
+  }
+  const float inv_cols = 1.0f / (float)cols;
+  int it = 0;
+  for (long long r = warp_global; r < rows; r += nwarps, ++it) {
+    const int st = it % kBwdStages;
     const float mu = mean[r], rs = rstd[r];
+    ptx::mbar_wait(&bars[st], (it / kBwdStages) & 1);
+    const uint4* xs = reinterpret_cast<const uint4*>(ring + st * slot_bytes);
+    const uint4* dys = xs + nc;
+    const uint4* adds = dys + nc;
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < kC8; ++i) {
       const int c = lane + 32 * i;
       if (c < nc) {
         float xv[8], dv[8];
-        unpack8(xp[i], xv);
-        unpack8(dp[i], dv);
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + 8 * c), g1 = *reinterpret_cast<const float4*>(gamma + 8 * c + 4);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        unpack8(xs[c], xv);
+        unpack8(dys[c], dv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          const float xh = (xv[e] * in_scale - mu) * rs, gd = dv[e] * g[e];
+          const float xh = (xv[e] * in_scale - mu) * rs, gd = dv[e] * g[i][e];
           s1 += gd;
           s2 = fmaf(gd, xh, s2);
           ag[i][e] = fmaf(dv[e], xh, ag[i][e]);
@@ -258,24 +370,22 @@ ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
     }
     const float m1 = warp_sum(s1) * inv_cols, m2 = warp_sum(s2) * inv_cols;
     const float k = rs * in_scale;
-    uint4* dxr = reinterpret_cast<uint4*>(dx + xoff);
+    uint4* dxr = reinterpret_cast<uint4*>(dx + ln_row_offset(r, rows, cols, n_inner, bstride));
 #pragma unroll
     for (int i = 0; i < kC8; ++i) {
       const int c = lane + 32 * i;
       if (c < nc) {
         float xv[8], dv[8], o[8];
-        unpack8(xp[i], xv);
-        unpack8(dp[i], dv);
-        const float4 g0 = *reinterpret_cast<const float4*>(gamma + 8 * c), g1 = *reinterpret_cast<const float4*>(gamma + 8 * c + 4);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        unpack8(xs[c], xv);
+        unpack8(dys[c], dv);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const float xh = (xv[e] * in_scale - mu) * rs;
-          o[e] = k * (dv[e] * g[e] - m1 - xh * m2);
+          o[e] = k * (dv[e] * g[i][e] - m1 - xh * m2);
         }
         if (dx_add) {
           float av[8];
-          unpack8(reinterpret_cast<const uint4*>(dx_add + xoff)[c], av);
+          unpack8(adds[c], av);
 #pragma unroll
           for (int e = 0; e < 8; ++e) o[e] += av[e];
         }
@@ -286,8 +396,13 @@ ln_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
         dxr[c] = pack8(o);
       }
     }
+    __syncwarp();                                     // every lane is done with the slot
+    const long long rn = r + kBwdStages * nwarps;
+    if (lane == 0 && rn < rows) issue(rn, st);
   }
   if (part) {
+    __syncthreads();                                  // the rings are dead: their place takes the per-warp partial sums
+    float* s_part = reinterpret_cast<float*>(ln_smem);
     float* sp = s_part + warp * kRows * cols;
 #pragma unroll
     for (int i = 0; i < kC8; ++i) {
@@ -704,6 +819,27 @@ int t4s_layernorm_fwd(const void* x, const float* gamma, const float* beta, void
   T4S_REQUIRE(cols % 4 == 0 && cols > 0 && cols <= 128 * kLnMaxV, "t4s_layernorm_fwd: cols must be a multiple of 4 and <= %d", 128 * kLnMaxV);
   if (n_inner <= 0) { n_inner = rows; x_bstride = 0; }
   T4S_REQUIRE(x_bstride % 4 == 0, "t4s_layernorm_fwd: batch stride must be a multiple of 4 elements");
+  const bool fast = dtype == T4S_BF16 && cols % 8 == 0 && cols <= 256 * kLnMaxC8 && x_bstride % 8 == 0 &&
+                    !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15);
+  if (fast) {
+    using B16 = __nv_bfloat16;
+    const size_t smem = ln_fwd_staged_smem(cols);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock, 2L * t4s::sm_count()));
+    auto launch = [&](auto kern) -> int {
+      if (smem > 48 * 1024) T4S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      kern<<<grid, kThreads, smem, t4s::as_stream(stream)>>>(static_cast<const B16*>(x), gamma, beta, static_cast<B16*>(y), mean, rstd, rows, cols, eps,
+                                                              in_scale, n_inner, x_bstride);
+      return T4S_OK;
+    };
+    int rc;
+    if (cols <= 256) rc = launch(ln_fwd_bf16_staged_kernel<1>);
+    else if (cols <= 512) rc = launch(ln_fwd_bf16_staged_kernel<2>);
+    else if (cols <= 768) rc = launch(ln_fwd_bf16_staged_kernel<3>);
+    else rc = launch(ln_fwd_bf16_staged_kernel<4>);
+    if (rc) return rc;
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (ln_fwd_kernel<T><<<grid_for_rows(rows), kThreads, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(x), gamma, beta, static_cast<T*>(y), mean, rstd, rows, cols, eps, in_scale,
                                 n_inner, x_bstride)));
@@ -726,13 +862,14 @@ int t4s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
   const int prows = dx_colsum ? 3 : 2;
   int grid = (int)std::max<long long>(1, std::min<long long>((rows + kWarpsPerBlock - 1) / kWarpsPerBlock, 2L * t4s::sm_count()));
   if (want_params) T4S_REQUIRE(ws && ws_bytes >= (size_t)grid * prows * cols * sizeof(float), "t4s_layernorm_bwd: workspace too small");
-  const size_t smem = want_params ? (size_t)kWarpsPerBlock * prows * cols * sizeof(float) : 0;
+  size_t smem = want_params ? (size_t)kWarpsPerBlock * prows * cols * sizeof(float) : 0;
   cudaStream_t st = t4s::as_stream(stream);
   const bool fast = dtype == T4S_BF16 && cols % 8 == 0 && cols <= 256 * kLnMaxC8 && x_bstride % 8 == 0 &&
                     !((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
                        reinterpret_cast<uintptr_t>(dx_add) | reinterpret_cast<uintptr_t>(gamma)) & 15);
   if (fast) {
     using B16 = __nv_bfloat16;
+    smem = ln_bwd_staged_smem(cols);     // the row rings; the partial sums reuse their place
     auto launch = [&](auto kern) -> int {
       if (smem > 48 * 1024) T4S_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       kern<<<grid, kThreads, smem, st>>>(static_cast<const B16*>(dy), static_cast<const B16*>(x), gamma, mean, rstd,
@@ -742,15 +879,15 @@ int t4s_layernorm_bwd(const void* dy, const void* x, const float* gamma, const f
     };
     int rc;
     if (dx_colsum) {
-      if (cols <= 256) rc = launch(ln_bwd_bf16_kernel<1, true>);
-      else if (cols <= 512) rc = launch(ln_bwd_bf16_kernel<2, true>);
-      else if (cols <= 768) rc = launch(ln_bwd_bf16_kernel<3, true>);
-      else rc = launch(ln_bwd_bf16_kernel<4, true>);
+      if (cols <= 256) rc = launch(ln_bwd_bf16_staged_kernel<1, true>);
+      else if (cols <= 512) rc = launch(ln_bwd_bf16_staged_kernel<2, true>);
+      else if (cols <= 768) rc = launch(ln_bwd_bf16_staged_kernel<3, true>);
+      else rc = launch(ln_bwd_bf16_staged_kernel<4, true>);
     } else {
-      if (cols <= 256) rc = launch(ln_bwd_bf16_kernel<1, false>);
-      else if (cols <= 512) rc = launch(ln_bwd_bf16_kernel<2, false>);
-      else if (cols <= 768) rc = launch(ln_bwd_bf16_kernel<3, false>);
-      else rc = launch(ln_bwd_bf16_kernel<4, false>);
+      if (cols <= 256) rc = launch(ln_bwd_bf16_staged_kernel<1, false>);
+      else if (cols <= 512) rc = launch(ln_bwd_bf16_staged_kernel<2, false>);
+      else if (cols <= 768) rc = launch(ln_bwd_bf16_staged_kernel<3, false>);
+      else rc = launch(ln_bwd_bf16_staged_kernel<4, false>);
     }
     if (rc) return rc;
   } else {
