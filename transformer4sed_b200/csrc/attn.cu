@@ -407,7 +407,8 @@ enum { bResFull = 0, bStrFull = 1, bStrEmpty = 4, bStatFull = 7, bStatEmpty = 9,
 __global__ void __launch_bounds__(fbw::kThreads, 1)
 attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
-                      const __grid_constant__ CUtensorMap tmDQ, const Args a, const int n_items) {
+                      const __grid_constant__ CUtensorMap tmDQ, const __grid_constant__ CUtensorMap tmDK,
+                      const __grid_constant__ CUtensorMap tmDV, const Args a, const int n_items) {
   using namespace fbw;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + oBar);
@@ -442,6 +443,8 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
   }
   if (warp == 8 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmDQ);
+    ptx::prefetch_tmap(&tmDK);
+    ptx::prefetch_tmap(&tmDV);
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
@@ -657,9 +660,33 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars[bAccFree]);
       const int row = t0 + r;
-      if (row < a.N) {
-        store_row32(a.dv + (long long)b * a.dv_bs + (long long)row * a.dv_ld + h * kHd + 32 * g, v, 1.f);
-        store_row32(a.dk + (long long)b * a.dk_bs + (long long)row * a.dk_ld + h * kHd + 32 * g, w, a.scale);
+      // This warp's 32 x 32 chunks of dV and dK leave through its (now idle) dQ staging box as two SWIZZLE_64B tiles and one TMA store
+      // each: asynchronous and in whole lines, where 16-byte row stores from 32 different rows stalled the warps at every work-item
+      // boundary (all CTAs reach it together).  Rows beyond the sequence are clipped by the tensor map.
+      if (ptx::elect_one()) ptx::bulk_wait_read_all();   // the item's last dQ reduce has read the box
+      __syncwarp();
+      {
+        uint4* dv4 = reinterpret_cast<uint4*>(dq_box + lane * 64);
+        uint4* dk4 = reinterpret_cast<uint4*>(dq_box + 2048 + lane * 64);
+        const int sw = (lane >> 1) & 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          dv4[q ^ sw] = make_uint4(pack_bf16(__uint_as_float(v[8 * q]), __uint_as_float(v[8 * q + 1])),
+                                   pack_bf16(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3])),
+                                   pack_bf16(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5])),
+                                   pack_bf16(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7])));
+          dk4[q ^ sw] = make_uint4(pack_bf16(__uint_as_float(w[8 * q]) * a.scale, __uint_as_float(w[8 * q + 1]) * a.scale),
+                                   pack_bf16(__uint_as_float(w[8 * q + 2]) * a.scale, __uint_as_float(w[8 * q + 3]) * a.scale),
+                                   pack_bf16(__uint_as_float(w[8 * q + 4]) * a.scale, __uint_as_float(w[8 * q + 5]) * a.scale),
+                                   pack_bf16(__uint_as_float(w[8 * q + 6]) * a.scale, __uint_as_float(w[8 * q + 7]) * a.scale));
+        }
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (ptx::elect_one()) {
+        ptx::tma_store_4d(&tmDV, dq_box, 32 * g, t0 + 32 * wq, h, b);
+        ptx::tma_store_4d(&tmDK, dq_box + 2048, 32 * g, t0 + 32 * wq, h, b);
+        ptx::bulk_commit();
       }
       if (a.colsum) {   // qkv bias gradient: column sums of this warp's 32 key rows
         const int D = a.H * kHd;
@@ -906,11 +933,28 @@ extern "C" int t4s_attn_bwd(const T4sAttnBwd* p, void* stream) {
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
       T4S_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled(dq32) failed with CUresult %d", (int)cr);
     }
+    // dK / dV leave through TMA tile stores: (d, token, head, clip) bf16 views with a [32 x 32] SWIZZLE_64B box
+    CUtensorMap tdk, tdv;
+    {
+      EncodeTiledFn enc = get_encode();
+      const struct { CUtensorMap* m; void* ptr; long long ld, bs; const char* name; } outs[2] = {{&tdk, p->dk, p->dk_ld, p->dk_bs, "dk"},
+                                                                                                 {&tdv, p->dv, p->dv_ld, p->dv_bs, "dv"}};
+      for (const auto& o : outs) {
+        T4S_REQUIRE(o.ptr && !(reinterpret_cast<uintptr_t>(o.ptr) & 15) && o.ld % 8 == 0 && o.bs % 8 == 0 && o.ld >= (long long)f->heads * kHd,
+                    "t4s_attn_bwd: %s needs a 16-byte aligned base and pitches that are multiples of 8 elements", o.name);
+        cuuint64_t dims[4] = {(cuuint64_t)kHd, (cuuint64_t)f->tokens, (cuuint64_t)f->heads, (cuuint64_t)f->batch};
+        cuuint64_t strides[3] = {(cuuint64_t)(o.ld * 2), (cuuint64_t)(kHd * 2), (cuuint64_t)(o.bs * 2)};
+        cuuint32_t box[4] = {32, 32, 1, 1}, estr[4] = {1, 1, 1, 1};
+        CUresult cr = enc(o.m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, o.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        T4S_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", o.name, (int)cr);
+      }
+    }
     T4S_CUDA(cudaMemsetAsync(p->dq32, 0, (size_t)f->batch * f->tokens * D * sizeof(float), st));
     T4S_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fbw::kSmem));
     const int n_items = a.n_tiles * f->heads * f->batch;
     const int pgrid = std::min(n_items, t4s::sm_count());
-    attn_bwd_fused_kernel<<<pgrid, fbw::kThreads, fbw::kSmem, st>>>(tq, tk, tv, tdo, tdq, a, n_items);
+    attn_bwd_fused_kernel<<<pgrid, fbw::kThreads, fbw::kSmem, st>>>(tq, tk, tv, tdo, tdq, tdk, tdv, a, n_items);
     T4S_LAUNCH_CHECK();
     if (p->dqkv_colsum) {
       const long long rows = (long long)f->batch * f->tokens;

@@ -90,6 +90,63 @@ __global__ void patch_small_grads_kernel(const float* __restrict__ tmp, float* _
   }
 }
 
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162 t;
+  t = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t*>(&t);
+  t = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t*>(&t);
+  return u;
+}
+// bf16 fast paths of the pooling / interpolation kernels below (C % 8 == 0, 16-byte aligned): a thread owns 8 adjacent channels of
+// one output position; same fp32 arithmetic in the same order as the scalar kernels, 32-bit index math.
+__global__ void __launch_bounds__(256) fpool_mean_fwd_bf16x8_kernel(const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ out, int B, int F,
+                                                                    int Tp, int c8n) {
+  const int total = B * Tp * c8n;
+  const float inv = 1.0f / (float)F;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / c8n, c = idx - r * c8n;
+    const int b = r / Tp, t = r - b * Tp;
+    const uint4* src = reinterpret_cast<const uint4*>(y) + ((long long)b * F * Tp + t) * c8n + c;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int f = 0; f < F; ++f) {
+      float v[8];
+      bf16x8_to_f32(src[(long long)f * Tp * c8n], v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    reinterpret_cast<uint4*>(out)[idx] = f32_to_bf16x8(acc);
+  }
+}
+__global__ void __launch_bounds__(256) fpool_mean_bwd_bf16x8_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dy, int B, int F,
+                                                                    int Tp, int c8n) {
+  const int total = B * Tp * c8n;
+  const float inv = 1.0f / (float)F;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / c8n, c = idx - r * c8n;
+    const int b = r / Tp, t = r - b * Tp;
+    float v[8];
+    bf16x8_to_f32(reinterpret_cast<const uint4*>(dout)[idx], v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] *= inv;
+    const uint4 o = f32_to_bf16x8(v);
+    uint4* dst = reinterpret_cast<uint4*>(dy) + ((long long)b * F * Tp + t) * c8n + c;
+    for (int f = 0; f < F; ++f) dst[(long long)f * Tp * c8n] = o;
+  }
+}
+
 // ---- frequency mean-pool: out[b, t, c] = mean_f y[b, f*Tp + t, c]   (passt_sed.py:206-208)
 template <typename T>
 __global__ void fpool_mean_fwd_kernel(const T* __restrict__ y, T* __restrict__ out, int B, int F, int Tp, int C) {
@@ -170,6 +227,54 @@ __global__ void pad_interp_bwd_kernel(const T* __restrict__ dout, T* __restrict_
   }
 }
 
+__global__ void __launch_bounds__(256) pad_interp_fwd_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int Tin,
+                                                                    int ratio, int c8n, int pad) {
+  const int L = Tin + pad, To = L * ratio, total = B * To * c8n;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / c8n, c = idx - r * c8n;
+    const int b = r / To, o = r - b * To;
+    int i0, i1;
+    float w;
+    interp_coeff(o, ratio, L, i0, i1, w);
+    const uint4* xb = reinterpret_cast<const uint4*>(x) + (long long)b * Tin * c8n + c;
+    float a0[8], a1[8];
+    bf16x8_to_f32(xb[(long long)min(i0, Tin - 1) * c8n], a0);
+    bf16x8_to_f32(xb[(long long)min(i1, Tin - 1) * c8n], a1);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) a0[e] = (1.0f - w) * a0[e] + w * a1[e];
+    reinterpret_cast<uint4*>(out)[idx] = f32_to_bf16x8(a0);
+  }
+}
+__global__ void __launch_bounds__(256) pad_interp_bwd_bf16x8_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int B, int Tin,
+                                                                    int ratio, int c8n, int pad) {
+  const int L = Tin + pad, To = L * ratio, total = B * Tin * c8n;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int r = idx / c8n, c = idx - r * c8n;
+    const int b = r / Tin, i = r - b * Tin;
+    const uint4* db = reinterpret_cast<const uint4*>(dout) + (long long)b * To * c8n + c;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int jhi = (pad && i == Tin - 1) ? Tin : i;
+    for (int j = i; j <= jhi; ++j) {
+      const int o_lo = max(0, (j - 1) * ratio), o_hi = min(To, (j + 2) * ratio);
+      for (int o = o_lo; o < o_hi; ++o) {
+        int i0, i1;
+        float w;
+        interp_coeff(o, ratio, L, i0, i1, w);
+        float g = 0.f;
+        if (i0 == j) g += 1.0f - w;
+        if (i1 == j) g += w;
+        if (g != 0.f) {
+          float v[8];
+          bf16x8_to_f32(db[(long long)o * c8n], v);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += g * v[e];
+        }
+      }
+    }
+    reinterpret_cast<uint4*>(dx)[idx] = f32_to_bf16x8(acc);
+  }
+}
+
 // ---- out[r, c] = scale * x[r*ld + c] + vec[c]
 template <typename T>
 __global__ void add_rowvec_kernel(const T* __restrict__ x, long long ld, const float* __restrict__ vec, T* __restrict__ out,
@@ -184,24 +289,6 @@ __global__ void add_rowvec_kernel(const T* __restrict__ x, long long ld, const f
 
 // bf16 fast path of the two strided element-wise kernels (cols % 8 == 0, pitches % 8 == 0, 16-byte aligned bases): a thread moves 8
 // elements per 16-byte access and keeps two independent chunks in flight; 32-bit index arithmetic (rows * cols / 8 < 2^31).
-__device__ __forceinline__ void bf16x8_to_f32(const uint4& u, float (&f)[8]) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(h[i]);
-    f[2 * i] = t.x;
-    f[2 * i + 1] = t.y;
-  }
-}
-__device__ __forceinline__ uint4 f32_to_bf16x8(const float (&f)[8]) {
-  uint4 u;
-  __nv_bfloat162 t;
-  t = __floats2bfloat162_rn(f[0], f[1]); u.x = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(f[2], f[3]); u.y = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(f[4], f[5]); u.z = *reinterpret_cast<uint32_t*>(&t);
-  t = __floats2bfloat162_rn(f[6], f[7]); u.w = *reinterpret_cast<uint32_t*>(&t);
-  return u;
-}
 // out[r*ldo + c] = alpha * x[r*ldx + c] + beta * y[r*ldy + c] + vec[c]   (y and / or vec may be NULL)
 __global__ void __launch_bounds__(256) axpby_bf16x8_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, const __nv_bfloat16* __restrict__ y,
                                                            long long ldy, const float* __restrict__ vec, __nv_bfloat16* __restrict__ out,
@@ -360,6 +447,12 @@ int t4s_patch_small_grads(const void* dx, int dtype, float* tmp, float* d_time, 
 
 int t4s_fpool_mean_fwd(const void* y, void* out, int dtype, int batch, int f_dim, int t_dim, int dim, void* stream) {
   T4S_REQUIRE(y && out, "t4s_fpool_mean_fwd: null pointer");
+  if (dtype == T4S_BF16 && dim % 8 == 0 && !((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) && (long long)batch * f_dim * t_dim * (dim / 8) < (1LL << 30)) {
+    fpool_mean_fwd_bf16x8_kernel<<<grid_for((long long)batch * t_dim * (dim / 8)), 256, 0, t4s::as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(y), static_cast<__nv_bfloat16*>(out), batch, f_dim, t_dim, dim / 8);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (fpool_mean_fwd_kernel<T><<<grid_for((long long)batch * t_dim * dim), 256, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(y), static_cast<T*>(out), batch, f_dim, t_dim, dim)));
   T4S_LAUNCH_CHECK();
@@ -368,6 +461,12 @@ int t4s_fpool_mean_fwd(const void* y, void* out, int dtype, int batch, int f_dim
 
 int t4s_fpool_mean_bwd(const void* dout, void* dy, int dtype, int batch, int f_dim, int t_dim, int dim, void* stream) {
   T4S_REQUIRE(dout && dy, "t4s_fpool_mean_bwd: null pointer");
+  if (dtype == T4S_BF16 && dim % 8 == 0 && !((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dy)) & 15) && (long long)batch * f_dim * t_dim * (dim / 8) < (1LL << 30)) {
+    fpool_mean_bwd_bf16x8_kernel<<<grid_for((long long)batch * t_dim * (dim / 8)), 256, 0, t4s::as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(dy), batch, f_dim, t_dim, dim / 8);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (fpool_mean_bwd_kernel<T><<<grid_for((long long)batch * f_dim * t_dim * dim), 256, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(dout), static_cast<T*>(dy), batch, f_dim, t_dim, dim)));
   T4S_LAUNCH_CHECK();
@@ -376,6 +475,12 @@ int t4s_fpool_mean_bwd(const void* dout, void* dy, int dtype, int batch, int f_d
 
 int t4s_pad_interp_fwd(const void* x, void* out, int dtype, int batch, int t_in, int ratio, int dim, int pad, void* stream) {
   T4S_REQUIRE(x && out && t_in > 0 && ratio >= 1 && (pad == 0 || pad == 1), "t4s_pad_interp_fwd: bad arguments");
+  if (dtype == T4S_BF16 && dim % 8 == 0 && !((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) && (long long)batch * (t_in + pad) * ratio * (dim / 8) < (1LL << 30)) {
+    pad_interp_fwd_bf16x8_kernel<<<grid_for((long long)batch * (t_in + pad) * ratio * (dim / 8)), 256, 0, t4s::as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), batch, t_in, ratio, dim / 8, pad);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (pad_interp_fwd_kernel<T><<<grid_for((long long)batch * (t_in + pad) * ratio * dim), 256, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(x), static_cast<T*>(out), batch, t_in, ratio, dim, pad)));
   T4S_LAUNCH_CHECK();
@@ -384,6 +489,12 @@ int t4s_pad_interp_fwd(const void* x, void* out, int dtype, int batch, int t_in,
 
 int t4s_pad_interp_bwd(const void* dout, void* dx, int dtype, int batch, int t_in, int ratio, int dim, int pad, void* stream) {
   T4S_REQUIRE(dout && dx && t_in > 0 && ratio >= 1 && (pad == 0 || pad == 1), "t4s_pad_interp_bwd: bad arguments");
+  if (dtype == T4S_BF16 && dim % 8 == 0 && !((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(dx)) & 15) && (long long)batch * (t_in + pad) * ratio * (dim / 8) < (1LL << 30)) {
+    pad_interp_bwd_bf16x8_kernel<<<grid_for((long long)batch * t_in * (dim / 8)), 256, 0, t4s::as_stream(stream)>>>(
+        static_cast<const __nv_bfloat16*>(dout), static_cast<__nv_bfloat16*>(dx), batch, t_in, ratio, dim / 8, pad);
+    T4S_LAUNCH_CHECK();
+    return T4S_OK;
+  }
   T4S_DISPATCH_DTYPE(dtype, (pad_interp_bwd_kernel<T><<<grid_for((long long)batch * t_in * dim), 256, 0, t4s::as_stream(stream)>>>(
                                 static_cast<const T*>(dout), static_cast<T*>(dx), batch, t_in, ratio, dim, pad)));
   T4S_LAUNCH_CHECK();
