@@ -650,7 +650,9 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         if (!tail) ++T;
       }
       // ---- dV / dK of this work item: each column half writes 32 of the 64 head-dim columns ----
+      T4S_TRACE_B(warp, T - 1, 6);
       ptx::mbar_wait(&bars[bAccFull], W & 1);
+      T4S_TRACE_B(warp, T - 1, 7);
       ptx::tc_fence_after();
       uint32_t v[32], w[32];
       ptx::tmem_ld_32x32(t_lane + 256 + 32 * g, v);
@@ -688,12 +690,14 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ptx::tma_store_4d(&tmDK, dq_box + 2048, 32 * g, t0 + 32 * wq, h, b);
         ptx::bulk_commit();
       }
+      T4S_TRACE_B(warp, T, 6);
       if (a.colsum) {   // qkv bias gradient: column sums of this warp's 32 key rows
         const int D = a.H * kHd;
         const float sv = warp_colsum32(v, row < a.N, lane), sk = warp_colsum32(w, row < a.N, lane);
         atomicAdd(a.colsum + 2 * D + h * kHd + 32 * g + lane, sv);
         atomicAdd(a.colsum + D + h * kHd + 32 * g + lane, sk * a.scale);
       }
+      T4S_TRACE_B(warp, T, 7);
     }
     if (ptx::elect_one()) ptx::bulk_wait_all();   // the staging boxes must outlive the last reduce
   }
