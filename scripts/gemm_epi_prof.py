@@ -26,7 +26,24 @@ def dgrad(colsum=True):
              colsum=db1 if colsum else None)
 
 
-for name, fn in (("fc1 forward (bias, GELU, 2 outputs)", fc1), ("fc2 dgrad (GELU', colsum)", dgrad), ("fc2 dgrad (GELU', no colsum)", lambda: dgrad(False))):
+def plain():
+    ops.gemm(ops.Op(x, M, D), ops.Op(w1, Hd, D), ops.Out(h, Hd), M, Hd, D)
+
+
+def bias_gelu_one():
+    ops.gemm(ops.Op(x, M, D), ops.Op(w1, Hd, D), ops.Out(h, Hd), M, Hd, D, bias=b1, act=ops.ACT_GELU)
+
+
+def bias_two():
+    ops.gemm(ops.Op(x, M, D), ops.Op(w1, Hd, D), ops.Out(h, Hd), M, Hd, D, bias=b1, aux=ops.Out(pre, Hd))
+
+
+def resid_add():
+    ops.gemm(ops.Op(x, M, D), ops.Op(w1, Hd, D), ops.Out(h, Hd), M, Hd, D, residual=ops.Out(pre, Hd))
+
+
+for name, fn in (("same shape, no epilogue work, 1 output", plain), ("bias + GELU, 1 output", bias_gelu_one), ("bias, 2 outputs, no GELU", bias_two),
+                 ("residual add (TMA-fed), 1 output", resid_add), ("fc1 forward (bias, GELU, 2 outputs)", fc1), ("fc2 dgrad (GELU', colsum)", dgrad), ("fc2 dgrad (GELU', no colsum)", lambda: dgrad(False))):
     fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
