@@ -399,7 +399,7 @@ constexpr int oRes = 0, oStr = oRes + 2 * kTileBytes, oP = oStr + kStr * 2 * kTi
               oStat = oDq + 8 * kDqBox, oBar = oStat + 2 * 2 * kTile * 4;
 constexpr int kSmem = oBar + 192;
 static_assert(kSmem <= 232448, "fused attention backward: shared memory");
-constexpr int kTmemCols = 512;  // S^T [0,128)  dP^T [128,256)  dV [256,320)  dK [320,384)  dQ tile [384,448)
+constexpr int kTmemCols = 512;  // S^T [0,128)  dP^T [128,256)  dV [256,320)  dK [320,384)  dQ tile [384,448)  P^T (bf16 pairs) [448,512)
 enum { bResFull = 0, bStrFull = 1, bStrEmpty = 4, bStatFull = 7, bStatEmpty = 9, bSFull = 11, bSFree = 12, bPFull = 13, bPvFree = 14, bDsFree = 15,
        bDqFull = 16, bDqFree = 17, bAccFull = 18, bAccFree = 19, bCount = 20 };
 }  // namespace fbw
@@ -538,7 +538,11 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
           bwd::mma_k128_amn(tmem + 384, sDs, r0, false);                                 // dQ_i tile = dS K_j
           ptx::tc_commit(&bars[bDsFree]);
           ptx::tc_commit(&bars[bDqFull]);
-          mma_k128_mn(tmem + 256, sP, cur + kTileBytes, kIdescPV, i > 0);                // dV += P^T dO_i
+          {                                                                              // dV += P^T dO_i, P^T from TMEM
+            const uint64_t bdesc = ptx::umma_desc_sw128(cur + kTileBytes, 8192, 1024);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) ptx::mma_f16_ts(tmem + 256, tmem + 448 + 8 * k, bdesc + 128 * k, kIdescPV, (i > 0 || k > 0) ? 1u : 0u);
+          }
           ptx::tc_commit(&bars[bPvFree]);
           ptx::tc_commit(&bars[bStrEmpty + st]);
           if (i == n_tiles - 1) ptx::tc_commit(&bars[bAccFull]);
@@ -633,9 +637,13 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         }
         if (!tail) T4S_TRACE_B(warp, T, 4);
         if (!tail) {
+          // P^T (bf16 pairs: this row's 64 queries -> 32 columns) goes to TMEM and is the A operand of dV += P^T dO from there: no
+          // shared-memory store and no operand fetch for it (the kernel is bound by the shared-memory pipe)
           ptx::mbar_wait(&bars[bPvFree], (T & 1) ^ 1);   // tile T-1's dV MMA has finished reading P
-          store_row_chunk(smem + oP, r, 64 * g, pp[0]);
-          store_row_chunk(smem + oP, r, 64 * g + 32, pp[1]);
+          ptx::tc_fence_after();
+          ptx::tmem_st_32x32(t_lane + 448 + 32 * g, reinterpret_cast<const uint32_t (&)[32]>(pp));
+          ptx::tmem_st_wait();
+          ptx::tc_fence_before();
         }
         ptx::fence_proxy_async();                        // one fence for P, dS and the dQ box
         __syncwarp();
