@@ -37,7 +37,7 @@ for w_ in (0, 5):
     print(f"softmax warp {w_}: tile: wait-start, S/dP ready, loaded, computed (dS stored), dq drained, handed over")
     for j in range(16):
         print(f"   T={20 + j}: " + " ".join(f"{at(w_, j, e) - t0:7d}" for e in range(6)))
-print("item epilogue of warp 0 (after T=29): tail done, AccFull seen, dV/dK store issued, column sums done:",
+print("item epilogue of warp 0 (after T=29): tail done, AccFull seen, column sums done, dV/dK store issued:",
       at(0, 9, 6) - t0, at(0, 9, 7) - t0, at(0, 10, 6) - t0, at(0, 10, 7) - t0)
 print("MMA warp: tile: loop top, S/dP(T+1) issued, P/dS(T) ready, dK/dQ/dV(T) issued")
 for j in range(16):

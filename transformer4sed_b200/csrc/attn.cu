@@ -670,6 +670,14 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&bars[bAccFree]);
       const int row = t0 + r;
+      // the column sums first: they only need the registers, and the tail's dQ reduce finishes reading the staging box meanwhile
+      if (a.colsum) {   // qkv bias gradient: column sums of this warp's 32 key rows
+        const int D = a.H * kHd;
+        const float sv = warp_colsum32(v, row < a.N, lane), sk = warp_colsum32(w, row < a.N, lane);
+        atomicAdd(a.colsum + 2 * D + h * kHd + 32 * g + lane, sv);
+        atomicAdd(a.colsum + D + h * kHd + 32 * g + lane, sk * a.scale);
+      }
+      T4S_TRACE_B(warp, T, 6);
       // This warp's 32 x 32 chunks of dV and dK leave through its (now idle) dQ staging box as two SWIZZLE_64B tiles and one TMA store
       // each: asynchronous and in whole lines, where 16-byte row stores from 32 different rows stalled the warps at every work-item
       // boundary (all CTAs reach it together).  Rows beyond the sequence are clipped by the tensor map.
@@ -697,13 +705,6 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         ptx::tma_store_4d(&tmDV, dq_box, 32 * g, t0 + 32 * wq, h, b);
         ptx::tma_store_4d(&tmDK, dq_box + 2048, 32 * g, t0 + 32 * wq, h, b);
         ptx::bulk_commit();
-      }
-      T4S_TRACE_B(warp, T, 6);
-      if (a.colsum) {   // qkv bias gradient: column sums of this warp's 32 key rows
-        const int D = a.H * kHd;
-        const float sv = warp_colsum32(v, row < a.N, lane), sk = warp_colsum32(w, row < a.N, lane);
-        atomicAdd(a.colsum + 2 * D + h * kHd + 32 * g + lane, sv);
-        atomicAdd(a.colsum + D + h * kHd + 32 * g + lane, sk * a.scale);
       }
       T4S_TRACE_B(warp, T, 7);
     }
