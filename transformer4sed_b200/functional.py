@@ -9,6 +9,7 @@ Precision modes (`set_precision`):
 """
 import ctypes
 import math
+import os
 
 import torch
 
@@ -545,6 +546,10 @@ class _Attention(torch.autograd.Function):
         return dqkv, None
 
 
+# fp32 copy of the attention output for delta = rowsum(dO * O) in the backward (T4S_ATTN_O32=0: delta from the bf16 output)
+_ATTN_O32 = os.environ.get("T4S_ATTN_O32", "1") != "0"
+
+
 def _attn_desc(qkv, o, lse, B, N, D, H, scale, o32=None):
     a = _lib.Attn()
     a.batch, a.heads, a.tokens, a.head_dim, a.scale = B, H, N, D // H, scale
@@ -575,7 +580,7 @@ class _FlashAttention(torch.autograd.Function):
             o = torch.empty(B, N, D, dtype=qkv.dtype, device=dev)
             lse = torch.empty(B, H, Nl, dtype=torch.float32, device=dev)
             # un-rounded copy of o for the backward's delta (kept only when a backward can follow)
-            o32 = torch.empty(B, N, D, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+            o32 = torch.empty(B, N, D, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] and _ATTN_O32 else None
             a = _attn_desc(qkv, o, lse, B, N, D, H, (D // H) ** -0.5, o32)
             _lib_call("t4s_attn_fwd", ctypes.byref(a), _st(), _key=(B, H, N))
         ctx.save_for_backward(qkv, o, lse, o32)
@@ -776,7 +781,7 @@ class _FlashRelPosAttention(torch.autograd.Function):
             _lib_call("t4s_add_rowvec", _p(qkv), 3 * D, _p(v.detach().reshape(-1)), _p(qv), B * T, D, 1.0, code, _st())
             o = torch.empty(B, T, D, dtype=dt, device=dev)
             lse = torch.empty(B, H, Nl, dtype=torch.float32, device=dev)
-            o32 = torch.empty(B, T, D, dtype=torch.float32, device=dev) if any(ctx.needs_input_grad[:4]) else None
+            o32 = torch.empty(B, T, D, dtype=torch.float32, device=dev) if any(ctx.needs_input_grad[:4]) and _ATTN_O32 else None
             a = _relattn_desc(qkv, qu, qv, p_lin, o, lse, B, T, D, H, (D // H) ** -0.5, o32)
             _lib_call("t4s_relattn_fwd", ctypes.byref(a), _st(), _key=(B, H, T))
         ctx.save_for_backward(qkv, p_lin, u, v, qu, qv, o, lse, o32)
