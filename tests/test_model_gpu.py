@@ -209,5 +209,13 @@ def test_mlm_pretrain_forward_matches_reference(golden):
         loss.backward()
         assert net.mask_token.grad is None   # upstream no-op masking: the mask token never reaches the decoder
         assert net.mlm_mlp[2].weight.grad is not None
+        # with the sliding-window fusion the mixed frame sequence is contiguous upstream (`mix_rate * x_local + ...` takes x_local's layout),
+        # `clone().reshape(-1, C)` is a view and the mask IS written: the mask token takes part and receives a gradient
+        net.zero_grad(set_to_none=True)
+        torch.manual_seed(9)
+        pred_w, other_w = net(mel, encoder_win=True)
+        assert torch.equal(other_w["mask_id_seq"].cpu(), other["mask_id_seq"].cpu())     # same draws, same mask
+        F.mse_loss(other_w["frame_before_mask"].detach(), pred_w, mask_ref.cuda()).backward()
+        assert net.mask_token.grad is not None and float(net.mask_token.grad.abs().sum()) > 0
     finally:
         F.set_precision("bf16")

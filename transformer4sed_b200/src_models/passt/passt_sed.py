@@ -115,10 +115,13 @@ class PaSST_SED(SEDModel):
         y = y.reshape(B, f_dim, t_dim, C).transpose(1, 2).reshape(B * t_dim, f_dim, C)
         return self.f_pool_module(y).reshape(B, t_dim, C)
 
-    def decoder_step(self, x, other_dict):
+    def decoder_step(self, x, other_dict, encoder_win=False):
         other_dict["frame_before_mask"] = x
         if self.mlm:
-            noop = self.strict_upstream and x.shape[0] > 1 and type(self) is PaSST_SED
+            # Upstream writes the mask through `token_seq.clone().reshape(-1, C)` (mask.py:65-79): a view only when the frame sequence is
+            # contiguous.  From the transposed interpolation output with B > 1 it is not (the write is lost: SURVEY §9.1); with the
+            # sliding-window fusion `mix_rate * x_local + ...` takes x_local's contiguous layout and the mask IS applied.
+            noop = self.strict_upstream and x.shape[0] > 1 and type(self) is PaSST_SED and not encoder_win
             x, mask_id_seq = self.mlm_tool.setence_mask(x, self.mask_token, apply=not noop)
             other_dict["mask_id_seq"] = mask_id_seq
         return self.decoder(x)
@@ -141,7 +144,7 @@ class PaSST_SED(SEDModel):
             slide_window_model = PasstWithSlide(net=self, win_param=win_param)
             x_local = self.slide_window_layer(slide_window_model(input, emb_len=x.shape[1]))
             x = F.lerp(x, x_local, mix_rate)
-        x = self.decoder_step(x, other_dict)
+        x = self.decoder_step(x, other_dict, encoder_win=bool(encoder_win))
         if self.at_adpater:
             other_dict = self.at_forward(frame, other_dict, skip=2)  # patch tokens only; no [B,1188,C] slice copy
         if self.mlm:
