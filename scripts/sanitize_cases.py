@@ -1,5 +1,5 @@
 """Small-shape launches of the mbarrier / TMA / TMEM kernels for compute-sanitizer (scripts/sanitize.sh): tcgen05 GEMM (single-CTA and
-CTA-pair tiles, split-K, staged epilogues), fused attention forward / backward (plain and Transformer-XL), the sliding-window kernels and
+CTA-pair tiles, split-K, staged epilogues), fused attention forward / backward (plain and Transformer-XL), the bulk-copy staged LayerNorm kernels and
 the post-processing kernels.  Every case is also checked against torch so a sanitizer-clean run is a correct run."""
 import sys
 
@@ -50,6 +50,18 @@ for (B, N, H) in ((2, 200, 2), (1, 37, 3), (1, 300, 1)):
     o2.backward(wgt)
     assert torch.isfinite(o2.float()).all() and torch.isfinite(qkv2.grad.float()).all() and torch.isfinite(p.grad.float()).all()
 print("attention cases ok", flush=True)
+
+# ---- LayerNorm through the bulk-copy staged kernels (ragged row counts, a sliced [B, skip:, C] view, with and without the residual gradient)
+for (B, N, C, skip) in ((3, 37, 768, 0), (2, 101, 384, 2), (1, 5, 256, 0)):
+    xs = torch.randn(B, N + skip, C, device=dev).to(torch.bfloat16).requires_grad_(True)
+    gam, bet = torch.nn.Parameter(torch.rand(C, device=dev) + 0.5), torch.nn.Parameter(torch.randn(C, device=dev) * 0.1)
+    y = F.layer_norm(xs, gam, bet, 1e-6, skip=skip)
+    y2, res = F.layer_norm_res(y, gam, bet, 1e-6)
+    ref = torch.nn.functional.layer_norm(xs.detach().float()[:, skip:], (C,), gam.detach(), bet.detach(), 1e-6)
+    assert rel(y.float(), ref) < 2e-2, (B, N, C, skip)
+    (y2.float().sum() + res.float().sum()).backward()
+    assert torch.isfinite(xs.grad.float()).all() and torch.isfinite(gam.grad).all()
+print("layernorm cases ok", flush=True)
 
 # ---- post-processing / scaler / losses
 from transformer4sed_b200.src_codec import decoder as D_  # noqa: E402
