@@ -15,8 +15,9 @@
 //   affected: the reference cancels in O / l); the O_g rows of a warp are then rescaled in place (tcgen05.ld / .st).  With the
 //   accumulator in TMEM there is no per-tile fold of O through registers.
 //   kRel: next to AC = (q+u) K^T the tensor core forms BD = (q+v) Pw^T against the 256-row position window of the tile; rel_shift
-//   is a per-row skew BD_shifted[r, c] = BD[r, 127 - r + c]: each thread parks 64 window columns of its row in a private,
-//   bank-conflict-free shared-memory row and reads 32 of them back at its own offset (twice per tile).
+//   is a per-row skew BD_shifted[r, c] = BD[r, 127 - r + c]: the multiples of 8 of the per-row offset are resolved by register selects,
+//   the rest by parking 40 window columns of the row in a private, bank-conflict-free shared-memory row and reading 32 of them back at
+//   the lane's offset (twice per tile).
 //   plain: the CTA carries TWO query tiles (two groups of 8 softmax warps, K / V tiles shared) and each group's P tile is double
 //   buffered, so a group never waits for its own P V product: while P_j V_j runs, the group is already in tile j+1's exponentials,
 //   and the other group keeps the MUFU pipe busy during this group's TMEM loads (r2a ncu: with one P tile per group the softmax
@@ -29,8 +30,8 @@ namespace t4s {
 namespace attn {
 namespace fwd2 {
 
-constexpr int kScrPitch = 68;                       // floats per parked row: 16-byte stores and 4-byte skewed reads conflict free
-constexpr int kWarpScratch = 32 * kScrPitch * 4;    // 8704 B
+constexpr int kScrPitch = 44;                       // floats per parked row (40 used)
+constexpr int kWarpScratch = (32 * kScrPitch + 24) * 4 + 32;   // 5760 B: 32 rows + the group shifts, padded to 64 bytes
 constexpr float kRescaleThreshold = 8.0f;           // log2 units
 
 template <bool kRel>
@@ -220,7 +221,10 @@ attn_fwd2_kernel(const __grid_constant__ Maps tm, const Args a) {
     const float sl2 = a.sl2;
     const uint64_t sl2_2 = ptx::pack2(sl2, sl2);
     float m = -INFINITY, l = 0.f;
-    float* scr = kRel ? reinterpret_cast<float*>(smem + L::oScr + (warp & 7) * kWarpScratch) + lane * kScrPitch : nullptr;
+    // scratch row of this lane: 40 floats at pitch 44, lane group l >> 3 shifted by 8 words each (16-byte stores and skewed 4-byte reads
+    // are bank conflict free)
+    float* scr = kRel ? reinterpret_cast<float*>(smem + L::oScr + (warp & 7) * kWarpScratch) + lane * kScrPitch + 8 * (lane >> 3) : nullptr;
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
 
     for (int j = 0; j < n_tiles; ++j) {
       const int nvalid = a.N - j * kTile - 64 * g;   // columns of this half that exist (may be <= 0 or >= 64)
@@ -250,12 +254,16 @@ attn_fwd2_kernel(const __grid_constant__ Maps tm, const Args a) {
           ptx::tmem_ld_32x32(t_lane + 256 + wb, x0);
           ptx::tmem_ld_32x32(t_lane + 256 + wb + 32, x1);
           ptx::tmem_ld_wait();
+          // window offset of lane l = 31 - l = 8 (3 - (l >> 3)) + 7 - (l & 7): the multiples of 8 are resolved by register selects on lane
+          // bits 4 and 3, so only 40 of the 64 window columns go through shared memory (10 STS.128 + 32 LDS instead of 16 + 32)
+          uint32_t a16[48], y[40];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            *reinterpret_cast<uint4*>(scr + 4 * k) = make_uint4(x0[4 * k], x0[4 * k + 1], x0[4 * k + 2], x0[4 * k + 3]);
-            *reinterpret_cast<uint4*>(scr + 32 + 4 * k) = make_uint4(x1[4 * k], x1[4 * k + 1], x1[4 * k + 2], x1[4 * k + 3]);
-          }
-          const volatile float* rd = scr + (31 - lane);
+          for (int k = 0; k < 48; ++k) a16[k] = b4 ? (k < 32 ? x0[k] : x1[k - 32]) : (k < 16 ? x0[k + 16] : x1[k - 16]);
+#pragma unroll
+          for (int k = 0; k < 40; ++k) y[k] = b3 ? a16[k] : a16[k + 8];
+#pragma unroll
+          for (int k = 0; k < 10; ++k) *reinterpret_cast<uint4*>(scr + 4 * k) = make_uint4(y[4 * k], y[4 * k + 1], y[4 * k + 2], y[4 * k + 3]);
+          const volatile float* rd = scr + (7 - (lane & 7));
 #pragma unroll
           for (int cc = 0; cc < 32; ++cc) s[32 * q + cc] += rd[cc];
         }

@@ -57,18 +57,19 @@ namespace bwd {
 // Pipeline of step t:   [S(t), BD(t) were issued during step t-1]  phase A: P = exp2(AC + shift(BD) - lse)  ->  dP(t), S(t+1)  ->
 // phase B: dS = P (dP - delta)  [BD(t+1) once dP is in registers]  ->  dQ += dS K  |  dV += P^T dO, dK += dS^T QU.
 // TMEM: S [0,128)   BD [128,384), its first half re-used for dP once the skew has consumed it   accumulators [384,512).
-// Skew scratch: a thread parks a 48-column BD window of its row (pitch 50 floats: 8-byte stores and 4-byte skewed reads are bank
-// conflict free) and reads 16 shifted values back, four times per tile.  Rows 0-19 of a warp live in the warp's own 4 KB block of the
-// P tile, which is dead between the dV MMA of step t-1 and the P store of step t (in the dQ kernel the P tile is not an operand: its
-// place is the dBD staging area, below); rows 20-31 live in a 2432-byte slot of their own whose first 32 bytes (the bank phase of row
-// 20 is 32) hold four of the mbarriers.
+// Skew scratch: a thread needs BD[r][127 - r + c] for the 16 columns c of a window; the coarse part of the per-row offset (multiples of 8) is
+// resolved by register selects, the fine part by parking 24 columns in a private shared-memory row (pitch 26 floats, lanes 16-31 shifted by
+// 8 words: 8-byte stores and 4-byte skewed reads are bank conflict free) and reading 16 back at the lane's offset, four times per tile.  The
+// rows live in the warp's own 4 KB block of the P tile, which is dead between the dV MMA of step t-1 and the P store of step t (in the dQ
+// kernel the P tile is not an operand: its place is the dBD staging area, below).  The mbarriers sit in the first 32 bytes of the 2432-byte
+// slots behind the dS tile (the slots held scratch rows 20-31 while a row was 48 columns wide).
 // dBD (dQ kernel): dS un-shifted back to position coordinates, dBD[i, T-1-i+j] = dS[i, j].  The two warps of a lane quarter stage their 32
 // rows x 128 columns row-contiguously (256 B per row, 16-byte chunks XOR-swizzled by the row) and each writes 16 whole rows.  A row whose
 // first destination column is odd is written one element to the left, the missing element being the last one of the same row from the
 // previous key tile (kept in a register), so that every store is a full 4-byte word: two-lane half-word stores at the ends of the
 // rows cost more than all the word stores together (measured: 4.4 k clk per step with them, 1.7 k without).
 constexpr int kBThreads = 320;
-constexpr int kPitch = 50;
+constexpr int kPitch = 26;
 constexpr int kScrSlot = 2432;
 constexpr int oOps = 0, oP = oOps + 9 * kTileBytes, oDs = oP + kPBytes, oScr = oDs + kPBytes;
 constexpr int kSmem = oScr + 8 * kScrSlot;
@@ -253,8 +254,9 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
     // this warp's rows of the P tile; dQ kernel: its half of the lane quarter's 8 KB dBD staging area
     unsigned char* blkP = smem + oP + (kDq ? wq * 8192 + g * 4096 : g * kTileBytes + wq * 4096);
     uint32_t cw[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // dQ kernel: last staged word of the odd rows this warp writes (previous key tile)
-    // rows 0-19: own P block; rows 20-31: own slot, placed so that row 20 keeps its bank phase (20 * 200 = 4000 = 32 mod 128)
-    float* scr = reinterpret_cast<float*>(lane < 20 ? blkP : smem + oScr + warp * kScrSlot + 32 - 4000) + lane * kPitch;
+    // scratch row of this lane: 24 floats at pitch 26, lanes 16-31 shifted by 8 words (conflict-free 8-byte stores and skewed 4-byte reads)
+    float* scr = reinterpret_cast<float*>(blkP) + lane * kPitch + ((lane & 16) >> 1);
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0;
     const float sl2 = a.sl2;
     const uint64_t sl2_2 = ptx::pack2(sl2, sl2);
     float my_lse = 0.f, my_delta = 0.f;
@@ -283,12 +285,18 @@ relattn_bwd_kernel(const __grid_constant__ CUtensorMap tmQU, const __grid_consta
         ptx::tmem_ld_32x32(t_lane + 128 + wb, y0);
         ptx::tmem_ld_32x16(t_lane + 128 + wb + 32, y1);
       };
+      // Lane l reads its 16 values at window offset 31 - l = 8 (3 - (l >> 3)) + 7 - (l & 7): the coarse part is resolved in registers (two
+      // levels of selects on lane bits 4 and 3), so that only 24 of the 48 window columns go through shared memory (12 STS.64 + 16 LDS per
+      // window instead of 24 + 16: the phase is bound by the shared-memory pipe).
       auto skew = [&](int q, const uint32_t (&y0)[32], const uint32_t (&y1)[16]) {
+        uint32_t a16[32], y[24];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) *reinterpret_cast<uint2*>(scr + 2 * k) = make_uint2(y0[2 * k], y0[2 * k + 1]);
+        for (int k = 0; k < 32; ++k) a16[k] = b4 ? y0[k] : (k < 16 ? y0[k + 16] : y1[k - 16]);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) *reinterpret_cast<uint2*>(scr + 32 + 2 * k) = make_uint2(y1[2 * k], y1[2 * k + 1]);
-        const volatile float* rd = scr + (31 - lane);
+        for (int k = 0; k < 24; ++k) y[k] = b3 ? a16[k] : a16[k + 8];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) *reinterpret_cast<uint2*>(scr + 2 * k) = make_uint2(y[2 * k], y[2 * k + 1]);
+        const volatile float* rd = scr + (7 - (lane & 7));
 #pragma unroll
         for (int cc = 0; cc < 16; ++cc) s[16 * q + cc] += rd[cc];
       };
