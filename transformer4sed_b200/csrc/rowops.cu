@@ -330,17 +330,19 @@ ln_bwd_bf16_staged_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
   if (lane == 0)
     for (int st = 0; st < kBwdStages; ++st)
       if (warp_global + st * nwarps < rows) issue(warp_global + st * nwarps, st);
-  float g[kC8][8], ag[kC8][8], ab[kC8][8], ad[kDxSum ? kC8 : 1][8];
+  // packed f32x2 arithmetic: pair j of a 16-byte chunk = elements (2j, 2j+1); the accumulators are pairs as well
+  uint64_t g2[kC8][4], ag2[kC8][4], ab2[kC8][4], ad2[kDxSum ? kC8 : 1][4];
 #pragma unroll
   for (int i = 0; i < kC8; ++i) {
     const int c = lane + 32 * i;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      g[i][e] = c < nc ? gamma[8 * c + e] : 0.f;
-      ag[i][e] = ab[i][e] = 0.f;
-      if (kDxSum) ad[i][e] = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      g2[i][j] = c < nc ? ptx::pack2(gamma[8 * c + 2 * j], gamma[8 * c + 2 * j + 1]) : ptx::pack2(0.f, 0.f);
+      ag2[i][j] = ab2[i][j] = ptx::pack2(0.f, 0.f);
+      if (kDxSum) ad2[i][j] = ptx::pack2(0.f, 0.f);
     }
   }
+  auto pair_of = [](uint32_t w) { return ptx::pack2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); };   // two bf16 -> f32x2
   const float inv_cols = 1.0f / (float)cols;
   int it = 0;
   for (long long r = warp_global; r < rows; r += nwarps, ++it) {
@@ -350,56 +352,73 @@ ln_bwd_bf16_staged_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloa
     const uint4* xs = reinterpret_cast<const uint4*>(ring + st * slot_bytes);
     const uint4* dys = xs + nc;
     const uint4* adds = dys + nc;
-    float s1 = 0.f, s2 = 0.f;
+    // xhat = x * (in_scale * rstd) - mean * rstd
+    const uint64_t xa = ptx::pack2(in_scale * rs, in_scale * rs), xb = ptx::pack2(-mu * rs, -mu * rs);
+    uint64_t s1p = ptx::pack2(0.f, 0.f), s2p = ptx::pack2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < kC8; ++i) {
       const int c = lane + 32 * i;
       if (c < nc) {
-        float xv[8], dv[8];
-        unpack8(xs[c], xv);
-        unpack8(dys[c], dv);
+        const uint4 xw = xs[c], dw = dys[c];
+        const uint32_t xv[4] = {xw.x, xw.y, xw.z, xw.w}, dv[4] = {dw.x, dw.y, dw.z, dw.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float xh = (xv[e] * in_scale - mu) * rs, gd = dv[e] * g[i][e];
-          s1 += gd;
-          s2 = fmaf(gd, xh, s2);
-          ag[i][e] = fmaf(dv[e], xh, ag[i][e]);
-          ab[i][e] += dv[e];
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t xh = ptx::fma2(pair_of(xv[j]), xa, xb), d = pair_of(dv[j]), gd = ptx::mul2(d, g2[i][j]);
+          s1p = ptx::add2(s1p, gd);
+          s2p = ptx::fma2(gd, xh, s2p);
+          ag2[i][j] = ptx::fma2(d, xh, ag2[i][j]);
+          ab2[i][j] = ptx::add2(ab2[i][j], d);
         }
       }
     }
-    const float m1 = warp_sum(s1) * inv_cols, m2 = warp_sum(s2) * inv_cols;
+    float s1a, s1b, s2a, s2b;
+    ptx::unpack2(s1p, s1a, s1b);
+    ptx::unpack2(s2p, s2a, s2b);
+    const float m1 = warp_sum(s1a + s1b) * inv_cols, m2 = warp_sum(s2a + s2b) * inv_cols;
+    // dx = k (g dy - m1 - xhat m2) = (g dy) k - k m1 - xhat (k m2),  k = rstd * in_scale
     const float k = rs * in_scale;
+    const uint64_t kk = ptx::pack2(k, k), nkm1 = ptx::pack2(-k * m1, -k * m1), nkm2 = ptx::pack2(-k * m2, -k * m2);
     uint4* dxr = reinterpret_cast<uint4*>(dx + ln_row_offset(r, rows, cols, n_inner, bstride));
 #pragma unroll
     for (int i = 0; i < kC8; ++i) {
       const int c = lane + 32 * i;
       if (c < nc) {
-        float xv[8], dv[8], o[8];
-        unpack8(xs[c], xv);
-        unpack8(dys[c], dv);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float xh = (xv[e] * in_scale - mu) * rs;
-          o[e] = k * (dv[e] * g[i][e] - m1 - xh * m2);
-        }
+        const uint4 xw = xs[c], dw = dys[c];
+        const uint32_t xv[4] = {xw.x, xw.y, xw.z, xw.w}, dv[4] = {dw.x, dw.y, dw.z, dw.w};
+        uint32_t av[4] = {0u, 0u, 0u, 0u};
         if (dx_add) {
-          float av[8];
-          unpack8(adds[c], av);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] += av[e];
+          const uint4 aw = adds[c];
+          av[0] = aw.x; av[1] = aw.y; av[2] = aw.z; av[3] = aw.w;
         }
-        if (kDxSum) {
+        uint32_t ow[4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) ad[i][e] += o[e];
+        for (int j = 0; j < 4; ++j) {
+          const uint64_t xh = ptx::fma2(pair_of(xv[j]), xa, xb);
+          uint64_t o = ptx::fma2(ptx::mul2(pair_of(dv[j]), g2[i][j]), kk, nkm1);
+          o = ptx::fma2(xh, nkm2, o);
+          if (dx_add) o = ptx::add2(o, pair_of(av[j]));
+          if (kDxSum) ad2[i][j] = ptx::add2(ad2[i][j], o);
+          float oa, ob;
+          ptx::unpack2(o, oa, ob);
+          __nv_bfloat162 t = __floats2bfloat162_rn(oa, ob);
+          ow[j] = *reinterpret_cast<uint32_t*>(&t);
         }
-        dxr[c] = pack8(o);
+        dxr[c] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
       }
     }
     __syncwarp();                                     // every lane is done with the slot
     const long long rn = r + kBwdStages * nwarps;
     if (lane == 0 && rn < rows) issue(rn, st);
   }
+  float ag[kC8][8], ab[kC8][8], ad[kDxSum ? kC8 : 1][8];
+#pragma unroll
+  for (int i = 0; i < kC8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ptx::unpack2(ag2[i][j], ag[i][2 * j], ag[i][2 * j + 1]);
+      ptx::unpack2(ab2[i][j], ab[i][2 * j], ab[i][2 * j + 1]);
+      if (kDxSum) ptx::unpack2(ad2[i][j], ad[i][2 * j], ad[i][2 * j + 1]);
+    }
   if (part) {
     __syncthreads();                                  // the rings are dead: their place takes the per-warp partial sums
     float* s_part = reinterpret_cast<float*>(ln_smem);
