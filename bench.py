@@ -283,6 +283,13 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     launches = lib.t4s_launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    # host side of one step: wall time until every launch of a step has been enqueued on an idle stream (no synchronisation inside;
+    # one step is fewer launches than the driver's queue holds).  The step is GPU-bound as long as this stays below ms_per_step.
+    barrier()
+    t_h0 = time.perf_counter()
+    train_step(wav_dev)
+    host_enqueue_ms = (time.perf_counter() - t_h0) * 1e3
+    barrier()
     # ---- timed region 2: end to end from pinned host memory (H2D of the clips + D2H of the loss every step) -------
     copy_stream = torch.cuda.Stream(dev)
     bufs = [torch.empty_like(wav_dev) for _ in range(2)]
@@ -350,6 +357,7 @@ def run_ours(args):
             cfg["tc_frac_of_sustained_bf16"] = value / world * 3 * FWD_GFLOP_PER_CLIP / 1e3 / pk["bf16_tflops_sustained"]
         elif roof is not None:
             cfg["tc_frac_of_sustained_bf16_gemm_flops_only"] = roof["gemm_tflop_per_step"] / (ms / args.steps / 1e3) / pk["bf16_tflops_sustained"]
+        cfg["host_enqueue_ms_per_step"] = host_enqueue_ms
         if in_sync is not None:
             cfg["params_in_sync"] = in_sync
         if strict is not None:
