@@ -33,3 +33,32 @@ def test_ops_fail_loudly_without_cuda():
     ext = PasstFeatureExtractor()
     with pytest.raises(_lib.T4sError):
         ext(torch.zeros(1, 32000))
+
+
+def test_packed_gemm_descriptor_matches_ctypes_layout():
+    """ops.gemm fills T4sGemm with one struct.pack_into call: the bytes must equal the ctypes structure built field by field."""
+    import torch
+    from transformer4sed_b200 import ops
+    from transformer4sed_b200._lib import Gemm, Matrix, Operand
+    a, b = torch.zeros(40, 24, dtype=torch.bfloat16), torch.zeros(56, 24, dtype=torch.bfloat16)
+    c, x, r = torch.zeros(40, 56), torch.zeros(40, 56, dtype=torch.bfloat16), torch.zeros(40, 56, dtype=torch.bfloat16)
+    bias, cs = torch.zeros(56), torch.zeros(56)
+    A, B = ops.Op(a, 40, 24, 3, nb1=2, stride1=5, nb2=3, stride2=7), ops.Op(b, 56, 24, 1, mn_major=True)
+    C, X, R = ops.Out(c, 56, 2, 11, 13), ops.Out(x, 56), ops.Out(r, 56, 4)
+    vals = ops._gemm_args(A, B, C, 40, 56, 24, 2, 3, bias, X, R, 0.5, ops.ACT_GELU, 4, 99, cs, (7, 30))
+    buf = (ctypes.c_char * ops._GEMM_PACK.size)()
+    ops._GEMM_PACK.pack_into(buf, 0, *vals)
+    g = Gemm()
+    g.M, g.N, g.K, g.in_dtype, g.nb1, g.nb2, g.split_k, g.c_split_stride = 40, 56, 24, ops.BF16, 2, 3, 4, 99
+    g.A, g.B, g.C, g.aux, g.residual = A.c(), B.c(), C.c(), X.c(), R.c()
+    g.bias, g.alpha, g.act, g.colsum = ctypes.c_void_p(bias.data_ptr()), 0.5, ops.ACT_GELU, ctypes.c_void_p(cs.data_ptr())
+    g.band_lo, g.band_hi = 7, 30
+    assert ops._GEMM_PACK.size == ctypes.sizeof(Gemm)
+    assert bytes(buf) == bytes(g)
+    # absent optional parts are all-zero, as the zero-initialised ctypes structure has them
+    vals = ops._gemm_args(A, B, C, 40, 56, 24, 1, 1, None, None, None, 1.0, ops.ACT_NONE, 1, 0, None, None)
+    ops._GEMM_PACK.pack_into(buf, 0, *vals)
+    g2 = Gemm()
+    g2.M, g2.N, g2.K, g2.in_dtype, g2.nb1, g2.nb2, g2.split_k = 40, 56, 24, ops.BF16, 1, 1, 1
+    g2.A, g2.B, g2.C, g2.alpha = A.c(), B.c(), C.c(), 1.0
+    assert bytes(buf) == bytes(g2)

@@ -105,7 +105,7 @@ def _declare(lib):
         "t4s_mel_forward": (I, [P, P, P, P, P, P, P, I, P, I, I, I, ctypes.POINTER(MelParams), P]),
         "t4s_mel_normalize": (I, [P, P, Z, P]),
         "t4s_amp_to_db": (I, [P, P, Z, F, F, F, F, P]),
-        "t4s_gemm": (I, [ctypes.POINTER(Gemm), P]),
+        "t4s_gemm": (I, [P, P]),   # T4sGemm* (ops.gemm packs the descriptor bytes itself)
         "t4s_reduce_splits": (I, [P, I, Z, P, I, P]),
         "t4s_attn_padded_len": (L, [I]),
         "t4s_attn_fwd": (I, [ctypes.POINTER(Attn), P]),

@@ -4,6 +4,8 @@ Everything here runs on the current CUDA stream of the tensor's device and raise
 failure; there is no CPU implementation.
 """
 import ctypes
+import struct
+import threading
 
 import torch
 
@@ -52,6 +54,55 @@ class Out:
 _NULL_MAT = Matrix(ctypes.c_void_p(0), 0, 0, 0, 0)
 
 
+# The T4sGemm descriptor is filled with ONE struct.pack_into call instead of ~45 ctypes attribute stores (11 us -> 2 us of host time per
+# GEMM; the 8-clip DASM step issues ~500 GEMMs and is host-bound).  The format string is derived from the ctypes layout, so the two
+# cannot drift apart (tests/test_abi.py compares the bytes).
+def _flat_fields(cls, base=0, prefix=""):
+    out = []
+    for name, typ in cls._fields_:
+        off = base + getattr(cls, name).offset
+        if isinstance(typ, type) and issubclass(typ, ctypes.Structure):
+            out += _flat_fields(typ, off, prefix + name + ".")
+        else:
+            out.append((prefix + name, off, typ))
+    return out
+
+
+def _packer(cls):
+    code = {ctypes.c_int: "i", ctypes.c_int64: "q", ctypes.c_void_p: "Q", ctypes.c_float: "f"}
+    fmt, pos = "=", 0
+    for _, off, typ in _flat_fields(cls):
+        if off > pos:
+            fmt += f"{off - pos}x"
+            pos = off
+        fmt += code[typ]
+        pos += ctypes.sizeof(typ)
+    if ctypes.sizeof(cls) > pos:
+        fmt += f"{ctypes.sizeof(cls) - pos}x"
+    return struct.Struct(fmt)
+
+
+_GEMM_PACK = _packer(Gemm)
+_tls = threading.local()
+
+
+def _gemm_args(A, B, C, M, N, K, nb1, nb2, bias, aux, residual, alpha, act, split_k, c_split_stride, colsum, band):
+    """Field values of T4sGemm in declaration order (include/t4s.h)."""
+    at, bt, ct = A.t, B.t, C.t
+    vals = [M, N, K, dtype_code(at.dtype), nb1, nb2, split_k, c_split_stride,
+            at.data_ptr() + A.offset * at.element_size(), A.rows, A.ld, A.nb1, A.stride1, A.nb2, A.stride2, int(A.mn_major),
+            bt.data_ptr() + B.offset * bt.element_size(), B.rows, B.ld, B.nb1, B.stride1, B.nb2, B.stride2, int(B.mn_major),
+            ct.data_ptr() + C.offset * ct.element_size(), dtype_code(ct.dtype), C.ld, C.stride1, C.stride2]
+    for m in (aux, residual):
+        if m is None:
+            vals += [0, 0, 0, 0, 0]
+        else:
+            vals += [m.t.data_ptr() + m.offset * m.t.element_size(), dtype_code(m.t.dtype), m.ld, m.stride1, m.stride2]
+    vals += [bias.data_ptr() if bias is not None else 0, float(alpha), act, colsum.data_ptr() if colsum is not None else 0,
+             int(band[0]) if band is not None else 0, int(band[1]) if band is not None else 0]
+    return vals
+
+
 def gemm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, bias=None, aux: Out = None, residual: Out = None, alpha=1.0,
          act=ACT_NONE, split_k=1, c_split_stride=0, colsum=None, band=None):
     """C[z] = act(alpha * A[z] @ B[z]^T + bias) + residual[z] on tensor cores (tcgen05).  `colsum` (fp32 [N], zeroed by the caller)
@@ -60,24 +111,18 @@ def gemm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, bias=None, aux: Out = None
     _lib.ensure_device(A.t)
     if A.t.dtype != B.t.dtype:
         raise _lib.T4sError("gemm operands must share a dtype")
-    g = Gemm()
-    g.M, g.N, g.K, g.in_dtype, g.nb1, g.nb2 = M, N, K, dtype_code(A.t.dtype), nb1, nb2
-    g.split_k, g.c_split_stride = split_k, c_split_stride
-    g.A, g.B, g.C = A.c(), B.c(), C.c()
-    g.aux = aux.c() if aux is not None else _NULL_MAT
-    g.residual = residual.c() if residual is not None else _NULL_MAT
     if bias is not None and bias.dtype != torch.float32:
         raise _lib.T4sError("gemm bias must be float32")
-    g.bias = ctypes.c_void_p(bias.data_ptr()) if bias is not None else ctypes.c_void_p(0)
-    g.alpha, g.act = float(alpha), act
-    g.colsum = ctypes.c_void_p(colsum.data_ptr()) if colsum is not None else ctypes.c_void_p(0)
-    g.band_lo, g.band_hi = (int(band[0]), int(band[1])) if band is not None else (0, 0)
+    buf = getattr(_tls, "gemm_buf", None)
+    if buf is None:
+        buf = _tls.gemm_buf = (ctypes.c_char * _GEMM_PACK.size)()
+    _GEMM_PACK.pack_into(buf, 0, *_gemm_args(A, B, C, M, N, K, nb1, nb2, bias, aux, residual, alpha, act, split_k, c_split_stride, colsum, band))
     with torch.cuda.device(A.t.device):
         if _lib.profiler is not None:
             key = (M, N, K, nb1 * nb2, "T" if A.mn_major else "N", "T" if B.mn_major else "N", split_k)
-            rc = _lib.profiler.timed("t4s_gemm", key, lambda: _lib.load().t4s_gemm(ctypes.byref(g), _lib.stream_ptr()))
+            rc = _lib.profiler.timed("t4s_gemm", key, lambda: _lib.load().t4s_gemm(buf, _lib.stream_ptr()))
         else:
-            rc = _lib.load().t4s_gemm(ctypes.byref(g), _lib.stream_ptr())
+            rc = _lib.load().t4s_gemm(buf, _lib.stream_ptr())
         _lib.check(rc, "t4s_gemm")
 
 
