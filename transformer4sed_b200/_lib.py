@@ -268,8 +268,31 @@ def ensure_device(t):
 
 
 def stream_ptr():
+    """Raw handle of the current stream of the current device (the C entry points torch itself uses: `torch.cuda.current_stream()`
+    costs several microseconds of Python per call, and it is called once per kernel launch)."""
     import torch
-    return c_void_p(torch.cuda.current_stream().cuda_stream)
+    return c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
+
+
+class _NullGuard:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL_GUARD = _NullGuard()
+
+
+def device_guard(device):
+    """`with device_guard(t.device):` = `with torch.cuda.device(t.device):` without the context-manager cost when that device is
+    already current (the normal case: one process per GPU)."""
+    import torch
+    idx = device.index if isinstance(device, torch.device) else device
+    if idx is None or idx == torch._C._cuda_getDevice():
+        return _NULL_GUARD
+    return torch.cuda.device(idx)
 
 
 def ptr(t):

@@ -98,7 +98,7 @@ def cast_weight(w: torch.Tensor) -> torch.Tensor:
 
 def convert(src, dst):
     _lib.ensure_device(src)
-    with torch.cuda.device(src.device):
+    with _lib.device_guard(src.device):
         _lib_call("t4s_convert", _p(src), ops.dtype_code(src.dtype), _p(dst), ops.dtype_code(dst.dtype), src.numel(), _st())
     return dst
 
@@ -139,7 +139,7 @@ def _split3(op: Op, K, pattern, nb1, nb2):
 def mm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, **kw):
     """Tensor-core GEMM honouring the precision mode."""
     if _MODE == "tf32x3" and A.t.dtype == torch.float32:
-        with torch.cuda.device(A.t.device):
+        with _lib.device_guard(A.t.device):
             A3, B3 = _split3(A, K, 0, nb1, nb2), _split3(B, K, 1, nb1, nb2)
         kw.pop("band", None)   # the [hi | lo | hi] operand has three copies of every k: the band hint does not carry over
         ops.gemm(A3, B3, C, M, N, 3 * K, nb1=nb1, nb2=nb2, **kw)
@@ -210,7 +210,7 @@ def colsum(x2d, cols=None, ld=None, rows=None):
     cols = x2d.shape[1] if cols is None else cols
     ld = x2d.stride(0) if ld is None else ld
     lib = _lib.load()
-    with torch.cuda.device(x2d.device):
+    with _lib.device_guard(x2d.device):
         nbytes = lib.t4s_colsum_workspace(rows, cols)
         ws = torch.empty(nbytes // 4, dtype=torch.float32, device=x2d.device)
         out = torch.empty(cols, dtype=torch.float32, device=x2d.device)
@@ -236,7 +236,7 @@ class _Linear(torch.autograd.Function):
         y = torch.empty(M, N, dtype=out_dtype, device=x.device)
         aux = torch.empty(M, N, dtype=x.dtype, device=x.device) if act == ops.ACT_GELU else None
         res2 = residual.reshape(M, N) if residual is not None else None
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             mm(Op(x2, M, x2.stride(0)), Op(wq, N, wq.stride(0)), Out(y, N), M, N, K, bias=b.detach() if b is not None else None,
                aux=Out(aux, N) if aux is not None else None, residual=Out(res2, res2.stride(0)) if res2 is not None else None, act=act)
         ctx.save_for_backward(x2, w, aux)
@@ -257,7 +257,7 @@ class _Linear(torch.autograd.Function):
             dy2 = dy2.contiguous()
         dev = x2.device
         d_res = None
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             if ctx.has_res:
                 d_res = dy if dy.dtype == ctx.res_dtype else convert(dy2, torch.empty(dy.shape, dtype=ctx.res_dtype, device=dev))
             if dy2.dtype != x2.dtype:
@@ -308,7 +308,7 @@ class _Mlp(torch.autograd.Function):
         M, Hd, N = x2.shape[0], w1.shape[0], w2.shape[0]
         w1q, w2q = cast_weight(w1), cast_weight(w2)
         dt, dev = x.dtype, x.device
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             h = torch.empty(M, Hd, dtype=dt, device=dev)
             pre = torch.empty(M, Hd, dtype=dt, device=dev)
             mm(Op(x2, M, x2.stride(0)), Op(w1q, Hd, w1q.stride(0)), Out(h, Hd), M, Hd, K, bias=b1.detach(), aux=Out(pre, Hd), act=ops.ACT_GELU)
@@ -331,7 +331,7 @@ class _Mlp(torch.autograd.Function):
         if dy2.stride(-1) != 1:
             dy2 = dy2.contiguous()
         ng = ctx.needs_input_grad
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             if dy2.dtype != x2.dtype:
                 dy2 = convert(dy2, torch.empty(M, N, dtype=x2.dtype, device=dev))
             w1q, w2q = cast_weight(w1), cast_weight(w2)
@@ -384,7 +384,7 @@ class _LayerNorm(torch.autograd.Function):
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
         xp = ctypes.c_void_p(x.data_ptr() + off * x.element_size())
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib_call("t4s_layernorm_fwd", xp, _p(gamma.detach()), _p(beta.detach()), _p(y), _p(mean), _p(rstd), rows, C, eps, in_scale,
                       ops.dtype_code(x.dtype), n_inner, bstride, _st())
         ctx.save_for_backward(x, gamma, mean, rstd)
@@ -400,7 +400,7 @@ class _LayerNorm(torch.autograd.Function):
             dy = convert(dy, torch.empty(dy.shape, dtype=x.dtype, device=x.device))
         lib = _lib.load()
         dev = x.device
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             dx = torch.zeros_like(x) if skip else torch.empty_like(x)
             want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
             dg = torch.empty(C, dtype=torch.float32, device=dev) if want else None
@@ -432,7 +432,7 @@ class _LayerNormRes(torch.autograd.Function):
         y = torch.empty_like(x)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib_call("t4s_layernorm_fwd", _p(x), _p(gamma.detach()), _p(beta.detach()), _p(y), _p(mean), _p(rstd), rows, C, eps, 1.0,
                       ops.dtype_code(x.dtype), 0, 0, _st())
         ctx.save_for_backward(x, gamma, mean, rstd)
@@ -454,7 +454,7 @@ class _LayerNormRes(torch.autograd.Function):
             if dres.dtype != x.dtype:
                 dres = convert(dres, torch.empty(dres.shape, dtype=x.dtype, device=dev))
         lib = _lib.load()
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             dx = torch.empty_like(x)
             want = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
             dg = torch.empty(C, dtype=torch.float32, device=dev) if want else None
@@ -504,7 +504,7 @@ class _Attention(torch.autograd.Function):
         Np = _pad8(N)
         scale = hd ** -0.5
         dt, dev = qkv.dtype, qkv.device
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             P = torch.empty(B, H, N, Np, dtype=dt, device=dev)
             mm(_heads(qkv, B, N, D, H, 0), _heads(qkv, B, N, D, H, 1), Out(P, Np, 0, N * Np, H * N * Np), N, N, hd, nb1=H, nb2=B, alpha=scale)
             _lib_call("t4s_softmax_fwd", _p(P), _p(P), B * H * N, N, Np, Np, ops.dtype_code(dt), _st())
@@ -528,7 +528,7 @@ class _Attention(torch.autograd.Function):
         do = do.contiguous()
         if do.dtype != dt:
             do = convert(do, torch.empty(do.shape, dtype=dt, device=dev))
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             dqkv = torch.empty_like(qkv)
             dP = torch.empty(B, H, N, Np, dtype=dt, device=dev)
             pmat = dict(nb1=H, stride1=N * Np, nb2=B, stride2=H * N * Np)
@@ -576,7 +576,7 @@ class _FlashAttention(torch.autograd.Function):
         dev = qkv.device
         lib = _lib.load()
         Nl = lib.t4s_attn_padded_len(N)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             o = torch.empty(B, N, D, dtype=qkv.dtype, device=dev)
             lse = torch.empty(B, H, Nl, dtype=torch.float32, device=dev)
             # un-rounded copy of o for the backward's delta (kept only when a backward can follow)
@@ -597,7 +597,7 @@ class _FlashAttention(torch.autograd.Function):
         do = do.contiguous()
         if do.dtype != qkv.dtype:
             do = convert(do, torch.empty(do.shape, dtype=qkv.dtype, device=dev))
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             dqkv = torch.empty_like(qkv)
             delta = torch.empty_like(lse)
             g = _lib.AttnBwd()
@@ -655,7 +655,7 @@ class _RelPosAttention(torch.autograd.Function):
         scale = hd ** -0.5
         dt, dev = qkv.dtype, qkv.device
         code = ops.dtype_code(dt)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             qu = torch.empty(B, T, D, dtype=dt, device=dev)
             qv = torch.empty(B, T, D, dtype=dt, device=dev)
             _lib_call("t4s_add_rowvec", _p(qkv), 3 * D, _p(u.detach().reshape(-1)), _p(qu), B * T, D, 1.0, code, _st())
@@ -689,7 +689,7 @@ class _RelPosAttention(torch.autograd.Function):
         do = do.contiguous()
         if do.dtype != dt:
             do = convert(do, torch.empty(do.shape, dtype=dt, device=dev))
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             qu = torch.empty(B, T, D, dtype=dt, device=dev)
             qv = torch.empty(B, T, D, dtype=dt, device=dev)
             _lib_call("t4s_add_rowvec", _p(qkv), 3 * D, _p(u.detach().reshape(-1)), _p(qu), B * T, D, 1.0, code, _st())
@@ -774,7 +774,7 @@ class _FlashRelPosAttention(torch.autograd.Function):
         code = ops.dtype_code(dt)
         lib = _lib.load()
         Nl = lib.t4s_attn_padded_len(T)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             qu = torch.empty(B, T, D, dtype=dt, device=dev)
             qv = torch.empty(B, T, D, dtype=dt, device=dev)
             _lib_call("t4s_add_rowvec", _p(qkv), 3 * D, _p(u.detach().reshape(-1)), _p(qu), B * T, D, 1.0, code, _st())
@@ -803,7 +803,7 @@ class _FlashRelPosAttention(torch.autograd.Function):
         do = do.contiguous()
         if do.dtype != dt:
             do = convert(do, torch.empty(do.shape, dtype=dt, device=dev))
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             dqkv = torch.empty_like(qkv)
             dqu = torch.empty(B, T, D, dtype=dt, device=dev)
             delta = torch.empty_like(lse)
@@ -893,7 +893,7 @@ class _PatchEmbed(torch.autograd.Function):
         dt, dev = act_dtype(), mel.device
         n_tok = 2 + F * Tp
         PP = P * P
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             A = torch.empty(nW * B * F * Tp, PP, dtype=dt, device=dev)
             if starts is None:
                 _lib_call("t4s_patch_im2col", _p(mel), ops.dtype_code(mel.dtype), _p(A), ops.dtype_code(dt), B, Hh, W, P, stride, F, Tp, _st())
@@ -929,7 +929,7 @@ class _PatchEmbed(torch.autograd.Function):
             dx = convert(dx, torch.empty(dx.shape, dtype=A.dtype, device=dev))
         ng = ctx.needs_input_grad
         PP = P * P
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             f32 = dict(dtype=torch.float32, device=dev)
             tmp = torch.empty(n_tok * D, **f32)
             shapes = (tshape if ng[3] else None, fshape if ng[4] else None, (D,) if ng[2] else None, cshape if ng[5] else None,
@@ -979,7 +979,7 @@ class _FpoolMean(torch.autograd.Function):
         y = y.contiguous()
         B, _, C = y.shape
         out = torch.empty(B, Tp, C, dtype=y.dtype, device=y.device)
-        with torch.cuda.device(y.device):
+        with _lib.device_guard(y.device):
             _lib_call("t4s_fpool_mean_fwd", _p(y), _p(out), ops.dtype_code(y.dtype), B, F, Tp, C, _st())
         ctx.cfg = (B, F, Tp, C)
         return out
@@ -989,7 +989,7 @@ class _FpoolMean(torch.autograd.Function):
         B, F, Tp, C = ctx.cfg
         dout = dout.contiguous()
         dy = torch.empty(B, F * Tp, C, dtype=dout.dtype, device=dout.device)
-        with torch.cuda.device(dout.device):
+        with _lib.device_guard(dout.device):
             _lib_call("t4s_fpool_mean_bwd", _p(dout), _p(dy), ops.dtype_code(dout.dtype), B, F, Tp, C, _st())
         return dy, None, None
 
@@ -1005,7 +1005,7 @@ class _PadInterp(torch.autograd.Function):
         x = x.contiguous()
         B, Tin, C = x.shape
         out = torch.empty(B, (Tin + pad) * ratio, C, dtype=x.dtype, device=x.device)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib_call("t4s_pad_interp_fwd", _p(x), _p(out), ops.dtype_code(x.dtype), B, Tin, ratio, C, pad, _st())
         ctx.cfg = (B, Tin, ratio, C, pad)
         return out
@@ -1015,7 +1015,7 @@ class _PadInterp(torch.autograd.Function):
         B, Tin, ratio, C, pad = ctx.cfg
         dout = dout.contiguous()
         dx = torch.empty(B, Tin, C, dtype=dout.dtype, device=dout.device)
-        with torch.cuda.device(dout.device):
+        with _lib.device_guard(dout.device):
             _lib_call("t4s_pad_interp_bwd", _p(dout), _p(dx), ops.dtype_code(dout.dtype), B, Tin, ratio, C, pad, _st())
         return dx, None, None
 
@@ -1048,7 +1048,7 @@ class _OverlapAdd(torch.autograd.Function):
         dt, dev = locals_[0].dtype, locals_[0].device
         segs, n = _segments(list(zip(locals_, spec)), B, C)
         out = torch.empty(B, frames, C, dtype=dt, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib_call("t4s_window_overlap_add_fwd", segs, n, _p(out), ops.dtype_code(dt), B, frames, C, _st())
         ctx.cfg = (frames, B, spec, [t.shape for t in locals_], dt)
         return out
@@ -1063,7 +1063,7 @@ class _OverlapAdd(torch.autograd.Function):
         C = dout.shape[-1]
         grads = [torch.empty(sh, dtype=dt, device=dev) for sh in shapes]
         segs, n = _segments(list(zip(grads, spec)), B, C)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib_call("t4s_window_overlap_add_bwd", _p(dout), segs, n, ops.dtype_code(dt), B, frames, C, _st())
         return (None, None, None) + tuple(grads)
 
@@ -1084,7 +1084,7 @@ class _Lerp(torch.autograd.Function):
             b = convert(b, torch.empty(b.shape, dtype=a.dtype, device=a.device))
         C = a.shape[-1]
         out = torch.empty_like(a)
-        with torch.cuda.device(a.device):
+        with _lib.device_guard(a.device):
             _lib_call("t4s_add2", _p(a), C, _p(b), C, _p(out), C, a.numel() // C, C, 1.0 - w, w, ops.dtype_code(a.dtype), _st())
         ctx.w = w
         return out
@@ -1095,7 +1095,7 @@ class _Lerp(torch.autograd.Function):
         C = dout.shape[-1]
         code = ops.dtype_code(dout.dtype)
         da = db = None
-        with torch.cuda.device(dout.device):
+        with _lib.device_guard(dout.device):
             if ctx.needs_input_grad[0]:
                 da = torch.empty_like(dout)
                 _lib_call("t4s_add_rowvec", _p(dout), C, ctypes.c_void_p(0), _p(da), dout.numel() // C, C, 1.0 - ctx.w, code, _st())
@@ -1122,7 +1122,7 @@ class _MaskRows(torch.autograd.Function):
         rows = x.numel() // C
         tok = token.detach().reshape(-1).float().contiguous()
         out = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib_call("t4s_mask_rows_fwd", _p(x), _p(tok), _p(kind), _p(src), _p(out), rows, C, ops.dtype_code(x.dtype), _st())
         ctx.save_for_backward(kind, src)
         ctx.cfg = (rows, C, token.shape, x.dtype)
@@ -1138,7 +1138,7 @@ class _MaskRows(torch.autograd.Function):
             dout = convert(dout, torch.empty(dout.shape, dtype=dt, device=dev))
         lib = _lib.load()
         copy_rows = torch.nonzero(kind == 2).reshape(-1)  # index bookkeeping (ascending); the arithmetic is in the kernel
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             dx = torch.empty_like(dout) if ctx.needs_input_grad[0] else None
             dtok = torch.empty(C, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
             nbytes = lib.t4s_mask_rows_bwd_workspace(rows, C)
@@ -1178,7 +1178,7 @@ class _Im2col3x3(torch.autograd.Function):
         Kp = _pad8(9 * C)
         dt = act_dtype()
         col = torch.empty(B * H * W, Kp, dtype=dt, device=x.device)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib_call("t4s_im2col3x3", _p(x), ops.dtype_code(x.dtype), sb, sh, sw, _p(col), ops.dtype_code(dt), B, H, W, C, Kp, _st())
         ctx.cfg = (B, H, W, C, Kp, mel_layout, x.dtype)
         return col
@@ -1190,7 +1190,7 @@ class _Im2col3x3(torch.autograd.Function):
             return None, None
         dcol = dcol.contiguous()
         din = torch.empty(B, H, W, C, dtype=dcol.dtype, device=dcol.device)
-        with torch.cuda.device(dcol.device):
+        with _lib.device_guard(dcol.device):
             _lib_call("t4s_col2im3x3", _p(dcol), _p(din), ops.dtype_code(dcol.dtype), B, H, W, C, Kp, _st())
         return (din if din.dtype == xdt else cast(din, xdt)), None
 
@@ -1221,7 +1221,7 @@ class _BatchNorm(torch.autograd.Function):
         y = torch.empty_like(x)
         mean = torch.empty(C, dtype=torch.float32, device=dev)
         rstd = torch.empty(C, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             nbytes = lib.t4s_chan_stats_workspace(rows, C)
             ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
             _lib_call("t4s_batchnorm_fwd", _p(x), _p(y), ops.dtype_code(x.dtype), rows, C, _p(gamma.detach()), _p(beta.detach()), _p(running_mean),
@@ -1243,7 +1243,7 @@ class _BatchNorm(torch.autograd.Function):
         dx = torch.empty_like(x)
         dg = torch.empty(C, dtype=torch.float32, device=dev)
         db = torch.empty(C, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             nbytes = lib.t4s_chan_stats_workspace(rows, C)
             ws = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=dev)
             _lib_call("t4s_batchnorm_bwd", _p(dy), _p(x), ops.dtype_code(x.dtype), rows, C, _p(gamma.detach()), _p(mean), _p(rstd),
@@ -1262,7 +1262,7 @@ class _Gate(torch.autograd.Function):
         _lib.ensure_device(y)
         y, lin = y.contiguous(), lin.contiguous()
         out = torch.empty_like(y)
-        with torch.cuda.device(y.device):
+        with _lib.device_guard(y.device):
             _lib_call("t4s_gate_fwd", _p(y), _p(lin), _p(out), y.numel(), p, seed, ops.dtype_code(y.dtype), _st())
         ctx.save_for_backward(y, lin)
         ctx.cfg = (p, seed)
@@ -1276,7 +1276,7 @@ class _Gate(torch.autograd.Function):
         if dout.dtype != y.dtype:
             dout = convert(dout, torch.empty(dout.shape, dtype=y.dtype, device=y.device))
         dy, dlin = torch.empty_like(y), torch.empty_like(y)
-        with torch.cuda.device(y.device):
+        with _lib.device_guard(y.device):
             _lib_call("t4s_gate_bwd", _p(dout), _p(y), _p(lin), _p(dy), _p(dlin), y.numel(), p, seed, ops.dtype_code(y.dtype), _st())
         return dy, dlin, None, None
 
@@ -1302,7 +1302,7 @@ class _AvgPool(torch.autograd.Function):
         x = x.contiguous()
         B, H, W, C = x.shape
         out = torch.empty(B, H // ph, W // pw, C, dtype=x.dtype, device=x.device)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib_call("t4s_avgpool_fwd", _p(x), _p(out), ops.dtype_code(x.dtype), B, H, W, C, ph, pw, _st())
         ctx.cfg = (B, H, W, C, ph, pw)
         return out
@@ -1312,7 +1312,7 @@ class _AvgPool(torch.autograd.Function):
         B, H, W, C, ph, pw = ctx.cfg
         dout = dout.contiguous()
         dx = torch.empty(B, H, W, C, dtype=dout.dtype, device=dout.device)
-        with torch.cuda.device(dout.device):
+        with _lib.device_guard(dout.device):
             _lib_call("t4s_avgpool_bwd", _p(dout), _p(dx), ops.dtype_code(dout.dtype), B, H, W, C, ph, pw, _st())
         return dx, None, None
 
@@ -1333,7 +1333,7 @@ class _ScaleAdd(torch.autograd.Function):
             b = convert(b, torch.empty(b.shape, dtype=a.dtype, device=a.device))
         w32 = w.detach().reshape(-1).float().contiguous()
         out = torch.empty_like(a)
-        with torch.cuda.device(a.device):
+        with _lib.device_guard(a.device):
             _lib_call("t4s_scale_add_fwd", _p(a), _p(b), _p(w32), _p(out), a.numel(), ops.dtype_code(a.dtype), _st())
         ctx.save_for_backward(b, w32)
         ctx.wshape = w.shape
@@ -1349,7 +1349,7 @@ class _ScaleAdd(torch.autograd.Function):
         db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
         dw = torch.empty(1, dtype=torch.float32, device=dev)
         ws = torch.empty(256, dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             _lib_call("t4s_scale_add_bwd", _p(dout), _p(b), _p(w32), _p(db), _p(dw), _p(ws), b.numel(), ops.dtype_code(b.dtype), _st())
         return (dout if ctx.needs_input_grad[0] else None), db, (dw.reshape(ctx.wshape) if ctx.needs_input_grad[2] else None)
 
@@ -1368,7 +1368,7 @@ class _L2Norm(torch.autograd.Function):
         rows = x.numel() // C
         y = torch.empty_like(x)
         inv = torch.empty(rows, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib_call("t4s_l2norm_fwd", _p(x), _p(y), _p(inv), rows, C, ops.dtype_code(x.dtype), _st())
         ctx.save_for_backward(y, inv)
         return y
@@ -1381,7 +1381,7 @@ class _L2Norm(torch.autograd.Function):
             dy = convert(dy, torch.empty(dy.shape, dtype=y.dtype, device=y.device))
         dx = torch.empty_like(y)
         C = y.shape[-1]
-        with torch.cuda.device(y.device):
+        with _lib.device_guard(y.device):
             _lib_call("t4s_l2norm_bwd", _p(dy), _p(y), _p(inv), _p(dx), y.numel() // C, C, ops.dtype_code(y.dtype), _st())
         return dx
 
@@ -1397,7 +1397,7 @@ class _ProtoAct(torch.autograd.Function):
         _lib.ensure_device(s)
         s = s.contiguous().float()
         p = torch.empty_like(s)
-        with torch.cuda.device(s.device):
+        with _lib.device_guard(s.device):
             _lib_call("t4s_proto_act_fwd", _p(s), _p(p), s.numel(), slope, temperature, _st())
         ctx.save_for_backward(s, p)
         ctx.cfg = (slope, temperature)
@@ -1409,7 +1409,7 @@ class _ProtoAct(torch.autograd.Function):
         slope, temperature = ctx.cfg
         dp = dp.contiguous().float()
         ds = torch.empty_like(s)
-        with torch.cuda.device(s.device):
+        with _lib.device_guard(s.device):
             _lib_call("t4s_proto_act_bwd", _p(s), _p(p), _p(dp), _p(ds), s.numel(), slope, temperature, _st())
         return ds, None, None
 
@@ -1449,7 +1449,7 @@ class _LoraLinear(torch.autograd.Function):
             x2 = x2.contiguous()
         M, N, r = x2.shape[0], w.shape[0], A.shape[0]
         dt, dev = x.dtype, x.device
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             Aq, Bq = to_plain(A, dt), to_plain(B, dt)
             weff = torch.empty(N, K, dtype=dt, device=dev)
             wq = cast_weight(w)
@@ -1475,7 +1475,7 @@ class _LoraLinear(torch.autograd.Function):
         if dy2.stride(-1) != 1:
             dy2 = dy2.contiguous()
         ng = ctx.needs_input_grad
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             if dy2.dtype != dt:
                 dy2 = convert(dy2, torch.empty(M, N, dtype=dt, device=dev))
             if act == ops.ACT_GELU:
@@ -1539,7 +1539,7 @@ class _Dropout(torch.autograd.Function):
         _lib.ensure_device(x)
         x = x.contiguous()
         out = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib_call("t4s_dropout", _p(x), _p(out), x.numel(), p, seed, ops.dtype_code(x.dtype), _st())
         ctx.cfg = (p, seed)
         return out
@@ -1549,7 +1549,7 @@ class _Dropout(torch.autograd.Function):
         p, seed = ctx.cfg
         dout = dout.contiguous()
         dx = torch.empty_like(dout)
-        with torch.cuda.device(dout.device):
+        with _lib.device_guard(dout.device):
             _lib_call("t4s_dropout", _p(dout), _p(dx), dout.numel(), p, seed, ops.dtype_code(dout.dtype), _st())
         return dx, None, None
 
@@ -1568,7 +1568,7 @@ class _Add(torch.autograd.Function):
         a, b = a.contiguous(), b.contiguous()
         C = a.shape[-1]
         out = torch.empty_like(a)
-        with torch.cuda.device(a.device):
+        with _lib.device_guard(a.device):
             _lib_call("t4s_add2", _p(a), C, _p(b), C, _p(out), C, a.numel() // C, C, 1.0, 1.0, ops.dtype_code(a.dtype), _st())
         return out
 
@@ -1596,7 +1596,7 @@ class _CrossAttention(torch.autograd.Function):
         scale = hd ** -0.5
         dt, dev = q.dtype, q.device
         code = ops.dtype_code(dt)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             P = torch.empty(B, H, Nq, Np, dtype=dt, device=dev)
             mm(Op(q, Nq, D, 0, nb1=H, stride1=hd, nb2=B, stride2=Nq * D), Op(kv, Nk, 2 * D, 0, nb1=H, stride1=hd, nb2=B, stride2=Nk * 2 * D),
                Out(P, Np, 0, Nq * Np, H * Nq * Np), Nq, Nk, hd, nb1=H, nb2=B, alpha=scale)
@@ -1630,7 +1630,7 @@ class _CrossAttention(torch.autograd.Function):
             do = convert(do, torch.empty(do.shape, dtype=dt, device=dev))
         if Pd is None:
             Pd = P
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             dq = torch.empty_like(q)
             dkv = torch.empty_like(kv)
             dP = torch.empty(B, H, Nq, Np, dtype=dt, device=dev)
@@ -1674,7 +1674,7 @@ class _QueryPool(torch.autograd.Function):
         strong = torch.empty(B, K, T, dtype=torch.float32, device=score.device)
         weak = torch.empty(B, K, dtype=torch.float32, device=score.device)
         pm = pad_mask.to(torch.uint8).contiguous() if pad_mask is not None else None
-        with torch.cuda.device(score.device):
+        with _lib.device_guard(score.device):
             _lib_call("t4s_query_pool_fwd", _p(score), _p(at_out), _p(pm), float(temp), _p(strong), _p(weak), B, T, K, _st())
         ctx.save_for_backward(score, at_out, strong, pm)
         ctx.temp = float(temp)
@@ -1688,7 +1688,7 @@ class _QueryPool(torch.autograd.Function):
         dat = torch.empty_like(at_out)
         ds = dstrong.contiguous().float() if dstrong is not None else None
         dw = dweak.contiguous().float() if dweak is not None else None
-        with torch.cuda.device(score.device):
+        with _lib.device_guard(score.device):
             _lib_call("t4s_query_pool_bwd", _p(score), _p(at_out), _p(strong), _p(ds), _p(dw), _p(pm), ctx.temp, _p(dscore), _p(dat), B, T, K, _st())
         return dscore, dat, None, None
 
@@ -1710,7 +1710,7 @@ class _QueryFrameScore(torch.autograd.Function):
         B, T, C = x.shape
         K = emb.shape[1]
         out = torch.empty(B, T, K, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             mm(Op(x, T, C, 0, nb1=B, stride1=T * C), Op(emb, K, C, 0, nb1=B, stride1=K * C), Out(out, K, 0, T * K), T, K, C, nb1=B)
         ctx.save_for_backward(x, emb)
         return out
@@ -1722,7 +1722,7 @@ class _QueryFrameScore(torch.autograd.Function):
         K = emb.shape[1]
         dt, dev = x.dtype, x.device
         Kp = _pad8(K)
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             # operand copy of the gradient in the activation dtype with a 16-byte row pitch (K = 407 is not a multiple of 8)
             d2 = torch.zeros(B, T, Kp, dtype=dt, device=dev)
             d32 = dout.contiguous().float()
@@ -1754,7 +1754,7 @@ class _SedPool(torch.autograd.Function):
         strong = torch.empty(B, K, T, dtype=torch.float32, device=logits.device)
         weak = torch.empty(B, K, dtype=torch.float32, device=logits.device)
         pm = pad_mask.to(torch.uint8).contiguous() if pad_mask is not None else None
-        with torch.cuda.device(logits.device):
+        with _lib.device_guard(logits.device):
             _lib_call("t4s_sed_pool_fwd", _p(logits), _p(pm), float(temp), _p(strong), _p(weak), B, T, K, _st())
         ctx.save_for_backward(strong, pm)
         ctx.temp = float(temp)
@@ -1767,7 +1767,7 @@ class _SedPool(torch.autograd.Function):
         dl = torch.empty(B, T, K, dtype=torch.float32, device=strong.device)
         ds = dstrong.contiguous().float() if dstrong is not None else None
         dw = dweak.contiguous().float() if dweak is not None else None
-        with torch.cuda.device(strong.device):
+        with _lib.device_guard(strong.device):
             _lib_call("t4s_sed_pool_bwd", _p(strong), _p(ds), _p(dw), _p(pm), ctx.temp, _p(dl), B, T, K, _st())
         return dl, None, None
 
@@ -1783,7 +1783,7 @@ class _Sigmoid(torch.autograd.Function):
         _lib.ensure_device(x)
         x = x.contiguous().float()
         y = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib_call("t4s_sigmoid_fwd", _p(x), _p(y), x.numel(), _st())
         ctx.save_for_backward(y)
         return y
@@ -1793,7 +1793,7 @@ class _Sigmoid(torch.autograd.Function):
         (y,) = ctx.saved_tensors
         dy = dy.contiguous().float()
         dx = torch.empty_like(y)
-        with torch.cuda.device(y.device):
+        with _lib.device_guard(y.device):
             _lib_call("t4s_sigmoid_bwd", _p(y), _p(dy), _p(dx), y.numel(), _st())
         return dx
 
@@ -1810,7 +1810,7 @@ class _Bce(torch.autograd.Function):
         y = y.contiguous().float()
         ws = torch.empty(512, dtype=torch.float32, device=p.device)
         out = torch.empty(2, dtype=torch.float32, device=p.device)
-        with torch.cuda.device(p.device):
+        with _lib.device_guard(p.device):
             _lib_call("t4s_bce_fwd", _p(p), _p(y), p.numel(), _p(ws), _p(out), _st())
         ctx.save_for_backward(p, y)
         return out[0]
@@ -1820,7 +1820,7 @@ class _Bce(torch.autograd.Function):
         p, y = ctx.saved_tensors
         dp = torch.empty_like(p)
         g = g.reshape(1).contiguous().float()
-        with torch.cuda.device(p.device):
+        with _lib.device_guard(p.device):
             _lib_call("t4s_bce_bwd", _p(p), _p(y), _p(g), p.numel(), _p(dp), _st())
         return dp, None
 
@@ -1843,7 +1843,7 @@ class _Mse(torch.autograd.Function):
         m = row_mask.reshape(-1).to(torch.uint8).contiguous() if row_mask is not None else None
         ws = torch.empty(512, dtype=torch.float32, device=a.device)
         out = torch.empty(2, dtype=torch.float32, device=a.device)
-        with torch.cuda.device(a.device):
+        with _lib.device_guard(a.device):
             _lib_call("t4s_mse_fwd", _p(a), _p(b), _p(m), rows, C, ops.dtype_code(a.dtype), _p(ws), _p(out), _st())
         ctx.save_for_backward(a, b, m, out)
         return out[0]
@@ -1856,7 +1856,7 @@ class _Mse(torch.autograd.Function):
         da = torch.empty_like(a) if ctx.needs_input_grad[0] else None
         db = torch.empty_like(b) if ctx.needs_input_grad[1] else None
         g = g.reshape(1).contiguous().float()
-        with torch.cuda.device(a.device):
+        with _lib.device_guard(a.device):
             _lib_call("t4s_mse_bwd", _p(a), _p(b), _p(m), rows, C, ops.dtype_code(a.dtype), _p(g), _p(out), _p(da), _p(db), _st())
         return da, db, None
 
@@ -1881,7 +1881,7 @@ class _AttnPool(torch.autograd.Function):
         ctxv = torch.empty(items, C, dtype=kv.dtype, device=kv.device)
         probs = torch.empty(items, H, K, dtype=torch.float32, device=kv.device)
         kp = ctypes.c_void_p(kv.data_ptr() + skip * C2 * kv.element_size())
-        with torch.cuda.device(kv.device):
+        with _lib.device_guard(kv.device):
             _lib_call("t4s_attnpool_fwd", kp, _p(q), _p(ctxv), _p(probs), items, K, C, H, K_all * C2, ops.dtype_code(kv.dtype), _st())
         ctx.save_for_backward(kv, q, probs)
         ctx.cfg = (H, skip)
@@ -1899,7 +1899,7 @@ class _AttnPool(torch.autograd.Function):
         dkv = torch.zeros_like(kv) if skip else torch.empty_like(kv)
         dq_part = torch.empty(items, C, dtype=torch.float32, device=kv.device)
         off = skip * C2 * kv.element_size()
-        with torch.cuda.device(kv.device):
+        with _lib.device_guard(kv.device):
             _lib_call("t4s_attnpool_bwd", ctypes.c_void_p(kv.data_ptr() + off), _p(q), _p(probs), _p(dctx),
                       ctypes.c_void_p(dkv.data_ptr() + off), _p(dq_part), items, K, C, H, K_all * C2, ops.dtype_code(kv.dtype), _st())
             dq = colsum(dq_part) if ctx.needs_input_grad[1] else None
@@ -1934,7 +1934,7 @@ class _ScaledLinear(torch.autograd.Function):
         wq = cast_weight(w.contiguous())
         bs = torch.empty(N, dtype=torch.float32, device=x.device)
         y = torch.empty(M, N, dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with _lib.device_guard(x.device):
             _lib_call("t4s_add_rowvec", _p(b.detach().contiguous()), N, ctypes.c_void_p(0), _p(bs), 1, N, float(s), ops.F32, _st())
             mm(Op(x, M, K), Op(wq, N, K), Out(y, N), M, N, K, bias=bs, alpha=float(s))
         ctx.save_for_backward(x, w)
@@ -1947,7 +1947,7 @@ class _ScaledLinear(torch.autograd.Function):
         M, K = x.shape
         N = w.shape[0]
         dev = x.device
-        with torch.cuda.device(dev):
+        with _lib.device_guard(dev):
             dys = torch.empty(M, N, dtype=x.dtype, device=dev)
             dy32 = dy.contiguous().float()
             tmp = torch.empty(M, N, dtype=torch.float32, device=dev)

@@ -117,7 +117,7 @@ def gemm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, bias=None, aux: Out = None
     if buf is None:
         buf = _tls.gemm_buf = (ctypes.c_char * _GEMM_PACK.size)()
     _GEMM_PACK.pack_into(buf, 0, *_gemm_args(A, B, C, M, N, K, nb1, nb2, bias, aux, residual, alpha, act, split_k, c_split_stride, colsum, band))
-    with torch.cuda.device(A.t.device):
+    with _lib.device_guard(A.t.device):
         if _lib.profiler is not None:
             key = (M, N, K, nb1 * nb2, "T" if A.mn_major else "N", "T" if B.mn_major else "N", split_k)
             rc = _lib.profiler.timed("t4s_gemm", key, lambda: _lib.load().t4s_gemm(buf, _lib.stream_ptr()))
@@ -128,7 +128,7 @@ def gemm(A: Op, B: Op, C: Out, M, N, K, nb1=1, nb2=1, bias=None, aux: Out = None
 
 def reduce_splits(ws, splits, n, out, accumulate=False):
     _lib.ensure_device(ws)
-    with torch.cuda.device(ws.device):
+    with _lib.device_guard(ws.device):
         _lib.check(_lib.load().t4s_reduce_splits(_lib.ptr(ws), splits, n, _lib.ptr(out), int(accumulate), _lib.stream_ptr()),
                    "t4s_reduce_splits")
 
