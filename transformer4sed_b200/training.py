@@ -154,6 +154,8 @@ class ParamArena:
                          torch.empty(len(layout), 3, dtype=torch.int64, device=dev), torch.cuda.Event()) for _ in range(2)]
         self._table_used = [False, False]
         self._table_turn = 0
+        self._layout_off = [off for _, off in layout]
+        self._layout_numel = [p.numel() for p, _ in layout]
         self._agreed = self._agreed_local = None
         self.buckets = None
         if overlap is None:
@@ -199,14 +201,19 @@ class ParamArena:
         t, t_dev, copied = self._tables[turn]
         if self._table_used[turn]:
             copied.synchronize()            # the upload that last read this pinned table has finished
-        for i, (p, off) in enumerate(self.layout):
+        # one vectorised store per column through the numpy view of the pinned table (an element-wise `t[i, j] = ...` costs a
+        # torch dispatch each: 3 ms of host time per step for the ~700 tensors of the PMAM / DASM models)
+        ptrs = []
+        for p, _ in self.layout:
             g = p.grad
             if g is not None and (g.dtype != torch.float32 or not g.is_contiguous()):
                 g = g.float().contiguous()
                 p.grad = g
-            t[i, 0] = g.data_ptr() if g is not None else 0
-            t[i, 1] = off
-            t[i, 2] = p.numel()
+            ptrs.append(g.data_ptr() if g is not None else 0)
+        tn = t.numpy()
+        tn[:, 0] = ptrs
+        tn[:, 1] = self._layout_off
+        tn[:, 2] = self._layout_numel
         with torch.cuda.device(self.device):
             t_dev.copy_(t, non_blocking=True)
             copied.record()
